@@ -1,0 +1,172 @@
+/*
+ * libb200vit — C ABI of the B200-native (sm_100a) ViT-B/16 / ViT-L/16 data2vec + uncertainty hot path.
+ *
+ * Every entry point replaces a group of ATen library calls that the reference
+ * (fx-erick/uncertainty-vit, pure PyTorch) issues on its hot path; the reference call site is cited
+ * beside each declaration as file:line into the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - the CALLER owns all memory (including workspaces); kernels never allocate or synchronise;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, <0 for a bad argument, >0 = cudaError_t of a failed launch;
+ *     b200vit_last_error() returns a thread-local message for the last non-zero return;
+ *   - bf16 tensors are raw uint16 storage (__nv_bfloat16), row-major, leading dimensions in ELEMENTS.
+ */
+#ifndef B200VIT_H_
+#define B200VIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VIT_ABI_VERSION 1
+
+const char* b200vit_last_error(void);
+int b200vit_abi_version(void);
+/* number of SMs of the current device (148 on B200); <0 when no CUDA device is usable */
+int b200vit_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM (tcgen05.mma, TMEM accumulators, TMA-fed, persistent, warp-specialised).
+ *   D[M,N] = A[M,K] * B[N,K]^T  with bf16 operands and fp32 accumulation.
+ * Replaces F.linear / nn.Linear in Attention.forward (modeling_finetune.py:149,186),
+ * Mlp.forward (modeling_finetune.py:76-81), lm_head (modeling_cyclical.py:219-225),
+ * PatchEmbed conv-as-GEMM (modeling_finetune.py:324), head (modeling_finetune.py:522)
+ * and the autograd backward of each (dgrad: a/b *_mn_major; wgrad: both mn-major + split_k).
+ * ---------------------------------------------------------------------------------------------- */
+enum b200vit_epilogue {
+  B200VIT_EPI_BF16 = 0,       /* out_bf16 = (acc + bias[n]) * colscale[n]           (bias/colscale optional) */
+  B200VIT_EPI_GELU = 1,       /* t = acc + bias; out2_bf16 = t (optional); out_bf16 = gelu_erf(t)            */
+  B200VIT_EPI_RESIDUAL = 2,   /* t = acc + bias; out2_bf16 = t (optional);
+                                 out_f32 = residual + rowscale[m / rows_per_scale] * colscale[n] * t         */
+  B200VIT_EPI_DGELU = 3,      /* out_bf16 = acc * gelu_erf'(aux[m,n])                                        */
+  B200VIT_EPI_F32 = 4,        /* out_f32 = acc + bias                                                        */
+  B200VIT_EPI_F32_ATOMIC = 5, /* out_f32 += alpha * acc  (red.global.add.v4; required with split_k)          */
+  B200VIT_EPI_ELU1 = 6        /* out_bf16 = elu(acc + bias) + 1   (cov-stream QKV, modeling_finetune_dist.py:127)    */
+};
+
+typedef struct b200vit_gemm_desc {
+  int32_t M, N, K;
+  const void* A;       /* a_mn_major == 0: [M, K] row-major (lda >= K);  1: stored as [K, M] row-major (lda >= M) */
+  int64_t lda;
+  int32_t a_mn_major;
+  const void* B;       /* b_mn_major == 0: [N, K] row-major (nn.Linear weight);  1: stored as [K, N] row-major    */
+  int64_t ldb;
+  int32_t b_mn_major;
+  int32_t epilogue;    /* enum b200vit_epilogue */
+  const float* bias;   /* [N] or NULL */
+  const float* colscale; /* [N] or NULL */
+  const float* rowscale; /* [ceil(M / rows_per_scale)] or NULL (drop-path keep/keep_prob per sample) */
+  int32_t rows_per_scale;
+  const float* residual; /* fp32 [M, ld_residual] */
+  int64_t ld_residual;
+  const void* aux;     /* bf16 [M, ld_aux] */
+  int64_t ld_aux;
+  float* out_f32;
+  int64_t ld_f32;
+  void* out_bf16;
+  int64_t ld_bf16;
+  void* out2_bf16;
+  int64_t ld2_bf16;
+  float alpha;
+  int32_t split_k;     /* F32_ATOMIC only: 0 = pick for wave efficiency, 1 = none, >1 = explicit number of K splits */
+  int32_t max_ctas;    /* 0: one CTA per SM */
+} b200vit_gemm_desc;
+
+int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (flash-style, one CTA per (batch, head), mma.sync bf16 tiles, online softmax, Philox dropout).
+ * Replaces Attention.forward lines 155-185 (modeling_finetune.py): q*scale, q k^T, + rel_pos_bias, softmax,
+ * attn_drop, attn @ v, transpose/reshape — and its autograd backward.
+ *   qkv   : bf16 [B, N, 3, H, 64] (the QKV GEMM output, no permute copy)
+ *   bias  : fp32 [H, N, ld_bias] or NULL      out : bf16 [B, N, H*64]      lse : fp32 [B, H, N]
+ *   keep_bits : packed dropout keep mask [B, H, N, 32] bytes (bit j%8 of byte j/8), written by fwd, read by bwd
+ *   keep_in   : optional injected keep mask uint8 [B, H, N, N]; NULL = Philox4x32-10 keyed on (seed, stream_id)
+ * N <= 208, head_dim == 64.
+ * ---------------------------------------------------------------------------------------------- */
+int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
+                     float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
+                     uint8_t* keep_bits, void* stream);
+/* dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, += ) is the gradient of
+ * relative_position_bias_table [num_bins, H]; rel_index int32 [N, N] is the reference's relative_position_index
+ * (modeling_finetune.py:339-353). */
+int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias, int64_t ld_bias,
+                     const uint8_t* keep_bits, const int32_t* rel_index, float* dtable, int32_t num_bins, int32_t B, int32_t H,
+                     int32_t N, int32_t head_dim, float scale, float p_drop, void* dqkv, void* stream);
+/* The Philox keep mask of b200vit_attn_fwd as uint8 [BH, N, N] (parity tests inject it into the CPU oracle). */
+int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound). C must be a multiple of 128 (<= 1024) for the LayerNorm kernels.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm (norm1/norm2/norm/fc_norm, modeling_finetune.py:270,280,420-421). Source row r is x[row_index[r]] when
+ * row_index != NULL (final-norm + masked-row gather of modeling_cyclical.py:219-224). Outputs are compact [rows, C]. */
+int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, const float* gamma, const float* beta, float eps,
+                          int32_t rows, int32_t C, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+/* dx[row_index[r]] += LN-backward(dy[r]) ; dgamma += ; dbeta += */
+int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
+                          const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma,
+                          float* dbeta, void* stream);
+/* backward of x + drop_path(gamma * t) (Block.forward, modeling_finetune.py:296-298):
+ * dt = rowscale[r / rows_per_scale] * gamma * dx (bf16); dgamma += sum rowscale * t * dx; dbias += sum dt */
+int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const void* t_bf16, const float* rowscale, int32_t rows_per_scale,
+                               const float* gamma, int32_t rows, int32_t C, void* dt_bf16, float* dgamma, float* dbias, void* stream);
+int b200vit_colsum_bf16(const void* x, int64_t ldx, int32_t rows, int32_t C, float* out_accum, void* stream);
+int b200vit_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* PatchEmbed (modeling_finetune.py:319-325) as im2col + GEMM: [B,Cin,H,W] fp32 -> [B*(H/P)*(W/P), Cin*P*P] bf16 */
+int b200vit_im2col_patches(const float* img, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t P, void* out_bf16, void* stream);
+/* cls concat + mask-token blend (+ pos_embed) (modeling_cyclical.py:175-194); mask uint8 [B*np] or NULL */
+int b200vit_assemble_tokens(const float* pe, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos_embed,
+                            int32_t B, int32_t np, int32_t C, float* x, void* stream);
+int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask, int32_t B, int32_t np, int32_t C, void* dpe_bf16, float* dcls,
+                                float* dmask_token, float* dpos_embed, void* stream);
+/* RelativePositionBias.forward (modeling_finetune.py:359-364): out[h,i,j] = table[index[i,j], h] */
+int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, float* out, void* stream);
+/* x[:, 1:].mean(1) (modeling_finetune.py:512-514) */
+int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int32_t C, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * data2vec step kernels
+ * ---------------------------------------------------------------------------------------------- */
+/* Target builder + loss (engine_for_cyclical.py:90-150), masked rows only: per row r (source row row_index[r] of each
+ * [*, ld_layer] fp32 teacher layer): t = LN?( mean_l LN?(layer_l[row]) ), eps 1e-5 no affine; loss = smooth_l1(y, t, beta)
+ * (or MSE) mean over R*C; dy = dloss/dy * grad_scale. layers_host is a HOST array of device pointers.
+ * Any of targets / dy_bf16 / dy_f32 / y may be NULL. row_loss: workspace of R floats; loss_out: device scalar. */
+int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
+                            const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
+                            float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
+                            void* stream);
+/* EMA teacher update e = d*e + (1-d)*m (engine_for_cyclical.py:182-185, timm ModelEmaV2._update) + bf16 shadow */
+int b200vit_ema_update(float* ema, const float* model, int64_t n, float decay, void* ema_bf16, void* stream);
+/* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
+int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
+/* clip + torch.optim.AdamW + bf16 weight shadow + EMA over flat arenas (utils.py:364-390, optim_factory.py:58-97).
+ * hp_lr_wd: device float2 {lr, weight_decay} per 1024-element chunk. grad_div: loss-scale divisor (unscale_). */
+int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
+                       float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
+                       float ema_decay, void* ema_bf16, void* stream);
+/* WassersteinLoss.forward + backward (distloss.py:13-30,73-79). work: 2R+8 floats. d_* are accumulated (+=). */
+int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
+                             int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,
+                             float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MC-sample uncertainty reduction (uncertainty_evaluations.py:77-85,110-202,270-272)
+ *   logits fp32 [S, N, K]; labels int32 [N].
+ *   mean_logits [N,K]; row_stats [N, 8] = {conf, pred, correct@1, correct@5, nll, entropy(pbar), variance, mutual_info};
+ *   hist [n_bins, 3] = {count, sum conf, sum correct} (+=, zero it first);
+ * b200vit_mc_finalize: summary[8] = {acc1 %, acc5 %, ECE, ECE(reference indexing quirk), NLL, mean entropy, mean variance, mean MI}
+ * ---------------------------------------------------------------------------------------------- */
+int b200vit_mc_reduce(const float* logits, const int32_t* labels, int32_t S, int32_t N, int32_t K, int32_t n_bins, float* mean_logits,
+                      float* row_stats, float* hist, void* stream);
+int b200vit_mc_finalize(const float* row_stats, const float* hist, int32_t N, int32_t n_bins, float* summary, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VIT_H_ */

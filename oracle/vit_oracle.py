@@ -1,0 +1,590 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+A plain fp32 PyTorch-on-CPU restatement of the reference's hot path (fx-erick/uncertainty-vit), written
+functionally over a state-dict that uses the reference's parameter names, with every source of
+randomness (drop-path keeps, dropout masks) INJECTED so that the CUDA path can be compared on identical noise.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.
+
+Parity pin: tools/make_golden.py imports the real reference classes (through oracle/ref_shim.py, in the build
+container where /root/reference exists), loads the same seeded state-dict, injects the same masks, and stores the
+reference outputs under tests/golden/; tests/test_oracle_golden.py checks this restatement against them.
+
+Each function cites the reference file:line it follows.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------------------
+# architecture description
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class Arch:
+    img_size: int = 224
+    patch_size: int = 16
+    in_chans: int = 3
+    embed_dim: int = 768
+    depth: int = 12
+    num_heads: int = 12
+    mlp_ratio: float = 4.0
+    num_classes: int = 1000
+    ln_eps: float = 1e-6          # partial(nn.LayerNorm, eps=1e-6): modeling_cyclical.py:293, modeling_finetune.py:1227
+    dist: bool = False            # dual-stream (--stochastic) model
+    kind: str = "cyclical"        # "cyclical" (data2vec student/teacher) | "finetune"
+
+    @property
+    def grid(self) -> int:
+        return self.img_size // self.patch_size
+
+    @property
+    def num_patches(self) -> int:
+        return self.grid * self.grid
+
+    @property
+    def tokens(self) -> int:
+        return self.num_patches + 1
+
+    @property
+    def hidden(self) -> int:
+        return int(self.embed_dim * self.mlp_ratio)
+
+
+VIT_B = dict(embed_dim=768, depth=12, num_heads=12)
+VIT_L = dict(embed_dim=1024, depth=24, num_heads=16)
+TINY = dict(img_size=64, embed_dim=128, depth=2, num_heads=2, num_classes=10)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# relative position index  (modeling_finetune.py:339-353) — integer, bit-exact
+# --------------------------------------------------------------------------------------------------------------
+def relative_position_index(wh: int, ww: int) -> torch.Tensor:
+    nrd = (2 * wh - 1) * (2 * ww - 1) + 3
+    idx = torch.zeros((wh * ww + 1, wh * ww + 1), dtype=torch.int64)
+    ys, xs = np.meshgrid(np.arange(wh), np.arange(ww), indexing="ij")
+    ys = torch.from_numpy(ys.reshape(-1))
+    xs = torch.from_numpy(xs.reshape(-1))
+    dy = ys[:, None] - ys[None, :] + (wh - 1)
+    dx = xs[:, None] - xs[None, :] + (ww - 1)
+    idx[1:, 1:] = dy * (2 * ww - 1) + dx
+    idx[0, :] = nrd - 3
+    idx[:, 0] = nrd - 2
+    idx[0, 0] = nrd - 1
+    return idx
+
+
+def rel_pos_bias(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """RelativePositionBias.forward (modeling_finetune.py:359-364): table[732,H] -> [H,N,N]."""
+    n = index.shape[0]
+    return table[index.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# seeded "lively" state-dict used by the parity tests (NOT the training init: gamma=1e-4 would hide the blocks)
+# --------------------------------------------------------------------------------------------------------------
+def state_names(arch: Arch) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(name, shape, role) in the reference's state_dict order."""
+    C, Hd, nh = arch.embed_dim, arch.hidden, arch.num_heads
+    P = arch.patch_size
+    out: List[Tuple[str, Tuple[int, ...], str]] = []
+    add = lambda n, s, r: out.append((n, tuple(s), r))
+    add("cls_token", (1, 1, C), "token")
+    if arch.dist:
+        add("cov_cls_token", (1, 1, C), "token")
+    if arch.kind == "cyclical":
+        add("mask_token", (1, 1, C), "token")
+        if arch.dist:
+            add("cov_mask_token", (1, 1, C), "token")
+    add("patch_embed.proj.weight", (C, arch.in_chans, P, P), "weight")
+    add("patch_embed.proj.bias", (C,), "bias")
+    if arch.dist:
+        add("cov_patch_embed.proj.weight", (C, arch.in_chans, P, P), "weight")
+        add("cov_patch_embed.proj.bias", (C,), "bias")
+    nrd = (2 * arch.grid - 1) ** 2 + 3
+    add("rel_pos_bias.relative_position_bias_table", (nrd, nh), "table")
+    for i in range(arch.depth):
+        p = f"blocks.{i}."
+        add(p + "gamma_1", (C,), "gamma")
+        add(p + "gamma_2", (C,), "gamma")
+        add(p + "norm1.weight", (C,), "ln_w")
+        add(p + "norm1.bias", (C,), "bias")
+        add(p + "attn.q_bias", (C,), "bias")
+        add(p + "attn.v_bias", (C,), "bias")
+        if arch.dist:
+            add(p + "attn.cov_q_bias", (C,), "bias")
+            add(p + "attn.cov_v_bias", (C,), "bias")
+        add(p + "attn.qkv.weight", (3 * C, C), "weight")
+        if arch.dist:
+            add(p + "attn.cov_qkv.weight", (3 * C, C), "weight")   # allocated but unused (quirk A.2-1)
+        add(p + "attn.proj.weight", (C, C), "weight")
+        add(p + "attn.proj.bias", (C,), "bias")
+        if arch.dist:
+            add(p + "attn.cov_proj.weight", (C, C), "weight")
+            add(p + "attn.cov_proj.bias", (C,), "bias")
+        add(p + "norm2.weight", (C,), "ln_w")
+        add(p + "norm2.bias", (C,), "bias")
+        add(p + "mlp.fc1.weight", (Hd, C), "weight")
+        add(p + "mlp.fc1.bias", (Hd,), "bias")
+        add(p + "mlp.fc2.weight", (C, Hd), "weight")
+        add(p + "mlp.fc2.bias", (C,), "bias")
+    if arch.kind == "cyclical":
+        add("norm.weight", (C,), "ln_w")
+        add("norm.bias", (C,), "bias")
+        add("lm_head.weight", (C, C), "weight")
+        add("lm_head.bias", (C,), "bias")
+        if arch.dist:
+            add("cov_lm_head.weight", (C, C), "weight")
+            add("cov_lm_head.bias", (C,), "bias")
+    else:
+        add("fc_norm.weight", (C,), "ln_w")
+        add("fc_norm.bias", (C,), "bias")
+        add("head.weight", (arch.num_classes, C), "weight")
+        add("head.bias", (arch.num_classes,), "bias")
+    return out
+
+
+def make_state(arch: Arch, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic test weights (torch CPU generator): every branch carries signal."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, role in state_names(arch):
+        if role == "weight":
+            fan_in = int(np.prod(shape[1:]))
+            t = torch.randn(shape, generator=g) * (0.7 / math.sqrt(fan_in))
+        elif role == "bias":
+            t = torch.randn(shape, generator=g) * 0.05
+        elif role == "gamma":
+            t = 0.25 + 0.5 * torch.rand(shape, generator=g)
+        elif role == "ln_w":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif role == "table":
+            t = torch.randn(shape, generator=g) * 0.3
+        else:  # token
+            t = torch.randn(shape, generator=g) * 0.5
+        sd[name] = t.float()
+    sd["rel_pos_bias.relative_position_index"] = relative_position_index(arch.grid, arch.grid)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------------------------
+# injected randomness
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class Noise:
+    """Injected stochastic-depth keeps and attention-dropout masks.
+
+    drop_path_keep[l] : float tensor [n_draws, B] in {0,1}; n_draws = 2 (det Block, modeling_finetune.py:296-297)
+                        or 4 (dist Block, modeling_finetune_dist.py:51-55), in call order.
+    drop_path_prob[l] : p_l = linspace(0, dpr, L)[l]  (modeling_finetune.py:401)
+    attn_keep[l]      : float tensor [B,H,N,N] in {0,1} (nn.Dropout(attn_drop) mask, modeling_finetune.py:183)
+    attn_drop         : p of that dropout
+    """
+    drop_path_keep: Optional[List[torch.Tensor]] = None
+    drop_path_prob: Optional[List[float]] = None
+    attn_keep: Optional[List[torch.Tensor]] = None
+    attn_drop: float = 0.0
+
+
+def _dp(x: torch.Tensor, noise: Optional[Noise], layer: int, draw: int) -> torch.Tensor:
+    """timm drop_path (modeling_finetune.py:51-62): x / keep_prob * mask[b], per sample."""
+    if noise is None or noise.drop_path_keep is None:
+        return x
+    p = noise.drop_path_prob[layer]
+    if p == 0.0:
+        return x
+    keep = noise.drop_path_keep[layer][draw].to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
+    return x / (1.0 - p) * keep
+
+
+def _attn_dropout(attn: torch.Tensor, noise: Optional[Noise], layer: int) -> torch.Tensor:
+    if noise is None or noise.attn_keep is None or noise.attn_drop == 0.0:
+        return attn
+    return attn * noise.attn_keep[layer].to(attn.dtype) / (1.0 - noise.attn_drop)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# blocks
+# --------------------------------------------------------------------------------------------------------------
+def _ln(x, w, b, eps):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def mlp(sd, p, x):
+    """Mlp.forward (modeling_finetune.py:75-82): fc2(GELU_erf(fc1 x))."""
+    h = F.linear(x, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+    h = F.gelu(h)
+    return F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+
+
+def attention(sd, p, x, bias, nh, noise, layer):
+    """Attention.forward (modeling_finetune.py:145-188)."""
+    B, N, C = x.shape
+    qb = torch.cat((sd[p + "attn.q_bias"], torch.zeros_like(sd[p + "attn.v_bias"]), sd[p + "attn.v_bias"]))
+    qkv = F.linear(x, sd[p + "attn.qkv.weight"], qb).reshape(B, N, 3, nh, -1).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    q = q * (q.shape[-1] ** -0.5)
+    attn = q @ k.transpose(-2, -1)
+    if bias is not None:
+        attn = attn + bias
+    attn = attn.softmax(dim=-1)
+    attn = _attn_dropout(attn, noise, layer)
+    x = (attn @ v).transpose(1, 2).reshape(B, N, -1)
+    return F.linear(x, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+
+
+def block(sd, i, x, bias, arch: Arch, noise: Optional[Noise]):
+    """Block.forward (modeling_finetune.py:290-299) -> (x, fc_feature)."""
+    p = f"blocks.{i}."
+    a = attention(sd, p, _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"], arch.ln_eps), bias, arch.num_heads,
+                  noise, i)
+    x = x + _dp(sd[p + "gamma_1"] * a, noise, i, 0)
+    f = _dp(sd[p + "gamma_2"] * mlp(sd, p, _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], arch.ln_eps)),
+            noise, i, 1)
+    return x + f, f
+
+
+def wasserstein_distance_matmul(m1, c1, m2, c2):
+    """uncertainty_evaluations.py:276-294."""
+    m1, m2, c1, c2 = torch.sigmoid(m1), torch.sigmoid(m2), torch.sigmoid(c1), torch.sigmoid(c2)
+    ret = -2 * m1 @ m2.transpose(-1, -2) + (m1 ** 2).sum(-1, keepdim=True) + (m2 ** 2).sum(-1, keepdim=True).transpose(-1, -2)
+    u1 = torch.sqrt(torch.clamp(c1, min=1e-24))
+    u2 = torch.sqrt(torch.clamp(c2, min=1e-24))
+    cov = -2 * u1 @ u2.transpose(-1, -2) + c1.sum(-1, keepdim=True) + c2.sum(-1, keepdim=True).transpose(-1, -2)
+    return ret + cov
+
+
+def dist_attention(sd, p, x, cx, bias, nh, noise, layer):
+    """dist Attention.forward (modeling_finetune_dist.py:111-179)."""
+    B, N, C = x.shape
+    z = torch.zeros_like(sd[p + "attn.v_bias"])
+    qb = torch.cat((sd[p + "attn.q_bias"], z, sd[p + "attn.v_bias"]))
+    cqb = torch.cat((sd[p + "attn.cov_q_bias"], z, sd[p + "attn.cov_v_bias"]))
+    W = sd[p + "attn.qkv.weight"]                      # the cov stream re-uses the MEAN weight (:127)
+    qkv = F.linear(x, W, qb).reshape(B, N, 3, nh, -1).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    cqkv = (F.elu(F.linear(cx, W, cqb)) + 1).reshape(B, N, 3, nh, -1).permute(2, 0, 3, 1, 4)
+    cq, ck, cv = cqkv[0], cqkv[1], cqkv[2]
+    q = q * (q.shape[-1] ** -0.5)
+    attn = torch.sigmoid(-wasserstein_distance_matmul(q, cq, k, ck) + 1e-24)
+    attn = attn + bias
+    attn = attn.softmax(dim=-1)
+    attn = _attn_dropout(attn, noise, layer)
+    om = (attn @ v).transpose(1, 2).reshape(B, N, -1)
+    oc = ((attn ** 2) @ cv).transpose(1, 2).reshape(B, N, -1)
+    return (F.linear(om, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]),
+            F.linear(oc, sd[p + "attn.cov_proj.weight"], sd[p + "attn.cov_proj.bias"]))
+
+
+def dist_block(sd, i, xm, xc, bias, arch: Arch, noise: Optional[Noise]):
+    """dist Block.forward (modeling_finetune_dist.py:41-59); 4 independent drop-path draws in this order."""
+    p = f"blocks.{i}."
+    n1 = lambda t: _ln(t, sd[p + "norm1.weight"], sd[p + "norm1.bias"], arch.ln_eps)
+    n2 = lambda t: _ln(t, sd[p + "norm2.weight"], sd[p + "norm2.bias"], arch.ln_eps)
+    m, c = dist_attention(sd, p, n1(xm), n1(xc), bias, arch.num_heads, noise, i)
+    xm = xm + _dp(sd[p + "gamma_1"] * m, noise, i, 0)
+    fm = _dp(sd[p + "gamma_2"] * mlp(sd, p, n2(xm)), noise, i, 1)
+    xc = xc + _dp(sd[p + "gamma_1"] * c, noise, i, 2)
+    fc = _dp(sd[p + "gamma_2"] * mlp(sd, p, n2(xc)), noise, i, 3)
+    return xm + fm, xc + fc
+
+
+# --------------------------------------------------------------------------------------------------------------
+# model wrappers
+# --------------------------------------------------------------------------------------------------------------
+def patch_embed(sd, prefix, x, arch: Arch):
+    """PatchEmbed.forward (modeling_finetune.py:319-325)."""
+    y = F.conv2d(x, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"], stride=arch.patch_size)
+    return y.flatten(2).transpose(1, 2)
+
+
+def _stem(sd, x, mask, arch: Arch, cov: bool):
+    pre = "cov_" if cov else ""
+    t = patch_embed(sd, pre + "patch_embed.", x, arch)
+    B = t.shape[0]
+    if mask is not None:
+        w = mask.reshape(B, -1, 1).to(t.dtype)
+        t = t * (1 - w) + sd[pre + "mask_token"].expand(B, t.shape[1], -1) * w   # modeling_cyclical.py:179-182
+    return torch.cat((sd[pre + "cls_token"].expand(B, -1, -1), t), dim=1)
+
+
+def cyclical_forward(sd, arch: Arch, x, bool_masked_pos, return_all_tokens=False, layer_results=None,
+                     noise: Optional[Noise] = None):
+    """VisionTransformerForCyclicalTraining.forward (modeling_cyclical.py:170-225) and the dist variant
+    (modeling_cyclical_dist.py:108-165)."""
+    bias = rel_pos_bias(sd["rel_pos_bias.relative_position_bias_table"], sd["rel_pos_bias.relative_position_index"])
+    if not arch.dist:
+        t = _stem(sd, x, bool_masked_pos, arch, False)
+        z = []
+        for i in range(arch.depth):
+            t, f = block(sd, i, t, bias, arch, noise)
+            if layer_results == "end":
+                z.append(t)
+            elif layer_results == "fc":
+                z.append(f)
+        if layer_results:
+            return [u[:, 1:] for u in z]
+        t = _ln(t, sd["norm.weight"], sd["norm.bias"], arch.ln_eps)[:, 1:]
+        if return_all_tokens:
+            return F.linear(t, sd["lm_head.weight"], sd["lm_head.bias"])
+        m = bool_masked_pos.flatten().bool()
+        return F.linear(t.reshape(-1, t.shape[-1])[m], sd["lm_head.weight"], sd["lm_head.bias"])
+    tm = _stem(sd, x, bool_masked_pos, arch, False)
+    tc = _stem(sd, x, bool_masked_pos, arch, True)
+    zm, zc = [], []
+    for i in range(arch.depth):
+        tm, tc = dist_block(sd, i, tm, tc, bias, arch, noise)
+        if layer_results == "end":
+            zm.append(tm)
+            zc.append(tc)
+    if layer_results:
+        return [u[:, 1:] for u in zm], [u[:, 1:] for u in zc]
+    tm = _ln(tm, sd["norm.weight"], sd["norm.bias"], arch.ln_eps)[:, 1:]
+    tc = _ln(tc, sd["norm.weight"], sd["norm.bias"], arch.ln_eps)[:, 1:]
+    if not return_all_tokens:
+        m = bool_masked_pos.flatten().bool()
+        tm = tm.reshape(-1, tm.shape[-1])[m]
+        tc = tc.reshape(-1, tc.shape[-1])[m]
+    return (F.linear(tm, sd["lm_head.weight"], sd["lm_head.bias"]),
+            F.linear(tc, sd["cov_lm_head.weight"], sd["cov_lm_head.bias"]))
+
+
+def finetune_forward(sd, arch: Arch, x, noise: Optional[Noise] = None):
+    """VisionTransformer.forward (modeling_finetune.py:476-523, mean-pool head) /
+    DistVisionTransformer.forward (modeling_finetune_dist.py:280-326)."""
+    bias = rel_pos_bias(sd["rel_pos_bias.relative_position_bias_table"], sd["rel_pos_bias.relative_position_index"])
+    fcn = lambda t: _ln(t, sd["fc_norm.weight"], sd["fc_norm.bias"], arch.ln_eps)
+    if not arch.dist:
+        t = _stem(sd, x, None, arch, False)
+        for i in range(arch.depth):
+            t, _ = block(sd, i, t, bias, arch, noise)
+        return F.linear(fcn(t[:, 1:].mean(1)), sd["head.weight"], sd["head.bias"])
+    tm = _stem(sd, x, None, arch, False)
+    tc = _stem(sd, x, None, arch, True)
+    for i in range(arch.depth):
+        tm, tc = dist_block(sd, i, tm, tc, bias, arch, noise)
+    fm, fc = fcn(tm[:, 1:].mean(1)), fcn(tc[:, 1:].mean(1))
+    return fm, fc, F.linear(fm, sd["head.weight"], sd["head.bias"])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# data2vec target builder, losses, EMA, optimiser   (engine_for_cyclical.py)
+# --------------------------------------------------------------------------------------------------------------
+def build_targets(layer_outputs: Sequence[torch.Tensor], target_layers: Sequence[int], bool_masked_pos,
+                  target_layer_norm_last=True, target_batch_norm=False, target_instance_norm=False,
+                  post_target_instance_norm=False, post_target_layer_norm=False):
+    """engine_for_cyclical.py:90-122. layer_outputs: list of [B,T,C] (cls already dropped)."""
+    fsz = layer_outputs[0].size(-1)
+    vals = [layer_outputs[i] for i in target_layers]
+    if target_instance_norm or target_batch_norm:
+        vals = [v.permute(0, 2, 1) for v in vals]
+    if target_batch_norm:
+        vals = [F.batch_norm(v.float(), running_mean=None, running_var=None, training=True) for v in vals]
+    if target_instance_norm:
+        vals = [F.instance_norm(v.float()) for v in vals]
+    if target_instance_norm or target_batch_norm:
+        vals = [v.permute(0, 2, 1) for v in vals]
+    if target_layer_norm_last:
+        vals = [F.layer_norm(v.float(), (fsz,)) for v in vals]
+    t = sum(vals) / len(target_layers)
+    if post_target_instance_norm:
+        t = F.instance_norm(t.permute(0, 2, 1).float()).permute(0, 2, 1)
+    if post_target_layer_norm:
+        t = F.layer_norm(t.float(), (fsz,))
+    return t.reshape(-1, fsz)[bool_masked_pos.flatten().bool()]
+
+
+def d2v_loss(outputs, targets, l1_beta=2.0, l2_loss=False):
+    """engine_for_cyclical.py:145-150 (+ logged z0, :130-133)."""
+    z0 = torch.sqrt(outputs.reshape(-1, outputs.size(-1)).var(dim=0) + 1e-6)
+    loss = F.mse_loss(outputs, targets) if l2_loss else F.smooth_l1_loss(outputs, targets, beta=l1_beta)
+    return loss, z0
+
+
+def wasserstein_distance(m1, c1, m2, c2):
+    """distloss.py:73-79."""
+    ret = ((m1 - m2) ** 2).sum(-1)
+    u1 = torch.sqrt(torch.clamp(c1, min=1e-24))
+    u2 = torch.sqrt(torch.clamp(c2, min=1e-24))
+    return ret + ((u1 - u2) ** 2).sum(-1)
+
+
+def wasserstein_loss(mean_out, cov_out, pos_mean, pos_cov, lam=1e-5):
+    """WassersteinLoss.forward (distloss.py:13-30)."""
+    a, b, g, h = (torch.sigmoid(t) for t in (mean_out, cov_out, pos_mean, pos_cov))
+    w = wasserstein_distance(a, b, g, h)
+    w = w / torch.max(torch.abs(w))
+    loss = -torch.log(torch.sigmoid(-w + 1e-24))
+    loss = loss / torch.max(torch.abs(loss))
+    return loss.sum() * lam
+
+
+def wasserstein_loss_finetune(mo, co, pm, pc, nm, nc, lam_ft=1e-4, lam_pvn=1e-4):
+    """WassersteinLossFineTuning.forward (distloss.py:39-70)."""
+    mo, co, pm, pc, nm, nc = (torch.sigmoid(t) for t in (mo, co, pm, pc, nm, nc))
+    pos = wasserstein_distance(mo, co, pm, pc)
+    neg = wasserstein_distance(mo, co, nm, nc)
+    pvn = wasserstein_distance(pm, pc, nm, nc)
+    pos = pos / pos.abs().max()
+    neg = neg / neg.abs().max()
+    pvn = pvn / pvn.abs().max()
+    loss = -torch.log(torch.sigmoid(neg - pos + 1e-24))
+    loss = (loss / loss.abs().max() * lam_ft).sum()
+    pl = torch.clamp(pos - pvn, 0)
+    pl = (pl / pl.abs().max() * lam_pvn).sum()
+    return loss + pl
+
+
+def ema_decay_at(it: int, decay_init: float, decay: float, ema_start_at: int) -> float:
+    """engine_for_cyclical.py:55-56."""
+    if it < ema_start_at:
+        return decay_init + it * (decay - decay_init) / ema_start_at
+    return decay
+
+
+def ema_update(ema: Dict[str, torch.Tensor], model: Dict[str, torch.Tensor], d: float) -> None:
+    """engine_for_cyclical.py:182-185 + timm ModelEmaV2._update: e.copy_(d*e + (1-d)*m) over the state_dict
+    (the int64 relative_position_index buffer round-trips unchanged)."""
+    with torch.no_grad():
+        for k in ema:
+            ema[k].copy_(d * ema[k] + (1.0 - d) * model[k])
+
+
+def clip_grad_norm(grads: Sequence[torch.Tensor], max_norm: float) -> Tuple[torch.Tensor, float]:
+    """torch.nn.utils.clip_grad_norm_ semantics (utils.py:374-377): coef = min(1, max_norm/(norm+1e-6))."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = float(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+    return total, coef
+
+
+def adamw_step(p, g, m, v, step: int, lr: float, wd: float, beta1=0.9, beta2=0.999, eps=1e-8) -> None:
+    """torch.optim.AdamW single-tensor update (optim_factory.py:152-153 -> optim.AdamW)."""
+    with torch.no_grad():
+        p.mul_(1 - lr * wd)
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1 = 1 - beta1 ** step
+        bc2 = 1 - beta2 ** step
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+def get_num_layer_for_vit(name: str, num_max_layer: int) -> int:
+    """optim_factory.py:33-44."""
+    if name in ("cls_token", "mask_token", "pos_embed"):
+        return 0
+    if name.startswith("patch_embed"):
+        return 0
+    if name.startswith("rel_pos_bias"):
+        return num_max_layer - 1
+    if name.startswith("blocks"):
+        return int(name.split(".")[1]) + 1
+    return num_max_layer - 1
+
+
+def is_no_decay(name: str, shape, skip=("pos_embed", "cls_token")) -> bool:
+    """optim_factory.py:66-67: 1-D params, *.bias and the skip list get weight_decay 0."""
+    return len(shape) == 1 or name.endswith(".bias") or name in skip
+
+
+# --------------------------------------------------------------------------------------------------------------
+# masking generator (masking_generator.py:29-92) with an injected python `random.Random`
+# --------------------------------------------------------------------------------------------------------------
+def blockwise_mask(rng, height=14, width=14, num_masking_patches=120, min_num_patches=16, max_num_patches=None,
+                   min_aspect=0.3, max_aspect=None) -> np.ndarray:
+    max_num_patches = num_masking_patches if max_num_patches is None else max_num_patches
+    max_aspect = max_aspect or 1 / min_aspect
+    log_ar = (math.log(min_aspect), math.log(max_aspect))
+    mask = np.zeros((height, width), dtype=int)
+    count = 0
+    while count < num_masking_patches:
+        max_mask = min(num_masking_patches - count, max_num_patches)
+        delta = 0
+        for _ in range(10):
+            target_area = rng.uniform(min_num_patches, max_mask)
+            ar = math.exp(rng.uniform(*log_ar))
+            h = int(round(math.sqrt(target_area * ar)))
+            w = int(round(math.sqrt(target_area / ar)))
+            if w < width and h < height:
+                top = rng.randint(0, height - h)
+                left = rng.randint(0, width - w)
+                num_masked = mask[top:top + h, left:left + w].sum()
+                if 0 < h * w - num_masked <= max_mask:
+                    for i in range(top, top + h):
+                        for j in range(left, left + w):
+                            if mask[i, j] == 0:
+                                mask[i, j] = 1
+                                delta += 1
+                if delta > 0:
+                    break
+        if delta == 0:
+            break
+        count += delta
+    return mask
+
+
+# --------------------------------------------------------------------------------------------------------------
+# MC-sample uncertainty metrics (uncertainty_evaluations.py)
+# --------------------------------------------------------------------------------------------------------------
+def ece(probs: torch.Tensor, labels: torch.Tensor, n_bins: int = 15, reference_indexing: bool = False) -> float:
+    """ECELoss.loss(probs, labels, logits=False) (uncertainty_evaluations.py:110-202): 15 uniform bins (lo,hi],
+    sum_b prop_b * |mean conf_b - mean acc_b|.
+
+    reference_indexing=True reproduces what the reference ACTUALLY computes with any torch whose
+    Tensor.__array_wrap__ turns numpy bool into uint8 (all releases to date): at :173-176 `in_bin` becomes a uint8
+    array, so `accuracies[in_bin]` at :184 is INTEGER fancy indexing (elements 0 and 1 of `accuracies`), i.e.
+    bin_acc_b = ((N - n_b) * acc[0] + n_b * acc[1]) / N, while bin_conf_b (a torch mask-index at :185) is the true bin
+    mean. The golden vector in tests/golden/metrics.pt pins this variant; the default is the documented ECE.
+    """
+    conf, pred = probs.max(dim=1)
+    acc = pred.eq(labels).numpy().astype(np.float64)
+    bounds = np.linspace(0, 1, n_bins + 1)
+    total = 0.0
+    confn = conf.numpy()
+    n = confn.shape[0]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        in_bin = np.greater(confn, lo.item()) * np.less_equal(confn, hi.item())
+        prop = np.mean(in_bin)
+        if prop.item() > 0:
+            if reference_indexing:
+                nb = int(in_bin.sum())
+                bin_acc = ((n - nb) * acc[0] + nb * acc[1]) / n
+            else:
+                bin_acc = np.mean(acc[in_bin])
+            total += prop * np.abs(np.mean(confn[in_bin]) - bin_acc)
+    return float(total)
+
+
+def nll(logits: torch.Tensor, labels: torch.Tensor) -> float:
+    """NLL (uncertainty_evaluations.py:270-272)."""
+    return float(-torch.log_softmax(logits.float(), 1).gather(1, labels[:, None]).mean())
+
+
+def accuracy_topk(logits: torch.Tensor, labels: torch.Tensor, topk=(1, 5)):
+    """timm.utils.accuracy (uncertainty_evaluations.py:81)."""
+    maxk = max(topk)
+    _, pred = logits.topk(maxk, 1, True, True)
+    correct = pred.t().eq(labels.reshape(1, -1).expand_as(pred.t()))
+    return [float(correct[:k].reshape(-1).float().sum() * 100.0 / labels.shape[0]) for k in topk]
+
+
+def mc_reduce(logits_snk: torch.Tensor, labels: torch.Tensor) -> Dict[str, object]:
+    """evaluate_MC_dropout reduction (uncertainty_evaluations.py:77-85): mean of LOGITS over S, then metrics.
+    entropy / variance / mutual information are extensions (no reference function: parity unpinned)."""
+    zbar = logits_snk.float().mean(0)
+    probs = torch.softmax(zbar, 1)
+    a1, a5 = accuracy_topk(zbar, labels, (1, min(5, zbar.shape[1])))
+    ps = torch.softmax(logits_snk.float(), -1)
+    pbar = ps.mean(0)
+    ent = -(pbar * torch.log(pbar.clamp_min(1e-30))).sum(-1)
+    ent_s = -(ps * torch.log(ps.clamp_min(1e-30))).sum(-1).mean(0)
+    var = ((ps - pbar) ** 2).mean(0).sum(-1)
+    return dict(mean_logits=zbar, acc1=a1, acc5=a5, ece=ece(probs, labels), ece_reference=ece(probs, labels, 15, True),
+                nll=nll(zbar, labels),
+                entropy=ent, variance=var, mutual_info=ent - ent_s, conf=probs.max(1).values, pred=probs.argmax(1))

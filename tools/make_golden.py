@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.pt from the REAL reference (build container only; needs /root/reference).
+
+For every case: build the reference class through oracle/ref_shim.py, load the seeded state-dict from
+oracle.vit_oracle.make_state, inject the same drop-path keeps / dropout masks on both sides, run the reference, store
+its outputs, and assert that the oracle restatement reproduces them (fp32, <= 2e-5 relative). The stored files hold
+only seeds, small inputs and outputs — weights are regenerated from the seed by the tests.
+
+    python tools/make_golden.py            # writes tests/golden/
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+from oracle import vit_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def make_noise(arch: O.Arch, B: int, dpr: float, attn_drop: float, seed: int) -> O.Noise:
+    g = torch.Generator().manual_seed(seed)
+    probs = [float(x) for x in torch.linspace(0, dpr, arch.depth)]
+    draws = 4 if arch.dist else 2
+    keeps = [(torch.rand(draws, B, generator=g) >= p).float() for p in probs]
+    N = arch.tokens
+    akeep = [(torch.rand(B, arch.num_heads, N, N, generator=g) >= attn_drop).float() for _ in range(arch.depth)]
+    return O.Noise(drop_path_keep=keeps, drop_path_prob=probs, attn_keep=akeep, attn_drop=attn_drop)
+
+
+class Injector:
+    """Feeds the oracle's Noise object to the reference in forward call order."""
+
+    def __init__(self, arch: O.Arch, noise: O.Noise):
+        self.arch, self.noise = arch, noise
+        self.reset()
+
+    def reset(self):
+        self.dp_calls = []
+        draws = 4 if self.arch.dist else 2
+        for l, p in enumerate(self.noise.drop_path_prob):
+            if p > 0:          # DropPath is nn.Identity when p == 0 (modeling_finetune.py:279)
+                for d in range(draws):
+                    self.dp_calls.append((l, d))
+        self.dp_i = 0
+        self.do_i = 0
+
+    def drop_path(self, x, p):
+        l, d = self.dp_calls[self.dp_i]
+        self.dp_i += 1
+        assert abs(p - self.noise.drop_path_prob[l]) < 1e-7
+        return self.noise.drop_path_keep[l][d]
+
+    def dropout(self, x, p):
+        l = self.do_i
+        self.do_i += 1
+        assert abs(p - self.noise.attn_drop) < 1e-7 and tuple(x.shape) == tuple(self.noise.attn_keep[l].shape)
+        return self.noise.attn_keep[l]
+
+    def __enter__(self):
+        self.reset()
+        ref_shim.DROP_PATH_HOOK = self.drop_path
+        ref_shim.DROPOUT_HOOK = self.dropout
+        return self
+
+    def __exit__(self, *a):
+        ref_shim.DROP_PATH_HOOK = None
+        ref_shim.DROPOUT_HOOK = None
+
+
+def build_reference(arch: O.Arch, dpr: float, attn_drop: float):
+    import modeling_cyclical
+    import modeling_cyclical_dist
+    import modeling_finetune
+    import modeling_finetune_dist
+    common = dict(img_size=arch.img_size, patch_size=arch.patch_size, embed_dim=arch.embed_dim, depth=arch.depth,
+                  num_heads=arch.num_heads, mlp_ratio=arch.mlp_ratio, qkv_bias=True,
+                  norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_path_rate=dpr, attn_drop_rate=attn_drop,
+                  use_shared_rel_pos_bias=True, use_abs_pos_emb=False, init_values=0.1)
+    if arch.kind == "cyclical":
+        cls = modeling_cyclical_dist.DistVisionTransformerForCyclicalTraining if arch.dist else \
+            modeling_cyclical.VisionTransformerForCyclicalTraining
+        return cls(**common)
+    cls = modeling_finetune_dist.DistVisionTransformer if arch.dist else modeling_finetune.VisionTransformer
+    return cls(num_classes=arch.num_classes, **common)
+
+
+def load_state(model, sd):
+    own = model.state_dict()
+    missing = [k for k in own if k not in sd]
+    extra = [k for k in sd if k not in own]
+    assert not missing and not extra, (missing, extra)
+    model.load_state_dict({k: v.clone() for k, v in sd.items()})
+
+
+def grad_digest(named_grads):
+    out = {}
+    for k, g in named_grads.items():
+        if g is None:
+            out[k] = None
+        else:
+            f = g.detach().flatten().float()
+            out[k] = dict(norm=float(f.double().norm()), head=f[:64].clone(), sum=float(f.double().sum()))
+    return out
+
+
+def case_cyclical(name, arch: O.Arch, B, dpr, attn_drop, seed, target_layers, lam=1e-5, check=True):
+    torch.manual_seed(seed)
+    sd = O.make_state(arch, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, 3, arch.img_size, arch.img_size, generator=g)
+    P = arch.num_patches
+    mask = torch.zeros(B, P, dtype=torch.int64)
+    for b in range(B):
+        k = max(1, int(P * 0.6) - b)                      # ragged: a different count per image
+        mask[b, torch.randperm(P, generator=g)[:k]] = 1
+    mask = mask.reshape(B, arch.grid, arch.grid)
+    noise = make_noise(arch, B, dpr, attn_drop, seed + 2)
+
+    ref = build_reference(arch, dpr, attn_drop)
+    load_state(ref, sd)
+    # teacher: eval mode, unmasked (engine_for_cyclical.py:68-88)
+    ref.eval()
+    with torch.no_grad():
+        t_ref = ref(x, bool_masked_pos=None, return_all_tokens=True, layer_results="end")
+    if arch.dist:
+        t_ref, tc_ref = t_ref
+    tgt_ref = O.build_targets(t_ref, target_layers, mask, post_target_layer_norm=True)
+    # student: train mode, masked, injected noise
+    ref.train()
+    with Injector(arch, noise):
+        out_ref = ref(x, bool_masked_pos=mask, return_all_tokens=False)
+    if arch.dist:
+        out_ref, cout_ref = out_ref
+        ctgt_ref = O.build_targets(tc_ref, target_layers, mask, post_target_layer_norm=True)
+    loss_ref = F.smooth_l1_loss(out_ref.float(), tgt_ref, beta=2.0)
+    if arch.dist:
+        import distloss
+        wl_ref = distloss.WassersteinLoss(lam)(out_ref.float(), cout_ref.float(), tgt_ref, ctgt_ref)
+        total_ref = loss_ref + wl_ref
+    else:
+        total_ref = loss_ref
+    total_ref.backward()
+    grads_ref = {k: p.grad for k, p in ref.named_parameters()}
+
+    gold = dict(arch=arch.__dict__.copy(), B=B, dpr=dpr, attn_drop=attn_drop, seed=seed, target_layers=list(target_layers),
+                x=x, mask=mask, noise=dict(keep=noise.drop_path_keep, prob=noise.drop_path_prob,
+                                           attn_keep=[k.to(torch.uint8) for k in noise.attn_keep], attn_drop=attn_drop),
+                teacher_layers=[t.clone() for t in t_ref] if arch.embed_dim <= 128 else None,
+                targets=tgt_ref, outputs=out_ref.detach(), loss=float(loss_ref), total_loss=float(total_ref),
+                grads=grad_digest(grads_ref), lam=lam,
+                state_checksum=float(sum(v.double().sum() for k, v in sd.items() if v.is_floating_point())))
+    if arch.dist:
+        gold.update(cov_outputs=cout_ref.detach(), cov_targets=ctgt_ref, wloss=float(wl_ref))
+
+    if check:
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+        with torch.no_grad():
+            t_o = O.cyclical_forward(sd, arch, x, None, return_all_tokens=True, layer_results="end")
+        if arch.dist:
+            t_o, tc_o = t_o
+        tgt_o = O.build_targets(t_o, target_layers, mask, post_target_layer_norm=True)
+        out_o = O.cyclical_forward(sdg, arch, x, mask, noise=noise)
+        if arch.dist:
+            out_o, cout_o = out_o
+            ctgt_o = O.build_targets(tc_o, target_layers, mask, post_target_layer_norm=True)
+        loss_o, _ = O.d2v_loss(out_o, tgt_o, 2.0)
+        tot_o = loss_o + (O.wasserstein_loss(out_o, cout_o, tgt_o, ctgt_o, lam) if arch.dist else 0.0)
+        tot_o.backward()
+        errs = dict(targets=rel_err(tgt_o, tgt_ref), out=rel_err(out_o, out_ref), loss=abs(float(tot_o) - float(total_ref)) / abs(float(total_ref)))
+        worst = 0.0
+        for k, gr in grads_ref.items():
+            go = sdg[k].grad
+            if gr is None:
+                assert go is None or float(go.abs().max()) == 0.0, k
+                continue
+            worst = max(worst, rel_err(go, gr))
+        errs["grad_worst"] = worst
+        print(f"[{name}] oracle vs reference: {errs}")
+        assert max(errs.values()) < 5e-5, errs
+    torch.save(gold, os.path.join(GOLD, name + ".pt"))
+    print(f"[{name}] loss={float(loss_ref):.6f} rows={out_ref.shape[0]} saved")
+
+
+def case_finetune(name, arch: O.Arch, B, seed, check=True):
+    sd = O.make_state(arch, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, 3, arch.img_size, arch.img_size, generator=g)
+    ref = build_reference(arch, 0.0, 0.0)
+    load_state(ref, sd)
+    ref.eval()
+    with torch.no_grad():
+        out = ref(x)
+        o = O.finetune_forward(sd, arch, x)
+    gold = dict(arch=arch.__dict__.copy(), B=B, seed=seed, x=x if x.numel() < 200000 else None)
+    if arch.dist:
+        gold.update(mean_feat=out[0], cov_feat=out[1], logits=out[2])
+        errs = [rel_err(a, b) for a, b in zip(o, out)]
+    else:
+        gold.update(logits=out)
+        errs = [rel_err(o, out)]
+    print(f"[{name}] oracle vs reference rel err {errs}")
+    assert max(errs) < 5e-5
+    torch.save(gold, os.path.join(GOLD, name + ".pt"))
+
+
+def case_metrics():
+    import distloss
+    import uncertainty_evaluations as U
+    g = torch.Generator().manual_seed(7)
+    S, N, K = 6, 96, 10
+    logits = torch.randn(S, N, K, generator=g) * 2.0
+    labels = torch.randint(0, K, (N,), generator=g)
+    # make ~60% of the mean predictions correct so that the accuracy bins are non-trivial
+    zbar = logits.mean(0)
+    flip = torch.rand(N, generator=g) < 0.6
+    labels = torch.where(flip, zbar.argmax(1), labels)
+    probs = torch.softmax(zbar, 1)
+    ece_ref = float(U.ECELoss().loss(probs, labels, logits=False))           # default logits=True path raises (§8c)
+    nll_ref = float(U.NLL(zbar, labels))
+    from timm.utils import accuracy
+    a1, a5 = [float(v) for v in accuracy(zbar, labels, topk=(1, 5))]
+    r = O.mc_reduce(logits, labels)
+    assert abs(r["ece_reference"] - ece_ref) < 1e-7 and abs(r["nll"] - nll_ref) < 1e-6 and abs(r["acc1"] - a1) < 1e-4 and abs(r["acc5"] - a5) < 1e-4
+    # Wasserstein losses
+    R, C = 40, 32
+    t = [torch.randn(R, C, generator=g) for _ in range(6)]
+    wl = float(distloss.WassersteinLoss(1e-5)(*t[:4]))
+    wlf = float(distloss.WassersteinLossFineTuning(1e-4, 1e-4)(*t))
+    assert abs(float(O.wasserstein_loss(*t[:4], 1e-5)) - wl) < 1e-9
+    assert abs(float(O.wasserstein_loss_finetune(*t, 1e-4, 1e-4)) - wlf) < 1e-9
+    wdm = U.wasserstein_distance_matmul(t[0][None], t[1][None], t[2][None], t[3][None])
+    assert rel_err(O.wasserstein_distance_matmul(t[0][None], t[1][None], t[2][None], t[3][None]), wdm) < 1e-6
+    torch.save(dict(logits=logits, labels=labels, ece_reference=ece_ref, ece=r["ece"], nll=nll_ref, acc1=a1, acc5=a5, w_inputs=t, wloss=wl,
+                    wloss_ft=wlf, wdm=wdm), os.path.join(GOLD, "metrics.pt"))
+    print(f"[metrics] ece={ece_ref:.6f} nll={nll_ref:.6f} acc1={a1:.2f} wl={wl:.3e} wlf={wlf:.3e}")
+
+
+def case_index_and_masks():
+    import modeling_finetune
+    from masking_generator import MaskingGenerator
+    for w in (4, 14):
+        ref = modeling_finetune.RelativePositionBias((w, w), 2).relative_position_index
+        assert torch.equal(ref, O.relative_position_index(w, w))
+    random.seed(123)
+    gen = MaskingGenerator((14, 14), num_masking_patches=120, max_num_patches=None, min_num_patches=16)
+    ref_masks = np.stack([gen() for _ in range(8)])
+    rng = random.Random(123)
+    mine = np.stack([O.blockwise_mask(rng) for _ in range(8)])
+    assert np.array_equal(ref_masks, mine), "masking generator restatement differs"
+    torch.save(dict(index14=O.relative_position_index(14, 14).to(torch.int16), masks=torch.from_numpy(ref_masks).to(torch.uint8),
+                    mask_seed=123), os.path.join(GOLD, "index_masks.pt"))
+    print("[index_masks] rel-pos index + 8 block-wise masks bit-exact; counts", ref_masks.reshape(8, -1).sum(1))
+
+
+def case_ema_adamw():
+    from timm.utils import ModelEmaV2
+    torch.manual_seed(3)
+    net = nn.Sequential(nn.Linear(16, 16), nn.LayerNorm(16), nn.Linear(16, 4))
+    ema = ModelEmaV2(net, 0.9998)
+    opt = torch.optim.AdamW(net.parameters(), lr=2e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+    mine = {k: v.clone() for k, v in net.state_dict().items()}
+    mine_ema = {k: v.clone() for k, v in mine.items()}
+    ms = {k: torch.zeros_like(v) for k, v in mine.items()}
+    vs = {k: torch.zeros_like(v) for k, v in mine.items()}
+    xs = torch.randn(5, 8, 16)
+    for step in range(1, 6):
+        opt.zero_grad()
+        net(xs[step - 1]).pow(2).mean().backward()
+        grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+        total = torch.nn.utils.clip_grad_norm_(net.parameters(), 0.05)
+        tot_o, coef = O.clip_grad_norm(list(grads.values()), 0.05)
+        assert abs(float(total) - float(tot_o)) < 1e-6
+        opt.step()
+        d = O.ema_decay_at(step, 0.999, 0.9998, 3)
+        ema._update(net, update_fn=lambda e, m: d * e + (1.0 - d) * m)
+        for k in mine:
+            O.adamw_step(mine[k], grads[k] * coef, ms[k], vs[k], step, 2e-3, 0.05)
+        O.ema_update(mine_ema, mine, d)
+    for k, v in net.state_dict().items():
+        assert rel_err(mine[k], v) < 1e-6, k
+        assert rel_err(mine_ema[k], ema.module.state_dict()[k]) < 1e-6, k
+    print("[ema_adamw] oracle AdamW+clip+EMA == torch.optim.AdamW + ModelEmaV2 over 5 steps")
+
+
+def main():
+    assert ref_shim.reference_available(), "needs /root/reference"
+    ref_shim.install()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    tiny = lambda **kw: O.Arch(**{**O.TINY, **kw})
+    case_index_and_masks()
+    case_metrics()
+    case_ema_adamw()
+    case_cyclical("tiny_det_cyclical", tiny(kind="cyclical"), B=3, dpr=0.2, attn_drop=0.1, seed=11, target_layers=[0, 1])
+    case_cyclical("tiny_dist_cyclical", tiny(kind="cyclical", dist=True), B=3, dpr=0.2, attn_drop=0.1, seed=12, target_layers=[0, 1])
+    case_finetune("tiny_det_finetune", tiny(kind="finetune"), B=3, seed=13)
+    case_finetune("tiny_dist_finetune", tiny(kind="finetune", dist=True), B=3, seed=14)
+    if "--fast" not in sys.argv:
+        case_finetune("vitb_dist_finetune_b8", O.Arch(kind="finetune", dist=True, **O.VIT_B), B=8, seed=0)   # config 1
+        case_cyclical("vitb_det_cyclical_b2", O.Arch(kind="cyclical", **O.VIT_B), B=2, dpr=0.25, attn_drop=0.05, seed=1,
+                      target_layers=[6, 7, 8, 9, 10, 11])
+    print("golden vectors written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

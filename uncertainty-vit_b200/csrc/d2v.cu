@@ -1,0 +1,438 @@
+// data2vec step kernels (HBM-bound, 128-bit vectorised):
+//   d2v_target_loss : per masked row, LayerNorm (eps 1e-5, no affine) of the EMA teacher's top-K block outputs, their mean,
+//                     optional post LayerNorm, smooth-L1(beta) / MSE against the student row, dLoss/dy   (engine_for_cyclical.py:90-150)
+//   ema_update      : e = d*e + (1-d)*m over a flat fp32 arena (+ bf16 shadow of e)                     (engine_for_cyclical.py:182-185)
+//   sumsq / adamw   : grad-norm, clip, AdamW, bf16 weight shadow and EMA in one pass over the arenas    (utils.py:364-390)
+//   wasserstein_loss: WassersteinLoss fwd/bwd (distloss.py:13-30)
+#include "../../include/b200vit.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXV = 8;  // float4 per lane -> C <= 1024
+constexpr int MAX_LAYERS = 24;
+
+struct LayerPtrs {
+  const float* p[MAX_LAYERS];
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// no-affine LayerNorm of NV float4 per lane, in place; F.layer_norm(x.float(), (C,)) eps=1e-5
+template <int NV>
+__device__ __forceinline__ void ln_inplace(float4 (&v)[NV], int C, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd; }
+}
+
+// One warp per masked row. layers[l] is a [B, T, C] fp32 residual stream (cls row included): source row = row_index[r].
+template <int NV>
+__global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, int num_layers, long long ld_layer,
+                                                              const int* __restrict__ row_index, const float* __restrict__ y,
+                                                              int R, int C, int ln_each, int ln_post, float beta, int l2_loss,
+                                                              float grad_scale, float* __restrict__ targets,
+                                                              bf16* __restrict__ dy_bf16, float* __restrict__ dy_f32,
+                                                              float* __restrict__ row_loss) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const long long src = row_index[r];
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < num_layers; ++l) {
+    const float* row = layers.p[l] + src * ld_layer;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = ld4_stream(row + (i * 32 + lane) * 4);
+    if (ln_each) ln_inplace<NV>(v, C, 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+  }
+  const float inv = 1.0f / num_layers;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { acc[i].x *= inv; acc[i].y *= inv; acc[i].z *= inv; acc[i].w *= inv; }
+  if (ln_post) ln_inplace<NV>(acc, C, 1e-5f);
+  float loss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (targets != nullptr) *reinterpret_cast<float4*>(targets + (long long)r * C + c) = acc[i];
+    if (y == nullptr) continue;
+    const float4 yv = ld4(y + (long long)r * C + c);
+    const float e[4] = {yv.x - acc[i].x, yv.y - acc[i].y, yv.z - acc[i].z, yv.w - acc[i].w};
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (l2_loss) {
+        loss += e[j] * e[j];
+        g[j] = 2.0f * e[j];
+      } else {
+        const float a = fabsf(e[j]);
+        // F.smooth_l1_loss: 0.5*e^2/beta if |e| < beta else |e| - 0.5*beta
+        loss += a < beta ? 0.5f * e[j] * e[j] / beta : a - 0.5f * beta;
+        g[j] = a < beta ? e[j] / beta : (e[j] > 0.f ? 1.0f : -1.0f);
+      }
+      g[j] *= grad_scale;
+    }
+    if (dy_bf16 != nullptr) {
+      uint2 u;
+      u.x = pack_bf16x2(g[0], g[1]);
+      u.y = pack_bf16x2(g[2], g[3]);
+      *reinterpret_cast<uint2*>(dy_bf16 + (long long)r * C + c) = u;
+    }
+    if (dy_f32 != nullptr) *reinterpret_cast<float4*>(dy_f32 + (long long)r * C + c) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+  loss = warp_sum(loss);
+  if (lane == 0 && row_loss != nullptr) row_loss[r] = loss;
+}
+
+// deterministic single-CTA sum: out[0] = scale * sum(v[0..n))
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = (float)(s * (double)scale);
+  }
+}
+
+// e = d*e + (1-d)*m ; optional bf16 shadow of e
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ e, const float* __restrict__ m, long long n4, float d,
+                                                  bf16* __restrict__ shadow) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float od = 1.0f - d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ld4(e + i * 4);
+    const float4 b = ld4_stream(m + i * 4);
+    // same expression as the reference lambda: cur_decay * e + (1. - cur_decay) * m
+    const float4 o = make_float4(d * a.x + od * b.x, d * a.y + od * b.y, d * a.z + od * b.z, d * a.w + od * b.w);
+    *reinterpret_cast<float4*>(e + i * 4) = o;
+    if (shadow != nullptr) {
+      uint2 u;
+      u.x = pack_bf16x2(o.x, o.y);
+      u.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(shadow + i * 4) = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld4(g + i * 4);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  __shared__ float sh[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+
+// Fused clip + AdamW (+ bf16 weight shadow, + EMA teacher update and its bf16 shadow) over flat arenas.
+// Hyper-parameters per 1024-element chunk: hp[chunk] = {lr, weight_decay} (param-group semantics of
+// optim_factory.py:58-97 and the per-step lr*lr_scale of engine_for_cyclical.py:47-53 are folded in by the host).
+// torch.optim.AdamW update order: p *= 1 - lr*wd ; m,v EMA ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n4, const float2* __restrict__ hp,
+                                                    float beta1, float beta2, float eps, float bc1, float sqrt_bc2,
+                                                    const float* __restrict__ gnorm_sq, float max_norm, float grad_div,
+                                                    bf16* __restrict__ p_shadow, float* __restrict__ ema, float ema_decay,
+                                                    bf16* __restrict__ ema_shadow) {
+  float coef = 1.0f / grad_div;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float norm = sqrtf(__ldg(gnorm_sq)) / grad_div;
+    coef *= fminf(1.0f, max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float od = 1.0f - ema_decay;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float2 h = __ldg(hp + (i >> 8));  // 1024 elements = 256 float4 per chunk
+    const float lr = h.x, wd = h.y;
+    float4 pv = ld4(p + i * 4);
+    const float4 gv = ld4_stream(g + i * 4);
+    float4 mv = ld4(m + i * 4), vv = ld4(v + i * 4);
+    float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gp[j] * coef;
+      pp[j] *= 1.0f - lr * wd;
+      mp[j] = beta1 * mp[j] + (1.0f - beta1) * gj;
+      vp[j] = beta2 * vp[j] + (1.0f - beta2) * gj * gj;
+      const float denom = sqrtf(vp[j]) / sqrt_bc2 + eps;
+      pp[j] -= (lr / bc1) * (mp[j] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i * 4) = pv;
+    *reinterpret_cast<float4*>(m + i * 4) = mv;
+    *reinterpret_cast<float4*>(v + i * 4) = vv;
+    if (p_shadow != nullptr) {
+      uint2 u;
+      u.x = pack_bf16x2(pv.x, pv.y);
+      u.y = pack_bf16x2(pv.z, pv.w);
+      *reinterpret_cast<uint2*>(p_shadow + i * 4) = u;
+    }
+    if (ema != nullptr) {
+      const float4 ev = ld4(ema + i * 4);
+      const float4 o = make_float4(ema_decay * ev.x + od * pv.x, ema_decay * ev.y + od * pv.y, ema_decay * ev.z + od * pv.z,
+                                   ema_decay * ev.w + od * pv.w);
+      *reinterpret_cast<float4*>(ema + i * 4) = o;
+      if (ema_shadow != nullptr) {
+        uint2 u;
+        u.x = pack_bf16x2(o.x, o.y);
+        u.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(ema_shadow + i * 4) = u;
+      }
+    }
+  }
+}
+
+// ---------------- WassersteinLoss (distloss.py:13-30) ----------------
+// pass 1: w_r = sum (s(a)-s(g))^2 + sum (sqrt(max(s(b),1e-24)) - sqrt(max(s(h),1e-24)))^2 ; one warp per row
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) wloss_rowdist_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                                                            const float* __restrict__ h, int R, int C, float* __restrict__ w) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 av = ld4(a + (long long)r * C + c), bv = ld4(b + (long long)r * C + c);
+    const float4 gv = ld4(g + (long long)r * C + c), hv = ld4(h + (long long)r * C + c);
+    const float* ap = &av.x; const float* bp = &bv.x; const float* gp = &gv.x; const float* hp = &hv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dm = sigm(ap[j]) - sigm(gp[j]);
+      const float dc = sqrtf(fmaxf(sigm(bp[j]), 1e-24f)) - sqrtf(fmaxf(sigm(hp[j]), 1e-24f));
+      s += dm * dm + dc * dc;
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) w[r] = s;
+}
+
+// pass 2 (single CTA): wmax = max|w| ; l_r = -log(sigmoid(-w_r/wmax + 1e-24)) ; lmax = max|l| ; loss = lam * sum l_r / lmax
+// and the row coefficients of dloss/dw_r INCLUDING the two max-normalisers (autograd differentiates through torch.max):
+//   stats[0]=loss, stats[1]=wmax, stats[2]=lmax, stats[3]=argmax_w, stats[4]=argmax_l ; coef[r] = dloss/dw_r
+__global__ void __launch_bounds__(1024) wloss_finalize_kernel(const float* __restrict__ w, int R, float lam, float* __restrict__ stats,
+                                                              float* __restrict__ coef) {
+  __shared__ float sh_v[32];
+  __shared__ int sh_i[32];
+  __shared__ float bc[4];
+  __shared__ int bi[2];
+  auto block_argmax = [&](float v, int idx) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sh_v[threadIdx.x >> 5] = v; sh_i[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      v = threadIdx.x < (blockDim.x >> 5) ? sh_v[threadIdx.x] : -1.f;
+      idx = threadIdx.x < (blockDim.x >> 5) ? sh_i[threadIdx.x] : 0x7fffffff;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+      }
+      if (threadIdx.x == 0) { sh_v[0] = v; sh_i[0] = idx; }
+    }
+    __syncthreads();
+  };
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh_v[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      v = threadIdx.x < (blockDim.x >> 5) ? sh_v[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) sh_v[0] = v;
+    }
+    __syncthreads();
+    const float r = sh_v[0];
+    __syncthreads();
+    return r;
+  };
+  float v = -1.f; int idx = 0x7fffffff;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) { const float a = fabsf(w[r]); if (a > v) { v = a; idx = r; } }
+  block_argmax(v, idx);
+  if (threadIdx.x == 0) { bc[0] = sh_v[0]; bi[0] = sh_i[0]; }
+  __syncthreads();
+  const float wmax = bc[0];
+  const int iw = bi[0];
+  // l_r and its max
+  v = -1.f; idx = 0x7fffffff;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float z = -w[r] / wmax + 1e-24f;
+    const float l = -logf(sigm(z));
+    if (fabsf(l) > v) { v = fabsf(l); idx = r; }
+  }
+  block_argmax(v, idx);
+  if (threadIdx.x == 0) { bc[1] = sh_v[0]; bi[1] = sh_i[0]; }
+  __syncthreads();
+  const float lmax = bc[1];
+  const int il = bi[1];
+  float sl = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) sl += -logf(sigm(-w[r] / wmax + 1e-24f));
+  const float sum_l = block_sum(sl);
+  // loss = lam * S / lmax with S = sum l_r, lmax = l_il (l >= 0).  dloss/dl_r = lam * (1/lmax - [r==il] * S / lmax^2)
+  // l_r = softplus(-z_r), z_r = -u_r + 1e-24, u_r = w_r / wmax (w >= 0 -> wmax = w_iw): dl/du_r = sigmoid(-z_r) = 1 - sigmoid(z_r)
+  // du_r/dw_k = [r==k]/wmax - [k==iw] * w_r / wmax^2
+  float part = 0.f;  // sum_r dloss/du_r * w_r
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float z = -w[r] / wmax + 1e-24f;
+    const float dl = lam * (1.0f / lmax - (r == il ? sum_l / (lmax * lmax) : 0.f));
+    const float du = dl * (1.0f - sigm(z));
+    coef[r] = du / wmax;
+    part += du * w[r];
+  }
+  const float tot = block_sum(part);
+  if (threadIdx.x == 0) {
+    coef[iw] -= tot / (wmax * wmax);
+    stats[0] = lam * sum_l / lmax; stats[1] = wmax; stats[2] = lmax; stats[3] = (float)iw; stats[4] = (float)il;
+  }
+}
+
+// pass 3: da, db (grads of the student mean / cov outputs) = coef[r] * dw_r/d(.) * grad_scale, ACCUMULATED into da/db
+__global__ void __launch_bounds__(256) wloss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                                                        const float* __restrict__ h, const float* __restrict__ coef, int R, int C,
+                                                        float grad_scale, float* __restrict__ da, float* __restrict__ db) {
+  const long long total = (long long)R * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int r = (int)(i / C);
+    const float k = coef[r] * grad_scale;
+    const float sa = sigm(a[i]), sg = sigm(g[i]), sb = sigm(b[i]), shh = sigm(h[i]);
+    da[i] += k * 2.0f * (sa - sg) * sa * (1.0f - sa);
+    const float ub = sqrtf(fmaxf(sb, 1e-24f)), uh = sqrtf(fmaxf(shh, 1e-24f));
+    // d sqrt(clamp(sb))/dsb = 0.5/ub where sb > 1e-24 (sigmoid of a finite float always is)
+    db[i] += k * 2.0f * (ub - uh) * (sb > 1e-24f ? 0.5f / ub : 0.f) * sb * (1.0f - sb);
+  }
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
+                                       const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
+                                       float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
+                                       void* stream) {
+  B200_CHECK_ARG(layers_host != nullptr && num_layers > 0 && num_layers <= MAX_LAYERS, "d2v_target_loss: 1..%d layers", MAX_LAYERS);
+  B200_CHECK_ARG(row_index != nullptr && C % 128 == 0 && C <= 128 * MAXV, "d2v_target_loss: C=%d must be a multiple of 128, <= %d", C, 128 * MAXV);
+  B200_CHECK_ARG(loss_out == nullptr || (row_loss != nullptr && y != nullptr), "d2v_target_loss: loss_out needs y and a row_loss workspace of R floats");
+  if (R == 0) return 0;
+  LayerPtrs lp;
+  for (int i = 0; i < num_layers; ++i) {
+    B200_CHECK_ARG(layers_host[i] != nullptr, "d2v_target_loss: layer %d is null", i);
+    lp.p[i] = layers_host[i];
+  }
+  const int grid = (R + 7) / 8;
+#define TL(NV) d2v_target_loss_kernel<NV><<<grid, 256, 0, STREAM>>>(lp, num_layers, ld_layer, row_index, y, R, C, ln_each, ln_post, beta, l2_loss, grad_scale, targets, static_cast<bf16*>(dy_bf16), dy_f32, row_loss)
+  switch (C / 128) {
+    case 1: TL(1); break; case 2: TL(2); break; case 3: TL(3); break; case 4: TL(4); break;
+    case 5: TL(5); break; case 6: TL(6); break; case 7: TL(7); break; default: TL(8); break;
+  }
+#undef TL
+  B200_CHECK_LAUNCH("d2v_target_loss");
+  if (loss_out != nullptr) {
+    reduce_sum_kernel<<<1, 1024, 0, STREAM>>>(row_loss, R, 1.0f / ((float)R * (float)C), loss_out);
+    B200_CHECK_LAUNCH("d2v_loss_reduce");
+  }
+  return 0;
+}
+
+extern "C" int b200vit_ema_update(float* ema, const float* model, int64_t n, float decay, void* ema_bf16, void* stream) {
+  B200_CHECK_ARG(ema != nullptr && model != nullptr && n >= 0 && n % 4 == 0, "ema_update: n=%lld must be a multiple of 4", (long long)n);
+  B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(ema) | reinterpret_cast<uintptr_t>(model)) & 15) == 0, "ema_update: arenas must be 16-byte aligned");
+  if (n == 0) return 0;
+  const int sms = b200vit_num_sms();
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  ema_kernel<<<(int)blocks, 256, 0, STREAM>>>(ema, model, n / 4, decay, static_cast<bf16*>(ema_bf16));
+  B200_CHECK_LAUNCH("ema_update");
+  return 0;
+}
+
+extern "C" int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* stream) {
+  B200_CHECK_ARG(g != nullptr && out_accum != nullptr && n >= 0 && n % 4 == 0, "sumsq: n must be a multiple of 4");
+  if (n == 0) return 0;
+  const int sms = b200vit_num_sms();
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  sumsq_kernel<<<(int)blocks, 256, 0, STREAM>>>(g, n / 4, out_accum);
+  B200_CHECK_LAUNCH("sumsq");
+  return 0;
+}
+
+extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
+                                  float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
+                                  float ema_decay, void* ema_bf16, void* stream) {
+  B200_CHECK_ARG(p != nullptr && g != nullptr && m != nullptr && v != nullptr && hp_lr_wd != nullptr, "adamw_step: null pointer");
+  B200_CHECK_ARG(n >= 0 && n % 1024 == 0, "adamw_step: arena length must be a multiple of 1024 (one {lr,wd} pair per 1024 elements)");
+  B200_CHECK_ARG(step >= 1, "adamw_step: step counts from 1");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  const int sms = b200vit_num_sms();
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, n / 4, reinterpret_cast<const float2*>(hp_lr_wd), beta1, beta2, eps, (float)bc1,
+                                                (float)sqrt(bc2), gnorm_sq, max_norm, grad_div > 0.f ? grad_div : 1.0f,
+                                                static_cast<bf16*>(p_bf16), ema, ema_decay, static_cast<bf16*>(ema_bf16));
+  B200_CHECK_LAUNCH("adamw_step");
+  return 0;
+}
+
+extern "C" int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
+                                        int32_t C, float lam, float grad_scale, float* work /* 2R+8 floats */, float* d_mean_out,
+                                        float* d_cov_out, float* loss_out, void* stream) {
+  B200_CHECK_ARG(mean_out && cov_out && pos_mean && pos_cov && work && loss_out, "wasserstein_loss: null pointer");
+  B200_CHECK_ARG(R > 0 && C % 4 == 0, "wasserstein_loss: bad shape R=%d C=%d", R, C);
+  float* w = work;
+  float* coef = work + R;
+  float* stats = work + 2 * R;
+  wloss_rowdist_kernel<<<(R + 7) / 8, 256, 0, STREAM>>>(mean_out, cov_out, pos_mean, pos_cov, R, C, w);
+  B200_CHECK_LAUNCH("wloss_rowdist");
+  wloss_finalize_kernel<<<1, 1024, 0, STREAM>>>(w, R, lam, stats, coef);
+  B200_CHECK_LAUNCH("wloss_finalize");
+  cudaMemcpyAsync(loss_out, stats, sizeof(float), cudaMemcpyDeviceToDevice, STREAM);
+  if (d_mean_out != nullptr && d_cov_out != nullptr) {
+    const int sms = b200vit_num_sms();
+    long long blocks = ((long long)R * C + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    wloss_bwd_kernel<<<(int)blocks, 256, 0, STREAM>>>(mean_out, cov_out, pos_mean, pos_cov, coef, R, C, grad_scale, d_mean_out, d_cov_out);
+    B200_CHECK_LAUNCH("wloss_bwd");
+  }
+  return 0;
+}

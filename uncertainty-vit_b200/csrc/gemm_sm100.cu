@@ -1,0 +1,470 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (SWIZZLE_128B) -> tcgen05.mma (cta_group::1,
+// 128x256x16, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with fused bias / GELU / layer-scale +
+// drop-path + residual / dGELU / fp32 / split-K atomic accumulation.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T
+//
+// Replaces every nn.Linear / F.linear of the reference hot path and their autograd backward:
+//   QKV, proj (modeling_finetune.py:149,186), fc1/fc2 (modeling_finetune.py:76-81), lm_head (modeling_cyclical.py:219-225),
+//   patch-embed conv-as-GEMM (modeling_finetune.py:324), head (modeling_finetune.py:522).
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
+// warps 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4 of the 256-column accumulator).
+#include <mutex>
+
+#include "../../include/b200vit.h"
+#include "ptx_sm100.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
+
+struct EpiParams {
+  int mode;
+  const float* bias;
+  const float* colscale;
+  const float* rowscale;
+  int rows_per_scale;
+  const float* residual;
+  long long ld_residual;
+  const bf16* aux;
+  long long ld_aux;
+  float* out_f32;
+  long long ld_f32;
+  bf16* out_bf16;
+  long long ld_bf16;
+  bf16* out2_bf16;
+  long long ld2_bf16;
+  float alpha;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, num_kb, split_k, kb_per_split;
+  EpiParams epi;
+};
+
+__device__ __forceinline__ void store_bf16x8(bf16* p, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Applies the fused epilogue to 32 consecutive accumulator columns [n0, n0+32) of row m.
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, int m, int n0, int N, float (&v)[32]) {
+  const int nvalid = min(32, N - n0);  // N % 8 == 0 is enforced on the host
+  if (e.mode == B200VIT_EPI_F32_ATOMIC) {
+    float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (j < nvalid) ptx::red_add_v4(dst + j, v[j] * e.alpha, v[j + 1] * e.alpha, v[j + 2] * e.alpha, v[j + 3] * e.alpha);
+    return;
+  }
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (j < nvalid) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+  }
+  switch (e.mode) {
+    case B200VIT_EPI_BF16: {
+      if (e.colscale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < nvalid) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(e.colscale + n0 + j));
+            v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
+          }
+      }
+      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      break;
+    }
+    case B200VIT_EPI_GELU: {
+      if (e.out2_bf16 != nullptr) {
+        bf16* dst2 = e.out2_bf16 + (long long)m * e.ld2_bf16 + n0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          if (j < nvalid) store_bf16x8(dst2 + j, v + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      break;
+    }
+    case B200VIT_EPI_RESIDUAL: {
+      if (e.out2_bf16 != nullptr) {
+        bf16* dst2 = e.out2_bf16 + (long long)m * e.ld2_bf16 + n0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          if (j < nvalid) store_bf16x8(dst2 + j, v + j);
+      }
+      const float rs = e.rowscale != nullptr ? __ldg(e.rowscale + m / e.rows_per_scale) : 1.0f;
+      const float* res = e.residual + (long long)m * e.ld_residual + n0;
+      float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (j < nvalid) {
+          float4 s = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.colscale != nullptr) s = __ldg(reinterpret_cast<const float4*>(e.colscale + n0 + j));
+          const float4 r = *reinterpret_cast<const float4*>(res + j);
+          float4 o;
+          o.x = fmaf(rs * s.x, v[j], r.x);
+          o.y = fmaf(rs * s.y, v[j + 1], r.y);
+          o.z = fmaf(rs * s.z, v[j + 2], r.z);
+          o.w = fmaf(rs * s.w, v[j + 3], r.w);
+          *reinterpret_cast<float4*>(dst + j) = o;
+        }
+      break;
+    }
+    case B200VIT_EPI_DGELU: {
+      const bf16* aux = e.aux + (long long)m * e.ld_aux + n0;
+      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (j < nvalid) {
+          const uint4 a = *reinterpret_cast<const uint4*>(aux + j);
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+          v[j] *= gelu_erf_grad(a0.x); v[j + 1] *= gelu_erf_grad(a0.y);
+          v[j + 2] *= gelu_erf_grad(a1.x); v[j + 3] *= gelu_erf_grad(a1.y);
+          v[j + 4] *= gelu_erf_grad(a2.x); v[j + 5] *= gelu_erf_grad(a2.y);
+          v[j + 6] *= gelu_erf_grad(a3.x); v[j + 7] *= gelu_erf_grad(a3.y);
+          store_bf16x8(dst + j, v + j);
+        }
+      break;
+    }
+    case B200VIT_EPI_ELU1: {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.0f : __expf(v[j]);   // elu(x)+1
+      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      break;
+    }
+    case B200VIT_EPI_F32:
+    default: {
+      float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (j < nvalid) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      break;
+    }
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_units = num_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int tile = u / p.split_k, split = u - tile * p.split_k;
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              ptx::tma_load_2d(smem_a(stage) + c * (BLOCK_K * 128), &tmap_a, full_bar(stage), m_blk * BLOCK_M + c * 64,
+                               kb * BLOCK_K);
+          } else {
+            ptx::tma_load_2d(smem_a(stage), &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              ptx::tma_load_2d(smem_b(stage) + c * (BLOCK_K * 128), &tmap_b, full_bar(stage), n_blk * BLOCK_N + c * 64,
+                               kb * BLOCK_K);
+          } else {
+            ptx::tma_load_2d(smem_b(stage), &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int tile = u / p.split_k, split = u - tile * p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: 32 B per UMMA_K inside the 128-byte swizzle row; MN-major: 16 k-rows x 128 B = 2048 B
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc(smem_a(stage) + k * 2048, BLOCK_K * 128, 1024)
+                                        : ptx::make_smem_desc(smem_a(stage) + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc(smem_b(stage) + k * 2048, BLOCK_K * 128, 1024)
+                                        : ptx::make_smem_desc(smem_b(stage) + k * 32, 16, 1024);
+            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= FIRST_EPI_WARP) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - FIRST_EPI_WARP;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                // column half of the accumulator
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int tile = u / p.split_k;
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const int m = m_blk * BLOCK_M + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 2; c += 32) {
+        const int n0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + c;
+        if (n0 >= p.N) break;              // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        if (m < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk(p.epi, m, n0, p.N, v);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart; box = box_inner x box_outer.
+int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+              uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    b200vit_set_error("gemm: cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -2;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200vit_set_error("gemm: cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu", (int)r, ptr,
+                      (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+    return -3;
+  }
+  return 0;
+}
+
+// split-K factor maximising wave efficiency on `sms` SMs (fewest splits on ties), >= 8 k-blocks per split.
+int pick_split_k(int tiles, int num_kb, int sms) {
+  if (tiles >= sms) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  const int max_split = num_kb / 8 > 0 ? num_kb / 8 : 1;
+  for (int s = 1; s <= max_split && s <= 64; ++s) {
+    const int units = tiles * s;
+    const int waves = (units + sms - 1) / sms;
+    const double eff = (double)units / ((double)waves * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;  // benign race: the attribute call is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      b200vit_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  B200_CHECK_LAUNCH("gemm_bf16");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  B200_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
+  B200_CHECK_ARG(d->N % 8 == 0, "gemm: N=%d must be a multiple of 8", d->N);
+  B200_CHECK_ARG(d->A != nullptr && d->B != nullptr, "gemm: null operand");
+  B200_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->B) & 15) == 0,
+                 "gemm: operands must be 16-byte aligned");
+  B200_CHECK_ARG(d->lda >= (d->a_mn_major ? d->M : d->K) && d->ldb >= (d->b_mn_major ? d->N : d->K), "gemm: leading dimension too small");
+  const int mode = d->epilogue;
+  B200_CHECK_ARG(mode >= 0 && mode <= B200VIT_EPI_ELU1, "gemm: unknown epilogue %d", mode);
+  const bool wants_bf16 = mode == B200VIT_EPI_BF16 || mode == B200VIT_EPI_GELU || mode == B200VIT_EPI_DGELU || mode == B200VIT_EPI_ELU1;
+  if (wants_bf16) B200_CHECK_ARG(d->out_bf16 != nullptr && d->ld_bf16 % 8 == 0 && d->ld_bf16 >= d->N, "gemm: bad out_bf16/ld_bf16");
+  if (!wants_bf16) B200_CHECK_ARG(d->out_f32 != nullptr && d->ld_f32 % 4 == 0 && d->ld_f32 >= d->N, "gemm: bad out_f32/ld_f32");
+  if (mode == B200VIT_EPI_RESIDUAL)
+    B200_CHECK_ARG(d->residual != nullptr && d->ld_residual % 4 == 0 && (d->rowscale == nullptr || d->rows_per_scale > 0),
+                   "gemm: RESIDUAL epilogue needs residual (+ rows_per_scale with rowscale)");
+  if (mode == B200VIT_EPI_DGELU) B200_CHECK_ARG(d->aux != nullptr && d->ld_aux % 8 == 0, "gemm: DGELU epilogue needs aux");
+  if (d->out2_bf16 != nullptr) B200_CHECK_ARG(d->ld2_bf16 % 8 == 0 && d->ld2_bf16 >= d->N, "gemm: bad ld2_bf16");
+  B200_CHECK_ARG(d->split_k <= 1 || mode == B200VIT_EPI_F32_ATOMIC, "gemm: split_k requires the F32_ATOMIC epilogue");
+
+  const int sms = b200vit_num_sms();
+  B200_CHECK_ARG(sms > 0, "gemm: no CUDA device");
+
+  GemmParams p;
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.tiles_m = (d->M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_n = (d->N + BLOCK_N - 1) / BLOCK_N;
+  p.num_kb = (d->K + BLOCK_K - 1) / BLOCK_K;
+  const int cap = d->max_ctas > 0 ? (d->max_ctas < sms ? d->max_ctas : sms) : sms;
+  int split = 1;
+  if (mode == B200VIT_EPI_F32_ATOMIC) split = d->split_k > 1 ? d->split_k : (d->split_k == 1 ? 1 : pick_split_k(p.tiles_m * p.tiles_n, p.num_kb, cap));
+  if (split > p.num_kb) split = p.num_kb;
+  p.kb_per_split = (p.num_kb + split - 1) / split;
+  p.split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.epi.mode = mode;
+  p.epi.bias = d->bias; p.epi.colscale = d->colscale; p.epi.rowscale = d->rowscale;
+  p.epi.rows_per_scale = d->rows_per_scale > 0 ? d->rows_per_scale : 1;
+  p.epi.residual = d->residual; p.epi.ld_residual = d->ld_residual;
+  p.epi.aux = static_cast<const bf16*>(d->aux); p.epi.ld_aux = d->ld_aux;
+  p.epi.out_f32 = d->out_f32; p.epi.ld_f32 = d->ld_f32;
+  p.epi.out_bf16 = static_cast<bf16*>(d->out_bf16); p.epi.ld_bf16 = d->ld_bf16;
+  p.epi.out2_bf16 = static_cast<bf16*>(d->out2_bf16); p.epi.ld2_bf16 = d->ld2_bf16;
+  p.epi.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major: inner = K, rows = M|N, box 64 x BLOCK;   MN-major: inner = M|N, rows = K, box 64 x BLOCK_K
+  rc = d->a_mn_major ? make_tmap(&ta, d->A, d->M, d->K, d->lda, 64, BLOCK_K) : make_tmap(&ta, d->A, d->K, d->M, d->lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  rc = d->b_mn_major ? make_tmap(&tb, d->B, d->N, d->K, d->ldb, 64, BLOCK_K) : make_tmap(&tb, d->B, d->K, d->N, d->ldb, BLOCK_K, BLOCK_N);
+  if (rc) return rc;
+
+  const int units = p.tiles_m * p.tiles_n * p.split_k;
+  const int grid = units < cap ? units : cap;
+  if (d->a_mn_major) return d->b_mn_major ? launch<true, true>(ta, tb, p, grid, stream) : launch<true, false>(ta, tb, p, grid, stream);
+  return d->b_mn_major ? launch<false, true>(ta, tb, p, grid, stream) : launch<false, false>(ta, tb, p, grid, stream);
+}

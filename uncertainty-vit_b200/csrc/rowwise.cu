@@ -1,0 +1,459 @@
+// Bandwidth-bound row kernels of the block forward/backward: LayerNorm fwd/bwd (with optional row gather/scatter),
+// layer-scale + drop-path backward with its column reductions, bf16 column sums, fp32->bf16 casts, patch im2col,
+// token assembly (cls concat + mask-token blend) and its backward, relative-position-bias gather, mean pooling.
+// All loads/stores are 128-bit; one warp owns one row; column reductions accumulate per CTA and finish with one
+// atomicAdd per column per CTA.
+#include "../../include/b200vit.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXV = 8;  // float4 per lane: C <= 32 * 4 * 8 = 1024
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_bf16x4(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x - mean) * rstd * gamma + beta   (nn.LayerNorm eps=1e-6, modeling_finetune.py:270,280)
+// two-pass variance in registers (matches ATen's fp32 result to ~1e-7)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ row_index,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                     int rows, int C, bf16* __restrict__ y, float* __restrict__ y32,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const long long src = row_index != nullptr ? row_index[warp] : warp;
+  const float* xr = x + src * ldx;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = ld4(xr + (i * 32 + lane) * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  if (lane == 0) {
+    if (mean_out != nullptr) mean_out[warp] = mean;
+    if (rstd_out != nullptr) rstd_out[warp] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gamma != nullptr) g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    if (beta != nullptr) b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y != nullptr) st_bf16x4(y + (long long)warp * C + c, o);
+    if (y32 != nullptr) st4(y32 + (long long)warp * C + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward. dx[src_row] += rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
+// dgamma += sum dy*xhat ; dbeta += sum dy.   Each warp loops over rows; per-CTA smem reduction; atomics at the end.
+// ------------------------------------------------------------------------------------------------
+template <int NV, typename DY>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, const float* __restrict__ x, long long ldx,
+                                                     const int* __restrict__ row_index, const float* __restrict__ gamma,
+                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                     int rows, int C, float* __restrict__ dx, long long lddx,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float red[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 g[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    g[i] = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const long long src = row_index != nullptr ? row_index[r] : r;
+    const float* xr = x + src * ldx;
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float4 xh[NV], d[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 xv = ld4(xr + c);
+      float4 dv;
+      if constexpr (sizeof(DY) == 2) dv = ld_bf16x4(reinterpret_cast<const bf16*>(dy) + (long long)r * C + c);
+      else dv = ld4(reinterpret_cast<const float*>(dy) + (long long)r * C + c);
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+      ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      d[i] = make_float4(dv.x * g[i].x, dv.y * g[i].y, dv.z * g[i].z, dv.w * g[i].w);
+      s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+      s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    float* dxr = dx + src * lddx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o = ld4(dxr + c);
+      o.x += rstd * (d[i].x - s1 - xh[i].x * s2);
+      o.y += rstd * (d[i].y - s1 - xh[i].y * s2);
+      o.z += rstd * (d[i].z - s1 - xh[i].z * s2);
+      o.w += rstd * (d[i].w - s1 - xh[i].w * s2);
+      st4(dxr + c, o);
+    }
+  }
+  if (dgamma != nullptr || dbeta != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&red[c], ag[i].x); atomicAdd(&red[c + 1], ag[i].y); atomicAdd(&red[c + 2], ag[i].z); atomicAdd(&red[c + 3], ag[i].w);
+      atomicAdd(&red[C + c], ab[i].x); atomicAdd(&red[C + c + 1], ab[i].y); atomicAdd(&red[C + c + 2], ab[i].z); atomicAdd(&red[C + c + 3], ab[i].w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (dgamma != nullptr) atomicAdd(dgamma + i, red[i]);
+      if (dbeta != nullptr) atomicAdd(dbeta + i, red[C + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of  x_out = x_in + rowscale[b] * gamma * t   (Block.forward, modeling_finetune.py:296-298):
+//   dt = rowscale*gamma*dx (bf16) ; dgamma += sum rowscale*t*dx ; dbias += sum dt      (dbias = grad of the branch's
+//   last Linear bias, i.e. column sum of dt)
+// ------------------------------------------------------------------------------------------------
+constexpr int CR_MAXG = 4;  // float4 groups per thread: C <= 4 * 4 * 256 = 4096
+
+__global__ void __launch_bounds__(256) scale_residual_bwd_kernel(const float* __restrict__ dx, long long lddx, const bf16* __restrict__ t,
+                                                                 const float* __restrict__ rowscale, int rows_per_scale,
+                                                                 const float* __restrict__ gamma, int rows, int C,
+                                                                 bf16* __restrict__ dt, float* __restrict__ dgamma, float* __restrict__ dbias) {
+  const int ngroups = C >> 2;
+  float4 ag[CR_MAXG], ab[CR_MAXG], gm[CR_MAXG];
+#pragma unroll
+  for (int i = 0; i < CR_MAXG; ++i) {
+    ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int gidx = threadIdx.x + i * 256;
+    gm[i] = (gidx < ngroups && gamma != nullptr) ? __ldg(reinterpret_cast<const float4*>(gamma) + gidx) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float rs = rowscale != nullptr ? __ldg(rowscale + r / rows_per_scale) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < CR_MAXG; ++i) {
+      const int gidx = threadIdx.x + i * 256;
+      if (gidx < ngroups) {
+        const float4 d = ld4(dx + (long long)r * lddx + gidx * 4);
+        const float4 tv = t != nullptr ? ld_bf16x4(t + (long long)r * C + gidx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 o = make_float4(rs * gm[i].x * d.x, rs * gm[i].y * d.y, rs * gm[i].z * d.z, rs * gm[i].w * d.w);
+        st_bf16x4(dt + (long long)r * C + gidx * 4, o);
+        ag[i].x += rs * tv.x * d.x; ag[i].y += rs * tv.y * d.y; ag[i].z += rs * tv.z * d.z; ag[i].w += rs * tv.w * d.w;
+        ab[i].x += o.x; ab[i].y += o.y; ab[i].z += o.z; ab[i].w += o.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CR_MAXG; ++i) {
+    const int gidx = threadIdx.x + i * 256;
+    if (gidx < ngroups) {
+      const int c = gidx * 4;
+      if (dgamma != nullptr) { atomicAdd(dgamma + c, ag[i].x); atomicAdd(dgamma + c + 1, ag[i].y); atomicAdd(dgamma + c + 2, ag[i].z); atomicAdd(dgamma + c + 3, ag[i].w); }
+      if (dbias != nullptr) { atomicAdd(dbias + c, ab[i].x); atomicAdd(dbias + c + 1, ab[i].y); atomicAdd(dbias + c + 2, ab[i].z); atomicAdd(dbias + c + 3, ab[i].w); }
+    }
+  }
+}
+
+// out[c] += sum_r x[r, c]   (bias gradients: fc1.bias from dpre, q_bias / v_bias from dqkv)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ out) {
+  const int ngroups = C >> 2;
+  float4 acc[CR_MAXG];
+#pragma unroll
+  for (int i = 0; i < CR_MAXG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < CR_MAXG; ++i) {
+      const int gidx = threadIdx.x + i * 256;
+      if (gidx < ngroups) {
+        const float4 v = ld_bf16x4(x + (long long)r * ldx + gidx * 4);
+        acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CR_MAXG; ++i) {
+    const int gidx = threadIdx.x + i * 256;
+    if (gidx < ngroups) {
+      const int c = gidx * 4;
+      atomicAdd(out + c, acc[i].x); atomicAdd(out + c + 1, acc[i].y); atomicAdd(out + c + 2, acc[i].z); atomicAdd(out + c + 3, acc[i].w);
+    }
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n4, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) st_bf16x4(dst + i * 4, ld4(src + i * 4));
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) dst[i] = __float2bfloat16(src[i]);
+}
+
+// images [B, Cin, H, W] fp32 -> patch matrix [B*gh*gw, Cin*P*P] bf16, k = (c, py, px) as Conv2d weight.flatten(1)
+// (PatchEmbed, modeling_finetune.py:319-325). One thread moves 4 consecutive pixels of a patch row.
+__global__ void im2col_kernel(const float* __restrict__ img, int B, int Cin, int H, int W, int P, bf16* __restrict__ out) {
+  const int gh = H / P, gw = W / P;
+  const int K = Cin * P * P;
+  const long long total4 = (long long)B * gh * gw * K / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long e = i * 4;
+    const int k = (int)(e % K);
+    const long long row = e / K;
+    const int px = k % P, py = (k / P) % P, c = k / (P * P);
+    const int gx = (int)(row % gw), gy = (int)((row / gw) % gh);
+    const int b = (int)(row / ((long long)gw * gh));
+    const float* s = img + (((long long)b * Cin + c) * H + gy * P + py) * W + gx * P + px;
+    st_bf16x4(out + e, ld4(s));
+  }
+}
+
+// x[b, 0] = cls ; x[b, 1+p] = pe[b,p] * (1 - w) + mask_token * w   (+ pos_embed)   (modeling_cyclical.py:175-194)
+__global__ void assemble_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ cls, const float* __restrict__ mask_token,
+                                       const uint8_t* __restrict__ mask, const float* __restrict__ pos, int B, int np, int C,
+                                       float* __restrict__ x) {
+  const int T = np + 1;
+  const int c4 = C >> 2;
+  const long long total = (long long)B * T * c4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % c4) * 4;
+    const long long row = i / c4;
+    const int t = (int)(row % T);
+    const int b = (int)(row / T);
+    float4 v;
+    if (t == 0) {
+      v = ld4(cls + c);
+    } else {
+      const long long prow = (long long)b * np + (t - 1);
+      v = ld4(pe + prow * C + c);
+      if (mask != nullptr) {
+        const float w = mask[prow] ? 1.0f : 0.0f;
+        const float4 m = ld4(mask_token + c);
+        v = make_float4(v.x * (1.f - w) + m.x * w, v.y * (1.f - w) + m.y * w, v.z * (1.f - w) + m.z * w, v.w * (1.f - w) + m.w * w);
+      }
+    }
+    if (pos != nullptr) {
+      const float4 p = ld4(pos + (long long)t * C + c);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    st4(x + row * C + c, v);
+  }
+}
+
+// backward of assemble_tokens: dpe = dx[:,1:] * (1-w) (bf16) ; dmask_token += sum dx*w ; dcls += sum_b dx[:,0] ; dpos += sum_b dx
+// grid.x strides over batch entries; thread = 4 channels.
+__global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, const uint8_t* __restrict__ mask, int B, int np, int C,
+                                           bf16* __restrict__ dpe, float* __restrict__ dcls, float* __restrict__ dmask_token,
+                                           float* __restrict__ dpos) {
+  const int T = np + 1;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  float4 am = make_float4(0.f, 0.f, 0.f, 0.f), ac = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float4 d0 = ld4(dx + ((long long)b * T) * C + c);
+    ac.x += d0.x; ac.y += d0.y; ac.z += d0.z; ac.w += d0.w;
+    if (dpos != nullptr) { atomicAdd(dpos + c, d0.x); atomicAdd(dpos + c + 1, d0.y); atomicAdd(dpos + c + 2, d0.z); atomicAdd(dpos + c + 3, d0.w); }
+    for (int p = 0; p < np; ++p) {
+      const long long prow = (long long)b * np + p;
+      const float4 d = ld4(dx + ((long long)b * T + 1 + p) * C + c);
+      const float w = (mask != nullptr && mask[prow]) ? 1.0f : 0.0f;
+      st_bf16x4(dpe + prow * C + c, make_float4(d.x * (1.f - w), d.y * (1.f - w), d.z * (1.f - w), d.w * (1.f - w)));
+      am.x += d.x * w; am.y += d.y * w; am.z += d.z * w; am.w += d.w * w;
+      if (dpos != nullptr) {
+        float* q = dpos + (long long)(1 + p) * C + c;
+        atomicAdd(q, d.x); atomicAdd(q + 1, d.y); atomicAdd(q + 2, d.z); atomicAdd(q + 3, d.w);
+      }
+    }
+  }
+  if (dcls != nullptr) { atomicAdd(dcls + c, ac.x); atomicAdd(dcls + c + 1, ac.y); atomicAdd(dcls + c + 2, ac.z); atomicAdd(dcls + c + 3, ac.w); }
+  if (dmask_token != nullptr && mask != nullptr) {
+    atomicAdd(dmask_token + c, am.x); atomicAdd(dmask_token + c + 1, am.y); atomicAdd(dmask_token + c + 2, am.z); atomicAdd(dmask_token + c + 3, am.w);
+  }
+}
+
+// RelativePositionBias.forward (modeling_finetune.py:359-364): out[h, i, j] = table[index[i, j], h]
+__global__ void rel_pos_bias_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, float* __restrict__ out) {
+  const int total = H * N * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int h = i / (N * N), ij = i - h * N * N;
+    out[i] = __ldg(table + (long long)index[ij] * H + h);
+  }
+}
+
+// out[b, c] = mean_{t=1..T-1} x[b, t, c]   (VisionTransformer.forward_features mean pooling, modeling_finetune.py:512-514)
+__global__ void meanpool_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const int b = blockIdx.x;
+  if (c >= C) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 1; t < T; ++t) {
+    const float4 v = ld4(x + ((long long)b * T + t) * C + c);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float inv = 1.0f / (T - 1);
+  st4(out + (long long)b * C + c, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+}
+
+int grid_for(long long work_items, int threads, int sms, int per_sm) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sms * per_sm;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, const float* gamma, const float* beta,
+                                     float eps, int32_t rows, int32_t C, void* y_bf16, float* y_f32, float* mean, float* rstd,
+                                     void* stream) {
+  B200_CHECK_ARG(x != nullptr && rows >= 0 && C > 0 && C % 128 == 0 && C <= 128 * LN_MAXV, "layernorm_fwd: C=%d must be a multiple of 128, <= %d", C, 128 * LN_MAXV);
+  B200_CHECK_ARG(y_bf16 != nullptr || y_f32 != nullptr, "layernorm_fwd: no output");
+  if (rows == 0) return 0;
+  const int grid = (rows + 7) / 8;
+#define LN_FWD(NV) ln_fwd_kernel<NV><<<grid, 256, 0, STREAM>>>(x, ldx, row_index, gamma, beta, eps, rows, C, static_cast<bf16*>(y_bf16), y_f32, mean, rstd)
+  switch (C / 128) {
+    case 1: LN_FWD(1); break; case 2: LN_FWD(2); break; case 3: LN_FWD(3); break; case 4: LN_FWD(4); break;
+    case 5: LN_FWD(5); break; case 6: LN_FWD(6); break; case 7: LN_FWD(7); break; default: LN_FWD(8); break;
+  }
+#undef LN_FWD
+  B200_CHECK_LAUNCH("layernorm_fwd");
+  return 0;
+}
+
+extern "C" int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index,
+                                     const float* gamma, const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx,
+                                     int64_t lddx, float* dgamma, float* dbeta, void* stream) {
+  B200_CHECK_ARG(dy != nullptr && x != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr, "layernorm_bwd: null pointer");
+  B200_CHECK_ARG(C > 0 && C % 128 == 0 && C <= 128 * LN_MAXV, "layernorm_bwd: C=%d must be a multiple of 128, <= %d", C, 128 * LN_MAXV);
+  if (rows == 0) return 0;
+  const int sms = b200vit_num_sms();
+  int grid = (rows + 7) / 8;
+  if (grid > sms * 4) grid = sms * 4;
+  const size_t smem = 2 * C * sizeof(float);
+#define LN_BWD(NV)                                                                                                              \
+  if (dy_is_f32) ln_bwd_kernel<NV, float><<<grid, 256, smem, STREAM>>>(static_cast<const float*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta); \
+  else ln_bwd_kernel<NV, bf16><<<grid, 256, smem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta)
+  switch (C / 128) {
+    case 1: LN_BWD(1); break; case 2: LN_BWD(2); break; case 3: LN_BWD(3); break; case 4: LN_BWD(4); break;
+    case 5: LN_BWD(5); break; case 6: LN_BWD(6); break; case 7: LN_BWD(7); break; default: LN_BWD(8); break;
+  }
+#undef LN_BWD
+  B200_CHECK_LAUNCH("layernorm_bwd");
+  return 0;
+}
+
+extern "C" int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const void* t_bf16, const float* rowscale, int32_t rows_per_scale,
+                                          const float* gamma, int32_t rows, int32_t C, void* dt_bf16, float* dgamma, float* dbias,
+                                          void* stream) {
+  B200_CHECK_ARG(dx != nullptr && dt_bf16 != nullptr, "scale_residual_bwd: null pointer");
+  B200_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 4 * 256 * CR_MAXG, "scale_residual_bwd: bad C=%d", C);
+  B200_CHECK_ARG(rowscale == nullptr || rows_per_scale > 0, "scale_residual_bwd: rows_per_scale must be > 0");
+  if (rows == 0) return 0;
+  const int sms = b200vit_num_sms();
+  int grid = rows < sms * 4 ? rows : sms * 4;
+  scale_residual_bwd_kernel<<<grid, 256, 0, STREAM>>>(dx, lddx, static_cast<const bf16*>(t_bf16), rowscale, rows_per_scale > 0 ? rows_per_scale : 1, gamma, rows, C,
+                                                       static_cast<bf16*>(dt_bf16), dgamma, dbias);
+  B200_CHECK_LAUNCH("scale_residual_bwd");
+  return 0;
+}
+
+extern "C" int b200vit_colsum_bf16(const void* x, int64_t ldx, int32_t rows, int32_t C, float* out, void* stream) {
+  B200_CHECK_ARG(x != nullptr && out != nullptr && C > 0 && C % 4 == 0 && C <= 4 * 256 * CR_MAXG && ldx % 4 == 0, "colsum_bf16: bad arguments (C=%d)", C);
+  if (rows == 0) return 0;
+  const int sms = b200vit_num_sms();
+  int grid = rows < sms * 4 ? rows : sms * 4;
+  colsum_bf16_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), ldx, rows, C, out);
+  B200_CHECK_LAUNCH("colsum_bf16");
+  return 0;
+}
+
+extern "C" int b200vit_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  B200_CHECK_ARG(src != nullptr && dst != nullptr && n >= 0, "cast: bad arguments");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cast: unaligned pointers");
+  if (n == 0) return 0;
+  const int sms = b200vit_num_sms();
+  cast_bf16_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, STREAM>>>(src, static_cast<bf16*>(dst), n / 4, n);
+  B200_CHECK_LAUNCH("cast_f32_to_bf16");
+  return 0;
+}
+
+extern "C" int b200vit_im2col_patches(const float* img, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t P, void* out_bf16, void* stream) {
+  B200_CHECK_ARG(img != nullptr && out_bf16 != nullptr && B > 0 && P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "im2col: bad arguments");
+  const int sms = b200vit_num_sms();
+  const long long total4 = (long long)B * Cin * H * W / 4;
+  im2col_kernel<<<grid_for(total4, 256, sms, 8), 256, 0, STREAM>>>(img, B, Cin, H, W, P, static_cast<bf16*>(out_bf16));
+  B200_CHECK_LAUNCH("im2col_patches");
+  return 0;
+}
+
+extern "C" int b200vit_assemble_tokens(const float* pe, const float* cls, const float* mask_token, const uint8_t* mask, const float* pos_embed,
+                                       int32_t B, int32_t np, int32_t C, float* x, void* stream) {
+  B200_CHECK_ARG(pe != nullptr && cls != nullptr && x != nullptr && C % 4 == 0, "assemble_tokens: bad arguments");
+  B200_CHECK_ARG(mask == nullptr || mask_token != nullptr, "assemble_tokens: mask without mask_token");
+  const int sms = b200vit_num_sms();
+  assemble_tokens_kernel<<<grid_for((long long)B * (np + 1) * (C / 4), 256, sms, 8), 256, 0, STREAM>>>(pe, cls, mask_token, mask, pos_embed, B, np, C, x);
+  B200_CHECK_LAUNCH("assemble_tokens");
+  return 0;
+}
+
+extern "C" int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask, int32_t B, int32_t np, int32_t C, void* dpe_bf16, float* dcls,
+                                           float* dmask_token, float* dpos_embed, void* stream) {
+  B200_CHECK_ARG(dx != nullptr && dpe_bf16 != nullptr && C % 4 == 0, "assemble_tokens_bwd: bad arguments");
+  const int threads = 64;
+  dim3 grid(B, (C / 4 + threads - 1) / threads);
+  assemble_tokens_bwd_kernel<<<grid, threads, 0, STREAM>>>(dx, mask, B, np, C, static_cast<bf16*>(dpe_bf16), dcls, dmask_token, dpos_embed);
+  B200_CHECK_LAUNCH("assemble_tokens_bwd");
+  return 0;
+}
+
+extern "C" int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, float* out, void* stream) {
+  B200_CHECK_ARG(table != nullptr && index != nullptr && out != nullptr && N > 0 && H > 0, "rel_pos_bias: bad arguments");
+  const int sms = b200vit_num_sms();
+  rel_pos_bias_kernel<<<grid_for((long long)H * N * N, 256, sms, 8), 256, 0, STREAM>>>(table, index, N, H, out);
+  B200_CHECK_LAUNCH("rel_pos_bias");
+  return 0;
+}
+
+extern "C" int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int32_t C, float* out, void* stream) {
+  B200_CHECK_ARG(x != nullptr && out != nullptr && T > 1 && C % 4 == 0, "meanpool_tokens: bad arguments");
+  const int threads = 64;
+  dim3 grid(B, (C / 4 + threads - 1) / threads);
+  meanpool_kernel<<<grid, threads, 0, STREAM>>>(x, B, T, C, out);
+  B200_CHECK_LAUNCH("meanpool_tokens");
+  return 0;
+}
