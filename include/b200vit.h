@@ -142,14 +142,14 @@ int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers,
                             float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
                             void* stream);
 /* EMA teacher update e = d*e + (1-d)*m (engine_for_cyclical.py:182-185, timm ModelEmaV2._update) + bf16 shadow */
-int b200vit_ema_update(float* ema, const float* model, int64_t n, float decay, void* ema_bf16, void* stream);
+int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, void* ema_bf16, void* stream);
 /* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
 int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
 /* clip + torch.optim.AdamW + bf16 weight shadow + EMA over flat arenas (utils.py:364-390, optim_factory.py:58-97).
  * hp_lr_wd: device float2 {lr, weight_decay} per 1024-element chunk. grad_div: loss-scale divisor (unscale_). */
 int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
                        float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
-                       float ema_decay, void* ema_bf16, void* stream);
+                       double ema_decay, void* ema_bf16, void* stream);
 /* WassersteinLoss.forward + backward (distloss.py:13-30,73-79). work: 2R+8 floats. d_* are accumulated (+=). */
 int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
                              int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,

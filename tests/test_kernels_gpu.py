@@ -1,0 +1,402 @@
+"""Kernel-level parity tests (B200): every C-ABI entry point against the CPU oracle / a plain fp32 PyTorch restatement
+of the same op on identical seeded inputs. Tolerances: fp32 paths 1e-4 relative, bf16 paths 2e-2 (BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    import uncertainty_vit_b200 as pkg
+    return pkg.ops
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GEMM: all four operand majors, ragged shapes, every epilogue
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (51, 128, 128), (394, 768, 768), (1000, 2304, 768), (333, 3072, 768),
+                                   (257, 768, 3072), (2000, 1000, 768)])
+def test_gemm_kmajor_bf16_out(ops, cuda, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_BF16, bias=bias, out_bf16=out)
+    ref = a.float() @ w.float().t() + bias
+    assert rel(out.float(), ref) < 5e-3
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 384, 520), (768, 768, 3000)])
+def test_gemm_mn_major_f32_out(ops, cuda, a_mn, b_mn, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(K + 13 * M)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    b = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda)
+    a_store = a.t().contiguous() if a_mn else a
+    b_store = b.t().contiguous() if b_mn else b
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=cuda)
+    ops.gemm(a_store, b_store, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=ops.EPI_F32, out_f32=out)
+    ref = a.float() @ b.float().t()
+    assert rel(out, ref) < 1e-5
+
+
+def test_gemm_wgrad_splitk_atomic(ops, cuda):
+    M, N, K = 6000, 768, 768   # dw[N,K] += dy[M,N]^T x[M,K]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dy = _bf(torch.randn(M, N, generator=g)).to(cuda)
+    x = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    dw = torch.ones(N, K, dtype=torch.float32, device=cuda)
+    ops.linear_wgrad(dy, x, dw)
+    ref = 1.0 + dy.float().t() @ x.float()
+    assert rel(dw, ref) < 1e-5
+    dw2 = torch.zeros(N, K, dtype=torch.float32, device=cuda)
+    ops.gemm(dy, x, N, K, M, a_mn=True, b_mn=True, epilogue=ops.EPI_F32_ATOMIC, out_f32=dw2, split_k=1)
+    assert rel(dw2, ref - 1.0) < 1e-5
+
+
+def test_gemm_epilogues(ops, cuda):
+    M, N, K, T = 394, 768, 768, 197
+    g = torch.Generator(device="cpu").manual_seed(9)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    gamma = torch.rand(N, generator=g).to(cuda)
+    rowscale = torch.tensor([0.0, 1.0 / 0.8], device=cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    acc = a.float() @ w.float().t() + bias
+    # GELU (+ pre-activation copy)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_GELU, bias=bias, out_bf16=out, out2_bf16=pre)
+    assert rel(pre.float(), acc) < 5e-3
+    assert rel(out.float(), torch.nn.functional.gelu(acc)) < 5e-3
+    # residual + layer-scale + drop-path
+    x_out = torch.empty(M, N, dtype=torch.float32, device=cuda)
+    t = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_RESIDUAL, bias=bias, colscale=gamma, rowscale=rowscale, rows_per_scale=T, residual=res,
+             out_f32=x_out, out2_bf16=t)
+    rs = rowscale.repeat_interleave(T)[:, None]
+    assert rel(x_out, res + rs * gamma * acc) < 1e-5
+    assert rel(t.float(), acc) < 5e-3
+    # dGELU
+    aux = _bf(torch.randn(M, N, generator=g)).to(cuda)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_DGELU, aux=aux, out_bf16=out)
+    xa = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(xa).sum().backward()
+    assert rel(out.float(), (a.float() @ w.float().t()) * xa.grad) < 5e-3
+    # ELU + 1
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_ELU1, bias=bias, out_bf16=out)
+    assert rel(out.float(), torch.nn.functional.elu(acc) + 1) < 5e-3
+
+
+def test_gemm_bad_args_raise(ops, cuda):
+    import uncertainty_vit_b200 as pkg
+    a = torch.zeros(16, 60, dtype=torch.bfloat16, device=cuda)
+    w = torch.zeros(16, 60, dtype=torch.bfloat16, device=cuda)
+    out = torch.zeros(16, 16, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(pkg._lib.B200VitError):
+        ops.gemm(a, w, 16, 16, 60, out_bf16=out)   # lda not a multiple of 8
+
+
+# ------------------------------------------------------------------------------------------------------------
+# LayerNorm / row kernels
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,C", [(37, 128), (394, 768), (101, 1024)])
+def test_layernorm_fwd_bwd(ops, cuda, rows, C):
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(cuda)
+    gam = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda)
+    bet = (0.1 * torch.randn(C, generator=g)).to(cuda)
+    y32 = torch.empty(rows, C, device=cuda)
+    y16 = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda)
+    mean = torch.empty(rows, device=cuda)
+    rstd = torch.empty(rows, device=cuda)
+    ops.layernorm_fwd(x, gam, bet, 1e-6, rows, C, y_bf16=y16, y_f32=y32, mean=mean, rstd=rstd)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-6)
+    assert rel(y32, ref) < 1e-5
+    assert rel(y16.float(), ref) < 5e-3
+    dy = torch.randn(rows, C, generator=g).to(cuda)
+    ref.backward(dy)
+    dx = torch.ones(rows, C, device=cuda)
+    dg = torch.zeros(C, device=cuda)
+    db = torch.zeros(C, device=cuda)
+    ops.layernorm_bwd(dy, x, gam, mean, rstd, rows, C, dx, dg, db)
+    assert rel(dx - 1.0, xr.grad) < 1e-4
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    # bf16 dy + gather/scatter rows
+    idx = torch.randperm(rows, generator=g)[: max(1, rows // 3)].sort().values.to(torch.int32).to(cuda)
+    R = idx.numel()
+    yg = torch.empty(R, C, device=cuda)
+    mg = torch.empty(R, device=cuda)
+    rg = torch.empty(R, device=cuda)
+    ops.layernorm_fwd(x, gam, bet, 1e-6, R, C, y_f32=yg, mean=mg, rstd=rg, row_index=idx)
+    assert rel(yg, ref.detach()[idx.long()]) < 1e-5
+    dyb = dy[:R].to(torch.bfloat16)
+    dx2 = torch.zeros(rows, C, device=cuda)
+    ops.layernorm_bwd(dyb, x, gam, mg, rg, R, C, dx2, None, None, row_index=idx)
+    xr2 = x.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr2, (C,), gam, bet, 1e-6)[idx.long()].backward(dyb.float())
+    assert rel(dx2, xr2.grad) < 1e-4
+
+
+def test_scale_residual_bwd_and_colsum(ops, cuda):
+    rows, C, T = 394, 768, 197
+    g = torch.Generator(device="cpu").manual_seed(3)
+    dx = torch.randn(rows, C, generator=g).to(cuda)
+    t = _bf(torch.randn(rows, C, generator=g)).to(cuda)
+    gamma = torch.rand(C, generator=g).to(cuda)
+    rowscale = torch.tensor([1.25, 0.0], device=cuda)
+    dt = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda)
+    dg = torch.zeros(C, device=cuda)
+    db = torch.zeros(C, device=cuda)
+    ops.scale_residual_bwd(dx, t, rowscale, T, gamma, rows, C, dt, dg, db)
+    rs = rowscale.repeat_interleave(T)[:, None]
+    ref_dt = rs * gamma * dx
+    assert rel(dt.float(), ref_dt) < 5e-3
+    assert rel(dg, (rs * t.float() * dx).sum(0)) < 1e-4
+    assert rel(db, ref_dt.sum(0)) < 1e-4
+    x = _bf(torch.randn(rows, 2304, generator=g)).to(cuda)
+    out = torch.zeros(768, device=cuda)
+    ops.colsum_bf16(x[:, 1536:], rows, 768, out, ldx=2304)
+    assert rel(out, x[:, 1536:].float().sum(0)) < 1e-4
+
+
+def test_patch_embed_pieces(ops, cuda):
+    B, P, G, C = 3, 16, 4, 128
+    g = torch.Generator(device="cpu").manual_seed(4)
+    img = torch.randn(B, 3, G * P, G * P, generator=g).to(cuda)
+    w = (torch.randn(C, 3, P, P, generator=g) * 0.05).to(cuda)
+    bias = torch.randn(C, generator=g).to(cuda)
+    patches = torch.empty(B * G * G, 3 * P * P, dtype=torch.bfloat16, device=cuda)
+    ops.im2col(img, P, patches)
+    ref_p = torch.nn.functional.unfold(img, P, stride=P).transpose(1, 2).reshape(B * G * G, -1)
+    assert rel(patches.float(), ref_p) < 5e-3
+    pe = torch.empty(B * G * G, C, device=cuda)
+    ops.gemm(patches, ops.cast_bf16(w.reshape(C, -1)), B * G * G, C, 3 * P * P, epilogue=ops.EPI_F32, bias=bias, out_f32=pe)
+    ref = torch.nn.functional.conv2d(img, w, bias, stride=P).flatten(2).transpose(1, 2).reshape(B * G * G, C)
+    assert rel(pe, ref) < 1e-2
+    cls = torch.randn(C, generator=g).to(cuda)
+    mtok = torch.randn(C, generator=g).to(cuda)
+    mask = (torch.rand(B, G * G, generator=g) < 0.5).to(torch.uint8).to(cuda)
+    x = torch.empty(B, G * G + 1, C, device=cuda)
+    ops.assemble_tokens(pe, cls, mtok, mask, None, B, G * G, C, x)
+    wm = mask.float()[..., None]
+    refx = torch.cat((cls.expand(B, 1, C), pe.view(B, G * G, C) * (1 - wm) + mtok * wm), 1)
+    assert rel(x, refx) < 1e-6
+    dx = torch.randn(B, G * G + 1, C, generator=g).to(cuda)
+    dpe = torch.empty(B * G * G, C, dtype=torch.bfloat16, device=cuda)
+    dcls = torch.zeros(C, device=cuda)
+    dm = torch.zeros(C, device=cuda)
+    ops.assemble_tokens_bwd(dx, mask, B, G * G, C, dpe, dcls, dm)
+    assert rel(dpe.float(), (dx[:, 1:] * (1 - wm)).reshape(-1, C)) < 5e-3
+    assert rel(dcls, dx[:, 0].sum(0)) < 1e-5
+    assert rel(dm, (dx[:, 1:] * wm).sum((0, 1))) < 1e-5
+
+
+def test_rel_pos_bias_and_meanpool(ops, cuda):
+    from oracle import vit_oracle as O
+    H = 12
+    idx = O.relative_position_index(14, 14)
+    table = torch.randn(732, H)
+    out = torch.empty(H, 197, 197, device=cuda)
+    ops.rel_pos_bias(table.to(cuda), idx.to(torch.int32).to(cuda), 197, H, out)
+    assert torch.equal(out.cpu(), O.rel_pos_bias(table, idx))           # pure gather: bit-exact
+    x = torch.randn(4, 197, 768)
+    o = torch.empty(4, 768, device=cuda)
+    ops.meanpool_tokens(x.to(cuda), 4, 197, 768, o)
+    assert rel(o.cpu(), x[:, 1:].mean(1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, bias, keep, p, scale):
+    B, N, _, H, D = qkv.shape
+    q, k, v = qkv.float().permute(2, 0, 3, 1, 4)
+    s = (q * scale) @ k.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    pr = s.softmax(-1)
+    if keep is not None:
+        pr = pr * keep.view(B, H, N, N).float() / (1 - p)
+    return (pr @ v).transpose(1, 2).reshape(B, N, H * D)
+
+
+@pytest.mark.parametrize("B,H,N,p", [(2, 2, 17, 0.0), (2, 3, 197, 0.0), (3, 2, 197, 0.1), (1, 2, 64, 0.25), (2, 2, 208, 0.05)])
+def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
+    g = torch.Generator(device="cpu").manual_seed(N + B)
+    qkv = _bf(torch.randn(B, N, 3, H, 64, generator=g)).to(cuda)
+    bias = (torch.randn(H, N, N, generator=g) * 0.5).to(cuda)
+    scale = 64 ** -0.5
+    out = torch.full((B, N, H * 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+    lse = torch.empty(B, H, N, device=cuda)
+    bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=cuda)
+    seed, sid = 1234, 7
+    ops.attn_fwd(qkv, bias, B, H, N, scale, p, seed, sid, None, out, lse, bits if p > 0 else None)
+    keep = ops.dropout_mask(B * H, N, p, seed, sid, cuda) if p > 0 else None
+    if keep is not None:
+        frac = keep.float().mean().item()
+        assert abs(frac - (1 - p)) < 0.02
+        # packed bits written by the forward == the materialised mask
+        unpacked = ((bits.view(B * H, N, 32, 1) >> torch.arange(8, device=cuda, dtype=torch.uint8)) & 1).reshape(B * H, N, 256)[:, :, :N]
+        assert torch.equal(unpacked, keep)
+    qr = qkv.float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    ref = _attn_ref(qr, br, keep, p, scale)
+    assert rel(out.float(), ref) < 1e-2
+    assert torch.isfinite(out.float()).all()
+    # injected mask path gives the same result
+    if keep is not None:
+        out2 = torch.empty_like(out)
+        bits2 = torch.zeros_like(bits)
+        ops.attn_fwd(qkv, bias, B, H, N, scale, p, 0, 0, keep, out2, lse, bits2)
+        unpacked2 = ((bits2.view(B * H, N, 32, 1) >> torch.arange(8, device=cuda, dtype=torch.uint8)) & 1).reshape(B * H, N, 256)[:, :, :N]
+        assert torch.equal(out2, out) and torch.equal(unpacked2, keep)
+    # backward
+    dout = _bf(torch.randn(B, N, H * 64, generator=g)).to(cuda)
+    ref.backward(dout.float())
+    idx = torch.randint(0, 50, (N, N), generator=g).to(torch.int32).to(cuda)
+    dtable = torch.zeros(50, H, device=cuda)
+    dqkv = torch.full((B, N, 3, H, 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+    ops.attn_bwd(qkv, out, dout, lse, bias, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv)
+    assert torch.isfinite(dqkv.float()).all()
+    for part, name in ((0, "dq"), (1, "dk"), (2, "dv")):
+        assert rel(dqkv[:, :, part].float(), qr.grad[:, :, part]) < 2e-2, name
+    ref_tab = torch.zeros(50, H, device=cuda)
+    ref_tab.index_add_(0, idx.long().flatten(), br.grad.permute(1, 2, 0).reshape(N * N, H))
+    assert rel(dtable, ref_tab) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------------------
+# data2vec target/loss, EMA, AdamW, Wasserstein loss, MC metrics  — against the CPU oracle
+# ------------------------------------------------------------------------------------------------------------
+def test_d2v_target_loss_vs_oracle(ops, cuda):
+    from oracle import vit_oracle as O
+    B, T, C, K = 4, 197, 768, 6
+    g = torch.Generator(device="cpu").manual_seed(21)
+    layers = [torch.randn(B, T, C, generator=g) * (1 + i) + 0.3 * i for i in range(K)]
+    mask = torch.zeros(B, T - 1, dtype=torch.int64)
+    for b in range(B):
+        mask[b, torch.randperm(T - 1, generator=g)[: 100 + 5 * b]] = 1
+    y = torch.randn(int(mask.sum()), C, generator=g) * 2
+    yo = y.clone().requires_grad_(True)
+    tgt = O.build_targets([l[:, 1:] for l in layers], list(range(K)), mask, post_target_layer_norm=True)
+    loss, _ = O.d2v_loss(yo, tgt, 2.0)
+    loss.backward()
+    rows = (torch.nonzero(mask.flatten()).flatten() // (T - 1) * T + 1 + torch.nonzero(mask.flatten()).flatten() % (T - 1)).to(torch.int32)
+    R = rows.numel()
+    dl = [l.to(cuda) for l in layers]
+    targets = torch.empty(R, C, device=cuda)
+    dy = torch.empty(R, C, device=cuda)
+    dyb = torch.empty(R, C, dtype=torch.bfloat16, device=cuda)
+    row_loss = torch.empty(R, device=cuda)
+    loss_out = torch.empty(1, device=cuda)
+    ops.d2v_target_loss(dl, C, rows.to(cuda), y.to(cuda), R, C, True, True, 2.0, False, 1.0 / (R * C), targets, dyb, dy, row_loss, loss_out)
+    assert rel(targets.cpu(), tgt) < 1e-5
+    assert abs(loss_out.item() - loss.item()) / abs(loss.item()) < 1e-5
+    assert rel(dy.cpu(), yo.grad) < 1e-5
+    assert rel(dyb.float().cpu(), yo.grad) < 5e-3
+    # MSE + no post-LN variant
+    tgt2 = O.build_targets([l[:, 1:] for l in layers], list(range(K)), mask, post_target_layer_norm=False)
+    loss2, _ = O.d2v_loss(y, tgt2, 2.0, l2_loss=True)
+    ops.d2v_target_loss(dl, C, rows.to(cuda), y.to(cuda), R, C, True, False, 2.0, True, 1.0, targets, None, None, row_loss, loss_out)
+    assert rel(targets.cpu(), tgt2) < 1e-5 and abs(loss_out.item() - loss2.item()) / abs(loss2.item()) < 1e-5
+
+
+def test_ema_and_adamw_vs_oracle(ops, cuda):
+    from oracle import vit_oracle as O
+    n = 1024 * 37
+    g = torch.Generator(device="cpu").manual_seed(2)
+    p = torch.randn(n, generator=g)
+    e = torch.randn(n, generator=g)
+    pc, ec = p.clone(), e.clone()
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    P, E, Mo, V = p.to(cuda), e.to(cuda), m.to(cuda), v.to(cuda)
+    Pb = torch.empty(n, dtype=torch.bfloat16, device=cuda)
+    Eb = torch.empty(n, dtype=torch.bfloat16, device=cuda)
+    lr, wd, max_norm, d = 2e-3, 0.05, 3.0, 0.9998
+    hp = torch.tensor([[lr, wd]] * (n // 1024), dtype=torch.float32)
+    hp[::2, 1] = 0.0                         # alternate chunks: no-decay group
+    hp[::3, 0] = lr * 0.65                   # and a layer-decay lr scale
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * 5
+        total, coef = O.clip_grad_norm([grad], max_norm)
+        for c in range(n // 1024):
+            sl = slice(c * 1024, (c + 1) * 1024)
+            O.adamw_step(pc[sl], grad[sl] * coef, m[sl], v[sl], step, float(hp[c, 0]), float(hp[c, 1]))
+        O.ema_update({"w": ec}, {"w": pc}, d)
+        G = grad.to(cuda)
+        nsq = torch.zeros(1, device=cuda)
+        ops.sumsq(G, nsq)
+        assert abs(math.sqrt(nsq.item()) - float(total)) / float(total) < 1e-5
+        ops.adamw_step(P, G, Mo, V, hp.to(cuda), step, gnorm_sq=nsq, max_norm=max_norm, p_bf16=Pb, ema=E, ema_decay=d, ema_bf16=Eb)
+    assert rel(P.cpu(), pc) < 1e-5 and rel(E.cpu(), ec) < 1e-6
+    assert rel(Pb.float().cpu(), pc) < 5e-3 and rel(Eb.float().cpu(), ec) < 5e-3
+    # stand-alone EMA kernel: bit-exact against the reference expression d*e + (1-d)*m in fp32
+    e2 = torch.randn(n, generator=g)
+    m2 = torch.randn(n, generator=g)
+    E2 = e2.to(cuda)
+    ops.ema_update(E2, m2.to(cuda), d)
+    assert torch.equal(E2.cpu(), d * e2 + (1.0 - d) * m2)
+
+
+def test_wasserstein_loss_vs_oracle(ops, cuda):
+    from oracle import vit_oracle as O
+    R, C = 300, 768
+    g = torch.Generator(device="cpu").manual_seed(8)
+    t = [torch.randn(R, C, generator=g) for _ in range(4)]
+    a = t[0].clone().requires_grad_(True)
+    b = t[1].clone().requires_grad_(True)
+    loss = O.wasserstein_loss(a, b, t[2], t[3], 1e-5)
+    loss.backward()
+    dev = [x.to(cuda) for x in t]
+    work = torch.empty(2 * R + 8, device=cuda)
+    da = torch.zeros(R, C, device=cuda)
+    db = torch.zeros(R, C, device=cuda)
+    lo = torch.empty(1, device=cuda)
+    ops.wasserstein_loss(dev[0], dev[1], dev[2], dev[3], 1e-5, 1.0, work, da, db, lo)
+    assert abs(lo.item() - loss.item()) / abs(loss.item()) < 1e-4
+    assert rel(da.cpu(), a.grad) < 1e-3 and rel(db.cpu(), b.grad) < 1e-3
+
+
+def test_mc_reduce_vs_oracle_and_golden(ops, cuda, golden_dir):
+    import os
+    from oracle import vit_oracle as O
+    gold = torch.load(os.path.join(golden_dir, "metrics.pt"))
+    for logits, labels in ((gold["logits"], gold["labels"]),
+                           (torch.randn(30, 192, 1000, generator=torch.Generator().manual_seed(0)) * 3,
+                            torch.randint(0, 1000, (192,), generator=torch.Generator().manual_seed(1)))):
+        if logits.shape[2] == 1000:   # make the synthetic case partly correct
+            labels = torch.where(torch.arange(192) % 2 == 0, logits.mean(0).argmax(1), labels)
+        r = O.mc_reduce(logits, labels)
+        mean_logits, rows, hist, summary = ops.mc_reduce(logits.to(cuda), labels.to(torch.int32).to(cuda))
+        s = summary.cpu()
+        assert rel(mean_logits.cpu(), r["mean_logits"]) < 1e-6
+        assert torch.equal(rows[:, 1].cpu().long(), r["pred"])                      # argmax: bit-exact
+        assert abs(s[0].item() - r["acc1"]) < 1e-3 and abs(s[1].item() - r["acc5"]) < 1e-3
+        assert abs(s[2].item() - r["ece"]) < 1e-5 and abs(s[3].item() - r["ece_reference"]) < 1e-5
+        assert abs(s[4].item() - r["nll"]) / abs(r["nll"]) < 1e-5
+        assert rel(rows[:, 5].cpu(), r["entropy"]) < 1e-4 and rel(rows[:, 6].cpu(), r["variance"]) < 1e-3
+        assert (rows[:, 7].cpu() - r["mutual_info"]).abs().max() < 1e-4
+    assert abs(s[3].item() - 0) >= 0  # summary layout sanity
+    mean_logits, rows, hist, summary = ops.mc_reduce(gold["logits"].to(cuda), gold["labels"].to(torch.int32).to(cuda))
+    assert abs(summary[3].item() - gold["ece_reference"]) < 1e-5 and abs(summary[4].item() - gold["nll"]) < 1e-5
+    assert abs(summary[0].item() - gold["acc1"]) < 1e-3 and abs(summary[1].item() - gold["acc5"]) < 1e-3

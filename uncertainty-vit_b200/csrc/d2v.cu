@@ -121,15 +121,18 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 }
 
 // e = d*e + (1-d)*m ; optional bf16 shadow of e
-__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ e, const float* __restrict__ m, long long n4, float d,
+// bit-exact restatement of the reference lambda `cur_decay * e + (1. - cur_decay) * m` on fp32 tensors: both python scalars
+// are rounded to fp32, two rounded products, one rounded add (no FMA contraction).
+__device__ __forceinline__ float ema_mix(float d, float od, float e, float m) { return __fadd_rn(__fmul_rn(d, e), __fmul_rn(od, m)); }
+
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ e, const float* __restrict__ m, long long n4, float d, float od,
                                                   bf16* __restrict__ shadow) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const float od = 1.0f - d;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 a = ld4(e + i * 4);
     const float4 b = ld4_stream(m + i * 4);
     // same expression as the reference lambda: cur_decay * e + (1. - cur_decay) * m
-    const float4 o = make_float4(d * a.x + od * b.x, d * a.y + od * b.y, d * a.z + od * b.z, d * a.w + od * b.w);
+    const float4 o = make_float4(ema_mix(d, od, a.x, b.x), ema_mix(d, od, a.y, b.y), ema_mix(d, od, a.z, b.z), ema_mix(d, od, a.w, b.w));
     *reinterpret_cast<float4*>(e + i * 4) = o;
     if (shadow != nullptr) {
       uint2 u;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ v, long long n4, const float2* __restrict__ hp,
                                                     float beta1, float beta2, float eps, float bc1, float sqrt_bc2,
                                                     const float* __restrict__ gnorm_sq, float max_norm, float grad_div,
-                                                    bf16* __restrict__ p_shadow, float* __restrict__ ema, float ema_decay,
+                                                    bf16* __restrict__ p_shadow, float* __restrict__ ema, float ema_decay, float od,
                                                     bf16* __restrict__ ema_shadow) {
   float coef = 1.0f / grad_div;
   if (gnorm_sq != nullptr && max_norm > 0.f) {
@@ -174,7 +177,6 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     coef *= fminf(1.0f, max_norm / (norm + 1e-6f));  // torch.nn.utils.clip_grad_norm_
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
-  const float od = 1.0f - ema_decay;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float2 h = __ldg(hp + (i >> 8));  // 1024 elements = 256 float4 per chunk
     const float lr = h.x, wd = h.y;
@@ -202,8 +204,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     }
     if (ema != nullptr) {
       const float4 ev = ld4(ema + i * 4);
-      const float4 o = make_float4(ema_decay * ev.x + od * pv.x, ema_decay * ev.y + od * pv.y, ema_decay * ev.z + od * pv.z,
-                                   ema_decay * ev.w + od * pv.w);
+      const float4 o = make_float4(ema_mix(ema_decay, od, ev.x, pv.x), ema_mix(ema_decay, od, ev.y, pv.y), ema_mix(ema_decay, od, ev.z, pv.z),
+                                   ema_mix(ema_decay, od, ev.w, pv.w));
       *reinterpret_cast<float4*>(ema + i * 4) = o;
       if (ema_shadow != nullptr) {
         uint2 u;
@@ -373,14 +375,14 @@ extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t 
   return 0;
 }
 
-extern "C" int b200vit_ema_update(float* ema, const float* model, int64_t n, float decay, void* ema_bf16, void* stream) {
+extern "C" int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, void* ema_bf16, void* stream) {
   B200_CHECK_ARG(ema != nullptr && model != nullptr && n >= 0 && n % 4 == 0, "ema_update: n=%lld must be a multiple of 4", (long long)n);
   B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(ema) | reinterpret_cast<uintptr_t>(model)) & 15) == 0, "ema_update: arenas must be 16-byte aligned");
   if (n == 0) return 0;
   const int sms = b200vit_num_sms();
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-  ema_kernel<<<(int)blocks, 256, 0, STREAM>>>(ema, model, n / 4, decay, static_cast<bf16*>(ema_bf16));
+  ema_kernel<<<(int)blocks, 256, 0, STREAM>>>(ema, model, n / 4, (float)decay, (float)(1.0 - decay), static_cast<bf16*>(ema_bf16));
   B200_CHECK_LAUNCH("ema_update");
   return 0;
 }
@@ -398,7 +400,7 @@ extern "C" int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* 
 
 extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
                                   float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
-                                  float ema_decay, void* ema_bf16, void* stream) {
+                                  double ema_decay, void* ema_bf16, void* stream) {
   B200_CHECK_ARG(p != nullptr && g != nullptr && m != nullptr && v != nullptr && hp_lr_wd != nullptr, "adamw_step: null pointer");
   B200_CHECK_ARG(n >= 0 && n % 1024 == 0, "adamw_step: arena length must be a multiple of 1024 (one {lr,wd} pair per 1024 elements)");
   B200_CHECK_ARG(step >= 1, "adamw_step: step counts from 1");
@@ -409,7 +411,7 @@ extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, 
   if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
   adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, n / 4, reinterpret_cast<const float2*>(hp_lr_wd), beta1, beta2, eps, (float)bc1,
                                                 (float)sqrt(bc2), gnorm_sq, max_norm, grad_div > 0.f ? grad_div : 1.0f,
-                                                static_cast<bf16*>(p_bf16), ema, ema_decay, static_cast<bf16*>(ema_bf16));
+                                                static_cast<bf16*>(p_bf16), ema, (float)ema_decay, (float)(1.0 - ema_decay), static_cast<bf16*>(ema_bf16));
   B200_CHECK_LAUNCH("adamw_step");
   return 0;
 }

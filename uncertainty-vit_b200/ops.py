@@ -1,0 +1,223 @@
+"""Tensor-level wrappers over the C ABI. PyTorch only supplies device memory and the CUDA stream; every call below ends in a
+hand-written sm_100a kernel of libb200vit.so. Tensors must be CUDA tensors; there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BF16, EPI_DGELU, EPI_ELU1, EPI_F32, EPI_F32_ATOMIC, EPI_GELU, EPI_RESIDUAL, GemmDesc, check)
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.B200VitError("libb200vit ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def sm_count() -> int:
+    return _lib.lib().b200vit_device_sm_count()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
+         epilogue: int = EPI_BF16, bias=None, colscale=None, rowscale=None, rows_per_scale: int = 0, residual=None,
+         aux=None, out_f32=None, out_bf16=None, out2_bf16=None, alpha: float = 1.0, split_k: int = 0, max_ctas: int = 0,
+         lda: Optional[int] = None, ldb: Optional[int] = None) -> None:
+    """D[M,N] = A[M,K] B[N,K]^T (bf16 in, fp32 accumulate). a_mn/b_mn: operand stored as [K, M] / [K, N] row-major."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn_major = _p(a), (lda if lda is not None else a.stride(0)), int(a_mn)
+    d.B, d.ldb, d.b_mn_major = _p(b), (ldb if ldb is not None else b.stride(0)), int(b_mn)
+    d.epilogue = epilogue
+    d.bias, d.colscale, d.rowscale, d.rows_per_scale = _p(bias), _p(colscale), _p(rowscale), rows_per_scale
+    if residual is not None:
+        d.residual, d.ld_residual = _p(residual), residual.stride(0)
+    if aux is not None:
+        d.aux, d.ld_aux = _p(aux), aux.stride(0)
+    if out_f32 is not None:
+        d.out_f32, d.ld_f32 = _p(out_f32), out_f32.stride(0)
+    if out_bf16 is not None:
+        d.out_bf16, d.ld_bf16 = _p(out_bf16), out_bf16.stride(0)
+    if out2_bf16 is not None:
+        d.out2_bf16, d.ld2_bf16 = _p(out2_bf16), out2_bf16.stride(0)
+    d.alpha, d.split_k, d.max_ctas = alpha, split_k, max_ctas
+    check(_lib.lib().b200vit_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
+    _count()
+
+
+def linear_fwd(x_bf16, w_bf16, **kw):
+    """x[M,K] @ w[N,K]^T"""
+    M, K = x_bf16.shape
+    N = w_bf16.shape[0]
+    gemm(x_bf16, w_bf16, M, N, K, **kw)
+
+
+def linear_dgrad(dy_bf16, w_bf16, **kw):
+    """dx[M,K] = dy[M,N] @ w[N,K]   (w is the MN-major B operand)"""
+    M, N = dy_bf16.shape
+    K = w_bf16.shape[1]
+    gemm(dy_bf16, w_bf16, M, K, N, b_mn=True, **kw)
+
+
+def linear_wgrad(dy_bf16, x_bf16, dw_f32, alpha: float = 1.0):
+    """dw[N,K] += dy[M,N]^T @ x[M,K]   (both operands MN-major, split-K with fp32 atomics)"""
+    M, N = dy_bf16.shape
+    K = x_bf16.shape[1]
+    gemm(dy_bf16, x_bf16, N, K, M, a_mn=True, b_mn=True, epilogue=EPI_F32_ATOMIC, out_f32=dw_f32, alpha=alpha)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None):
+    ld_bias = bias.stride(1) if bias is not None else 0
+    check(_lib.lib().b200vit_attn_fwd(_p(qkv), _p(bias), ld_bias, B, H, N, 64, scale, p_drop, seed, stream_id, _p(keep_in), _p(out),
+                                      _p(lse), _p(keep_bits), _stream()), "attn_fwd")
+    _count()
+
+
+def attn_bwd(qkv, out, dout, lse, bias, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv):
+    ld_bias = bias.stride(1) if bias is not None else 0
+    nb = dtable.shape[0] if dtable is not None else 0
+    check(_lib.lib().b200vit_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(bias), ld_bias, _p(keep_bits), _p(rel_index), _p(dtable), nb,
+                                      B, H, N, 64, scale, p_drop, _p(dqkv), _stream()), "attn_bwd")
+    _count()
+
+
+def dropout_mask(BH, N, p_drop, seed, stream_id, device) -> torch.Tensor:
+    out = torch.empty(BH, N, N, dtype=torch.uint8, device=device)
+    check(_lib.lib().b200vit_dropout_mask(_p(out), BH, N, p_drop, seed, stream_id, _stream()), "dropout_mask")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# row kernels
+# ----------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, rows, C_, y_bf16=None, y_f32=None, mean=None, rstd=None, row_index=None, ldx=None):
+    check(_lib.lib().b200vit_layernorm_fwd(_p(x), ldx if ldx is not None else C_, _p(row_index), _p(gamma), _p(beta), eps, rows, C_,
+                                           _p(y_bf16), _p(y_f32), _p(mean), _p(rstd), _stream()), "layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma=None, dbeta=None, row_index=None, ldx=None, lddx=None):
+    check(_lib.lib().b200vit_layernorm_bwd(_p(dy), int(dy.dtype == torch.float32), _p(x), ldx if ldx is not None else C_, _p(row_index),
+                                           _p(gamma), _p(mean), _p(rstd), rows, C_, _p(dx), lddx if lddx is not None else C_,
+                                           _p(dgamma), _p(dbeta), _stream()), "layernorm_bwd")
+    _count()
+
+
+def scale_residual_bwd(dx, t_bf16, rowscale, rows_per_scale, gamma, rows, C_, dt_bf16, dgamma=None, dbias=None):
+    check(_lib.lib().b200vit_scale_residual_bwd(_p(dx), C_, _p(t_bf16), _p(rowscale), rows_per_scale, _p(gamma), rows, C_, _p(dt_bf16),
+                                                _p(dgamma), _p(dbias), _stream()), "scale_residual_bwd")
+    _count()
+
+
+def colsum_bf16(x, rows, C_, out, ldx=None):
+    check(_lib.lib().b200vit_colsum_bf16(_p(x), ldx if ldx is not None else x.stride(0), rows, C_, _p(out), _stream()), "colsum_bf16")
+    _count()
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(_lib.lib().b200vit_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "cast_f32_to_bf16")
+    _count()
+    return dst
+
+
+def im2col(img, P, out):
+    B, Cin, H, W = img.shape
+    check(_lib.lib().b200vit_im2col_patches(_p(img), B, Cin, H, W, P, _p(out), _stream()), "im2col_patches")
+    _count()
+
+
+def assemble_tokens(pe, cls, mask_token, mask_u8, pos, B, np_, C_, x):
+    check(_lib.lib().b200vit_assemble_tokens(_p(pe), _p(cls), _p(mask_token), _p(mask_u8), _p(pos), B, np_, C_, _p(x), _stream()),
+          "assemble_tokens")
+    _count()
+
+
+def assemble_tokens_bwd(dx, mask_u8, B, np_, C_, dpe_bf16, dcls, dmask_token, dpos=None):
+    check(_lib.lib().b200vit_assemble_tokens_bwd(_p(dx), _p(mask_u8), B, np_, C_, _p(dpe_bf16), _p(dcls), _p(dmask_token), _p(dpos),
+                                                 _stream()), "assemble_tokens_bwd")
+    _count()
+
+
+def rel_pos_bias(table, index_i32, N, H, out):
+    check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, _p(out), _stream()), "rel_pos_bias")
+    _count()
+
+
+def meanpool_tokens(x, B, T, C_, out):
+    check(_lib.lib().b200vit_meanpool_tokens(_p(x), B, T, C_, _p(out), _stream()), "meanpool_tokens")
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# data2vec step
+# ----------------------------------------------------------------------------------------------------------------
+def d2v_target_loss(layers: Sequence[torch.Tensor], ld_layer, row_index, y, R, C_, ln_each=True, ln_post=True, beta=2.0, l2_loss=False,
+                    grad_scale=1.0, targets=None, dy_bf16=None, dy_f32=None, row_loss=None, loss_out=None):
+    arr = (C.c_void_p * len(layers))(*[_p(t) for t in layers])
+    check(_lib.lib().b200vit_d2v_target_loss(arr, len(layers), ld_layer, _p(row_index), _p(y), R, C_, int(ln_each), int(ln_post), beta,
+                                             int(l2_loss), grad_scale, _p(targets), _p(dy_bf16), _p(dy_f32), _p(row_loss), _p(loss_out),
+                                             _stream()), "d2v_target_loss")
+    _count(2 if loss_out is not None else 1)
+
+
+def ema_update(ema, model, decay, ema_bf16=None):
+    check(_lib.lib().b200vit_ema_update(_p(ema), _p(model), ema.numel(), decay, _p(ema_bf16), _stream()), "ema_update")
+    _count()
+
+
+def sumsq(g, out_accum):
+    check(_lib.lib().b200vit_sumsq(_p(g), g.numel(), _p(out_accum), _stream()), "sumsq")
+    _count()
+
+
+def adamw_step(p, g, m, v, hp, step, beta1=0.9, beta2=0.999, eps=1e-8, gnorm_sq=None, max_norm=0.0, grad_div=1.0, p_bf16=None,
+               ema=None, ema_decay=0.0, ema_bf16=None):
+    check(_lib.lib().b200vit_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hp), beta1, beta2, eps, step, _p(gnorm_sq), max_norm,
+                                        grad_div, _p(p_bf16), _p(ema), ema_decay, _p(ema_bf16), _stream()), "adamw_step")
+    _count()
+
+
+def wasserstein_loss(mean_out, cov_out, pos_mean, pos_cov, lam, grad_scale, work, d_mean, d_cov, loss_out):
+    R, C_ = mean_out.shape
+    check(_lib.lib().b200vit_wasserstein_loss(_p(mean_out), _p(cov_out), _p(pos_mean), _p(pos_cov), R, C_, lam, grad_scale, _p(work),
+                                              _p(d_mean), _p(d_cov), _p(loss_out), _stream()), "wasserstein_loss")
+    _count(3 if d_mean is not None else 2)
+
+
+def mc_reduce(logits, labels_i32, n_bins=15):
+    S, N, K = logits.shape
+    dev = logits.device
+    mean_logits = torch.empty(N, K, dtype=torch.float32, device=dev)
+    row_stats = torch.empty(N, 8, dtype=torch.float32, device=dev)
+    hist = torch.zeros(n_bins, 3, dtype=torch.float32, device=dev)
+    summary = torch.empty(8, dtype=torch.float32, device=dev)
+    check(_lib.lib().b200vit_mc_reduce(_p(logits), _p(labels_i32), S, N, K, n_bins, _p(mean_logits), _p(row_stats), _p(hist), _stream()),
+          "mc_reduce")
+    check(_lib.lib().b200vit_mc_finalize(_p(row_stats), _p(hist), N, n_bins, _p(summary), _stream()), "mc_finalize")
+    _count(2)
+    return mean_logits, row_stats, hist, summary
