@@ -125,6 +125,9 @@ int b200vit_assemble_tokens(const float* pe, const float* cls, const float* mask
                             int32_t B, int32_t np, int32_t C, float* x, void* stream);
 int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask, int32_t B, int32_t np, int32_t C, void* dpe_bf16, float* dcls,
                                 float* dmask_token, float* dpos_embed, void* stream);
+/* DropPath (timm drop_path, modeling_finetune.py:51-62): out[l, d, b] = keep / (1 - p_l), keep ~ Bernoulli(1 - p_l) from
+ * Philox4x32-10 keyed on (seed; l, d, b). probs_host: HOST array of L drop probabilities (linspace(0, rate, L), :401). */
+int b200vit_drop_path_scales(const float* probs_host, int32_t L, int32_t draws, int32_t B, uint64_t seed, float* out, void* stream);
 /* RelativePositionBias.forward (modeling_finetune.py:359-364): out[h,i,j] = table[index[i,j], h] */
 int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, float* out, void* stream);
 /* x[:, 1:].mean(1) (modeling_finetune.py:512-514) */

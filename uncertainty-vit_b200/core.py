@@ -1,0 +1,350 @@
+"""Forward / backward schedules of the ViT hot path over the C-ABI kernels (no autograd, no torch math).
+
+`vit_forward` / `vit_backward` take a ParamSource (fp32 master tensors + bf16 shadows, addressed by the REFERENCE's state-dict
+names) so the same schedule serves the nn.Module boundary (modeling.py, through torch.autograd.Function) and
+the flat-arena training engine (engine.py).
+
+Math restated from: Block.forward (modeling_finetune.py:290-299), Attention.forward (:145-188), Mlp.forward (:75-82),
+VisionTransformerForCyclicalTraining.forward_features/forward (modeling_cyclical.py:170-225),
+VisionTransformer.forward_features/forward (modeling_finetune.py:476-523).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_BF16, EPI_DGELU, EPI_F32, EPI_GELU, EPI_RESIDUAL, B200VitError
+
+
+@dataclass
+class VitConfig:
+    img_size: int = 224
+    patch_size: int = 16
+    in_chans: int = 3
+    embed_dim: int = 768
+    depth: int = 12
+    num_heads: int = 12
+    mlp_ratio: float = 4.0
+    num_classes: int = 1000
+    ln_eps: float = 1e-6
+    kind: str = "cyclical"          # "cyclical" | "finetune"
+    dist: bool = False
+    drop_path_rate: float = 0.0
+    attn_drop_rate: float = 0.0
+    has_gamma: bool = True
+    use_abs_pos_emb: bool = False
+
+    @property
+    def grid(self):
+        return self.img_size // self.patch_size
+
+    @property
+    def num_patches(self):
+        return self.grid * self.grid
+
+    @property
+    def tokens(self):
+        return self.num_patches + 1
+
+    @property
+    def hidden(self):
+        return int(self.embed_dim * self.mlp_ratio)
+
+    @property
+    def drop_path_probs(self) -> List[float]:
+        return [float(x) for x in torch.linspace(0, self.drop_path_rate, self.depth)]   # modeling_finetune.py:401
+
+
+class ParamSource:
+    """fp32 master parameters and their bf16 GEMM shadows by reference state-dict name."""
+
+    def f32(self, name: str) -> Optional[torch.Tensor]:
+        raise NotImplementedError
+
+    def bf16(self, name: str) -> torch.Tensor:
+        raise NotImplementedError
+
+    def qkv_bias(self, prefix: str, cov: bool = False) -> torch.Tensor:
+        """cat(q_bias, 0, v_bias) fp32 [3C] (modeling_finetune.py:148)."""
+        raise NotImplementedError
+
+    def rel_index_i32(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def head_padded(self):
+        """(head.weight bf16 [Kp, C], head.bias fp32 [Kp]) with Kp = num_classes rounded up to 8, padding rows zero."""
+        raise NotImplementedError
+
+
+@dataclass
+class Noise:
+    """Randomness of one training forward. Defaults = device Philox streams; any field may be injected (parity tests)."""
+    seed: int = 0
+    drop_path_scale: Optional[torch.Tensor] = None      # fp32 [L, draws, B] = keep / (1 - p_l)
+    attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
+    drop_path_active: bool = True
+    attn_drop_active: bool = True
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one block
+# ------------------------------------------------------------------------------------------------------------------
+def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: Optional[torch.Tensor], *, save: bool,
+                  dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
+                  x_mid: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """x_in: fp32 [B*T, C] residual stream. Returns the saved tensors (x_out under 'x_out')."""
+    T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
+    M = B * T
+    dev = x_in.device
+    p = f"blocks.{i}."
+    bf = torch.bfloat16
+    h1 = _empty((M, C), bf, dev)
+    mean1 = _empty((M,), torch.float32, dev)
+    rstd1 = _empty((M,), torch.float32, dev)
+    ops.layernorm_fwd(x_in, ps.f32(p + "norm1.weight"), ps.f32(p + "norm1.bias"), cfg.ln_eps, M, C, y_bf16=h1, mean=mean1, rstd=rstd1)
+    qkv = _empty((M, 3 * C), bf, dev)
+    ops.gemm(h1, ps.bf16(p + "attn.qkv.weight"), M, 3 * C, C, epilogue=EPI_BF16, bias=ps.qkv_bias(p), out_bf16=qkv)
+    attn_out = _empty((M, C), bf, dev)
+    lse = _empty((B, H, T), torch.float32, dev) if save else None
+    keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
+    ops.attn_fwd(qkv, bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, attn_out, lse, keep_bits)
+    if x_mid is None:
+        x_mid = _empty((M, C), torch.float32, dev)
+    t1 = _empty((M, C), bf, dev) if save else None
+    dp1 = dp_scale[0] if dp_scale is not None else None
+    dp2 = dp_scale[1] if dp_scale is not None else None
+    g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
+    g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
+    ops.gemm(attn_out, ps.bf16(p + "attn.proj.weight"), M, C, C, epilogue=EPI_RESIDUAL, bias=ps.f32(p + "attn.proj.bias"), colscale=g1,
+             rowscale=dp1, rows_per_scale=T, residual=x_in, out_f32=x_mid, out2_bf16=t1)
+    h2 = _empty((M, C), bf, dev)
+    mean2 = _empty((M,), torch.float32, dev)
+    rstd2 = _empty((M,), torch.float32, dev)
+    ops.layernorm_fwd(x_mid, ps.f32(p + "norm2.weight"), ps.f32(p + "norm2.bias"), cfg.ln_eps, M, C, y_bf16=h2, mean=mean2, rstd=rstd2)
+    act = _empty((M, Hd), bf, dev)
+    pre = _empty((M, Hd), bf, dev) if save else None
+    ops.gemm(h2, ps.bf16(p + "mlp.fc1.weight"), M, Hd, C, epilogue=EPI_GELU, bias=ps.f32(p + "mlp.fc1.bias"), out_bf16=act, out2_bf16=pre)
+    if x_out is None:
+        x_out = _empty((M, C), torch.float32, dev)
+    t2 = _empty((M, C), bf, dev) if save else None
+    ops.gemm(act, ps.bf16(p + "mlp.fc2.weight"), M, C, Hd, epilogue=EPI_RESIDUAL, bias=ps.f32(p + "mlp.fc2.bias"), colscale=g2,
+             rowscale=dp2, rows_per_scale=T, residual=x_mid, out_f32=x_out, out2_bf16=t2)
+    if not save:
+        return {"x_out": x_out, "x_mid": x_mid}
+    return dict(x_in=x_in, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, attn_out=attn_out, lse=lse, keep_bits=keep_bits, t1=t1, x_mid=x_mid,
+                h2=h2, mean2=mean2, rstd2=rstd2, act=act, pre=pre, t2=t2, x_out=x_out, dp1=dp1, dp2=dp2, p_attn=p_attn)
+
+
+def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.Tensor], dx: torch.Tensor, B: int,
+                   bias: Optional[torch.Tensor], grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor]):
+    """dx: fp32 [B*T, C] gradient of the block output; updated IN PLACE to the gradient of the block input."""
+    T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
+    M = B * T
+    p = f"blocks.{i}."
+    g = lambda n: grads.get(p + n)
+    dt, dpre, dh, dqkv = ws["dt"], ws["dpre"], ws["dh"], ws["dqkv"]
+    g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
+    g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
+    # ---- MLP branch: x_out = x_mid + dp2 * gamma_2 * (fc2(gelu(fc1(LN2 x_mid))))
+    ops.scale_residual_bwd(dx, s["t2"], s["dp2"], T, g2, M, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
+    ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
+    ops.colsum_bf16(dpre, M, Hd, g("mlp.fc1.bias"))
+    ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
+    ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
+    ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M, C, dx, g("norm2.weight"), g("norm2.bias"))
+    # ---- attention branch: x_mid = x_in + dp1 * gamma_1 * proj(attn(LN1 x_in))
+    ops.scale_residual_bwd(dx, s["t1"], s["dp1"], T, g1, M, C, dt, g("gamma_1") if cfg.has_gamma else None, g("attn.proj.bias"))
+    ops.linear_wgrad(dt, s["attn_out"], g("attn.proj.weight"))
+    ops.gemm(dt, ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
+    ops.attn_bwd(s["qkv"], s["attn_out"], dh, s["lse"], bias, s["keep_bits"], ps.rel_index_i32() if dtable is not None else None, dtable,
+                 B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv)
+    ops.colsum_bf16(dqkv, M, C, g("attn.q_bias"), ldx=3 * C)
+    ops.colsum_bf16(dqkv[:, 2 * C:], M, C, g("attn.v_bias"), ldx=3 * C)
+    ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))
+    ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
+    ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"))
+
+
+def backward_workspace(cfg: VitConfig, B: int, dev) -> Dict[str, torch.Tensor]:
+    M, C, Hd = B * cfg.tokens, cfg.embed_dim, cfg.hidden
+    bf = torch.bfloat16
+    return dict(dt=_empty((M, C), bf, dev), dpre=_empty((M, Hd), bf, dev), dh=_empty((M, C), bf, dev), dqkv=_empty((M, 3 * C), bf, dev))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stem / bias
+# ------------------------------------------------------------------------------------------------------------------
+def patches_bf16(cfg: VitConfig, images: torch.Tensor) -> torch.Tensor:
+    B = images.shape[0]
+    K = cfg.in_chans * cfg.patch_size * cfg.patch_size
+    out = _empty((B * cfg.num_patches, K), torch.bfloat16, images.device)
+    ops.im2col(images, cfg.patch_size, out)
+    return out
+
+
+def stem_forward(ps: ParamSource, cfg: VitConfig, patches: torch.Tensor, B: int, mask_u8: Optional[torch.Tensor], x: Optional[torch.Tensor] = None,
+                 prefix: str = "") -> torch.Tensor:
+    C, npat = cfg.embed_dim, cfg.num_patches
+    dev = patches.device
+    pe = _empty((B * npat, C), torch.float32, dev)
+    ops.gemm(patches, ps.bf16(prefix + "patch_embed.proj.weight"), B * npat, C, patches.shape[1], epilogue=EPI_F32,
+             bias=ps.f32(prefix + "patch_embed.proj.bias"), out_f32=pe)
+    if x is None:
+        x = _empty((B * cfg.tokens, C), torch.float32, dev)
+    ops.assemble_tokens(pe, ps.f32(prefix + "cls_token"), ps.f32(prefix + "mask_token") if mask_u8 is not None else None, mask_u8,
+                        ps.f32("pos_embed") if cfg.use_abs_pos_emb else None, B, npat, C, x)
+    return x
+
+
+def stem_backward(ps: ParamSource, cfg: VitConfig, patches: torch.Tensor, dx: torch.Tensor, B: int, mask_u8, grads, prefix: str = ""):
+    C, npat = cfg.embed_dim, cfg.num_patches
+    dpe = _empty((B * npat, C), torch.bfloat16, dx.device)
+    ops.assemble_tokens_bwd(dx, mask_u8, B, npat, C, dpe, grads.get(prefix + "cls_token"), grads.get(prefix + "mask_token"),
+                            grads.get("pos_embed") if cfg.use_abs_pos_emb else None)
+    ops.linear_wgrad(dpe, patches, grads[prefix + "patch_embed.proj.weight"].view(C, -1))
+    ops.colsum_bf16(dpe, B * npat, C, grads[prefix + "patch_embed.proj.bias"])
+
+
+def rel_bias(ps: ParamSource, cfg: VitConfig, dev) -> Optional[torch.Tensor]:
+    table = ps.f32("rel_pos_bias.relative_position_bias_table")
+    if table is None:
+        return None
+    T, H = cfg.tokens, cfg.num_heads
+    out = _empty((H, T, T), torch.float32, dev)
+    ops.rel_pos_bias(table, ps.rel_index_i32(), T, H, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# whole network
+# ------------------------------------------------------------------------------------------------------------------
+def make_drop_path_scales(cfg: VitConfig, B: int, noise: Noise, dev, draws: int = 2) -> Optional[torch.Tensor]:
+    if not noise.drop_path_active or cfg.drop_path_rate <= 0.0:
+        return None
+    if noise.drop_path_scale is not None:
+        return noise.drop_path_scale
+    return ops.drop_path_scales(cfg.drop_path_probs, draws, B, noise.seed, dev)
+
+
+def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u8: Optional[torch.Tensor] = None,
+                row_index: Optional[torch.Tensor] = None, mode: str = "masked", train: bool = False, save: bool = False,
+                noise: Optional[Noise] = None, collect: Optional[List[int]] = None, collect_what: str = "end",
+                patches: Optional[torch.Tensor] = None):
+    """Deterministic (single-stream) ViT.
+    mode: 'masked'  -> lm_head(norm(x)[:,1:][mask])            [R, C]   (row_index = flat rows b*T+1+p of the masked patches)
+          'all'     -> lm_head(norm(x)[:,1:])                  [B, np, C]
+          'layers'  -> residual streams of the blocks in `collect` (fp32 [B, T, C], cls row included), no head
+          'logits'  -> head(fc_norm(mean_{t>=1} x))            [B, K]   (fine-tune model)
+          'features'-> fc_norm(mean_{t>=1} x)                  [B, C]
+    Returns (output, ctx); ctx holds what vit_backward needs when save=True."""
+    if images.dtype != torch.float32 or not images.is_contiguous():
+        images = images.float().contiguous()
+    B = images.shape[0]
+    T, C = cfg.tokens, cfg.embed_dim
+    dev = images.device
+    noise = noise or Noise()
+    if patches is None:
+        patches = patches_bf16(cfg, images)
+    x = stem_forward(ps, cfg, patches, B, mask_u8)
+    bias = rel_bias(ps, cfg, dev)
+    dps = make_drop_path_scales(cfg, B, noise, dev) if train else None
+    p_attn = cfg.attn_drop_rate if noise.attn_drop_active else 0.0
+    saved = []
+    layers: Dict[int, torch.Tensor] = {}
+    collect = collect or []
+    for i in range(cfg.depth):
+        keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
+        s = block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn, seed=noise.seed,
+                          keep_in=keep_in)
+        if i in collect:
+            if collect_what == "fc":      # fc_feature = x_out - x_mid (modeling_cyclical.py:203-205); rarely used
+                layers[i] = (s["x_out"] - s["x_mid"]).view(B, T, C)
+            else:
+                layers[i] = s["x_out"].view(B, T, C)
+        x = s["x_out"]
+        if save:
+            saved.append(s)
+    ctx = dict(B=B, saved=saved, patches=patches, mask_u8=mask_u8, row_index=row_index, mode=mode, bias=bias, x_final=x) if save else None
+    if mode == "layers":
+        return layers, ctx
+    if mode in ("masked", "all"):
+        if mode == "all":
+            row_index = all_patch_rows(B, T, dev)
+        R = row_index.numel()
+        hn = _empty((R, C), torch.bfloat16, dev)
+        mean = _empty((R,), torch.float32, dev)
+        rstd = _empty((R,), torch.float32, dev)
+        out = _empty((R, C), torch.float32, dev)
+        if R > 0:
+            ops.layernorm_fwd(x, ps.f32("norm.weight"), ps.f32("norm.bias"), cfg.ln_eps, R, C, y_bf16=hn, mean=mean, rstd=rstd, row_index=row_index)
+            ops.gemm(hn, ps.bf16("lm_head.weight"), R, C, C, epilogue=EPI_F32, bias=ps.f32("lm_head.bias"), out_f32=out)
+        if save:
+            ctx.update(hn=hn, hmean=mean, hrstd=rstd, row_index=row_index)
+        return (out.view(B, T - 1, C) if mode == "all" else out), ctx
+    if mode in ("logits", "features"):
+        pooled = _empty((B, C), torch.float32, dev)
+        ops.meanpool_tokens(x, B, T, C, pooled)
+        feat = _empty((B, C), torch.float32, dev)
+        fb = _empty((B, C), torch.bfloat16, dev)
+        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, B, C, y_bf16=fb, y_f32=feat)
+        if mode == "features":
+            return feat, ctx
+        K = cfg.num_classes
+        w, hb = ps.head_padded()           # [Kp, C] bf16 / [Kp] fp32, rows >= K zero (GEMM needs N % 8 == 0)
+        Kp = w.shape[0]
+        logits = _empty((B, Kp), torch.float32, dev)
+        ops.gemm(fb, w, B, Kp, C, epilogue=EPI_F32, bias=hb, out_f32=logits)
+        return logits[:, :K], ctx
+    raise B200VitError(f"unknown forward mode {mode!r}")
+
+
+_ROWS_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def all_patch_rows(B: int, T: int, dev) -> torch.Tensor:
+    key = (B, T, str(dev))
+    t = _ROWS_CACHE.get(key)
+    if t is None:
+        r = torch.arange(B * T, dtype=torch.int32).view(B, T)[:, 1:].reshape(-1).contiguous()
+        t = r.to(dev)
+        _ROWS_CACHE[key] = t
+    return t
+
+
+def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads: Dict[str, torch.Tensor], dout_is_bf16_rows: bool = False):
+    """Accumulates parameter gradients into `grads` (fp32 tensors by reference name, caller zero-initialises).
+    dout: gradient of the forward output ('masked'/'all' modes): fp32 or bf16 [R, C]."""
+    B = ctx["B"]
+    T, C = cfg.tokens, cfg.embed_dim
+    M = B * T
+    dev = dout.device
+    mode = ctx["mode"]
+    if mode not in ("masked", "all"):
+        raise B200VitError(f"backward is implemented for the data2vec modes ('masked', 'all'), not {mode!r}")
+    row_index = ctx["row_index"]
+    R = row_index.numel()
+    dy = dout.reshape(R, C)
+    if dy.dtype != torch.bfloat16:
+        dy = ops.cast_bf16(dy.contiguous())
+    dx = torch.zeros((M, C), dtype=torch.float32, device=dev)
+    if R > 0:
+        ops.linear_wgrad(dy, ctx["hn"], grads["lm_head.weight"])
+        ops.colsum_bf16(dy, R, C, grads["lm_head.bias"])
+        dhn = _empty((R, C), torch.bfloat16, dev)
+        ops.gemm(dy, ps.bf16("lm_head.weight"), R, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dhn)
+        ops.layernorm_bwd(dhn, ctx["x_final"], ps.f32("norm.weight"), ctx["hmean"], ctx["hrstd"], R, C, dx, grads["norm.weight"], grads["norm.bias"],
+                          row_index=row_index)
+    ws = backward_workspace(cfg, B, dev)
+    dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    for i in reversed(range(cfg.depth)):
+        block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
+        ctx["saved"][i] = None   # free activations as we go
+    stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)

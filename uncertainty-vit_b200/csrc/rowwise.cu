@@ -457,3 +457,32 @@ extern "C" int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int
   B200_CHECK_LAUNCH("meanpool_tokens");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Stochastic depth keep/keep_prob per (layer, draw, sample): timm drop_path semantics (modeling_finetune.py:51-62),
+// uniform numbers from Philox4x32-10 keyed on (seed; layer, draw, sample) instead of torch's global generator.
+// ------------------------------------------------------------------------------------------------
+struct DropPathProbs { float p[64]; };
+__global__ void drop_path_scales_kernel(DropPathProbs probs, int L, int draws, int B, unsigned long long seed, float* __restrict__ out) {
+  const int total = L * draws * B;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i % B, d = (i / B) % draws, l = i / (B * draws);
+    const float p = probs.p[l];
+    const Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)d, (uint32_t)l, 0xD509A7u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u = (r.x >> 8) * (1.0f / 16777216.0f);    // [0,1)
+    out[i] = (p <= 0.f) ? 1.0f : (u >= p ? 1.0f / (1.0f - p) : 0.0f);
+  }
+}
+
+extern "C" int b200vit_drop_path_scales(const float* probs_host, int32_t L, int32_t draws, int32_t B, uint64_t seed, float* out, void* stream) {
+  B200_CHECK_ARG(probs_host != nullptr && out != nullptr && L > 0 && L <= 64 && draws > 0 && B > 0, "drop_path_scales: bad arguments (L <= 64)");
+  DropPathProbs pr;
+  for (int i = 0; i < L; ++i) {
+    B200_CHECK_ARG(probs_host[i] >= 0.f && probs_host[i] < 1.f, "drop_path_scales: p[%d] out of range", i);
+    pr.p[i] = probs_host[i];
+  }
+  const int total = L * draws * B;
+  drop_path_scales_kernel<<<(total + 255) / 256, 256, 0, STREAM>>>(pr, L, draws, B, seed, out);
+  B200_CHECK_LAUNCH("drop_path_scales");
+  return 0;
+}

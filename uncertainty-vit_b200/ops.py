@@ -163,6 +163,16 @@ def assemble_tokens_bwd(dx, mask_u8, B, np_, C_, dpe_bf16, dcls, dmask_token, dp
     _count()
 
 
+def drop_path_scales(probs, draws, B, seed, device) -> torch.Tensor:
+    """[L, draws, B] fp32 keep/(1-p) factors (device Philox; no torch RNG involved)."""
+    L = len(probs)
+    out = torch.empty(L, draws, B, dtype=torch.float32, device=device)
+    arr = (C.c_float * L)(*[float(p) for p in probs])
+    check(_lib.lib().b200vit_drop_path_scales(arr, L, draws, B, seed, _p(out), _stream()), "drop_path_scales")
+    _count()
+    return out
+
+
 def rel_pos_bias(table, index_i32, N, H, out):
     check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, _p(out), _stream()), "rel_pos_bias")
     _count()
