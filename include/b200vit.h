@@ -149,8 +149,10 @@ int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, 
 /* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
 int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
 /* clip + torch.optim.AdamW + bf16 weight shadow + EMA over flat arenas (utils.py:364-390, optim_factory.py:58-97).
- * hp_lr_wd: device float2 {lr, weight_decay} per 1024-element chunk. grad_div: loss-scale divisor (unscale_). */
-int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
+ * hp_lr_wd: device float2 {lr_scale, wd_scale} per 1024-element chunk (param groups); lr / weight_decay: this step's
+ * schedule values (engine_for_cyclical.py:47-53). grad_div: divisor applied to g first (loss scale x world size). */
+int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float lr, float weight_decay,
+                       float beta1, float beta2,
                        float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
                        double ema_decay, void* ema_bf16, void* stream);
 /* WassersteinLoss.forward + backward (distloss.py:13-30,73-79). work: 2R+8 floats. d_* are accumulated (+=). */

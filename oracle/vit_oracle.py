@@ -588,3 +588,35 @@ def mc_reduce(logits_snk: torch.Tensor, labels: torch.Tensor) -> Dict[str, objec
     return dict(mean_logits=zbar, acc1=a1, acc5=a5, ece=ece(probs, labels), ece_reference=ece(probs, labels, 15, True),
                 nll=nll(zbar, labels),
                 entropy=ent, variance=var, mutual_info=ent - ent_s, conf=probs.max(1).values, pred=probs.argmax(1))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# one full data2vec optimisation step (engine_for_cyclical.py:45-186) — used by the engine parity test and as the
+# CPU baseline ("port") that bench.py times on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def d2v_step(sd: Dict[str, torch.Tensor], ema: Dict[str, torch.Tensor], opt: Dict[str, Dict[str, torch.Tensor]], arch: Arch, x, mask,
+             step: int, noise: Optional[Noise] = None, target_layers=(6, 7, 8, 9, 10, 11), lr=2e-3, wd=0.05, clip=3.0, ema_decay=0.9998,
+             l1_beta=2.0, return_grads: bool = False):
+    """sd / ema: float state dicts (updated IN PLACE); opt: {'m': {...}, 'v': {...}}. Returns (loss, grad_norm[, grads])."""
+    with torch.no_grad():
+        t = cyclical_forward(ema, arch, x, None, return_all_tokens=True, layer_results="end")
+    tgt = build_targets(t, list(target_layers), mask, post_target_layer_norm=True)
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
+    out = cyclical_forward(leaf, arch, x, mask, noise=noise)
+    loss, _ = d2v_loss(out.float(), tgt, l1_beta)
+    loss.backward()
+    grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(sd[k])) for k in names}
+    total, coef = clip_grad_norm(list(grads.values()), clip)
+    for k in names:
+        decay = 0.0 if is_no_decay(k, sd[k].shape) else wd
+        adamw_step(sd[k], grads[k] * coef, opt["m"][k], opt["v"][k], step, lr, decay)
+    ema_update({k: ema[k] for k in names}, sd, ema_decay)
+    if return_grads:
+        return float(loss), float(total), grads
+    return float(loss), float(total)
+
+
+def new_opt_state(sd):
+    return {"m": {k: torch.zeros_like(v) for k, v in sd.items() if v.is_floating_point()},
+            "v": {k: torch.zeros_like(v) for k, v in sd.items() if v.is_floating_point()}}

@@ -333,21 +333,21 @@ def test_ema_and_adamw_vs_oracle(ops, cuda):
     Pb = torch.empty(n, dtype=torch.bfloat16, device=cuda)
     Eb = torch.empty(n, dtype=torch.bfloat16, device=cuda)
     lr, wd, max_norm, d = 2e-3, 0.05, 3.0, 0.9998
-    hp = torch.tensor([[lr, wd]] * (n // 1024), dtype=torch.float32)
+    hp = torch.tensor([[1.0, 1.0]] * (n // 1024), dtype=torch.float32)
     hp[::2, 1] = 0.0                         # alternate chunks: no-decay group
-    hp[::3, 0] = lr * 0.65                   # and a layer-decay lr scale
+    hp[::3, 0] = 0.65                        # and a layer-decay lr scale
     for step in range(1, 4):
         grad = torch.randn(n, generator=g) * 5
         total, coef = O.clip_grad_norm([grad], max_norm)
         for c in range(n // 1024):
             sl = slice(c * 1024, (c + 1) * 1024)
-            O.adamw_step(pc[sl], grad[sl] * coef, m[sl], v[sl], step, float(hp[c, 0]), float(hp[c, 1]))
+            O.adamw_step(pc[sl], grad[sl] * coef, m[sl], v[sl], step, lr * float(hp[c, 0]), wd * float(hp[c, 1]))
         O.ema_update({"w": ec}, {"w": pc}, d)
         G = grad.to(cuda)
         nsq = torch.zeros(1, device=cuda)
         ops.sumsq(G, nsq)
         assert abs(math.sqrt(nsq.item()) - float(total)) / float(total) < 1e-5
-        ops.adamw_step(P, G, Mo, V, hp.to(cuda), step, gnorm_sq=nsq, max_norm=max_norm, p_bf16=Pb, ema=E, ema_decay=d, ema_bf16=Eb)
+        ops.adamw_step(P, G, Mo, V, hp.to(cuda), step, lr, wd, gnorm_sq=nsq, max_norm=max_norm, p_bf16=Pb, ema=E, ema_decay=d, ema_bf16=Eb)
     assert rel(P.cpu(), pc) < 1e-5 and rel(E.cpu(), ec) < 1e-6
     assert rel(Pb.float().cpu(), pc) < 5e-3 and rel(Eb.float().cpu(), ec) < 5e-3
     # stand-alone EMA kernel: bit-exact against the reference expression d*e + (1-d)*m in fp32

@@ -51,7 +51,7 @@ _PROTOS = {
     "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "b200vit_ema_update": (i32, [vp, vp, i64, C.c_double, vp, vp]),
     "b200vit_sumsq": (i32, [vp, i64, vp, vp]),
-    "b200vit_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, i32, vp, f32, f32, vp, vp, C.c_double, vp, vp]),
+    "b200vit_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, C.c_double, vp, vp]),
     "b200vit_wasserstein_loss": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
     "b200vit_mc_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "b200vit_mc_finalize": (i32, [vp, vp, i32, i32, vp, vp]),

@@ -162,12 +162,13 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 // Fused clip + AdamW (+ bf16 weight shadow, + EMA teacher update and its bf16 shadow) over flat arenas.
-// Hyper-parameters per 1024-element chunk: hp[chunk] = {lr, weight_decay} (param-group semantics of
-// optim_factory.py:58-97 and the per-step lr*lr_scale of engine_for_cyclical.py:47-53 are folded in by the host).
+// Per 1024-element chunk: hp[chunk] = {lr_scale, wd_scale}; lr = base_lr * lr_scale, weight_decay = base_wd * wd_scale
+// (param groups of optim_factory.py:58-97: wd_scale 0 for 1-D / bias / skip-list params, lr_scale = layer decay; the
+// per-step schedule values of engine_for_cyclical.py:47-53 arrive as base_lr / base_wd).
 // torch.optim.AdamW update order: p *= 1 - lr*wd ; m,v EMA ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n4, const float2* __restrict__ hp,
-                                                    float beta1, float beta2, float eps, float bc1, float sqrt_bc2,
+                                                    float base_lr, float base_wd, float beta1, float beta2, float eps, float bc1, float sqrt_bc2,
                                                     const float* __restrict__ gnorm_sq, float max_norm, float grad_div,
                                                     bf16* __restrict__ p_shadow, float* __restrict__ ema, float ema_decay, float od,
                                                     bf16* __restrict__ ema_shadow) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float2 h = __ldg(hp + (i >> 8));  // 1024 elements = 256 float4 per chunk
-    const float lr = h.x, wd = h.y;
+    const float lr = base_lr * h.x, wd = base_wd * h.y;
     float4 pv = ld4(p + i * 4);
     const float4 gv = ld4_stream(g + i * 4);
     float4 mv = ld4(m + i * 4), vv = ld4(v + i * 4);
@@ -398,7 +399,7 @@ extern "C" int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* 
   return 0;
 }
 
-extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float beta1, float beta2,
+extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hp_lr_wd, float lr, float weight_decay, float beta1, float beta2,
                                   float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
                                   double ema_decay, void* ema_bf16, void* stream) {
   B200_CHECK_ARG(p != nullptr && g != nullptr && m != nullptr && v != nullptr && hp_lr_wd != nullptr, "adamw_step: null pointer");
@@ -409,7 +410,7 @@ extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, 
   const int sms = b200vit_num_sms();
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, n / 4, reinterpret_cast<const float2*>(hp_lr_wd), beta1, beta2, eps, (float)bc1,
+  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, n / 4, reinterpret_cast<const float2*>(hp_lr_wd), lr, weight_decay, beta1, beta2, eps, (float)bc1,
                                                 (float)sqrt(bc2), gnorm_sq, max_norm, grad_div > 0.f ? grad_div : 1.0f,
                                                 static_cast<bf16*>(p_bf16), ema, (float)ema_decay, (float)(1.0 - ema_decay), static_cast<bf16*>(ema_bf16));
   B200_CHECK_LAUNCH("adamw_step");

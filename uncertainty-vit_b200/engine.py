@@ -1,0 +1,261 @@
+"""data2vec pre-training step engine (the hot loop of engine_for_cyclical.train_one_epoch, :45-186) over flat device arenas.
+
+One step = EMA-teacher forward (eval, unmasked) -> target builder + smooth-L1 (one kernel, masked rows only) -> student
+forward/backward -> [NCCL all-reduce of the flat gradient arena] -> grad-norm -> fused clip + AdamW + bf16 shadows + EMA.
+No host synchronisation inside the step; the loss is read back once at the end (the reference's loss.item(), :164).
+
+The model's nn.Parameters are re-pointed at views of the arenas, so state_dict()/checkpoints/other code see live values.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import core, ops
+from ._lib import B200VitError
+from .core import Noise, VitConfig
+
+CHUNK = 1024
+
+
+def get_num_layer_for_vit(var_name: str, num_max_layer: int) -> int:
+    """optim_factory.py:33-44."""
+    if var_name in ("cls_token", "mask_token", "pos_embed"):
+        return 0
+    if var_name.startswith("patch_embed"):
+        return 0
+    if var_name.startswith("rel_pos_bias"):
+        return num_max_layer - 1
+    if var_name.startswith("blocks"):
+        return int(var_name.split(".")[1]) + 1
+    return num_max_layer - 1
+
+
+def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epochs=0, start_warmup_value=0, warmup_steps=-1):
+    """utils.py:408-425."""
+    warmup_schedule = np.array([])
+    warmup_iters = warmup_epochs * niter_per_ep
+    if warmup_steps > 0:
+        warmup_iters = warmup_steps
+    if warmup_epochs > 0 or warmup_steps > 0:
+        warmup_schedule = np.linspace(start_warmup_value, base_value, warmup_iters)
+    iters = np.arange(epochs * niter_per_ep - warmup_iters)
+    schedule = np.array([final_value + 0.5 * (base_value - final_value) * (1 + math.cos(math.pi * i / (len(iters)))) for i in iters])
+    schedule = np.concatenate((warmup_schedule, schedule))
+    assert len(schedule) == epochs * niter_per_ep
+    return schedule
+
+
+class ArenaParams(core.ParamSource):
+    """ParamSource over one fp32 arena + its bf16 shadow arena."""
+
+    def __init__(self, layout: Dict[str, tuple], f32: torch.Tensor, bf16: torch.Tensor, rel_index: torch.Tensor, num_classes_pad=None):
+        self.layout, self.a32, self.a16, self._rel = layout, f32, bf16, rel_index
+        self._v32: Dict[str, torch.Tensor] = {}
+        self._v16: Dict[str, torch.Tensor] = {}
+
+    def f32(self, name):
+        v = self._v32.get(name)
+        if v is None:
+            ent = self.layout.get(name)
+            if ent is None:
+                return None
+            off, shape = ent
+            v = self.a32[off: off + int(np.prod(shape))].view(shape)
+            self._v32[name] = v
+        return v
+
+    def bf16(self, name):
+        v = self._v16.get(name)
+        if v is None:
+            off, shape = self.layout[name]
+            v = self.a16[off: off + int(np.prod(shape))].view(shape[0], -1)
+            self._v16[name] = v
+        return v
+
+    def qkv_bias(self, prefix, cov=False):
+        return self.f32(prefix + ("attn.__cov_qkv_bias" if cov else "attn.__qkv_bias"))
+
+    def rel_index_i32(self):
+        return self._rel
+
+
+class D2VEngine:
+    """Owns arenas + optimizer state for a data2vec student and its EMA teacher."""
+
+    def __init__(self, model, *, lr=2e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, clip_grad=3.0, ema_decay=0.9998,
+                 ema_decay_init=0.999, ema_start_at=0, target_layers: Sequence[int] = (6, 7, 8, 9, 10, 11), l1_beta=2.0, l2_loss=False,
+                 target_layer_norm_last=True, post_target_layer_norm=True, layer_decay: Optional[float] = None, loss_scale=-1.0,
+                 skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0):
+        self.model = model
+        self.cfg: VitConfig = model.cfg
+        if self.cfg.dist:
+            raise NotImplementedError("the fused engine covers the deterministic data2vec step; the dual-stream model trains through autograd")
+        dev = model.cls_token.device
+        if dev.type != "cuda":
+            raise B200VitError("D2VEngine needs the model on a CUDA (B200) device")
+        self.dev = dev
+        self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad
+        self.ema_decay, self.ema_decay_init, self.ema_start_at = ema_decay, ema_decay_init, ema_start_at
+        self.target_layers = list(target_layers)
+        self.l1_beta, self.l2_loss, self.ln_each, self.ln_post = l1_beta, l2_loss, target_layer_norm_last, post_target_layer_norm
+        self.loss_scale = loss_scale
+        self.world_size, self.pg = world_size, process_group
+        self.seed = seed
+        self.it = 0
+        # ---- layout: every segment starts on a CHUNK boundary; (q_bias | 0 | v_bias) of a block form ONE segment so that the
+        # QKV GEMM bias cat(q_bias, zeros, v_bias) (modeling_finetune.py:148) is a plain arena view
+        named = dict(model.named_parameters())
+        L = self.cfg.depth + 2
+        layout: Dict[str, tuple] = {}
+        chunks_hp: List[tuple] = []
+        off = 0
+        skip = set(skip_weight_decay)
+
+        def add(name, shape, lr_scale, wd_scale):
+            nonlocal off
+            n = int(np.prod(shape))
+            layout[name] = (off, tuple(shape))
+            nch = (n + CHUNK - 1) // CHUNK
+            chunks_hp.extend([(lr_scale, wd_scale)] * nch)
+            off += nch * CHUNK
+
+        done = set()
+        for name, p in named.items():
+            if name in done:
+                continue
+            layer_id = get_num_layer_for_vit(name, L)
+            lr_scale = 1.0 if layer_decay is None else layer_decay ** (L - 1 - layer_id)
+            no_decay = p.dim() == 1 or name.endswith(".bias") or name in skip            # optim_factory.py:66-67
+            if name.endswith("attn.q_bias"):
+                prefix = name[: -len("q_bias")]
+                C = p.numel()
+                add(prefix + "__qkv_bias", (3 * C,), lr_scale, 0.0)
+                base = layout[prefix + "__qkv_bias"][0]
+                layout[prefix + "q_bias"] = (base, (C,))
+                layout[prefix + "v_bias"] = (base + 2 * C, (C,))
+                done.update({prefix + "q_bias", prefix + "v_bias"})
+                continue
+            add(name, p.shape, lr_scale, 0.0 if no_decay else 1.0)
+        self.layout, self.n = layout, off
+        f32 = lambda: torch.zeros(off, dtype=torch.float32, device=dev)
+        self.p32, self.g32, self.m32, self.v32, self.e32 = f32(), f32(), f32(), f32(), f32()
+        self.p16 = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.e16 = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.hp = torch.tensor(chunks_hp, dtype=torch.float32, device=dev).contiguous()
+        with torch.no_grad():
+            for name, p in named.items():
+                o, shape = layout[name]
+                view = self.p32[o: o + p.numel()].view(shape)
+                view.copy_(p.detach())
+                p.data = view                     # the module now aliases the arena
+        self.e32.copy_(self.p32)                  # ModelEmaV2: deepcopy of the student at construction (run_cyclical.py:503)
+        ops.cast_bf16(self.p32, self.p16)
+        ops.cast_bf16(self.e32, self.e16)
+        rel = model.rel_pos_bias.relative_position_index.to(torch.int32).contiguous() if model.rel_pos_bias is not None else None
+        self.student = ArenaParams(layout, self.p32, self.p16, rel)
+        self.teacher = ArenaParams(layout, self.e32, self.e16, rel)
+        self.grads = {name: self.g32[o: o + int(np.prod(s))].view(s) for name, (o, s) in layout.items()}
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.opt_step = 0
+        self.cur_decay = ema_decay
+        if hasattr(model, "_ps"):
+            model._ps.invalidate()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+        return {name: self.e32[o: o + int(np.prod(s))].view(s) for name, (o, s) in self.layout.items() if "__" not in name}
+
+    @staticmethod
+    def rows_from_host_mask(mask: np.ndarray, T: int) -> np.ndarray:
+        """mask: [B, np] {0,1} on the HOST -> flat stream rows b*T+1+p in the reference's boolean-gather order."""
+        b, p = np.nonzero(mask.reshape(mask.shape[0], -1))
+        return (b * T + 1 + p).astype(np.int32)
+
+    def decay_at(self, it: int) -> float:
+        """engine_for_cyclical.py:55-56."""
+        if it < self.ema_start_at:
+            return self.ema_decay_init + it * (self.ema_decay - self.ema_decay_init) / self.ema_start_at
+        return self.ema_decay
+
+    def step(self, images: torch.Tensor, mask_u8: torch.Tensor, rows: torch.Tensor, *, lr: Optional[float] = None,
+             weight_decay: Optional[float] = None, noise: Optional[Noise] = None) -> torch.Tensor:
+        """One optimisation step on device-resident inputs. images fp32 [B,3,H,W]; mask_u8 uint8 [B*np]; rows int32 [R].
+        Returns the device scalar loss (no sync)."""
+        cfg = self.cfg
+        B = images.shape[0]
+        C, T = cfg.embed_dim, cfg.tokens
+        R = rows.numel()
+        lr = self.lr if lr is None else lr
+        wd = self.wd if weight_decay is None else weight_decay
+        self.cur_decay = self.decay_at(self.it)
+        if noise is None:
+            noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
+        patches = core.patches_bf16(cfg, images)
+        # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88
+        layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers, patches=patches)
+        # student: :124-128
+        out, ctx = core.vit_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise,
+                                    patches=patches)
+        # targets + loss + dLoss/dy: :90-150 (masked rows only; LayerNorm is per row)
+        dy = torch.empty((R, C), dtype=torch.bfloat16, device=self.dev)
+        row_loss = torch.empty((R,), dtype=torch.float32, device=self.dev)
+        ls = self.loss_scale if self.loss_scale != -1 else 1.0
+        ops.d2v_target_loss([layers[i].view(B * T, C) for i in self.target_layers], C, rows, out, R, C, self.ln_each, self.ln_post, self.l1_beta,
+                            self.l2_loss, ls / (R * C), None, dy, None, row_loss, self.loss_dev)
+        del layers
+        self.g32.zero_()
+        core.vit_backward(self.student, cfg, ctx, dy, self.grads)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.g32, group=self.pg)       # DDP gradient mean = sum / world (folded into grad_div)
+        self.gnorm_sq.zero_()
+        ops.sumsq(self.g32, self.gnorm_sq)
+        self.opt_step += 1
+        do_ema = self.cur_decay != 1
+        ops.adamw_step(self.p32, self.g32, self.m32, self.v32, self.hp, self.opt_step, lr, wd, self.betas[0], self.betas[1], self.eps,
+                       gnorm_sq=self.gnorm_sq, max_norm=self.clip if self.clip else 0.0, grad_div=float(self.world_size), p_bf16=self.p16,
+                       ema=self.e32 if do_ema else None, ema_decay=self.cur_decay, ema_bf16=self.e16 if do_ema else None)
+        self.it += 1
+        return self.loss_dev
+
+    def grad_norm(self) -> torch.Tensor:
+        return torch.sqrt(self.gnorm_sq) / self.world_size
+
+    def step_host(self, images_pinned: torch.Tensor, mask_host: np.ndarray, **kw) -> float:
+        """The reference-facing call: HOST batch in (pinned images + integer mask as the data loader yields them,
+        engine_for_cyclical.py:58-60), loss value out (:164). Host->device copies and the loss read-back are inside."""
+        B = images_pinned.shape[0]
+        m = np.ascontiguousarray(mask_host.reshape(B, -1).astype(np.uint8))
+        rows = torch.from_numpy(self.rows_from_host_mask(m, self.cfg.tokens))
+        images = images_pinned.to(self.dev, non_blocking=True)
+        mask_u8 = torch.from_numpy(m.reshape(-1)).to(self.dev, non_blocking=True)
+        rows = rows.to(self.dev, non_blocking=True)
+        loss = self.step(images, mask_u8, rows, **kw)
+        return float(loss.item())
+
+
+def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,
+                    wd_schedule_values=None, print_freq: int = 10, log=print) -> Dict[str, float]:
+    """Loop of engine_for_cyclical.train_one_epoch (:45-225) over the fused engine: per-step lr/wd from the schedule tables,
+    EMA-decay anneal, non-finite loss aborts (:166-168)."""
+    total, n = 0.0, 0
+    for step, (batch, _) in enumerate(data_loader):
+        it = start_steps + step
+        samples, bool_masked_pos = batch
+        lr = float(lr_schedule_values[it]) if lr_schedule_values is not None else None
+        wd = float(wd_schedule_values[it]) if wd_schedule_values is not None else None
+        engine.it = it
+        if not samples.is_pinned():
+            samples = samples.pin_memory()
+        loss = engine.step_host(samples, np.asarray(bool_masked_pos), lr=lr, weight_decay=wd)
+        if not math.isfinite(loss):
+            raise FloatingPointError(f"Loss is {loss}, stopping training")
+        total += loss
+        n += 1
+        if step % print_freq == 0:
+            log(f"Epoch: [{epoch}] step {step} loss {loss:.4f} ema_decay {engine.cur_decay:.6f}")
+    return {"loss": total / max(n, 1), "cur_decay": engine.cur_decay}

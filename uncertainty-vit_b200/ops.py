@@ -205,9 +205,9 @@ def sumsq(g, out_accum):
     _count()
 
 
-def adamw_step(p, g, m, v, hp, step, beta1=0.9, beta2=0.999, eps=1e-8, gnorm_sq=None, max_norm=0.0, grad_div=1.0, p_bf16=None,
+def adamw_step(p, g, m, v, hp, step, lr, weight_decay, beta1=0.9, beta2=0.999, eps=1e-8, gnorm_sq=None, max_norm=0.0, grad_div=1.0, p_bf16=None,
                ema=None, ema_decay=0.0, ema_bf16=None):
-    check(_lib.lib().b200vit_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hp), beta1, beta2, eps, step, _p(gnorm_sq), max_norm,
+    check(_lib.lib().b200vit_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hp), lr, weight_decay, beta1, beta2, eps, step, _p(gnorm_sq), max_norm,
                                         grad_div, _p(p_bf16), _p(ema), ema_decay, _p(ema_bf16), _stream()), "adamw_step")
     _count()
 
