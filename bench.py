@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Headline benchmark: ViT-B/16 data2vec pre-training step (BASELINE.json configs[1]) in img/s.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm (CPU oracle port) on the host cores
+
+One "step" = EMA-teacher forward + target builder / smooth-L1 + student forward/backward + [NCCL grad all-reduce] + clip + AdamW +
+EMA on one batch of 128 synthetic 224x224 images per GPU with exactly 120 masked patches per image (README recipe:
+drop_path 0.25, attn_drop 0.05, layer-scale 1e-4, target_layers 6-11, post LayerNorm targets, l1_beta 2, EMA 0.9998, clip 3, wd 0.05).
+`value`   : device-timed (CUDA events) with the batch already resident in HBM.
+`e2e`     : the same step through D2VEngine.step_host(): pinned host batch -> device copy and loss read-back inside the timed region.
+`roofline`: all launches of the tcgen05 GEMM kernel inside instrumented steps: algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 128
+MASKED = 120
+CPU_SAMPLE_BATCH = 8
+
+
+def synth_batch(B, seed, pin=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, 224, 224, generator=g)
+    mask = np.zeros((B, 196), dtype=np.uint8)
+    for b in range(B):
+        mask[b, torch.randperm(196, generator=g)[:MASKED].numpy()] = 1
+    return (x.pin_memory() if pin else x), mask.reshape(B, 14, 14)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"], source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        hi = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm; the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    from oracle import vit_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    arch = O.Arch(kind="cyclical", **O.VIT_B)
+    sd = O.make_state(arch, 0)
+    ema = {k: v.clone() for k, v in sd.items()}
+    opt = O.new_opt_state(sd)
+    x, mask = synth_batch(batch, 0, pin=False)
+    mask_t = torch.from_numpy(mask.astype(np.int64))
+    g = torch.Generator().manual_seed(1)
+    probs = [float(p) for p in torch.linspace(0, 0.25, arch.depth)]
+    noise = O.Noise(drop_path_keep=[(torch.rand(2, batch, generator=g) >= p).float() for p in probs], drop_path_prob=probs,
+                    attn_keep=[(torch.rand(batch, arch.num_heads, arch.tokens, arch.tokens, generator=g) >= 0.05).float() for _ in range(arch.depth)],
+                    attn_drop=0.05)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.d2v_step(sd, ema, opt, arch, x, mask_t, i + 1, noise)
+        times.append(time.perf_counter() - t0)
+    t = times[warmup:]
+    return batch * len(t) / sum(t), sum(t) / len(t), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 4))
+    v, sec, cores = cpu_reference_steps(steps, min(args.warmup, 1))
+    sample = f"{steps} full data2vec steps of {CPU_SAMPLE_BATCH} images (fp32, oracle port of the reference algorithm), {cores} threads"
+    print(json.dumps({"impl": "reference", "metric": "data2vec ViT-B/16 pretrain throughput", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+                      "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "beit_base_patch16_224 data2vec cyclical pretrain step, 120 masked patches, target_layers 6-11, EMA 0.9998",
+                                 "batch_per_step": CPU_SAMPLE_BATCH},
+                      "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import engine as E, modeling as M
+    ops = pkg.ops
+
+    torch.manual_seed(0 + rank)                                   # run_cyclical.py:315 seed + rank
+    model = M.create_model("beit_base_patch16_224", pretrained=False, drop_path_rate=0.25, drop_rate=0.0, use_shared_rel_pos_bias=True,
+                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05).to(dev)
+    if world > 1:                                                 # DDP broadcasts rank 0's parameters at construction
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    eng = E.D2VEngine(model, lr=2e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.9998, ema_decay_init=0.999, ema_start_at=0,
+                      target_layers=[6, 7, 8, 9, 10, 11], l1_beta=2.0, post_target_layer_norm=True, world_size=world, seed=rank)
+    lr_sched = E.cosine_scheduler(2e-3, 1e-5, 800, 10, warmup_epochs=10)       # per-step lr as the runner computes it
+    host = [synth_batch(BATCH, 100 * rank + i) for i in range(2)]
+    dev_batches = []
+    for x, m in host:
+        mu8 = np.ascontiguousarray(m.reshape(BATCH, -1))
+        dev_batches.append((x.to(dev), torch.from_numpy(mu8.reshape(-1)).to(dev), torch.from_numpy(eng.rows_from_host_mask(mu8, 197)).to(dev)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lr_at = lambda i: float(lr_sched[min(i + 50, len(lr_sched) - 1)])
+    for i in range(args.warmup):
+        eng.step(*dev_batches[i % 2], lr=lr_at(i))
+    barrier()
+    # ---- value: K steps, inputs resident in HBM, CUDA events
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = eng.step(*dev_batches[i % 2], lr=lr_at(i))
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = (ops.LAUNCHES - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss.item())
+    # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs
+    for i in range(2):
+        eng.step_host(*host[i % 2], lr=lr_at(i))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.step_host(*host[i % 2], lr=lr_at(i))
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    h2d = host[0][0].numel() * 4 + BATCH * 196 + BATCH * MASKED * 4
+    # ---- roofline: CUDA events around every tcgen05 GEMM launch inside 2 instrumented steps
+    roof = None
+    if rank == 0:
+        ops.GEMM_TIMING = []
+        for i in range(2):
+            eng.step(*dev_batches[i % 2], lr=lr_at(i))
+        torch.cuda.synchronize()
+        rec, ops.GEMM_TIMING = ops.GEMM_TIMING, None
+        flops = sum(f for _, _, f in rec)
+        t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+        pk = peaks()
+        achieved = flops / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05, all 4 operand-major instantiations)", "launches_timed": len(rec),
+                "gemm_ms_per_step": t_ms / 2, "gemm_share_of_step": (t_ms / 2) / ms, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
+                "frac_of_burst": achieved / pk["bf16_burst"]}
+    barrier()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference_steps(2, 1)
+        cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+               "sample": f"2 full data2vec steps of {CPU_SAMPLE_BATCH} images after 1 warm-up ({sec:.2f} s/step), fp32 oracle port, {cores} threads"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "data2vec ViT-B/16 pretrain throughput", "value": world * BATCH / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "beit_base_patch16_224 data2vec cyclical pretrain step (run_cyclical.py recipe), batch 128/GPU, 120 masked patches, "
+                                   "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
+                       "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"},
+            "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+            "step_tflops_algorithmic": 140.93e9 * BATCH / (ms * 1e-3) / 1e12}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback); use --impl reference for the host baseline")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

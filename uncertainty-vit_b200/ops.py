@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import (EPI_BF16, EPI_DGELU, EPI_ELU1, EPI_F32, EPI_F32_ATOMIC, EPI_GELU, EPI_RESIDUAL, GemmDesc, check)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+GEMM_TIMING = None  # bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per GEMM launch
 
 
 def _count(n: int = 1) -> None:
@@ -60,7 +61,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if out2_bf16 is not None:
         d.out2_bf16, d.ld2_bf16 = _p(out2_bf16), out2_bf16.stride(0)
     d.alpha, d.split_k, d.max_ctas = alpha, split_k, max_ctas
-    check(_lib.lib().b200vit_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
+    if GEMM_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.lib().b200vit_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
+        e1.record()
+        GEMM_TIMING.append((e0, e1, 2.0 * M * N * K))
+    else:
+        check(_lib.lib().b200vit_gemm_bf16(C.byref(d), _stream()), "gemm_bf16")
     _count()
 
 
