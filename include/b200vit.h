@@ -75,6 +75,7 @@ typedef struct b200vit_gemm_desc {
   float alpha;
   int32_t split_k;     /* F32_ATOMIC only: 0 = pick for wave efficiency, 1 = none, >1 = explicit number of K splits */
   int32_t max_ctas;    /* 0: one CTA per SM */
+  float* colsum;       /* optional fp32 [N]: += column sums of the values written (fused bias gradient, e.g. fc1.bias from dGELU) */
 } b200vit_gemm_desc;
 
 int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
@@ -92,12 +93,15 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                      float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
                      uint8_t* keep_bits, void* stream);
-/* dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, += ) is the gradient of
- * relative_position_bias_table [num_bins, H]; rel_index int32 [N, N] is the reference's relative_position_index
- * (modeling_finetune.py:339-353). */
+/* dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, +=) is the gradient of
+ * relative_position_bias_table [num_bins, H]: the kernel stores dS^T as bf16 into ds_work [B, H, N, ld_ds] (ld_ds even,
+ * >= N rounded up to 16) and a second kernel reduces it over the batch and scatter-adds through rel_index int32 [N, N]
+ * (the reference's relative_position_index, modeling_finetune.py:339-353). dq_bias / dv_bias (optional, +=, [H*64]) are the
+ * q_bias / v_bias gradients (column sums of dQ / dV; modeling_finetune.py:148). */
 int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias, int64_t ld_bias,
-                     const uint8_t* keep_bits, const int32_t* rel_index, float* dtable, int32_t num_bins, int32_t B, int32_t H,
-                     int32_t N, int32_t head_dim, float scale, float p_drop, void* dqkv, void* stream);
+                     const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
+                     float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
+                     void* dqkv, void* stream);
 /* The Philox keep mask of b200vit_attn_fwd as uint8 [BH, N, N] (parity tests inject it into the CPU oracle). */
 int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 

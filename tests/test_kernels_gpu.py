@@ -98,6 +98,9 @@ def test_gemm_epilogues(ops, cuda):
     xa = aux.float().requires_grad_(True)
     torch.nn.functional.gelu(xa).sum().backward()
     assert rel(out.float(), (a.float() @ w.float().t()) * xa.grad) < 5e-3
+    cs = torch.zeros(N, device=cuda)
+    ops.gemm(a, w, M, N, K, epilogue=ops.EPI_DGELU, aux=aux, out_bf16=out, colsum=cs)
+    assert rel(cs, ((a.float() @ w.float().t()) * xa.grad).sum(0)) < 2e-3
     # ELU + 1
     out = torch.empty(M, N, dtype=torch.bfloat16, device=cuda)
     ops.gemm(a, w, M, N, K, epilogue=ops.EPI_ELU1, bias=bias, out_bf16=out)
@@ -275,8 +278,11 @@ def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
     idx = torch.randint(0, 50, (N, N), generator=g).to(torch.int32).to(cuda)
     dtable = torch.zeros(50, H, device=cuda)
     dqkv = torch.full((B, N, 3, H, 64), float("nan"), dtype=torch.bfloat16, device=cuda)
-    ops.attn_bwd(qkv, out, dout, lse, bias, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv)
+    dqb = torch.zeros(H * 64, device=cuda)
+    dvb = torch.zeros(H * 64, device=cuda)
+    ops.attn_bwd(qkv, out, dout, lse, bias, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv, dq_bias=dqb, dv_bias=dvb)
     assert torch.isfinite(dqkv.float()).all()
+    assert rel(dqb, qr.grad[:, :, 0].sum((0, 1)).flatten()) < 2e-2 and rel(dvb, qr.grad[:, :, 2].sum((0, 1)).flatten()) < 2e-2
     for part, name in ((0, "dq"), (1, "dk"), (2, "dv")):
         assert rel(dqkv[:, :, part].float(), qr.grad[:, :, part]) < 2e-2, name
     ref_tab = torch.zeros(50, H, device=cuda)

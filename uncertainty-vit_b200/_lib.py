@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
                 ("out_f32", vp), ("ld_f32", i64),
                 ("out_bf16", vp), ("ld_bf16", i64),
                 ("out2_bf16", vp), ("ld2_bf16", i64),
-                ("alpha", f32), ("split_k", i32), ("max_ctas", i32)]
+                ("alpha", f32), ("split_k", i32), ("max_ctas", i32), ("colsum", vp)]
 
 
 _PROTOS = {
@@ -35,7 +35,7 @@ _PROTOS = {
     "b200vit_device_sm_count": (i32, []),
     "b200vit_gemm_bf16": (i32, [C.POINTER(GemmDesc), vp]),
     "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, u32, vp, vp, vp, vp, vp]),
-    "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, vp]),
+    "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp]),
     "b200vit_dropout_mask": (i32, [vp, i32, i32, f32, u64, u32, vp]),
     "b200vit_layernorm_fwd": (i32, [vp, i64, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]),
     "b200vit_layernorm_bwd": (i32, [vp, i32, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, vp]),

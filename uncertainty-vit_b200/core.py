@@ -155,8 +155,7 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
     # ---- MLP branch: x_out = x_mid + dp2 * gamma_2 * (fc2(gelu(fc1(LN2 x_mid))))
     ops.scale_residual_bwd(dx, s["t2"], s["dp2"], T, g2, M, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
     ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
-    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
-    ops.colsum_bf16(dpre, M, Hd, g("mlp.fc1.bias"))
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre, colsum=g("mlp.fc1.bias"))
     ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
     ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M, C, dx, g("norm2.weight"), g("norm2.bias"))
@@ -165,9 +164,7 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
     ops.linear_wgrad(dt, s["attn_out"], g("attn.proj.weight"))
     ops.gemm(dt, ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.attn_bwd(s["qkv"], s["attn_out"], dh, s["lse"], bias, s["keep_bits"], ps.rel_index_i32() if dtable is not None else None, dtable,
-                 B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv)
-    ops.colsum_bf16(dqkv, M, C, g("attn.q_bias"), ldx=3 * C)
-    ops.colsum_bf16(dqkv[:, 2 * C:], M, C, g("attn.v_bias"), ldx=3 * C)
+                 B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv, ds_work=ws.get("ds"), dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"))
     ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))
     ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"))
@@ -176,7 +173,9 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
 def backward_workspace(cfg: VitConfig, B: int, dev) -> Dict[str, torch.Tensor]:
     M, C, Hd = B * cfg.tokens, cfg.embed_dim, cfg.hidden
     bf = torch.bfloat16
-    return dict(dt=_empty((M, C), bf, dev), dpre=_empty((M, Hd), bf, dev), dh=_empty((M, C), bf, dev), dqkv=_empty((M, 3 * C), bf, dev))
+    T = cfg.tokens
+    return dict(dt=_empty((M, C), bf, dev), dpre=_empty((M, Hd), bf, dev), dh=_empty((M, C), bf, dev), dqkv=_empty((M, 3 * C), bf, dev),
+                ds=torch.zeros((B, cfg.num_heads, T, (T + 15) // 16 * 16), dtype=bf, device=dev))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -259,9 +259,10 @@ struct AttnBwdParams {
   const float* bias;     // [H, N, ld_bias] or null
   long long ld_bias;
   const uint8_t* keep_bits;  // [B, H, N, 32] or null (p_drop == 0)
-  const int* rel_index;  // [N, N] int32 (bias-table bin of (i, j)) or null
-  float* dtable;         // [num_bins, H] fp32, accumulated (+=) ; or null
-  int num_bins;
+  bf16* ds_out;          // [B, H, N(key), ld_ds(query)] bf16 dS^T for the rel-pos-bias gradient, or null
+  int ld_ds;
+  float* dq_bias;        // [H*64] += column sums of dQ (q_bias gradient) or null
+  float* dv_bias;        // [H*64] += column sums of dV (v_bias gradient) or null
   bf16* dqkv;            // [B, N, 3, H, 64]
   int B, H, N;
   float scale, p_drop;
@@ -277,7 +278,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   float* sLse = sdQ + NMAX * HD;                                // [NMAX] (log2 domain)
   float* sD = sLse + NMAX;                                      // [NMAX]
   bf16* sStage = reinterpret_cast<bf16*>(sD + NMAX);            // [BWD_WARPS][16][24]
-  float* sTab = reinterpret_cast<float*>(sStage + BWD_WARPS * 16 * 24);  // [num_bins]
 
   const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh - b * p.H;
@@ -295,8 +295,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   load_tile_rows(sdO, gdo, o_stride, N, n_pad);
   for (int i = threadIdx.x; i < n_pad * HD; i += blockDim.x) sdQ[i] = 0.f;
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) sLse[i] = i < N ? p.lse[(long long)bh * N + i] * LOG2E : 0.f;
-  if (p.dtable != nullptr)
-    for (int i = threadIdx.x; i < p.num_bins; i += blockDim.x) sTab[i] = 0.f;
   cp_async_wait_all();
   __syncthreads();
   // D_i = sum_d dO[i,d] * O[i,d]  (8 lanes per row)
@@ -326,22 +324,25 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
   const float sl2 = p.scale * LOG2E;
 
-  if (warp < ntile) {
-    const int jt = warp;
-    const int jA = jt * 16 + qrow, jB = jA + 8;  // the two key rows this thread owns in C fragments
-    uint32_t ka[4][4], va[4][4];
+  const bool active = warp < ntile;
+  const int jt = active ? warp : 0;
+  const int jA = jt * 16 + qrow, jB = jA + 8;  // the two key rows this thread owns in C fragments
+  uint32_t ka[4][4], va[4][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      ldsm_x4(smem_u32(sK + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
-      ldsm_x4(smem_u32(sV + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
-    }
-    float dv[8][4], dk[8][4];
+  for (int ks = 0; ks < 4; ++ks) {
+    ldsm_x4(smem_u32(sK + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
+    ldsm_x4(smem_u32(sV + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
+  }
+  float dv[8][4], dk[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
-    bf16* stage = sStage + warp * 16 * 24;
+  for (int i = 0; i < 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
+  bf16* stage = sStage + warp * 16 * 24;
 
-    for (int step = 0; step < ntile; ++step) {
-      int it = step + jt;            // rotate the start so that concurrent warps hit different dQ tiles
+  // Every warp owns one 16-key tile; in step s it visits query tile (s + jt) mod ntile, so within a step the warps touch
+  // DISJOINT dQ tiles and the shared-memory accumulation needs no atomics (block barrier between steps).
+  for (int step = 0; step < ntile; ++step) {
+    if (active) {
+      int it = step + jt;
       if (it >= ntile) it -= ntile;
       // S^T = K_j Q_i^T and dP^T = V_j dO_i^T : [16 keys x 16 queries]
       float st[2][4], dp[2][4];
@@ -362,15 +363,16 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
       float pt[2][4], ds[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
+        const int ibase = it * 16 + n * 8 + quad * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int i = it * 16 + n * 8 + quad * 2 + (e & 1);   // query
+          const int i = ibase + (e & 1);                        // query
           const int j = (e < 2) ? jA : jB;                      // key
-          float pv = 0.f, dsv = 0.f, ptv = 0.f;
+          float dsv = 0.f, ptv = 0.f;
           if (i < N && j < N) {
             float sv = st[n][e] * sl2;
             if (p.bias != nullptr) sv += __ldg(p.bias + ((long long)h * N + i) * p.ld_bias + j) * LOG2E;
-            pv = exp2f(sv - sLse[i]);
+            const float pv = exp2f(sv - sLse[i]);
             float keepf = 1.0f;
             if (drop) {
               const uint8_t byte = p.keep_bits[((long long)bh * N + i) * 32 + (j >> 3)];
@@ -378,7 +380,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
             }
             ptv = pv * keepf;
             dsv = pv * (dp[n][e] * keepf - sD[i]);
-            if (p.dtable != nullptr) atomicAdd(sTab + p.rel_index[i * N + j], dsv);
           }
           pt[n][e] = ptv;
           ds[n][e] = dsv;
@@ -389,6 +390,12 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
       const uint32_t pa2 = pack_bf16x2(pt[1][0], pt[1][1]), pa3 = pack_bf16x2(pt[1][2], pt[1][3]);
       const uint32_t da0 = pack_bf16x2(ds[0][0], ds[0][1]), da1 = pack_bf16x2(ds[0][2], ds[0][3]);
       const uint32_t da2 = pack_bf16x2(ds[1][0], ds[1][1]), da3 = pack_bf16x2(ds[1][2], ds[1][3]);
+      if (p.ds_out != nullptr) {   // dS^T for the relative-position-bias gradient (reduced over the batch by a second kernel)
+        bf16* d0 = p.ds_out + ((long long)bh * N + jA) * p.ld_ds + it * 16 + quad * 2;
+        bf16* d1 = p.ds_out + ((long long)bh * N + jB) * p.ld_ds + it * 16 + quad * 2;
+        if (jA < N) { *reinterpret_cast<uint32_t*>(d0) = da0; *reinterpret_cast<uint32_t*>(d0 + 8) = da2; }
+        if (jB < N) { *reinterpret_cast<uint32_t*>(d1) = da1; *reinterpret_cast<uint32_t*>(d1 + 8) = da3; }
+      }
       // dV_j += P~^T dO_i ; dK_j += dS^T Q_i   (B = [query][d] row-major -> ldmatrix.trans)
 #pragma unroll
       for (int dpair = 0; dpair < 4; ++dpair) {
@@ -417,13 +424,17 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
         ldsm_x4_t(smem_u32(sK + (jt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dpair * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
         mma16816(dq0, sa0, sa1, sa2, sa3, b0, b1);
         mma16816(dq1, sa0, sa1, sa2, sa3, b2, b3);
-        float* q0 = sdQ + (it * 16 + qrow) * HD + dpair * 16 + quad * 2;
-        atomicAdd(q0, dq0[0]); atomicAdd(q0 + 1, dq0[1]);
-        atomicAdd(q0 + 8 * HD, dq0[2]); atomicAdd(q0 + 8 * HD + 1, dq0[3]);
-        atomicAdd(q0 + 8, dq1[0]); atomicAdd(q0 + 9, dq1[1]);
-        atomicAdd(q0 + 8 * HD + 8, dq1[2]); atomicAdd(q0 + 8 * HD + 9, dq1[3]);
+        float2* q0 = reinterpret_cast<float2*>(sdQ + (it * 16 + qrow) * HD + dpair * 16 + quad * 2);
+        float2 v;
+        v = q0[0]; v.x += dq0[0]; v.y += dq0[1]; q0[0] = v;
+        v = q0[4 * HD]; v.x += dq0[2]; v.y += dq0[3]; q0[4 * HD] = v;          // row + 8  (float2 units: 8 * HD / 2)
+        v = q0[4]; v.x += dq1[0]; v.y += dq1[1]; q0[4] = v;                    // cols + 8
+        v = q0[4 * HD + 4]; v.x += dq1[2]; v.y += dq1[3]; q0[4 * HD + 4] = v;
       }
     }
+    __syncthreads();
+  }
+  if (active) {
     // write dK (scaled) and dV for this key tile
     bf16* gdk = p.dqkv + (long long)b * N * row_stride + p.H * HD + h * HD;
     bf16* gdv = gdk + p.H * HD;
@@ -438,31 +449,63 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
         *reinterpret_cast<uint32_t*>(gdk + (long long)jB * row_stride + c) = pack_bf16x2(dk[dt][2] * p.scale, dk[dt][3] * p.scale);
         *reinterpret_cast<uint32_t*>(gdv + (long long)jB * row_stride + c) = pack_bf16x2(dv[dt][2], dv[dt][3]);
       }
+      if (p.dv_bias != nullptr) {   // v_bias gradient: column sums of dV over this tile's keys (rows >= N are exactly zero)
+        float s0 = dv[dt][0] + dv[dt][2], s1 = dv[dt][1] + dv[dt][3];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (qrow == 0) { atomicAdd(p.dv_bias + h * HD + c, s0); atomicAdd(p.dv_bias + h * HD + c + 1, s1); }
+      }
     }
   }
   __syncthreads();
-  // dQ (scaled) -> global
+  // dQ (scaled) -> global ; q_bias gradient = column sums (blockDim % 16 == 0, so a thread's column group is fixed)
   bf16* gdq = p.dqkv + (long long)b * N * row_stride + h * HD;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int idx = threadIdx.x; idx < N * 16; idx += blockDim.x) {
     const int r = idx >> 4, c = (idx & 15) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(sdQ + r * HD + c);
+    float4 v = *reinterpret_cast<const float4*>(sdQ + r * HD + c);
+    v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
     uint2 u;
-    u.x = pack_bf16x2(v.x * p.scale, v.y * p.scale);
-    u.y = pack_bf16x2(v.z * p.scale, v.w * p.scale);
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(gdq + (long long)r * row_stride + c) = u;
   }
-  if (p.dtable != nullptr)
-    for (int i = threadIdx.x; i < p.num_bins; i += blockDim.x) {
-      const float v = sTab[i];
-      if (v != 0.f) atomicAdd(p.dtable + (long long)i * p.H + h, v);
+  if (p.dq_bias != nullptr) {
+    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+    if ((threadIdx.x & 31) < 16) {
+      float* dst = p.dq_bias + h * HD + (threadIdx.x & 15) * 4;
+      atomicAdd(dst, cs.x); atomicAdd(dst + 1, cs.y); atomicAdd(dst + 2, cs.z); atomicAdd(dst + 3, cs.w);
     }
+  }
+}
+
+// Relative-position-bias table gradient: dtable[index[i, j], h] += sum_b dS[b, h, i, j]  (dS^T stored [B, H, j, ld] by attn_bwd)
+__global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restrict__ ds, int B, int H, int N, int ld,
+                                                           const int* __restrict__ rel_index, float* __restrict__ dtable) {
+  const int half = ld >> 1;                       // pairs of queries
+  const long long total = (long long)H * N * half;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int ip = (int)(t % half);
+    const int j = (int)((t / half) % N);
+    const int h = (int)(t / ((long long)half * N));
+    const int i = ip * 2;
+    if (i >= N) continue;
+    float s0 = 0.f, s1 = 0.f;
+    const bf16* src = ds + ((long long)h * N + j) * ld + i;
+    const long long bstride = (long long)H * N * ld;
+    for (int b = 0; b < B; ++b) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + b * bstride));
+      s0 += v.x; s1 += v.y;
+    }
+    atomicAdd(dtable + (long long)rel_index[i * N + j] * H + h, s0);
+    if (i + 1 < N) atomicAdd(dtable + (long long)rel_index[(i + 1) * N + j] * H + h, s1);
+  }
 }
 
 constexpr size_t FWD_SMEM = 3 * NMAX * PITCH * sizeof(bf16);
-size_t bwd_smem(int num_bins) {
-  return 4 * NMAX * PITCH * sizeof(bf16) + NMAX * HD * sizeof(float) + 2 * NMAX * sizeof(float) + BWD_WARPS * 16 * 24 * sizeof(bf16) +
-         (size_t)num_bins * sizeof(float);
-}
+constexpr size_t BWD_SMEM = 4 * NMAX * PITCH * sizeof(bf16) + NMAX * HD * sizeof(float) + 2 * NMAX * sizeof(float) + BWD_WARPS * 16 * 24 * sizeof(bf16);
 
 }  // namespace
 
@@ -491,26 +534,34 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
 }
 
 extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias, int64_t ld_bias,
-                                const uint8_t* keep_bits, const int32_t* rel_index, float* dtable, int32_t num_bins, int32_t B, int32_t H,
-                                int32_t N, int32_t head_dim, float scale, float p_drop, void* dqkv, void* stream) {
+                                const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
+                                float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
+                                void* dqkv, void* stream) {
   B200_CHECK_ARG(qkv && out && dout && lse && dqkv, "attn_bwd: null pointer");
   B200_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim %d unsupported (64 only)", head_dim);
   B200_CHECK_ARG(N > 0 && N <= NMAX, "attn_bwd: N=%d unsupported (1..%d)", N, NMAX);
   B200_CHECK_ARG(p_drop == 0.f || keep_bits != nullptr, "attn_bwd: dropout needs keep_bits from the forward");
-  B200_CHECK_ARG(dtable == nullptr || (rel_index != nullptr && num_bins > 0 && num_bins <= 4096), "attn_bwd: dtable needs rel_index and 1..4096 bins");
-  const size_t smem = bwd_smem(dtable != nullptr ? num_bins : 0);
-  static size_t configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int n_pad = (N + 15) / 16 * 16;
+  B200_CHECK_ARG(dtable == nullptr || (rel_index != nullptr && ds_work != nullptr && ld_ds >= n_pad && ld_ds % 2 == 0),
+                 "attn_bwd: dtable needs rel_index and a bf16 workspace [B,H,N,ld_ds] with even ld_ds >= %d", n_pad);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
     if (e != cudaSuccess) { b200vit_set_error("attn_bwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
+    configured = true;
   }
   AttnBwdParams p;
   p.qkv = static_cast<const bf16*>(qkv); p.out = static_cast<const bf16*>(out); p.dout = static_cast<const bf16*>(dout); p.lse = lse;
-  p.bias = bias; p.ld_bias = ld_bias; p.keep_bits = keep_bits; p.rel_index = rel_index; p.dtable = dtable; p.num_bins = num_bins;
+  p.bias = bias; p.ld_bias = ld_bias; p.keep_bits = keep_bits;
+  p.ds_out = dtable != nullptr ? static_cast<bf16*>(ds_work) : nullptr; p.ld_ds = ld_ds; p.dq_bias = dq_bias; p.dv_bias = dv_bias;
   p.dqkv = static_cast<bf16*>(dqkv); p.B = B; p.H = H; p.N = N; p.scale = scale; p.p_drop = p_drop;
-  attn_bwd_kernel<<<B * H, BWD_WARPS * 32, smem, STREAM>>>(p);
+  attn_bwd_kernel<<<B * H, BWD_WARPS * 32, BWD_SMEM, STREAM>>>(p);
   B200_CHECK_LAUNCH("attn_bwd");
+  if (dtable != nullptr) {
+    const int sms = b200vit_num_sms();
+    relbias_grad_kernel<<<sms * 8, 256, 0, STREAM>>>(static_cast<const bf16*>(ds_work), B, H, N, ld_ds, rel_index, dtable);
+    B200_CHECK_LAUNCH("relbias_grad");
+  }
   return 0;
 }
 

@@ -29,7 +29,9 @@ constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // 32 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 
 struct EpiParams {
@@ -49,6 +51,7 @@ struct EpiParams {
   bf16* out2_bf16;
   long long ld2_bf16;
   float alpha;
+  float* colsum;
 };
 
 struct GemmParams {
@@ -57,123 +60,61 @@ struct GemmParams {
   EpiParams epi;
 };
 
-__device__ __forceinline__ void store_bf16x8(bf16* p, const float* v) {
-  uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
+__device__ __forceinline__ void store_bf16x4(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
 }
 
-// Applies the fused epilogue to 32 consecutive accumulator columns [n0, n0+32) of row m.
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, int m, int n0, int N, float (&v)[32]) {
-  const int nvalid = min(32, N - n0);  // N % 8 == 0 is enforced on the host
+// Fused epilogue on 4 consecutive accumulator columns [n, n+4) of row m (coalesced layout: 8 lanes cover 32 columns of a row,
+// a warp instruction covers 4 rows x 128 B). `bias4` / `cs4` are the lane's per-chunk constants. Returns the value written
+// (for the fused column sums).
+__device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, float4 v, const float4& bias4, const float4& cs4) {
   if (e.mode == B200VIT_EPI_F32_ATOMIC) {
-    float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      if (j < nvalid) ptx::red_add_v4(dst + j, v[j] * e.alpha, v[j + 1] * e.alpha, v[j + 2] * e.alpha, v[j + 3] * e.alpha);
-    return;
+    ptx::red_add_v4(e.out_f32 + (long long)m * e.ld_f32 + n, v.x * e.alpha, v.y * e.alpha, v.z * e.alpha, v.w * e.alpha);
+    return v;
   }
-  if (e.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      if (j < nvalid) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-  }
+  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
   switch (e.mode) {
     case B200VIT_EPI_BF16: {
-      if (e.colscale != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < nvalid) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(e.colscale + n0 + j));
-            v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
-          }
-      }
-      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
+      store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
     case B200VIT_EPI_GELU: {
-      if (e.out2_bf16 != nullptr) {
-        bf16* dst2 = e.out2_bf16 + (long long)m * e.ld2_bf16 + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          if (j < nvalid) store_bf16x8(dst2 + j, v + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      if (e.out2_bf16 != nullptr) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, v);
+      v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+      store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
     case B200VIT_EPI_RESIDUAL: {
-      if (e.out2_bf16 != nullptr) {
-        bf16* dst2 = e.out2_bf16 + (long long)m * e.ld2_bf16 + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          if (j < nvalid) store_bf16x8(dst2 + j, v + j);
-      }
+      if (e.out2_bf16 != nullptr) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, v);
       const float rs = e.rowscale != nullptr ? __ldg(e.rowscale + m / e.rows_per_scale) : 1.0f;
-      const float* res = e.residual + (long long)m * e.ld_residual + n0;
-      float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (j < nvalid) {
-          float4 s = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (e.colscale != nullptr) s = __ldg(reinterpret_cast<const float4*>(e.colscale + n0 + j));
-          const float4 r = *reinterpret_cast<const float4*>(res + j);
-          float4 o;
-          o.x = fmaf(rs * s.x, v[j], r.x);
-          o.y = fmaf(rs * s.y, v[j + 1], r.y);
-          o.z = fmaf(rs * s.z, v[j + 2], r.z);
-          o.w = fmaf(rs * s.w, v[j + 3], r.w);
-          *reinterpret_cast<float4*>(dst + j) = o;
-        }
+      const float4 r = *reinterpret_cast<const float4*>(e.residual + (long long)m * e.ld_residual + n);
+      v = make_float4(fmaf(rs * cs4.x, v.x, r.x), fmaf(rs * cs4.y, v.y, r.y), fmaf(rs * cs4.z, v.z, r.z), fmaf(rs * cs4.w, v.w, r.w));
+      *reinterpret_cast<float4*>(e.out_f32 + (long long)m * e.ld_f32 + n) = v;
       break;
     }
     case B200VIT_EPI_DGELU: {
-      const bf16* aux = e.aux + (long long)m * e.ld_aux + n0;
-      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (j < nvalid) {
-          const uint4 a = *reinterpret_cast<const uint4*>(aux + j);
-          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-          v[j] *= gelu_erf_grad(a0.x); v[j + 1] *= gelu_erf_grad(a0.y);
-          v[j + 2] *= gelu_erf_grad(a1.x); v[j + 3] *= gelu_erf_grad(a1.y);
-          v[j + 4] *= gelu_erf_grad(a2.x); v[j + 5] *= gelu_erf_grad(a2.y);
-          v[j + 6] *= gelu_erf_grad(a3.x); v[j + 7] *= gelu_erf_grad(a3.y);
-          store_bf16x8(dst + j, v + j);
-        }
+      const uint2 a = *reinterpret_cast<const uint2*>(e.aux + (long long)m * e.ld_aux + n);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+      v = make_float4(v.x * gelu_erf_grad(a0.x), v.y * gelu_erf_grad(a0.y), v.z * gelu_erf_grad(a1.x), v.w * gelu_erf_grad(a1.y));
+      store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
     case B200VIT_EPI_ELU1: {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.0f : __expf(v[j]);   // elu(x)+1
-      bf16* dst = e.out_bf16 + (long long)m * e.ld_bf16 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (j < nvalid) store_bf16x8(dst + j, v + j);
+      v = make_float4(v.x > 0.f ? v.x + 1.0f : __expf(v.x), v.y > 0.f ? v.y + 1.0f : __expf(v.y), v.z > 0.f ? v.z + 1.0f : __expf(v.z),
+                      v.w > 0.f ? v.w + 1.0f : __expf(v.w));   // elu(x) + 1
+      store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
     case B200VIT_EPI_F32:
-    default: {
-      float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (j < nvalid) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    default:
+      *reinterpret_cast<float4*>(e.out_f32 + (long long)m * e.ld_f32 + n) = v;
       break;
-    }
   }
+  return v;
 }
 
 template <bool A_MN, bool B_MN>
@@ -189,6 +130,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  const uint32_t stage_base = bar_base + 256u;    // epilogue transpose staging: NUM_EPI_WARPS x 32 x 32 fp32
   auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_STAGE_BYTES; };
 
@@ -295,6 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int ew = warp - FIRST_EPI_WARP;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = ew >> 2;                // column half of the accumulator
+    float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - ptx::smem_u32(smem_raw))) + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -302,8 +245,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int m = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int m_base = m_blk * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+      const int cg = lane & 7, sub = lane >> 3;      // coalesced view: column group (4 cols) and row-within-4
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 2; c += 32) {
         const int n0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + c;
@@ -311,12 +255,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
-        if (m < p.M) {
-          float v[32];
+        // transpose through shared memory: lane = row on the TMEM side, lane = (row % 4, 4-column group) on the global side
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_chunk(p.epi, m, n0, p.N, v);
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+        __syncwarp();
+        const int n = n0 + cg * 4;
+        const bool col_ok = n < p.N;       // N % 8 == 0: a 4-column group is entirely valid or not
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (col_ok) {
+          if (p.epi.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
+          if (p.epi.colscale != nullptr) cs4 = __ldg(reinterpret_cast<const float4*>(p.epi.colscale + n));
         }
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = rr * 4 + sub;
+          const float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((cg ^ (row & 7)) << 2));
+          const int m = m_base + row;
+          if (col_ok && m < p.M) {
+            const float4 o = epilogue4(p.epi, m, n, v, bias4, cs4);
+            csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
+          }
+        }
+        if (p.epi.colsum != nullptr) {     // fused bias gradient: column sums of the values written by this tile
+#pragma unroll
+          for (int o = 8; o < 32; o <<= 1) {
+            csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+            csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+          }
+          if (sub == 0 && col_ok) ptx::red_add_v4(p.epi.colsum + n, csum.x, csum.y, csum.z, csum.w);
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -454,6 +425,7 @@ extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
   p.epi.out_bf16 = static_cast<bf16*>(d->out_bf16); p.epi.ld_bf16 = d->ld_bf16;
   p.epi.out2_bf16 = static_cast<bf16*>(d->out2_bf16); p.epi.ld2_bf16 = d->ld2_bf16;
   p.epi.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+  p.epi.colsum = d->colsum;
 
   CUtensorMap ta, tb;
   int rc;

@@ -41,7 +41,7 @@ def sm_count() -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          epilogue: int = EPI_BF16, bias=None, colscale=None, rowscale=None, rows_per_scale: int = 0, residual=None,
          aux=None, out_f32=None, out_bf16=None, out2_bf16=None, alpha: float = 1.0, split_k: int = 0, max_ctas: int = 0,
-         lda: Optional[int] = None, ldb: Optional[int] = None) -> None:
+         lda: Optional[int] = None, ldb: Optional[int] = None, colsum=None) -> None:
     """D[M,N] = A[M,K] B[N,K]^T (bf16 in, fp32 accumulate). a_mn/b_mn: operand stored as [K, M] / [K, N] row-major."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     d = GemmDesc()
@@ -61,6 +61,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if out2_bf16 is not None:
         d.out2_bf16, d.ld2_bf16 = _p(out2_bf16), out2_bf16.stride(0)
     d.alpha, d.split_k, d.max_ctas = alpha, split_k, max_ctas
+    d.colsum = _p(colsum)
     if GEMM_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -103,12 +104,16 @@ def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in
     _count()
 
 
-def attn_bwd(qkv, out, dout, lse, bias, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv):
+def attn_bwd(qkv, out, dout, lse, bias, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv, ds_work=None, dq_bias=None, dv_bias=None):
     ld_bias = bias.stride(1) if bias is not None else 0
-    nb = dtable.shape[0] if dtable is not None else 0
-    check(_lib.lib().b200vit_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(bias), ld_bias, _p(keep_bits), _p(rel_index), _p(dtable), nb,
-                                      B, H, N, 64, scale, p_drop, _p(dqkv), _stream()), "attn_bwd")
-    _count()
+    ld_ds = 0
+    if dtable is not None:
+        ld_ds = (N + 15) // 16 * 16
+        if ds_work is None:
+            ds_work = torch.empty((B, H, N, ld_ds), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.lib().b200vit_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(bias), ld_bias, _p(keep_bits), _p(ds_work), ld_ds, _p(rel_index),
+                                      _p(dtable), _p(dq_bias), _p(dv_bias), B, H, N, 64, scale, p_drop, _p(dqkv), _stream()), "attn_bwd")
+    _count(2 if dtable is not None else 1)
 
 
 def dropout_mask(BH, N, p_drop, seed, stream_id, device) -> torch.Tensor:
