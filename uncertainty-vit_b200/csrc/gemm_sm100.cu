@@ -1,6 +1,8 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (SWIZZLE_128B) -> tcgen05.mma (cta_group::1,
-// 128x256x16, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with fused bias / GELU / layer-scale +
-// drop-path + residual / dGELU / fp32 / split-K atomic accumulation.
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> shared memory (SWIZZLE_128B) -> tcgen05.mma.cta_group::2
+// (a CTA pair on one TPC computes a 256x256 tile: 256x256x16 UMMA, each CTA stages 128 rows of A and 128 rows of B, so the
+// L2->SMEM operand traffic per flop is 2/3 of the single-CTA 128x256 tile), fp32 accumulators in TMEM (double-buffered),
+// tcgen05.ld epilogue transposed through shared memory for coalesced I/O with fused bias / GELU / layer-scale + drop-path +
+// residual / dGELU / ELU+1 / fp32 / split-K atomic accumulation.
 //
 //   D[M,N] = A[M,K] * B[N,K]^T
 //
@@ -17,17 +19,19 @@
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
+constexpr int BLOCK_M = 128;   // rows per CTA; a CTA pair (cta_group::2) owns a 256 x 256 output tile
+constexpr int PAIR_M = 256;
+constexpr int BLOCK_N = 256;   // tile width; each CTA of the pair stages HALF_N rows of B
+constexpr int HALF_N = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // 32 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
@@ -136,6 +140,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();   // 0 = leader of the pair (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -143,21 +150,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(full_bar(s), 1);      // leader: its own arrive.expect_tx; bytes from BOTH CTAs' TMA loads
+      ptx::mbar_init(empty_bar(s), 1);     // per CTA: multicast tcgen05.commit of the leader
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
-      ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+      ptx::mbar_init(tfull_bar(a), 1);                     // per CTA: multicast commit
+      ptx::mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);    // leader: epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -166,47 +173,47 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_units = num_tiles * p.split_k;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
+    // ===================== TMA producer (one lane per CTA; both CTAs credit the leader's full barrier) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int u = pair; u < num_units; u += num_pairs) {
         const int tile = u / p.split_k, split = u - tile * p.split_k;
         const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int m0 = m_blk * PAIR_M + (int)cta_rank * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * HALF_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BLOCK_M / 64; ++c)
-              ptx::tma_load_2d(smem_a(stage) + c * (BLOCK_K * 128), &tmap_a, full_bar(stage), m_blk * BLOCK_M + c * 64,
-                               kb * BLOCK_K);
+              ptx::tma_load_2d_2sm(smem_a(stage) + c * (BLOCK_K * 128), &tmap_a, full_bar(stage), m0 + c * 64, kb * BLOCK_K);
           } else {
-            ptx::tma_load_2d(smem_a(stage), &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            ptx::tma_load_2d_2sm(smem_a(stage), &tmap_a, full_bar(stage), kb * BLOCK_K, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              ptx::tma_load_2d(smem_b(stage) + c * (BLOCK_K * 128), &tmap_b, full_bar(stage), n_blk * BLOCK_N + c * 64,
-                               kb * BLOCK_K);
+            for (int c = 0; c < HALF_N / 64; ++c)
+              ptx::tma_load_2d_2sm(smem_b(stage) + c * (BLOCK_K * 128), &tmap_b, full_bar(stage), n0 + c * 64, kb * BLOCK_K);
           } else {
-            ptx::tma_load_2d(smem_b(stage), &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+            ptx::tma_load_2d_2sm(smem_b(stage), &tmap_b, full_bar(stage), kb * BLOCK_K, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ===================== MMA issuer (one lane of the LEADER CTA) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR_M, BLOCK_N, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int u = pair; u < num_units; u += num_pairs) {
         const int tile = u / p.split_k, split = u - tile * p.split_k;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -223,12 +230,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                         : ptx::make_smem_desc(smem_a(stage) + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? ptx::make_smem_desc(smem_b(stage) + k * 2048, BLOCK_K * 128, 1024)
                                         : ptx::make_smem_desc(smem_b(stage) + k * 32, 16, 1024);
-            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          ptx::umma_commit_2sm(empty_bar(stage), 3);  // frees this smem slot in BOTH CTAs once the MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        ptx::umma_commit_2sm(tfull_bar(acc), 3);      // accumulators complete -> both CTAs' epilogues
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -240,12 +247,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - ptx::smem_u32(smem_raw))) + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = pair; u < num_units; u += num_pairs) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int m_base = m_blk * BLOCK_M + quarter * 32;
+      const int m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
       const int cg = lane & 7, sub = lane >> 3;      // coalesced view: column group (4 cols) and row-within-4
 #pragma unroll 1
@@ -291,16 +298,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA thread waits for both CTAs' epilogues
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();     // the peer may still be reading this CTA's smem / signalling its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -373,8 +380,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
     }
     configured = true;
   }
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
-  B200_CHECK_LAUNCH("gemm_bf16");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN>, ta, tb, p);
+  if (e != cudaSuccess) {
+    b200vit_set_error("gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
   return 0;
 }
 
@@ -407,10 +429,11 @@ extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
 
   GemmParams p;
   p.M = d->M; p.N = d->N; p.K = d->K;
-  p.tiles_m = (d->M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_m = (d->M + PAIR_M - 1) / PAIR_M;
   p.tiles_n = (d->N + BLOCK_N - 1) / BLOCK_N;
   p.num_kb = (d->K + BLOCK_K - 1) / BLOCK_K;
-  const int cap = d->max_ctas > 0 ? (d->max_ctas < sms ? d->max_ctas : sms) : sms;
+  int cap = (d->max_ctas > 0 ? (d->max_ctas < sms ? d->max_ctas : sms) : sms) / 2;   // CTA pairs
+  if (cap < 1) cap = 1;
   int split = 1;
   if (mode == B200VIT_EPI_F32_ATOMIC) split = d->split_k > 1 ? d->split_k : (d->split_k == 1 ? 1 : pick_split_k(p.tiles_m * p.tiles_n, p.num_kb, cap));
   if (split > p.num_kb) split = p.num_kb;
@@ -432,11 +455,11 @@ extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
   // K-major: inner = K, rows = M|N, box 64 x BLOCK;   MN-major: inner = M|N, rows = K, box 64 x BLOCK_K
   rc = d->a_mn_major ? make_tmap(&ta, d->A, d->M, d->K, d->lda, 64, BLOCK_K) : make_tmap(&ta, d->A, d->K, d->M, d->lda, BLOCK_K, BLOCK_M);
   if (rc) return rc;
-  rc = d->b_mn_major ? make_tmap(&tb, d->B, d->N, d->K, d->ldb, 64, BLOCK_K) : make_tmap(&tb, d->B, d->K, d->N, d->ldb, BLOCK_K, BLOCK_N);
+  rc = d->b_mn_major ? make_tmap(&tb, d->B, d->N, d->K, d->ldb, 64, BLOCK_K) : make_tmap(&tb, d->B, d->K, d->N, d->ldb, BLOCK_K, HALF_N);
   if (rc) return rc;
 
   const int units = p.tiles_m * p.tiles_n * p.split_k;
-  const int grid = units < cap ? units : cap;
+  const int grid = 2 * (units < cap ? units : cap);
   if (d->a_mn_major) return d->b_mn_major ? launch<true, true>(ta, tb, p, grid, stream) : launch<true, false>(ta, tb, p, grid, stream);
   return d->b_mn_major ? launch<false, true>(ta, tb, p, grid, stream) : launch<false, false>(ta, tb, p, grid, stream);
 }
