@@ -75,6 +75,7 @@ typedef struct b200vit_gemm_desc {
   float alpha;
   int32_t split_k;     /* F32_ATOMIC only: 0 = pick for wave efficiency, 1 = none, >1 = explicit number of K splits */
   int32_t max_ctas;    /* 0: one CTA per SM */
+  int32_t debug_flags; /* 0 in production; bit 0 = skip the epilogue's global I/O (roofline experiments only) */
   float* colsum;       /* optional fp32 [N]: += column sums of the values written (fused bias gradient, e.g. fc1.bias from dGELU) */
 } b200vit_gemm_desc;
 

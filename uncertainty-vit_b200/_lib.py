@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
                 ("out_f32", vp), ("ld_f32", i64),
                 ("out_bf16", vp), ("ld_bf16", i64),
                 ("out2_bf16", vp), ("ld2_bf16", i64),
-                ("alpha", f32), ("split_k", i32), ("max_ctas", i32), ("colsum", vp)]
+                ("alpha", f32), ("split_k", i32), ("max_ctas", i32), ("debug_flags", i32), ("colsum", vp)]
 
 
 _PROTOS = {

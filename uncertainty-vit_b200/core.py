@@ -155,7 +155,8 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
     # ---- MLP branch: x_out = x_mid + dp2 * gamma_2 * (fc2(gelu(fc1(LN2 x_mid))))
     ops.scale_residual_bwd(dx, s["t2"], s["dp2"], T, g2, M, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
     ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
-    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre, colsum=g("mlp.fc1.bias"))
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
+    ops.colsum_bf16(dpre, M, Hd, g("mlp.fc1.bias"))
     ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
     ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M, C, dx, g("norm2.weight"), g("norm2.bias"))

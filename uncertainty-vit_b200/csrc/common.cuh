@@ -57,14 +57,29 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// exact (erf) GELU and its derivative, as torch.nn.GELU() (reference modeling_finetune.py:65-82)
+// erf-GELU (torch.nn.GELU(), reference modeling_finetune.py:65-82) and its derivative. erfc(|u|) by Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below the bf16 resolution of the tensors it feeds): 2 MUFU + ~10 FMA per element instead of
+// erff()'s branchy ~25 — the GEMM epilogue that applies it is instruction-issue bound otherwise.
+__device__ __forceinline__ float erfc_abs_as(float a /* >= 0 */, float& e /* out: exp(-a^2) */) {
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  e = __expf(-a * a);
+  return p * t * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  float e;
+  const float q = 0.5f * erfc_abs_as(fabsf(x) * 0.70710678118654752f, e);   // 0.5 * erfc(|x|/sqrt2)
+  const float cdf = x >= 0.f ? 1.0f - q : q;
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;                                                                    // e = exp(-x^2/2)
+  const float q = 0.5f * erfc_abs_as(fabsf(x) * 0.70710678118654752f, e);
+  const float cdf = x >= 0.f ? 1.0f - q : q;
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
 // Philox4x32-10 (counter-based; Salmon et al. 2011). Same constants as cuRAND / torch.

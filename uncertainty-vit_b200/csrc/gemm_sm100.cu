@@ -56,6 +56,7 @@ struct EpiParams {
   long long ld2_bf16;
   float alpha;
   float* colsum;
+  int debug_skip_io;   // profiling only: drain TMEM but skip the epilogue's global loads/stores
 };
 
 struct GemmParams {
@@ -71,16 +72,39 @@ __device__ __forceinline__ void store_bf16x4(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Per-row operand of the epilogue that lives in global memory (residual fp32x4 / aux bf16x4), prefetched one 32-column
+// chunk ahead so that its latency never sits on the TMEM-drain critical path.
+struct EpiPrefetch {
+  float4 v;   // residual (RESIDUAL) or the 4 aux values converted to fp32 (DGELU)
+};
+
+template <int MODE>
+__device__ __forceinline__ EpiPrefetch epi_prefetch(const EpiParams& e, int m, int n, bool ok) {
+  EpiPrefetch pf;
+  pf.v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!ok) return pf;
+  if (MODE == B200VIT_EPI_RESIDUAL) {
+    pf.v = *reinterpret_cast<const float4*>(e.residual + (long long)m * e.ld_residual + n);
+  } else if (MODE == B200VIT_EPI_DGELU) {
+    const uint2 a = *reinterpret_cast<const uint2*>(e.aux + (long long)m * e.ld_aux + n);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+    pf.v = make_float4(a0.x, a0.y, a1.x, a1.y);
+  }
+  return pf;
+}
+
 // Fused epilogue on 4 consecutive accumulator columns [n, n+4) of row m (coalesced layout: 8 lanes cover 32 columns of a row,
-// a warp instruction covers 4 rows x 128 B). `bias4` / `cs4` are the lane's per-chunk constants. Returns the value written
+// a warp instruction covers 4 rows x 128 B). bias4 / cs4 / rs / pf were loaded ahead of time. Returns the value written
 // (for the fused column sums).
-__device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, float4 v, const float4& bias4, const float4& cs4) {
-  if (e.mode == B200VIT_EPI_F32_ATOMIC) {
+template <int MODE>
+__device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, float4 v, const float4& bias4, const float4& cs4, float rs,
+                                            const EpiPrefetch& pf) {
+  if (MODE == B200VIT_EPI_F32_ATOMIC) {
     ptx::red_add_v4(e.out_f32 + (long long)m * e.ld_f32 + n, v.x * e.alpha, v.y * e.alpha, v.z * e.alpha, v.w * e.alpha);
     return v;
   }
   v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-  switch (e.mode) {
+  switch (MODE) {
     case B200VIT_EPI_BF16: {
       v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
       store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
@@ -94,16 +118,12 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
     }
     case B200VIT_EPI_RESIDUAL: {
       if (e.out2_bf16 != nullptr) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, v);
-      const float rs = e.rowscale != nullptr ? __ldg(e.rowscale + m / e.rows_per_scale) : 1.0f;
-      const float4 r = *reinterpret_cast<const float4*>(e.residual + (long long)m * e.ld_residual + n);
-      v = make_float4(fmaf(rs * cs4.x, v.x, r.x), fmaf(rs * cs4.y, v.y, r.y), fmaf(rs * cs4.z, v.z, r.z), fmaf(rs * cs4.w, v.w, r.w));
+      v = make_float4(fmaf(rs * cs4.x, v.x, pf.v.x), fmaf(rs * cs4.y, v.y, pf.v.y), fmaf(rs * cs4.z, v.z, pf.v.z), fmaf(rs * cs4.w, v.w, pf.v.w));
       *reinterpret_cast<float4*>(e.out_f32 + (long long)m * e.ld_f32 + n) = v;
       break;
     }
     case B200VIT_EPI_DGELU: {
-      const uint2 a = *reinterpret_cast<const uint2*>(e.aux + (long long)m * e.ld_aux + n);
-      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
-      v = make_float4(v.x * gelu_erf_grad(a0.x), v.y * gelu_erf_grad(a0.y), v.z * gelu_erf_grad(a1.x), v.w * gelu_erf_grad(a1.y));
+      v = make_float4(v.x * gelu_erf_grad(pf.v.x), v.y * gelu_erf_grad(pf.v.y), v.z * gelu_erf_grad(pf.v.z), v.w * gelu_erf_grad(pf.v.w));
       store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
@@ -121,7 +141,7 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
   return v;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -247,20 +267,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - ptx::smem_u32(smem_raw))) + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int cg = lane & 7, sub = lane >> 3;      // coalesced view: 4-column group and row-within-4 of this lane
+    constexpr int CHUNKS = BLOCK_N / 2 / 32;       // 4 chunks of 32 columns per warp
+    const bool io = !p.epi.debug_skip_io;
     for (int u = pair; u < num_units; u += num_pairs) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
+      const int n_base = n_blk * BLOCK_N + half * (BLOCK_N / 2) + cg * 4;
+      // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for the MMAs of this tile,
+      // and for chunk c+1 while chunk c is being processed (no global-load latency on the TMEM-drain critical path)
+      auto load_cols = [&](int n, float4& b4, float4& c4) {
+        b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        c4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (MODE != B200VIT_EPI_F32_ATOMIC && n < p.N && io) {
+          if (p.epi.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
+          if ((MODE == B200VIT_EPI_BF16 || MODE == B200VIT_EPI_RESIDUAL) && p.epi.colscale != nullptr)
+            c4 = __ldg(reinterpret_cast<const float4*>(p.epi.colscale + n));
+        }
+      };
+      float4 bias4, cs4;
+      load_cols(n_base, bias4, cs4);
+      float rs[8];
+      EpiPrefetch pf[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int m = m_base + rr * 4 + sub;
+        rs[rr] = (MODE == B200VIT_EPI_RESIDUAL && p.epi.rowscale != nullptr && m < p.M) ? __ldg(p.epi.rowscale + m / p.epi.rows_per_scale) : 1.0f;
+        pf[rr] = epi_prefetch<MODE>(p.epi, m, n_base, io && m < p.M && n_base < p.N);
+      }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
-      const int cg = lane & 7, sub = lane >> 3;      // coalesced view: column group (4 cols) and row-within-4
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 2; c += 32) {
-        const int n0 = n_blk * BLOCK_N + half * (BLOCK_N / 2) + c;
-        if (n0 >= p.N) break;              // warp-uniform
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n = n_base + c * 32;
+        if (n - cg * 4 >= p.N) break;      // warp-uniform: this 32-column chunk lies outside the matrix
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
         ptx::tmem_ld_wait();
         // transpose through shared memory: lane = row on the TMEM side, lane = (row % 4, 4-column group) on the global side
 #pragma unroll
@@ -268,21 +312,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           *reinterpret_cast<float4*>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
         __syncwarp();
-        const int n = n0 + cg * 4;
-        const bool col_ok = n < p.N;       // N % 8 == 0: a 4-column group is entirely valid or not
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (col_ok) {
-          if (p.epi.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
-          if (p.epi.colscale != nullptr) cs4 = __ldg(reinterpret_cast<const float4*>(p.epi.colscale + n));
+        float4 bias_n, cs_n;
+        EpiPrefetch nxt[8];
+        const bool more = c + 1 < CHUNKS;
+        load_cols(more ? n + 32 : p.N, bias_n, cs_n);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int m = m_base + rr * 4 + sub;
+          nxt[rr] = epi_prefetch<MODE>(p.epi, m, n + 32, more && io && m < p.M && n + 32 < p.N);
         }
+        const bool col_ok = n < p.N;       // N % 8 == 0: a 4-column group is entirely valid or not
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
           const int row = rr * 4 + sub;
           const float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((cg ^ (row & 7)) << 2));
           const int m = m_base + row;
-          if (col_ok && m < p.M) {
-            const float4 o = epilogue4(p.epi, m, n, v, bias4, cs4);
+          if (col_ok && m < p.M && io) {
+            const float4 o = epilogue4<MODE>(p.epi, m, n, v, bias4, cs4, rs[rr], pf[rr]);
             csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
           }
         }
@@ -294,6 +341,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           if (sub == 0 && col_ok) ptx::red_add_v4(p.epi.colsum + n, csum.x, csum.y, csum.z, csum.w);
         }
+        bias4 = bias_n;
+        cs4 = cs_n;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) pf[rr] = nxt[rr];
         __syncwarp();
       }
       ptx::tc_fence_before();
@@ -369,11 +420,11 @@ int pick_split_k(int tiles, int num_kb, int sms) {
   return best;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       b200vit_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -392,12 +443,25 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN>, ta, tb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, MODE>, ta, tb, p);
   if (e != cudaSuccess) {
     b200vit_set_error("gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
     return (int)e;
   }
   return 0;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
+  switch (mode) {
+    case B200VIT_EPI_BF16: return launch<A_MN, B_MN, B200VIT_EPI_BF16>(ta, tb, p, grid, stream);
+    case B200VIT_EPI_GELU: return launch<A_MN, B_MN, B200VIT_EPI_GELU>(ta, tb, p, grid, stream);
+    case B200VIT_EPI_RESIDUAL: return launch<A_MN, B_MN, B200VIT_EPI_RESIDUAL>(ta, tb, p, grid, stream);
+    case B200VIT_EPI_DGELU: return launch<A_MN, B_MN, B200VIT_EPI_DGELU>(ta, tb, p, grid, stream);
+    case B200VIT_EPI_F32: return launch<A_MN, B_MN, B200VIT_EPI_F32>(ta, tb, p, grid, stream);
+    case B200VIT_EPI_F32_ATOMIC: return launch<A_MN, B_MN, B200VIT_EPI_F32_ATOMIC>(ta, tb, p, grid, stream);
+    default: return launch<A_MN, B_MN, B200VIT_EPI_ELU1>(ta, tb, p, grid, stream);
+  }
 }
 
 }  // namespace
@@ -449,6 +513,7 @@ extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
   p.epi.out2_bf16 = static_cast<bf16*>(d->out2_bf16); p.epi.ld2_bf16 = d->ld2_bf16;
   p.epi.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
   p.epi.colsum = d->colsum;
+  p.epi.debug_skip_io = d->debug_flags & 1;
 
   CUtensorMap ta, tb;
   int rc;
@@ -460,6 +525,6 @@ extern "C" int b200vit_gemm_bf16(const b200vit_gemm_desc* d, void* stream_) {
 
   const int units = p.tiles_m * p.tiles_n * p.split_k;
   const int grid = 2 * (units < cap ? units : cap);
-  if (d->a_mn_major) return d->b_mn_major ? launch<true, true>(ta, tb, p, grid, stream) : launch<true, false>(ta, tb, p, grid, stream);
-  return d->b_mn_major ? launch<false, true>(ta, tb, p, grid, stream) : launch<false, false>(ta, tb, p, grid, stream);
+  if (d->a_mn_major) return d->b_mn_major ? launch_mode<true, true>(mode, ta, tb, p, grid, stream) : launch_mode<true, false>(mode, ta, tb, p, grid, stream);
+  return d->b_mn_major ? launch_mode<false, true>(mode, ta, tb, p, grid, stream) : launch_mode<false, false>(mode, ta, tb, p, grid, stream);
 }

@@ -41,7 +41,7 @@ def sm_count() -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          epilogue: int = EPI_BF16, bias=None, colscale=None, rowscale=None, rows_per_scale: int = 0, residual=None,
          aux=None, out_f32=None, out_bf16=None, out2_bf16=None, alpha: float = 1.0, split_k: int = 0, max_ctas: int = 0,
-         lda: Optional[int] = None, ldb: Optional[int] = None, colsum=None) -> None:
+         lda: Optional[int] = None, ldb: Optional[int] = None, colsum=None, debug_flags: int = 0) -> None:
     """D[M,N] = A[M,K] B[N,K]^T (bf16 in, fp32 accumulate). a_mn/b_mn: operand stored as [K, M] / [K, N] row-major."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     d = GemmDesc()
@@ -62,6 +62,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
         d.out2_bf16, d.ld2_bf16 = _p(out2_bf16), out2_bf16.stride(0)
     d.alpha, d.split_k, d.max_ctas = alpha, split_k, max_ctas
     d.colsum = _p(colsum)
+    d.debug_flags = debug_flags
     if GEMM_TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
