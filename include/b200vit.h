@@ -86,7 +86,8 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
  * Replaces Attention.forward lines 155-185 (modeling_finetune.py): q*scale, q k^T, + rel_pos_bias, softmax,
  * attn_drop, attn @ v, transpose/reshape — and its autograd backward.
  *   qkv   : bf16 [B, N, 3, H, 64] (the QKV GEMM output, no permute copy)
- *   bias  : fp32 [H, N, ld_bias] or NULL      out : bf16 [B, N, H*64]      lse : fp32 [B, H, N]
+ *   bias  : fp32 [H, N, ld_bias] = log2(e) * rel_pos_bias, -inf in columns [N, ld_bias) (b200vit_rel_pos_bias out_fwd), or NULL
+ *   out : bf16 [B, N, H*64]      lse : fp32 [B, H, N]
  *   keep_bits : packed dropout keep mask [B, H, N, 32] bytes (bit j%8 of byte j/8), written by fwd, read by bwd
  *   keep_in   : optional injected keep mask uint8 [B, H, N, N]; NULL = Philox4x32-10 keyed on (seed, stream_id)
  * N <= 208, head_dim == 64.
@@ -94,12 +95,13 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                      float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
                      uint8_t* keep_bits, void* stream);
-/* dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, +=) is the gradient of
- * relative_position_bias_table [num_bins, H]: the kernel stores dS^T as bf16 into ds_work [B, H, N, ld_ds] (ld_ds even,
+/* bias_t: the TRANSPOSED padded bias (b200vit_rel_pos_bias out_bwd_t) or NULL.
+ * dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, +=) is the gradient of
+ * relative_position_bias_table [num_bins, H]: the kernel stores dS^T as bf16 into ds_work [B, H, N, ld_ds] (ld_ds % 8 == 0,
  * >= N rounded up to 16) and a second kernel reduces it over the batch and scatter-adds through rel_index int32 [N, N]
  * (the reference's relative_position_index, modeling_finetune.py:339-353). dq_bias / dv_bias (optional, +=, [H*64]) are the
  * q_bias / v_bias gradients (column sums of dQ / dV; modeling_finetune.py:148). */
-int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias, int64_t ld_bias,
+int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
                      const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                      float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                      void* dqkv, void* stream);
@@ -133,8 +135,12 @@ int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask, int32_t B,
 /* DropPath (timm drop_path, modeling_finetune.py:51-62): out[l, d, b] = keep / (1 - p_l), keep ~ Bernoulli(1 - p_l) from
  * Philox4x32-10 keyed on (seed; l, d, b). probs_host: HOST array of L drop probabilities (linspace(0, rate, L), :401). */
 int b200vit_drop_path_scales(const float* probs_host, int32_t L, int32_t draws, int32_t B, uint64_t seed, float* out, void* stream);
-/* RelativePositionBias.forward (modeling_finetune.py:359-364): out[h,i,j] = table[index[i,j], h] */
-int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, float* out, void* stream);
+/* RelativePositionBias.forward (modeling_finetune.py:359-364) in the padded layouts the attention kernels read:
+ *   out_fwd  [H, N, ld]: scale * table[index[i,j], h] for j < N, -inf for N <= j < ld  (key mask baked into the padding)
+ *   out_bwd_t[H, N, ld]: the transpose (row = key j, column = query i), 0 in the padding.   Either may be NULL.
+ * The attention kernels expect scale = log2(e) and ld = N rounded up to 16. */
+int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t ld, float scale, float* out_fwd,
+                         float* out_bwd_t, void* stream);
 /* x[:, 1:].mean(1) (modeling_finetune.py:512-514) */
 int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int32_t C, float* out, void* stream);
 

@@ -218,9 +218,12 @@ def test_rel_pos_bias_and_meanpool(ops, cuda):
     H = 12
     idx = O.relative_position_index(14, 14)
     table = torch.randn(732, H)
-    out = torch.empty(H, 197, 197, device=cuda)
-    ops.rel_pos_bias(table.to(cuda), idx.to(torch.int32).to(cuda), 197, H, out)
-    assert torch.equal(out.cpu(), O.rel_pos_bias(table, idx))           # pure gather: bit-exact
+    fwd, bwd = ops.rel_pos_bias(table.to(cuda), idx.to(torch.int32).to(cuda), 197, H)
+    ref = O.rel_pos_bias(table, idx)
+    assert tuple(fwd.shape) == (H, 197, 208)
+    assert torch.equal(fwd[:, :, :197].cpu(), ref * torch.tensor(ops.LOG2E))          # gather + one fp32 multiply: bit-exact
+    assert torch.equal(bwd[:, :, :197].cpu(), (ref * torch.tensor(ops.LOG2E)).transpose(1, 2))
+    assert torch.isinf(fwd[:, :, 197:]).all() and (bwd[:, :, 197:] == 0).all()
     x = torch.randn(4, 197, 768)
     o = torch.empty(4, 768, device=cuda)
     ops.meanpool_tokens(x.to(cuda), 4, 197, 768, o)
@@ -252,7 +255,8 @@ def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
     lse = torch.empty(B, H, N, device=cuda)
     bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=cuda)
     seed, sid = 1234, 7
-    ops.attn_fwd(qkv, bias, B, H, N, scale, p, seed, sid, None, out, lse, bits if p > 0 else None)
+    bias_f, bias_t = ops.pad_attn_bias(bias)
+    ops.attn_fwd(qkv, bias_f, B, H, N, scale, p, seed, sid, None, out, lse, bits if p > 0 else None)
     keep = ops.dropout_mask(B * H, N, p, seed, sid, cuda) if p > 0 else None
     if keep is not None:
         frac = keep.float().mean().item()
@@ -269,7 +273,7 @@ def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
     if keep is not None:
         out2 = torch.empty_like(out)
         bits2 = torch.zeros_like(bits)
-        ops.attn_fwd(qkv, bias, B, H, N, scale, p, 0, 0, keep, out2, lse, bits2)
+        ops.attn_fwd(qkv, bias_f, B, H, N, scale, p, 0, 0, keep, out2, lse, bits2)
         unpacked2 = ((bits2.view(B * H, N, 32, 1) >> torch.arange(8, device=cuda, dtype=torch.uint8)) & 1).reshape(B * H, N, 256)[:, :, :N]
         assert torch.equal(out2, out) and torch.equal(unpacked2, keep)
     # backward
@@ -280,7 +284,7 @@ def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
     dqkv = torch.full((B, N, 3, H, 64), float("nan"), dtype=torch.bfloat16, device=cuda)
     dqb = torch.zeros(H * 64, device=cuda)
     dvb = torch.zeros(H * 64, device=cuda)
-    ops.attn_bwd(qkv, out, dout, lse, bias, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv, dq_bias=dqb, dv_bias=dvb)
+    ops.attn_bwd(qkv, out, dout, lse, bias_t, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv, dq_bias=dqb, dv_bias=dvb)
     assert torch.isfinite(dqkv.float()).all()
     assert rel(dqb, qr.grad[:, :, 0].sum((0, 1)).flatten()) < 2e-2 and rel(dvb, qr.grad[:, :, 2].sum((0, 1)).flatten()) < 2e-2
     for part, name in ((0, "dq"), (1, "dk"), (2, "dv")):

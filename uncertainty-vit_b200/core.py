@@ -85,8 +85,8 @@ class Noise:
     seed: int = 0
     drop_path_scale: Optional[torch.Tensor] = None      # fp32 [L, draws, B] = keep / (1 - p_l)
     attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
-    drop_path_active: bool = True
-    attn_drop_active: bool = True
+    drop_path_active: bool = True                       # applies only to training forwards
+    attn_drop_active: Optional[bool] = None             # None: follow `train`; True: dropout even in eval (MC-dropout, enable_dropout())
 
 
 def _empty(shape, dtype, dev):
@@ -213,14 +213,12 @@ def stem_backward(ps: ParamSource, cfg: VitConfig, patches: torch.Tensor, dx: to
     ops.colsum_bf16(dpe, B * npat, C, grads[prefix + "patch_embed.proj.bias"])
 
 
-def rel_bias(ps: ParamSource, cfg: VitConfig, dev) -> Optional[torch.Tensor]:
+def rel_bias(ps: ParamSource, cfg: VitConfig, dev, want_bwd: bool = True):
+    """(bias_fwd, bias_bwd_t) padded log2(e)-scaled relative position bias, or (None, None)."""
     table = ps.f32("rel_pos_bias.relative_position_bias_table")
     if table is None:
-        return None
-    T, H = cfg.tokens, cfg.num_heads
-    out = _empty((H, T, T), torch.float32, dev)
-    ops.rel_pos_bias(table, ps.rel_index_i32(), T, H, out)
-    return out
+        return None, None
+    return ops.rel_pos_bias(table, ps.rel_index_i32(), cfg.tokens, cfg.num_heads, want_bwd)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -254,9 +252,10 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
     if patches is None:
         patches = patches_bf16(cfg, images)
     x = stem_forward(ps, cfg, patches, B, mask_u8)
-    bias = rel_bias(ps, cfg, dev)
+    bias, bias_t = rel_bias(ps, cfg, dev, want_bwd=save)
     dps = make_drop_path_scales(cfg, B, noise, dev) if train else None
-    p_attn = cfg.attn_drop_rate if noise.attn_drop_active else 0.0
+    attn_drop_on = train if noise.attn_drop_active is None else noise.attn_drop_active
+    p_attn = cfg.attn_drop_rate if attn_drop_on else 0.0
     saved = []
     layers: Dict[int, torch.Tensor] = {}
     collect = collect or []
@@ -272,7 +271,7 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
         x = s["x_out"]
         if save:
             saved.append(s)
-    ctx = dict(B=B, saved=saved, patches=patches, mask_u8=mask_u8, row_index=row_index, mode=mode, bias=bias, x_final=x) if save else None
+    ctx = dict(B=B, saved=saved, patches=patches, mask_u8=mask_u8, row_index=row_index, mode=mode, bias=bias_t, x_final=x) if save else None
     if mode == "layers":
         return layers, ctx
     if mode in ("masked", "all"):

@@ -2,9 +2,12 @@
 //   S = scale * q k^T + rel_pos_bias[h] ; P = softmax_j(S) ; P~ = dropout(P) ; O = P~ v
 // (Attention.forward, modeling_finetune.py:145-188). One CTA per (batch, head); Q/K/V staged in shared memory with
 // cp.async, mma.sync m16n8k16 bf16 tensor-core tiles, online softmax with quad-shuffle row reductions, counter-based
-// Philox dropout (or an injected keep-mask), relative-position-bias add from the L2-resident [H,N,N] tensor.
-// Backward recomputes P from the saved log-sum-exp, owns one 16-key tile per warp (dK/dV in registers), accumulates dQ
-// in shared memory, and scatter-adds dS straight into the relative_position_bias_table gradient (732 bins per head).
+// Philox dropout (or an injected keep-mask), relative-position-bias add from an L2-resident, log2(e)-prescaled, -inf padded
+// [H, N, ld] tensor (the key mask is baked into the padding).
+// Backward: phase 1 — every warp owns one 16-key tile (dK/dV accumulate in registers), recomputes P from the saved
+// log-sum-exp and parks dS^T as bf16 in shared memory; phase 2 — every warp owns one 16-query tile and forms dQ = dS K from
+// that shared dS^T (no atomics anywhere). dS^T is also streamed out coalesced for the relative-position-bias table gradient,
+// which a second kernel reduces over the batch and scatter-adds through the reference's relative_position_index.
 #include "../../include/b200vit.h"
 #include "common.cuh"
 
@@ -13,7 +16,8 @@ namespace {
 constexpr int HD = 64;            // head dim
 constexpr int PITCH = HD + 8;     // smem row pitch in bf16 (144 B: conflict-free ldmatrix)
 constexpr int NMAX = 208;         // 13 tiles of 16
-constexpr int FWD_WARPS = 7;
+constexpr int DSP = NMAX + 8;     // bf16 row pitch of the shared dS^T matrix (432 B = 27 x 16 B: conflict-free ldmatrix)
+constexpr int FWD_WARPS = 8;
 constexpr int BWD_WARPS = 13;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -33,6 +37,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2(float x) {   // 2^x, one MUFU; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Loads rows [0,N) x 64 bf16 of a [*, row_stride] global matrix into smem [NMAX][PITCH]; rows >= N zero-filled up to n_pad.
 __device__ __forceinline__ void load_tile_rows(bf16* s, const bf16* g, long long row_stride, int N, int n_pad) {
@@ -43,12 +52,12 @@ __device__ __forceinline__ void load_tile_rows(bf16* s, const bf16* g, long long
   }
 }
 
-// keep-bit of element (i, j) of head bh: 16-bit lanes of Philox4x32-10; one call covers the 8 values a thread owns in
-// four consecutive 8-key tiles for one row (see DESIGN.md "dropout stream").
+// Dropout stream: keep-bit of element (i, j) of head bh comes from a 16-bit lane of Philox4x32-7 (the Crush-resistant
+// round count of Salmon et al.); one call yields the 8 values a thread owns in four consecutive 8-key tiles of one row.
 __device__ __forceinline__ Philox4 dropout_group(uint64_t seed, uint32_t stream, uint32_t bh, uint32_t i, uint32_t quad, uint32_t group) {
-  return philox4x32_10(bh, i, quad * 8u + group, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return philox4x32<7>(bh, i, quad * 8u + group, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-__device__ __forceinline__ uint32_t dropout_u16(const Philox4& r, int idx /*0..7*/) {
+__device__ __forceinline__ uint32_t dropout_u16(const Philox4& r, int idx /*0..7, compile-time*/) {
   const uint32_t w = idx < 4 ? (idx < 2 ? r.x : r.y) : (idx < 6 ? r.z : r.w);
   return (idx & 1) ? (w >> 16) : (w & 0xffffu);
 }
@@ -58,7 +67,7 @@ __device__ __forceinline__ uint32_t dropout_u16(const Philox4& r, int idx /*0..7
 // ------------------------------------------------------------------------------------------------
 struct AttnFwdParams {
   const bf16* qkv;      // [B, N, 3, H, 64]
-  const float* bias;    // [H, N, ld_bias] or null
+  const float* bias;    // [H, N, ld_bias] * log2(e), columns [N, n_pad) = -inf ; or null
   long long ld_bias;
   bf16* out;            // [B, N, H*64]
   float* lse;           // [B, H, N]  natural-log log-sum-exp of the biased, scaled scores
@@ -70,6 +79,133 @@ struct AttnFwdParams {
   uint32_t stream_id;
 };
 
+struct FwdRowState {
+  float o[8][4];
+  float m[2], l[2];
+};
+
+// One chunk of NTS 8-key tiles starting at key j0 for the 16-query tile of this warp.
+template <int NTS, bool DROP, bool HAS_BIAS>
+__device__ __forceinline__ void fwd_chunk(const AttnFwdParams& p, const bf16* sK, const bf16* sV, const uint32_t (&qa)[4][4], FwdRowState& st,
+                                          int j0, int i0, int i1, const float* brow0, const float* brow1, int bh, int lane, float sl2,
+                                          uint32_t thresh) {
+  const int quad = lane & 3;
+  const int N = p.N;
+  float2 bv0[NTS], bv1[NTS];
+  if (HAS_BIAS) {   // requested first: the L2 latency overlaps the QK^T tensor work
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      bv0[nt] = __ldg(reinterpret_cast<const float2*>(brow0 + j0 + nt * 8 + quad * 2));
+      bv1[nt] = __ldg(reinterpret_cast<const float2*>(brow1 + j0 + nt * 8 + quad * 2));
+    }
+  }
+  float s[NTS][4];
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+  for (int np = 0; np < NTS / 2; ++np) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(smem_u32(sK + (j0 + np * 16 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
+      mma16816(s[np * 2], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+      mma16816(s[np * 2 + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+    }
+  }
+  float mx0 = st.m[0], mx1 = st.m[1];
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) {
+    if (HAS_BIAS) {   // bias is pre-multiplied by log2(e); padding columns hold -inf (key mask)
+      s[nt][0] = fmaf(s[nt][0], sl2, bv0[nt].x); s[nt][1] = fmaf(s[nt][1], sl2, bv0[nt].y);
+      s[nt][2] = fmaf(s[nt][2], sl2, bv1[nt].x); s[nt][3] = fmaf(s[nt][3], sl2, bv1[nt].y);
+    } else {
+      const int j = j0 + nt * 8 + quad * 2;
+      s[nt][0] = j < N ? s[nt][0] * sl2 : -INFINITY; s[nt][1] = j + 1 < N ? s[nt][1] * sl2 : -INFINITY;
+      s[nt][2] = j < N ? s[nt][2] * sl2 : -INFINITY; s[nt][3] = j + 1 < N ? s[nt][3] * sl2 : -INFINITY;
+    }
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float c0 = ex2(st.m[0] - mx0), c1 = ex2(st.m[1] - mx1);   // first chunk: ex2(-inf) = 0
+  st.m[0] = mx0; st.m[1] = mx1;
+  st.l[0] *= c0; st.l[1] *= c1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { st.o[i][0] *= c0; st.o[i][1] *= c0; st.o[i][2] *= c1; st.o[i][3] *= c1; }
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) {
+    s[nt][0] = ex2(s[nt][0] - mx0); s[nt][1] = ex2(s[nt][1] - mx0);
+    s[nt][2] = ex2(s[nt][2] - mx1); s[nt][3] = ex2(s[nt][3] - mx1);
+    l0 += s[nt][0] + s[nt][1];
+    l1 += s[nt][2] + s[nt][3];
+  }
+  st.l[0] += l0; st.l[1] += l1;
+  if (DROP) {
+#pragma unroll
+    for (int g = 0; g < (NTS + 3) / 4; ++g) {
+      uint32_t w0 = 0u, w1 = 0u;   // keep bits of rows i0 / i1 for keys j0 + g*32 .. +31 (this thread: 2 bits per 8-key tile)
+      if (p.keep_in == nullptr) {
+        const Philox4 r0 = dropout_group(p.seed, p.stream_id, bh, i0, quad, (j0 >> 5) + g);
+        const Philox4 r1 = dropout_group(p.seed, p.stream_id, bh, i1, quad, (j0 >> 5) + g);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+          if (g * 4 + n4 < NTS) {
+            const int sh = n4 * 8 + quad * 2;
+            w0 |= (dropout_u16(r0, n4 * 2) >= thresh ? 1u : 0u) << sh;
+            w0 |= (dropout_u16(r0, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
+            w1 |= (dropout_u16(r1, n4 * 2) >= thresh ? 1u : 0u) << sh;
+            w1 |= (dropout_u16(r1, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+          if (g * 4 + n4 < NTS) {
+            const int j = j0 + (g * 4 + n4) * 8 + quad * 2;
+            const int sh = n4 * 8 + quad * 2;
+            if (i0 < N && j < N && p.keep_in[((long long)bh * N + i0) * N + j]) w0 |= 1u << sh;
+            if (i0 < N && j + 1 < N && p.keep_in[((long long)bh * N + i0) * N + j + 1]) w0 |= 2u << sh;
+            if (i1 < N && j < N && p.keep_in[((long long)bh * N + i1) * N + j]) w1 |= 1u << sh;
+            if (i1 < N && j + 1 < N && p.keep_in[((long long)bh * N + i1) * N + j + 1]) w1 |= 2u << sh;
+          }
+        }
+      }
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) {
+        if (g * 4 + n4 < NTS) {
+          const int nt = g * 4 + n4, sh = n4 * 8 + quad * 2;
+          if (!((w0 >> sh) & 1u)) s[nt][0] = 0.f;
+          if (!((w0 >> sh) & 2u)) s[nt][1] = 0.f;
+          if (!((w1 >> sh) & 1u)) s[nt][2] = 0.f;
+          if (!((w1 >> sh) & 2u)) s[nt][3] = 0.f;
+        }
+      }
+      w0 |= __shfl_xor_sync(0xffffffffu, w0, 1); w0 |= __shfl_xor_sync(0xffffffffu, w0, 2);
+      w1 |= __shfl_xor_sync(0xffffffffu, w1, 1); w1 |= __shfl_xor_sync(0xffffffffu, w1, 2);
+      if (quad == 0) {
+        if (i0 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i0) * 32 + (j0 >> 3) + g * 4) = w0;
+        if (i1 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i1) * 32 + (j0 >> 3) + g * 4) = w1;
+      }
+    }
+  }
+  // O += P~ V   (the 1/(1-p) rescale of the kept probabilities is folded into the final normalisation)
+#pragma unroll
+  for (int kk = 0; kk < NTS / 2; ++kk) {
+    const uint32_t a0 = pack_bf16x2(s[kk * 2][0], s[kk * 2][1]), a1 = pack_bf16x2(s[kk * 2][2], s[kk * 2][3]);
+    const uint32_t a2 = pack_bf16x2(s[kk * 2 + 1][0], s[kk * 2 + 1][1]), a3 = pack_bf16x2(s[kk * 2 + 1][2], s[kk * 2 + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_u32(sV + (j0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      mma16816(st.o[dp * 2], a0, a1, a2, a3, b0, b1);
+      mma16816(st.o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+template <bool DROP, bool HAS_BIAS>
 __global__ void __launch_bounds__(FWD_WARPS * 32, 2) attn_fwd_kernel(const AttnFwdParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* sQ = reinterpret_cast<bf16*>(smem);
@@ -90,146 +226,49 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 2) attn_fwd_kernel(const AttnF
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quad = lane & 3, qrow = lane >> 2;
-  const bool drop = p.p_drop > 0.f;
-  const float inv_keep = drop ? 1.0f / (1.0f - p.p_drop) : 1.0f;
+  const float inv_keep = DROP ? 1.0f / (1.0f - p.p_drop) : 1.0f;
   const uint32_t thresh = (uint32_t)(p.p_drop * 65536.0f + 0.5f);
   const float sl2 = p.scale * LOG2E;
 
   for (int mt = warp; mt < ntile; mt += FWD_WARPS) {
-    // Q fragments for this 16-row tile: 4 k-steps
     uint32_t qa[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
       ldsm_x4(smem_u32(sQ + (mt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
-    float o[8][4];
+    FwdRowState st;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+    for (int i = 0; i < 8; ++i) st.o[i][0] = st.o[i][1] = st.o[i][2] = st.o[i][3] = 0.f;
+    st.m[0] = st.m[1] = -INFINITY;
+    st.l[0] = st.l[1] = 0.f;
     const int i0 = mt * 16 + qrow, i1 = i0 + 8;
-
-    for (int j0 = 0; j0 < n_pad; j0 += 64) {
-      const int nts = min(8, (n_pad - j0) >> 3);  // valid 8-key tiles in this chunk (even)
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (np * 2 < nts) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(smem_u32(sK + (j0 + np * 16 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
-            mma16816(s[np * 2], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
-            mma16816(s[np * 2 + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
-          }
-        }
-      }
-      // scale (log2 domain), bias, key masking, running max
-      float mx[2] = {mrow[0], mrow[1]};
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int j = j0 + nt * 8 + quad * 2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int jj = j + (e & 1);
-          const int ii = (e < 2) ? i0 : i1;
-          float v = s[nt][e] * sl2;
-          if (p.bias != nullptr && jj < N && ii < N) v += __ldg(p.bias + ((long long)h * N + ii) * p.ld_bias + jj) * LOG2E;
-          if (jj >= N || nt >= nts) v = -INFINITY;
-          s[nt][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      }
-      float corr[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        corr[r] = (mrow[r] == -INFINITY) ? 0.f : exp2f(mrow[r] - mx[r]);
-        mrow[r] = mx[r];
-        lrow[r] *= corr[r];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
-      // probabilities, row sums, dropout
-      uint32_t bits[2][2] = {{0u, 0u}, {0u, 0u}};  // [row][word]: bit (nt%4)*8 + quad*2 + lo of word nt/4
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        Philox4 r0, r1;
-        if (drop && p.keep_in == nullptr) {
-          r0 = dropout_group(p.seed, p.stream_id, bh, i0, quad, (j0 >> 5) + g);
-          r1 = dropout_group(p.seed, p.stream_id, bh, i1, quad, (j0 >> 5) + g);
-        }
-#pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) {
-          const int nt = g * 4 + n4;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float pv = exp2f(s[nt][e] - mrow[e >> 1]);   // -inf -> 0
-            lrow[e >> 1] += pv;
-            float outv = pv;
-            if (drop) {
-              const int jj = j0 + nt * 8 + quad * 2 + (e & 1);
-              const int ii = (e < 2) ? i0 : i1;
-              bool keep;
-              if (p.keep_in != nullptr) keep = (jj < N && ii < N) ? p.keep_in[(((long long)bh * N + ii) * N) + jj] != 0 : false;
-              else keep = dropout_u16(e < 2 ? r0 : r1, n4 * 2 + (e & 1)) >= thresh;
-              if (keep) bits[e >> 1][g] |= 1u << (n4 * 8 + quad * 2 + (e & 1));
-              outv = keep ? pv * inv_keep : 0.f;
-            }
-            s[nt][e] = outv;
-          }
-        }
-      }
-      if (drop && p.keep_bits != nullptr) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint32_t w = bits[r][g];
-            w |= __shfl_xor_sync(0xffffffffu, w, 1);
-            w |= __shfl_xor_sync(0xffffffffu, w, 2);
-            const int ii = r == 0 ? i0 : i1;
-            if (quad == 0 && ii < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + ii) * 32 + (j0 >> 3) + g * 4) = w;
-          }
-      }
-      // O += P~ V
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kk * 2 < nts) {
-          const uint32_t a0 = pack_bf16x2(s[kk * 2][0], s[kk * 2][1]), a1 = pack_bf16x2(s[kk * 2][2], s[kk * 2][3]);
-          const uint32_t a2 = pack_bf16x2(s[kk * 2 + 1][0], s[kk * 2 + 1][1]), a3 = pack_bf16x2(s[kk * 2 + 1][2], s[kk * 2 + 1][3]);
-#pragma unroll
-          for (int dp = 0; dp < 4; ++dp) {
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(smem_u32(sV + (j0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-            mma16816(o[dp * 2], a0, a1, a2, a3, b0, b1);
-            mma16816(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
-          }
-        }
-      }
+    const float* brow0 = HAS_BIAS ? p.bias + ((long long)h * N + min(i0, N - 1)) * p.ld_bias : nullptr;
+    const float* brow1 = HAS_BIAS ? p.bias + ((long long)h * N + min(i1, N - 1)) * p.ld_bias : nullptr;
+    int j0 = 0;
+    for (; j0 + 64 <= n_pad; j0 += 64) fwd_chunk<8, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh);
+    switch ((n_pad - j0) >> 3) {   // tail: only the 8-key tiles that exist
+      case 6: fwd_chunk<6, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
+      case 4: fwd_chunk<4, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
+      case 2: fwd_chunk<2, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
+      default: break;
     }
-    // finalise: row sums across the quad, normalise, store
+    // finalise: row sums across the quad, normalise (and apply the dropout rescale), store
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
-      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+      st.l[r] += __shfl_xor_sync(0xffffffffu, st.l[r], 1);
+      st.l[r] += __shfl_xor_sync(0xffffffffu, st.l[r], 2);
     }
-    const float inv0 = 1.0f / lrow[0], inv1 = 1.0f / lrow[1];
+    const float inv0 = inv_keep / st.l[0], inv1 = inv_keep / st.l[1];
     bf16* orow0 = p.out + ((long long)b * N + i0) * (p.H * HD) + h * HD;
     bf16* orow1 = p.out + ((long long)b * N + i1) * (p.H * HD) + h * HD;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       const int c = dt * 8 + quad * 2;
-      if (i0 < N) *reinterpret_cast<uint32_t*>(orow0 + c) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
-      if (i1 < N) *reinterpret_cast<uint32_t*>(orow1 + c) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+      if (i0 < N) *reinterpret_cast<uint32_t*>(orow0 + c) = pack_bf16x2(st.o[dt][0] * inv0, st.o[dt][1] * inv0);
+      if (i1 < N) *reinterpret_cast<uint32_t*>(orow1 + c) = pack_bf16x2(st.o[dt][2] * inv1, st.o[dt][3] * inv1);
     }
     if (quad == 0 && p.lse != nullptr) {
-      if (i0 < N) p.lse[(long long)bh * N + i0] = (mrow[0] + log2f(lrow[0])) / LOG2E;
-      if (i1 < N) p.lse[(long long)bh * N + i1] = (mrow[1] + log2f(lrow[1])) / LOG2E;
+      if (i0 < N) p.lse[(long long)bh * N + i0] = (st.m[0] + log2f(st.l[0])) / LOG2E;
+      if (i1 < N) p.lse[(long long)bh * N + i1] = (st.m[1] + log2f(st.l[1])) / LOG2E;
     }
   }
 }
@@ -244,7 +283,22 @@ __global__ void dropout_mask_kernel(uint8_t* out, int BH, int N, float p_drop, u
     const int bh = (int)(idx / ((long long)N * N));
     const int jt = j >> 3, quad = (j & 7) >> 1, lo = j & 1;
     const Philox4 r = dropout_group(seed, stream_id, bh, i, quad, jt >> 2);
-    out[idx] = dropout_u16(r, (jt & 3) * 2 + lo) >= thresh ? 1 : 0;
+    const int v = (jt & 3) * 2 + lo;
+    const uint32_t w = v < 4 ? (v < 2 ? r.x : r.y) : (v < 6 ? r.z : r.w);
+    out[idx] = ((v & 1) ? (w >> 16) : (w & 0xffffu)) >= thresh ? 1 : 0;
+  }
+}
+
+// RelativePositionBias.forward (modeling_finetune.py:359-364) in the layout the attention kernels read:
+//   out_fwd[h, i, j] = scale * table[index[i, j], h] for j < N, -inf for N <= j < ld     (forward: key mask baked in)
+//   out_bwd[h, j, i] = scale * table[index[i, j], h] for i < N, 0 for N <= i < ld        (backward: transposed)
+__global__ void rel_pos_bias_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, int ld, float scale,
+                                    float* __restrict__ out_fwd, float* __restrict__ out_bwd) {
+  const int total = H * N * ld;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int c = t % ld, r = (t / ld) % N, h = t / (ld * N);
+    if (out_fwd != nullptr) out_fwd[t] = c < N ? scale * __ldg(table + (long long)index[r * N + c] * H + h) : -INFINITY;
+    if (out_bwd != nullptr) out_bwd[t] = c < N ? scale * __ldg(table + (long long)index[c * N + r] * H + h) : 0.f;
   }
 }
 
@@ -256,7 +310,7 @@ struct AttnBwdParams {
   const bf16* out;       // [B, N, H*64]   forward output
   const bf16* dout;      // [B, N, H*64]
   const float* lse;      // [B, H, N]
-  const float* bias;     // [H, N, ld_bias] or null
+  const float* bias_t;   // [H, N(key j), ld_bias(query i)] * log2(e), transposed ; or null
   long long ld_bias;
   const uint8_t* keep_bits;  // [B, H, N, 32] or null (p_drop == 0)
   bf16* ds_out;          // [B, H, N(key), ld_ds(query)] bf16 dS^T for the rel-pos-bias gradient, or null
@@ -274,10 +328,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   bf16* sK = sQ + NMAX * PITCH;
   bf16* sV = sK + NMAX * PITCH;
   bf16* sdO = sV + NMAX * PITCH;
-  float* sdQ = reinterpret_cast<float*>(sdO + NMAX * PITCH);   // [NMAX][64]
-  float* sLse = sdQ + NMAX * HD;                                // [NMAX] (log2 domain)
+  bf16* sdS = sdO + NMAX * PITCH;                               // [NMAX(key j)][DSP(query i)]  dS^T
+  float* sLse = reinterpret_cast<float*>(sdS + NMAX * DSP);     // [NMAX] (log2 domain)
   float* sD = sLse + NMAX;                                      // [NMAX]
-  bf16* sStage = reinterpret_cast<bf16*>(sD + NMAX);            // [BWD_WARPS][16][24]
 
   const int bh = blockIdx.x;
   const int b = bh / p.H, h = bh - b * p.H;
@@ -293,7 +346,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   load_tile_rows(sK, gq + p.H * HD, row_stride, N, n_pad);
   load_tile_rows(sV, gq + 2 * p.H * HD, row_stride, N, n_pad);
   load_tile_rows(sdO, gdo, o_stride, N, n_pad);
-  for (int i = threadIdx.x; i < n_pad * HD; i += blockDim.x) sdQ[i] = 0.f;
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) sLse[i] = i < N ? p.lse[(long long)bh * N + i] * LOG2E : 0.f;
   cp_async_wait_all();
   __syncthreads();
@@ -323,61 +375,66 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
   const bool drop = p.p_drop > 0.f && p.keep_bits != nullptr;
   const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
   const float sl2 = p.scale * LOG2E;
-
   const bool active = warp < ntile;
-  const int jt = active ? warp : 0;
-  const int jA = jt * 16 + qrow, jB = jA + 8;  // the two key rows this thread owns in C fragments
-  uint32_t ka[4][4], va[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    ldsm_x4(smem_u32(sK + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
-    ldsm_x4(smem_u32(sV + (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8), va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
-  }
-  float dv[8][4], dk[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
-  bf16* stage = sStage + warp * 16 * 24;
 
-  // Every warp owns one 16-key tile; in step s it visits query tile (s + jt) mod ntile, so within a step the warps touch
-  // DISJOINT dQ tiles and the shared-memory accumulation needs no atomics (block barrier between steps).
-  for (int step = 0; step < ntile; ++step) {
-    if (active) {
-      int it = step + jt;
-      if (it >= ntile) it -= ntile;
+  // ================= phase 1: this warp owns key tile jt; loop over query tiles =================
+  if (active) {
+    const int jt = warp;
+    const int jA = jt * 16 + qrow, jB = jA + 8;  // the two key rows this thread owns in C fragments
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; }
+    const float* btA = p.bias_t != nullptr ? p.bias_t + ((long long)h * N + min(jA, N - 1)) * p.ld_bias : nullptr;
+    const float* btB = p.bias_t != nullptr ? p.bias_t + ((long long)h * N + min(jB, N - 1)) * p.ld_bias : nullptr;
+    const uint8_t* kb_base = drop ? p.keep_bits + (long long)bh * N * 32 + jt * 2 : nullptr;
+
+#pragma unroll 1
+    for (int it = 0; it < ntile; ++it) {
+      const int ia = it * 16 + quad * 2;   // queries ia, ia+1 (n-tile 0) and ia+8, ia+9 (n-tile 1)
+      // operands of the element-wise phase are requested before the MMAs so their latency overlaps the tensor work
+      float2 bA[2], bB[2];
+      uint32_t kw[2][2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        bA[n] = btA != nullptr ? __ldg(reinterpret_cast<const float2*>(btA + ia + n * 8)) : make_float2(0.f, 0.f);
+        bB[n] = btB != nullptr ? __ldg(reinterpret_cast<const float2*>(btB + ia + n * 8)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = ia + n * 8 + e;
+          kw[n][e] = (drop && i < N) ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(kb_base + (long long)i * 32)) : 0xffffu;
+        }
+      }
       // S^T = K_j Q_i^T and dP^T = V_j dO_i^T : [16 keys x 16 queries]
       float st[2][4], dp[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) { st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1, b2, b3;
-        const int off = (it * 16 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(smem_u32(sQ + off), b0, b1, b2, b3);
-        mma16816(st[0], ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3], b0, b1);
-        mma16816(st[1], ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3], b2, b3);
-        ldsm_x4(smem_u32(sdO + off), b0, b1, b2, b3);
-        mma16816(dp[0], va[ks][0], va[ks][1], va[ks][2], va[ks][3], b0, b1);
-        mma16816(dp[1], va[ks][0], va[ks][1], va[ks][2], va[ks][3], b2, b3);
+        uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+        const int aoff = (jt * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8;
+        const int boff = (it * 16 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(smem_u32(sK + aoff), a0, a1, a2, a3);
+        ldsm_x4(smem_u32(sQ + boff), b0, b1, b2, b3);
+        mma16816(st[0], a0, a1, a2, a3, b0, b1);
+        mma16816(st[1], a0, a1, a2, a3, b2, b3);
+        ldsm_x4(smem_u32(sV + aoff), a0, a1, a2, a3);
+        ldsm_x4(smem_u32(sdO + boff), b0, b1, b2, b3);
+        mma16816(dp[0], a0, a1, a2, a3, b0, b1);
+        mma16816(dp[1], a0, a1, a2, a3, b2, b3);
       }
-      // elementwise: P, dropout, dS
+      // elementwise: P, dropout, dS.  C layout: rows = keys (jA: e<2, jB: e>=2), cols = queries ia + n*8 + (e&1)
       float pt[2][4], ds[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        const int ibase = it * 16 + n * 8 + quad * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int i = ibase + (e & 1);                        // query
-          const int j = (e < 2) ? jA : jB;                      // key
-          float dsv = 0.f, ptv = 0.f;
+          const int i = ia + n * 8 + (e & 1);
+          const int j = (e < 2) ? jA : jB;
+          const float bias = (e < 2) ? ((e & 1) ? bA[n].y : bA[n].x) : ((e & 1) ? bB[n].y : bB[n].x);
+          float ptv = 0.f, dsv = 0.f;
           if (i < N && j < N) {
-            float sv = st[n][e] * sl2;
-            if (p.bias != nullptr) sv += __ldg(p.bias + ((long long)h * N + i) * p.ld_bias + j) * LOG2E;
-            const float pv = exp2f(sv - sLse[i]);
-            float keepf = 1.0f;
-            if (drop) {
-              const uint8_t byte = p.keep_bits[((long long)bh * N + i) * 32 + (j >> 3)];
-              keepf = ((byte >> (j & 7)) & 1) ? inv_keep : 0.f;
-            }
+            const float pv = ex2(fmaf(st[n][e], sl2, bias) - sLse[i]);
+            const float keepf = ((kw[n][e & 1] >> (qrow + (e < 2 ? 0 : 8))) & 1u) ? inv_keep : 0.f;
             ptv = pv * keepf;
             dsv = pv * (dp[n][e] * keepf - sD[i]);
           }
@@ -390,12 +447,11 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
       const uint32_t pa2 = pack_bf16x2(pt[1][0], pt[1][1]), pa3 = pack_bf16x2(pt[1][2], pt[1][3]);
       const uint32_t da0 = pack_bf16x2(ds[0][0], ds[0][1]), da1 = pack_bf16x2(ds[0][2], ds[0][3]);
       const uint32_t da2 = pack_bf16x2(ds[1][0], ds[1][1]), da3 = pack_bf16x2(ds[1][2], ds[1][3]);
-      if (p.ds_out != nullptr) {   // dS^T for the relative-position-bias gradient (reduced over the batch by a second kernel)
-        bf16* d0 = p.ds_out + ((long long)bh * N + jA) * p.ld_ds + it * 16 + quad * 2;
-        bf16* d1 = p.ds_out + ((long long)bh * N + jB) * p.ld_ds + it * 16 + quad * 2;
-        if (jA < N) { *reinterpret_cast<uint32_t*>(d0) = da0; *reinterpret_cast<uint32_t*>(d0 + 8) = da2; }
-        if (jB < N) { *reinterpret_cast<uint32_t*>(d1) = da1; *reinterpret_cast<uint32_t*>(d1 + 8) = da3; }
-      }
+      // park dS^T [key][query] for phase 2 (dQ) and for the bias-table gradient
+      *reinterpret_cast<uint32_t*>(sdS + jA * DSP + ia) = da0;
+      *reinterpret_cast<uint32_t*>(sdS + jB * DSP + ia) = da1;
+      *reinterpret_cast<uint32_t*>(sdS + jA * DSP + ia + 8) = da2;
+      *reinterpret_cast<uint32_t*>(sdS + jB * DSP + ia + 8) = da3;
       // dV_j += P~^T dO_i ; dK_j += dS^T Q_i   (B = [query][d] row-major -> ldmatrix.trans)
 #pragma unroll
       for (int dpair = 0; dpair < 4; ++dpair) {
@@ -408,34 +464,8 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
         mma16816(dk[dpair * 2], da0, da1, da2, da3, b0, b1);
         mma16816(dk[dpair * 2 + 1], da0, da1, da2, da3, b2, b3);
       }
-      // dQ_i += dS K_j : stage dS^T [key][query] in smem, reload transposed as A (m = query, k = key)
-      __syncwarp();
-      *reinterpret_cast<uint32_t*>(stage + qrow * 24 + quad * 2) = da0;
-      *reinterpret_cast<uint32_t*>(stage + (qrow + 8) * 24 + quad * 2) = da1;
-      *reinterpret_cast<uint32_t*>(stage + qrow * 24 + 8 + quad * 2) = da2;
-      *reinterpret_cast<uint32_t*>(stage + (qrow + 8) * 24 + 8 + quad * 2) = da3;
-      __syncwarp();
-      uint32_t sa0, sa1, sa2, sa3;
-      ldsm_x4_t(smem_u32(stage + ((lane >> 4) * 8 + (lane & 7)) * 24 + ((lane >> 3) & 1) * 8), sa0, sa1, sa2, sa3);
-#pragma unroll
-      for (int dpair = 0; dpair < 4; ++dpair) {
-        float dq0[4] = {0.f, 0.f, 0.f, 0.f}, dq1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(sK + (jt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dpair * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-        mma16816(dq0, sa0, sa1, sa2, sa3, b0, b1);
-        mma16816(dq1, sa0, sa1, sa2, sa3, b2, b3);
-        float2* q0 = reinterpret_cast<float2*>(sdQ + (it * 16 + qrow) * HD + dpair * 16 + quad * 2);
-        float2 v;
-        v = q0[0]; v.x += dq0[0]; v.y += dq0[1]; q0[0] = v;
-        v = q0[4 * HD]; v.x += dq0[2]; v.y += dq0[3]; q0[4 * HD] = v;          // row + 8  (float2 units: 8 * HD / 2)
-        v = q0[4]; v.x += dq1[0]; v.y += dq1[1]; q0[4] = v;                    // cols + 8
-        v = q0[4 * HD + 4]; v.x += dq1[2]; v.y += dq1[3]; q0[4 * HD + 4] = v;
-      }
     }
-    __syncthreads();
-  }
-  if (active) {
-    // write dK (scaled) and dV for this key tile
+    // write dK (scaled) and dV for this key tile ; v_bias gradient = column sums of dV (rows >= N are exactly zero)
     bf16* gdk = p.dqkv + (long long)b * N * row_stride + p.H * HD + h * HD;
     bf16* gdv = gdk + p.H * HD;
 #pragma unroll
@@ -449,7 +479,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
         *reinterpret_cast<uint32_t*>(gdk + (long long)jB * row_stride + c) = pack_bf16x2(dk[dt][2] * p.scale, dk[dt][3] * p.scale);
         *reinterpret_cast<uint32_t*>(gdv + (long long)jB * row_stride + c) = pack_bf16x2(dv[dt][2], dv[dt][3]);
       }
-      if (p.dv_bias != nullptr) {   // v_bias gradient: column sums of dV over this tile's keys (rows >= N are exactly zero)
+      if (p.dv_bias != nullptr) {
         float s0 = dv[dt][0] + dv[dt][2], s1 = dv[dt][1] + dv[dt][3];
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
@@ -458,25 +488,47 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
     }
   }
   __syncthreads();
-  // dQ (scaled) -> global ; q_bias gradient = column sums (blockDim % 16 == 0, so a thread's column group is fixed)
-  bf16* gdq = p.dqkv + (long long)b * N * row_stride + h * HD;
-  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int idx = threadIdx.x; idx < N * 16; idx += blockDim.x) {
-    const int r = idx >> 4, c = (idx & 15) * 4;
-    float4 v = *reinterpret_cast<const float4*>(sdQ + r * HD + c);
-    v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-    uint2 u;
-    u.x = pack_bf16x2(v.x, v.y);
-    u.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(gdq + (long long)r * row_stride + c) = u;
+
+  // ================= phase 2: this warp owns query tile it; dQ_i = sum_j dS_ij K_j from the shared dS^T =================
+  if (active) {
+    const int it = warp;
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll 1
+    for (int jt = 0; jt < ntile; ++jt) {
+      uint32_t a0, a1, a2, a3;   // A[m = query][k = key] = transposed read of dS^T[key][query]
+      ldsm_x4_t(smem_u32(sdS + (jt * 16 + (lane >> 4) * 8 + (lane & 7)) * DSP + it * 16 + ((lane >> 3) & 1) * 8), a0, a1, a2, a3);
+#pragma unroll
+      for (int dpair = 0; dpair < 4; ++dpair) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(sK + (jt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dpair * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+        mma16816(dq[dpair * 2], a0, a1, a2, a3, b0, b1);
+        mma16816(dq[dpair * 2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    bf16* gdq = p.dqkv + (long long)b * N * row_stride + h * HD;
+    const int iA = it * 16 + qrow, iB = iA + 8;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int c = dt * 8 + quad * 2;
+      const float v0 = dq[dt][0] * p.scale, v1 = dq[dt][1] * p.scale, v2 = dq[dt][2] * p.scale, v3 = dq[dt][3] * p.scale;
+      if (iA < N) *reinterpret_cast<uint32_t*>(gdq + (long long)iA * row_stride + c) = pack_bf16x2(v0, v1);
+      if (iB < N) *reinterpret_cast<uint32_t*>(gdq + (long long)iB * row_stride + c) = pack_bf16x2(v2, v3);
+      if (p.dq_bias != nullptr) {   // q_bias gradient (rows >= N of dS are exactly zero)
+        float s0 = v0 + v2, s1 = v1 + v3;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (qrow == 0) { atomicAdd(p.dq_bias + h * HD + c, s0); atomicAdd(p.dq_bias + h * HD + c + 1, s1); }
+      }
+    }
   }
-  if (p.dq_bias != nullptr) {
-    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-    if ((threadIdx.x & 31) < 16) {
-      float* dst = p.dq_bias + h * HD + (threadIdx.x & 15) * 4;
-      atomicAdd(dst, cs.x); atomicAdd(dst + 1, cs.y); atomicAdd(dst + 2, cs.z); atomicAdd(dst + 3, cs.w);
+  // dS^T rows -> global, coalesced 16-byte chunks (for the relative-position-bias table gradient)
+  if (p.ds_out != nullptr) {
+    const int chunks = n_pad >> 3;
+    for (int idx = threadIdx.x; idx < N * chunks; idx += blockDim.x) {
+      const int j = idx / chunks, c = (idx - j * chunks) * 8;
+      *reinterpret_cast<uint4*>(p.ds_out + ((long long)bh * N + j) * p.ld_ds + c) = *reinterpret_cast<const uint4*>(sdS + j * DSP + c);
     }
   }
 }
@@ -505,7 +557,19 @@ __global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restric
 }
 
 constexpr size_t FWD_SMEM = 3 * NMAX * PITCH * sizeof(bf16);
-constexpr size_t BWD_SMEM = 4 * NMAX * PITCH * sizeof(bf16) + NMAX * HD * sizeof(float) + 2 * NMAX * sizeof(float) + BWD_WARPS * 16 * 24 * sizeof(bf16);
+constexpr size_t BWD_SMEM = 4 * NMAX * PITCH * sizeof(bf16) + NMAX * DSP * sizeof(bf16) + 2 * NMAX * sizeof(float);
+
+template <bool DROP, bool HAS_BIAS>
+cudaError_t launch_fwd(const AttnFwdParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DROP, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  attn_fwd_kernel<DROP, HAS_BIAS><<<p.B * p.H, FWD_WARPS * 32, FWD_SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
 
 }  // namespace
 
@@ -519,21 +583,20 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
   B200_CHECK_ARG(N > 0 && N <= NMAX, "attn_fwd: N=%d unsupported (1..%d)", N, NMAX);
   B200_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "attn_fwd: bad p_drop");
   B200_CHECK_ARG(p_drop == 0.f || keep_bits != nullptr, "attn_fwd: dropout needs the keep_bits buffer [B,H,N,32]");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-    if (e != cudaSuccess) { b200vit_set_error("attn_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
-  }
+  const int n_pad = (N + 15) / 16 * 16;
+  B200_CHECK_ARG(bias == nullptr || (ld_bias >= n_pad && ld_bias % 2 == 0 && (reinterpret_cast<uintptr_t>(bias) & 7) == 0),
+                 "attn_fwd: bias must be the padded layout of b200vit_rel_pos_bias ([H,N,ld], ld even >= %d, 8-byte aligned)", n_pad);
   AttnFwdParams p;
   p.qkv = static_cast<const bf16*>(qkv); p.bias = bias; p.ld_bias = ld_bias; p.out = static_cast<bf16*>(out); p.lse = lse;
   p.keep_bits = keep_bits; p.keep_in = keep_in; p.B = B; p.H = H; p.N = N; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.stream_id = stream_id;
-  attn_fwd_kernel<<<B * H, FWD_WARPS * 32, FWD_SMEM, STREAM>>>(p);
-  B200_CHECK_LAUNCH("attn_fwd");
+  cudaError_t e;
+  if (p_drop > 0.f) e = bias != nullptr ? launch_fwd<true, true>(p, STREAM) : launch_fwd<true, false>(p, STREAM);
+  else e = bias != nullptr ? launch_fwd<false, true>(p, STREAM) : launch_fwd<false, false>(p, STREAM);
+  if (e != cudaSuccess) { b200vit_set_error("attn_fwd: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 
-extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias, int64_t ld_bias,
+extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
                                 const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                                 float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                                 void* dqkv, void* stream) {
@@ -542,8 +605,11 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   B200_CHECK_ARG(N > 0 && N <= NMAX, "attn_bwd: N=%d unsupported (1..%d)", N, NMAX);
   B200_CHECK_ARG(p_drop == 0.f || keep_bits != nullptr, "attn_bwd: dropout needs keep_bits from the forward");
   const int n_pad = (N + 15) / 16 * 16;
-  B200_CHECK_ARG(dtable == nullptr || (rel_index != nullptr && ds_work != nullptr && ld_ds >= n_pad && ld_ds % 2 == 0),
-                 "attn_bwd: dtable needs rel_index and a bf16 workspace [B,H,N,ld_ds] with even ld_ds >= %d", n_pad);
+  B200_CHECK_ARG(bias_t == nullptr || (ld_bias >= n_pad && ld_bias % 2 == 0 && (reinterpret_cast<uintptr_t>(bias_t) & 7) == 0),
+                 "attn_bwd: bias_t must be the transposed padded layout of b200vit_rel_pos_bias ([H,N,ld], ld even >= %d)", n_pad);
+  B200_CHECK_ARG(dtable == nullptr || (rel_index != nullptr && ds_work != nullptr && ld_ds >= n_pad && ld_ds % 8 == 0 &&
+                                       (reinterpret_cast<uintptr_t>(ds_work) & 15) == 0),
+                 "attn_bwd: dtable needs rel_index and a 16-byte aligned bf16 workspace [B,H,N,ld_ds] with ld_ds %% 8 == 0, >= %d", n_pad);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
@@ -552,7 +618,7 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   }
   AttnBwdParams p;
   p.qkv = static_cast<const bf16*>(qkv); p.out = static_cast<const bf16*>(out); p.dout = static_cast<const bf16*>(dout); p.lse = lse;
-  p.bias = bias; p.ld_bias = ld_bias; p.keep_bits = keep_bits;
+  p.bias_t = bias_t; p.ld_bias = ld_bias; p.keep_bits = keep_bits;
   p.ds_out = dtable != nullptr ? static_cast<bf16*>(ds_work) : nullptr; p.ld_ds = ld_ds; p.dq_bias = dq_bias; p.dv_bias = dv_bias;
   p.dqkv = static_cast<bf16*>(dqkv); p.B = B; p.H = H; p.N = N; p.scale = scale; p.p_drop = p_drop;
   attn_bwd_kernel<<<B * H, BWD_WARPS * 32, BWD_SMEM, STREAM>>>(p);
@@ -570,5 +636,15 @@ extern "C" int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p
   const int sms = b200vit_num_sms();
   dropout_mask_kernel<<<sms * 8, 256, 0, STREAM>>>(out, BH, N, p_drop, seed, stream_id);
   B200_CHECK_LAUNCH("dropout_mask");
+  return 0;
+}
+
+extern "C" int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t ld, float scale, float* out_fwd,
+                                    float* out_bwd_t, void* stream) {
+  B200_CHECK_ARG(table != nullptr && index != nullptr && (out_fwd != nullptr || out_bwd_t != nullptr) && N > 0 && H > 0 && ld >= N,
+                 "rel_pos_bias: bad arguments");
+  const int sms = b200vit_num_sms();
+  rel_pos_bias_kernel<<<sms * 4, 256, 0, STREAM>>>(table, index, N, H, ld, scale, out_fwd, out_bwd_t);
+  B200_CHECK_LAUNCH("rel_pos_bias");
   return 0;
 }

@@ -305,15 +305,6 @@ __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dx, const u
   }
 }
 
-// RelativePositionBias.forward (modeling_finetune.py:359-364): out[h, i, j] = table[index[i, j], h]
-__global__ void rel_pos_bias_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, float* __restrict__ out) {
-  const int total = H * N * N;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int h = i / (N * N), ij = i - h * N * N;
-    out[i] = __ldg(table + (long long)index[ij] * H + h);
-  }
-}
-
 // out[b, c] = mean_{t=1..T-1} x[b, t, c]   (VisionTransformer.forward_features mean pooling, modeling_finetune.py:512-514)
 __global__ void meanpool_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
@@ -438,14 +429,6 @@ extern "C" int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask,
   dim3 grid(B, (C / 4 + threads - 1) / threads);
   assemble_tokens_bwd_kernel<<<grid, threads, 0, STREAM>>>(dx, mask, B, np, C, static_cast<bf16*>(dpe_bf16), dcls, dmask_token, dpos_embed);
   B200_CHECK_LAUNCH("assemble_tokens_bwd");
-  return 0;
-}
-
-extern "C" int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, float* out, void* stream) {
-  B200_CHECK_ARG(table != nullptr && index != nullptr && out != nullptr && N > 0 && H > 0, "rel_pos_bias: bad arguments");
-  const int sms = b200vit_num_sms();
-  rel_pos_bias_kernel<<<grid_for((long long)H * N * N, 256, sms, 8), 256, 0, STREAM>>>(table, index, N, H, out);
-  B200_CHECK_LAUNCH("rel_pos_bias");
   return 0;
 }
 

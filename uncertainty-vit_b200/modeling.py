@@ -113,9 +113,8 @@ class RelativePositionBias(nn.Module):
 
     def forward(self):
         T, H = self.relative_position_index.shape[0], self.relative_position_bias_table.shape[1]
-        out = torch.empty(H, T, T, dtype=torch.float32, device=self.relative_position_bias_table.device)
-        ops.rel_pos_bias(self.relative_position_bias_table.detach(), self.relative_position_index.to(torch.int32), T, H, out)
-        return out
+        fwd, _ = ops.rel_pos_bias(self.relative_position_bias_table.detach(), self.relative_position_index.to(torch.int32), T, H, False)
+        return fwd[:, :, :T] / ops.LOG2E            # [H, T, T] in natural units, as the reference module returns
 
 
 # ------------------------------------------------------------------------------------------------------------------

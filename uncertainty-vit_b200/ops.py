@@ -105,7 +105,8 @@ def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in
     _count()
 
 
-def attn_bwd(qkv, out, dout, lse, bias, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv, ds_work=None, dq_bias=None, dv_bias=None):
+def attn_bwd(qkv, out, dout, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv, ds_work=None, dq_bias=None, dv_bias=None):
+    bias = bias_t
     ld_bias = bias.stride(1) if bias is not None else 0
     ld_ds = 0
     if dtable is not None:
@@ -187,9 +188,32 @@ def drop_path_scales(probs, draws, B, seed, device) -> torch.Tensor:
     return out
 
 
-def rel_pos_bias(table, index_i32, N, H, out):
-    check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, _p(out), _stream()), "rel_pos_bias")
+LOG2E = 1.4426950408889634
+
+
+def attn_ld(N: int) -> int:
+    return (N + 15) // 16 * 16
+
+
+def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True):
+    """(bias_fwd [H,N,ld], bias_bwd_t [H,N,ld] or None) in the padded, log2(e)-scaled layout of the attention kernels."""
+    ld = attn_ld(N)
+    fwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device)
+    bwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device) if want_bwd else None
+    check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, ld, LOG2E, _p(fwd), _p(bwd), _stream()), "rel_pos_bias")
     _count()
+    return fwd, bwd
+
+
+def pad_attn_bias(bias: torch.Tensor):
+    """Generic [H,N,N] additive bias -> the kernels' padded layouts (torch ops; tests / non-table biases only)."""
+    H, N, _ = bias.shape
+    ld = attn_ld(N)
+    fwd = torch.full((H, N, ld), float("-inf"), dtype=torch.float32, device=bias.device)
+    fwd[:, :, :N] = bias * LOG2E
+    bwd = torch.zeros((H, N, ld), dtype=torch.float32, device=bias.device)
+    bwd[:, :, :N] = bias.transpose(1, 2) * LOG2E
+    return fwd.contiguous(), bwd.contiguous()
 
 
 def meanpool_tokens(x, B, T, C_, out):
