@@ -175,3 +175,39 @@ def test_registry_boundary(pkg, cuda):
     assert isinstance(f, M.VisionTransformer) and f.head.out_features == 1000
     with pytest.raises(pkg._lib.B200VitError):
         m(torch.zeros(1, 3, 224, 224), None)            # CPU tensor: no fallback
+
+
+def test_mc_dropout_eval_matches_oracle_on_same_masks(pkg, cuda, golden_dir):
+    """evaluate_MC_dropout semantics (uncertainty_evaluations.py:42-89): S passes with attention dropout ON in eval mode (enable_dropout),
+    DropPath OFF; logits per pass against the oracle run with the SAME Philox masks (materialised by b200vit_dropout_mask); metrics from
+    b200vit_mc_reduce against the oracle's reduction."""
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import mc
+    gold = torch.load(os.path.join(golden_dir, "tiny_det_finetune.pt"))
+    gold = dict(gold, dpr=0.2, attn_drop=0.1)
+    model, arch, sd = _build_from_gold(pkg, gold, cuda)
+    x = gold["x"].to(cuda)
+    labels = torch.tensor([1, 3, 5])
+    S = 4
+    model.eval()
+    mc.enable_dropout(model)
+    assert model.blocks[0].attn.attn_drop.training and not model.blocks[1].drop_path.training
+    res = mc.evaluate_mc_dropout(model, [(x, labels)], S)
+    # re-run the passes manually to capture per-pass logits and the exact masks of each pass
+    model._seed_calls = 0
+    per_pass = []
+    for s in range(S):
+        model.eval(); mc.enable_dropout(model)
+        noise_seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (s + 1)) & 0xFFFFFFFFFFFFFFFF
+        with torch.no_grad():
+            logits = model(x)
+        keeps = [pkg.ops.dropout_mask(gold["B"] * arch.num_heads, arch.tokens, 0.1, noise_seed, l, cuda).view(gold["B"], arch.num_heads, arch.tokens, arch.tokens)
+                 for l in range(arch.depth)]
+        onoise = O.Noise(attn_keep=[k.float().cpu() for k in keeps], attn_drop=0.1)
+        ref = O.finetune_forward(sd, arch, gold["x"], noise=onoise)
+        assert rel(logits.cpu(), ref) < 2e-2, s
+        per_pass.append(ref)
+    r = O.mc_reduce(torch.stack(per_pass), labels)
+    assert rel(res["mean_logits"].cpu(), r["mean_logits"]) < 2e-2
+    assert abs(res["nll"] - r["nll"]) / abs(r["nll"]) < 2e-2 and abs(res["ece"] - r["ece"]) < 2e-2
+    assert not torch.equal(per_pass[0], per_pass[1])
