@@ -140,7 +140,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=120))
     import uncertainty_vit_b200 as pkg
     from uncertainty_vit_b200 import engine as E, modeling as M
     ops = pkg.ops
@@ -206,9 +206,10 @@ def run_b200(args):
     roof = None
     if rank == 0:
         ops.GEMM_TIMING = []
-        for i in range(2):
-            eng.step(*dev_batches[i % 2], lr=lr_at(i))
-        torch.cuda.synchronize()
+    for i in range(2):                       # every rank steps (the step contains the gradient all-reduce); rank 0 records
+        eng.step(*dev_batches[i % 2], lr=lr_at(i))
+    torch.cuda.synchronize()
+    if rank == 0:
         rec, ops.GEMM_TIMING = ops.GEMM_TIMING, None
         flops = sum(f for _, _, f in rec)
         t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
