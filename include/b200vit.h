@@ -105,6 +105,13 @@ int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const f
                      const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                      float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                      void* dqkv, void* stream);
+/* Wasserstein-distance attention of the dual-stream (--stochastic) model: dist Attention.forward (modeling_finetune_dist.py:111-179)
+ * with wasserstein_distance_matmul (uncertainty_evaluations.py:276-294). qkv_mean / qkv_cov: bf16 [B, N, 3, H, 64]; qkv_cov holds
+ * elu(.)+1 already (GEMM epilogue B200VIT_EPI_ELU1). bias (required) in the padded layout of b200vit_rel_pos_bias.
+ * out_mean = P~ v, out_cov = (P~)^2 cv, both bf16 [B, N, H*64]. */
+int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N,
+                      int32_t head_dim, float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in,
+                      void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
 /* The Philox keep mask of b200vit_attn_fwd as uint8 [BH, N, N] (parity tests inject it into the CPU oracle). */
 int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 

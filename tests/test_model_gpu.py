@@ -211,3 +211,55 @@ def test_mc_dropout_eval_matches_oracle_on_same_masks(pkg, cuda, golden_dir):
     assert rel(res["mean_logits"].cpu(), r["mean_logits"]) < 2e-2
     assert abs(res["nll"] - r["nll"]) / abs(r["nll"]) < 2e-2 and abs(res["ece"] - r["ece"]) < 2e-2
     assert not torch.equal(per_pass[0], per_pass[1])
+
+
+def _build_dist(pkg, gold, cuda):
+    from functools import partial
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import modeling_dist as MD
+    a = gold["arch"]
+    arch = O.Arch(**a)
+    kw = dict(img_size=a["img_size"], patch_size=16, embed_dim=a["embed_dim"], depth=a["depth"], num_heads=a["num_heads"], mlp_ratio=4,
+              qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), use_shared_rel_pos_bias=True, use_abs_pos_emb=False,
+              init_values=0.1, drop_path_rate=gold.get("dpr", 0.0), attn_drop_rate=gold.get("attn_drop", 0.0))
+    model = MD.DistVisionTransformerForCyclicalTraining(**kw) if arch.kind == "cyclical" else MD.DistVisionTransformer(num_classes=a["num_classes"], **kw)
+    sd = O.make_state(arch, gold["seed"])
+    model.load_state_dict(sd, strict=True)            # identical names/shapes incl. the unused cov_qkv.weight
+    return model.to(cuda), arch, sd
+
+
+def test_dist_finetune_forward_against_reference_golden(pkg, cuda, golden_dir):
+    """BASELINE.json configs[0]: dual-stream (--stochastic) fine-tune-mode forward, B=8, ViT-B/16, 1000 classes — and the tiny case."""
+    for name in ("tiny_dist_finetune", "vitb_dist_finetune_b8"):
+        gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+        model, arch, sd = _build_dist(pkg, gold, cuda)
+        if gold["x"] is None:
+            x = torch.randn(gold["B"], 3, arch.img_size, arch.img_size, generator=torch.Generator().manual_seed(gold["seed"] + 1))
+        else:
+            x = gold["x"]
+        model.eval()
+        with torch.no_grad():
+            mean_feat, cov_feat, logits = model(x.to(cuda))
+        assert rel(mean_feat.cpu(), gold["mean_feat"]) < 2e-2, name
+        assert rel(cov_feat.cpu(), gold["cov_feat"]) < 2e-2, name
+        assert rel(logits.cpu(), gold["logits"]) < 2e-2, name
+        assert torch.equal(logits.argmax(1).cpu(), gold["logits"].argmax(1)) or name.startswith("tiny")
+
+
+def test_dist_cyclical_forward_against_reference_golden(pkg, cuda, golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "tiny_dist_cyclical.pt"))
+    model, arch, sd = _build_dist(pkg, gold, cuda)
+    x, mask = gold["x"].to(cuda), gold["mask"].to(cuda)
+    model.eval()
+    with torch.no_grad():
+        lm, lc = model(x, None, return_all_tokens=True, layer_results="end")
+    from oracle import vit_oracle as O
+    tgt = O.build_targets([t.cpu() for t in lm], gold["target_layers"], gold["mask"], post_target_layer_norm=True)
+    ctgt = O.build_targets([t.cpu() for t in lc], gold["target_layers"], gold["mask"], post_target_layer_norm=True)
+    assert rel(tgt, gold["targets"]) < 2e-2 and rel(ctgt, gold["cov_targets"]) < 2e-2
+    model.train()
+    n = gold["noise"]
+    model.inject_noise(drop_path_keep=n["keep"], attn_keep=n["attn_keep"])
+    with torch.no_grad():
+        om, oc = model(x, mask)
+    assert rel(om.cpu(), gold["outputs"]) < 2e-2 and rel(oc.cpu(), gold["cov_outputs"]) < 2e-2

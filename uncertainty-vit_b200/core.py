@@ -347,3 +347,128 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
         block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
         ctx["saved"][i] = None   # free activations as we go
     stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# dual-stream ("--stochastic") network: mean and covariance streams stacked along the row dimension ([2*B*T, C]: rows
+# [0, M) = mean, [M, 2M) = covariance). The streams share norm1/norm2, qkv.weight (quirk §A.2-1), the MLP and gamma_1/2,
+# so LayerNorm, fc1 and fc2 run ONCE over the stacked rows; QKV / proj differ only in bias / epilogue / weight.
+# dist Block.forward (modeling_finetune_dist.py:41-59), dist Attention.forward (:111-179),
+# DistVisionTransformerForCyclicalTraining.forward (modeling_cyclical_dist.py:108-165), DistVisionTransformer.forward (:280-326)
+# ------------------------------------------------------------------------------------------------------------------
+def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: torch.Tensor, *, save: bool,
+                       dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+    T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
+    M = B * T
+    M2 = 2 * M
+    dev = x_in.device
+    p = f"blocks.{i}."
+    bf = torch.bfloat16
+    h1 = _empty((M2, C), bf, dev)
+    mean1 = _empty((M2,), torch.float32, dev)
+    rstd1 = _empty((M2,), torch.float32, dev)
+    ops.layernorm_fwd(x_in, ps.f32(p + "norm1.weight"), ps.f32(p + "norm1.bias"), cfg.ln_eps, M2, C, y_bf16=h1, mean=mean1, rstd=rstd1)
+    qkv = _empty((M2, 3 * C), bf, dev)
+    w = ps.bf16(p + "attn.qkv.weight")
+    ops.gemm(h1[:M], w, M, 3 * C, C, epilogue=EPI_BF16, bias=ps.qkv_bias(p), out_bf16=qkv[:M])
+    ops.gemm(h1[M:], w, M, 3 * C, C, epilogue=ops.EPI_ELU1, bias=ps.qkv_bias(p, cov=True), out_bf16=qkv[M:])     # elu(.)+1 (:127)
+    att = _empty((M2, C), bf, dev)
+    lse = _empty((B, H, T), torch.float32, dev) if save else None
+    keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
+    ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits)
+    x_mid = _empty((M2, C), torch.float32, dev)
+    t1 = _empty((M2, C), bf, dev) if save else None
+    g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
+    g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
+    dpv = (lambda d: dp_scale[d]) if dp_scale is not None else (lambda d: None)
+    ops.gemm(att[:M], ps.bf16(p + "attn.proj.weight"), M, C, C, epilogue=EPI_RESIDUAL, bias=ps.f32(p + "attn.proj.bias"), colscale=g1,
+             rowscale=dpv(0), rows_per_scale=T, residual=x_in[:M], out_f32=x_mid[:M], out2_bf16=t1[:M] if save else None)
+    ops.gemm(att[M:], ps.bf16(p + "attn.cov_proj.weight"), M, C, C, epilogue=EPI_RESIDUAL, bias=ps.f32(p + "attn.cov_proj.bias"), colscale=g1,
+             rowscale=dpv(2), rows_per_scale=T, residual=x_in[M:], out_f32=x_mid[M:], out2_bf16=t1[M:] if save else None)
+    h2 = _empty((M2, C), bf, dev)
+    mean2 = _empty((M2,), torch.float32, dev)
+    rstd2 = _empty((M2,), torch.float32, dev)
+    ops.layernorm_fwd(x_mid, ps.f32(p + "norm2.weight"), ps.f32(p + "norm2.bias"), cfg.ln_eps, M2, C, y_bf16=h2, mean=mean2, rstd=rstd2)
+    act = _empty((M2, Hd), bf, dev)
+    pre = _empty((M2, Hd), bf, dev) if save else None
+    ops.gemm(h2, ps.bf16(p + "mlp.fc1.weight"), M2, Hd, C, epilogue=EPI_GELU, bias=ps.f32(p + "mlp.fc1.bias"), out_bf16=act, out2_bf16=pre)
+    x_out = _empty((M2, C), torch.float32, dev)
+    t2 = _empty((M2, C), bf, dev) if save else None
+    dp_mlp = torch.cat((dp_scale[1], dp_scale[3])).contiguous() if dp_scale is not None else None      # draws 1 (mean) and 3 (cov)
+    ops.gemm(act, ps.bf16(p + "mlp.fc2.weight"), M2, C, Hd, epilogue=EPI_RESIDUAL, bias=ps.f32(p + "mlp.fc2.bias"), colscale=g2,
+             rowscale=dp_mlp, rows_per_scale=T, residual=x_mid, out_f32=x_out, out2_bf16=t2)
+    if not save:
+        return {"x_out": x_out, "x_mid": x_mid}
+    return dict(x_in=x_in, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, keep_bits=keep_bits, t1=t1, x_mid=x_mid, h2=h2,
+                mean2=mean2, rstd2=rstd2, act=act, pre=pre, t2=t2, x_out=x_out, dp_attn_m=dpv(0), dp_attn_c=dpv(2), dp_mlp=dp_mlp, p_attn=p_attn)
+
+
+def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u8: Optional[torch.Tensor] = None,
+                 row_index: Optional[torch.Tensor] = None, mode: str = "masked", train: bool = False, save: bool = False,
+                 noise: Optional[Noise] = None, collect: Optional[List[int]] = None):
+    """Dual-stream ViT. Modes as vit_forward; outputs are (mean, cov) pairs:
+       'masked' / 'all' -> (lm_head(norm(xm)[rows]), cov_lm_head(norm(xc)[rows])); 'layers' -> ({i: xm_i}, {i: xc_i});
+       'logits' -> (fc_norm(mean-pool xm), fc_norm(mean-pool xc), head(mean feature))  (modeling_finetune_dist.py:311-326)."""
+    if images.dtype != torch.float32 or not images.is_contiguous():
+        images = images.float().contiguous()
+    B = images.shape[0]
+    T, C = cfg.tokens, cfg.embed_dim
+    M = B * T
+    dev = images.device
+    noise = noise or Noise()
+    patches = patches_bf16(cfg, images)
+    x = _empty((2 * M, C), torch.float32, dev)
+    stem_forward(ps, cfg, patches, B, mask_u8, x=x[:M])
+    stem_forward(ps, cfg, patches, B, mask_u8, x=x[M:], prefix="cov_")
+    bias, bias_t = rel_bias(ps, cfg, dev, want_bwd=save)
+    if bias is None:
+        raise B200VitError("the dual-stream model needs use_shared_rel_pos_bias=True (the reference adds rel_pos_bias unconditionally)")
+    dps = make_drop_path_scales(cfg, B, noise, dev, draws=4) if train else None
+    attn_drop_on = train if noise.attn_drop_active is None else noise.attn_drop_active
+    p_attn = cfg.attn_drop_rate if attn_drop_on else 0.0
+    saved, lm, lc = [], {}, {}
+    collect = collect or []
+    for i in range(cfg.depth):
+        keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
+        s = dist_block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn,
+                               seed=noise.seed, keep_in=keep_in)
+        x = s["x_out"]
+        if i in collect:
+            lm[i] = x[:M].view(B, T, C)
+            lc[i] = x[M:].view(B, T, C)
+        if save:
+            saved.append(s)
+    ctx = dict(B=B, saved=saved, patches=patches, mask_u8=mask_u8, row_index=row_index, mode=mode, bias=bias_t, x_final=x) if save else None
+    if mode == "layers":
+        return (lm, lc), ctx
+    if mode in ("masked", "all"):
+        if mode == "all":
+            row_index = all_patch_rows(B, T, dev)
+        R = row_index.numel()
+        rows2 = torch.cat((row_index, row_index + M)).contiguous()
+        hn = _empty((2 * R, C), torch.bfloat16, dev)
+        mean = _empty((2 * R,), torch.float32, dev)
+        rstd = _empty((2 * R,), torch.float32, dev)
+        om = _empty((R, C), torch.float32, dev)
+        oc = _empty((R, C), torch.float32, dev)
+        if R > 0:
+            ops.layernorm_fwd(x, ps.f32("norm.weight"), ps.f32("norm.bias"), cfg.ln_eps, 2 * R, C, y_bf16=hn, mean=mean, rstd=rstd, row_index=rows2)
+            ops.gemm(hn[:R], ps.bf16("lm_head.weight"), R, C, C, epilogue=EPI_F32, bias=ps.f32("lm_head.bias"), out_f32=om)
+            ops.gemm(hn[R:], ps.bf16("cov_lm_head.weight"), R, C, C, epilogue=EPI_F32, bias=ps.f32("cov_lm_head.bias"), out_f32=oc)
+        if save:
+            ctx.update(hn=hn, hmean=mean, hrstd=rstd, row_index=row_index, rows2=rows2)
+        if mode == "all":
+            return (om.view(B, T - 1, C), oc.view(B, T - 1, C)), ctx
+        return (om, oc), ctx
+    if mode == "logits":
+        pooled = _empty((2 * B, C), torch.float32, dev)
+        ops.meanpool_tokens(x, 2 * B, T, C, pooled)
+        feat = _empty((2 * B, C), torch.float32, dev)
+        fb = _empty((2 * B, C), torch.bfloat16, dev)
+        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, 2 * B, C, y_bf16=fb, y_f32=feat)
+        w, hb = ps.head_padded()
+        Kp = w.shape[0]
+        logits = _empty((B, Kp), torch.float32, dev)
+        ops.gemm(fb[:B], w, B, Kp, C, epilogue=EPI_F32, bias=hb, out_f32=logits)
+        return (feat[:B], feat[B:], logits[:, :cfg.num_classes]), ctx
+    raise B200VitError(f"unknown forward mode {mode!r}")

@@ -118,6 +118,13 @@ def attn_bwd(qkv, out, dout, lse, bias_t, keep_bits, rel_index, dtable, B, H, N,
     _count(2 if dtable is not None else 1)
 
 
+def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out_mean=None, out_cov=None, lse=None,
+              keep_bits=None):
+    check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), B, H, N, 64, scale, p_drop, seed, stream_id,
+                                       _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), _stream()), "wattn_fwd")
+    _count()
+
+
 def dropout_mask(BH, N, p_drop, seed, stream_id, device) -> torch.Tensor:
     out = torch.empty(BH, N, N, dtype=torch.uint8, device=device)
     check(_lib.lib().b200vit_dropout_mask(_p(out), BH, N, p_drop, seed, stream_id, _stream()), "dropout_mask")
