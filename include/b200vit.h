@@ -112,6 +112,15 @@ int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const f
 int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N,
                       int32_t head_dim, float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in,
                       void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
+/* Backward of b200vit_wattn_fwd (two kernels: key-tile owners -> dV, dCV, dK, dCK and dD^T; query-tile owners -> dQ, dCQ).
+ * dqkv_cov is the gradient w.r.t. the PRE-activation of elu(.)+1, i.e. ready for the QKV wgrad / dgrad GEMMs.
+ * work_dD / work_dA: bf16 workspaces [B, H, N, ld_ds] (dA only when dtable != NULL). Bias gradients (optional, +=, [H*64]):
+ * dq_bias / dv_bias (q_bias, v_bias) and dcq_bias / dcv_bias (cov_q_bias, cov_v_bias). */
+int b200vit_wattn_bwd(const void* qkv_mean, const void* qkv_cov, const void* out_mean, const void* out_cov, const void* dout_mean,
+                      const void* dout_cov, const float* lse, const float* bias_t, int64_t ld_bias, const uint8_t* keep_bits,
+                      void* work_dD, void* work_dA, int32_t ld_ds, const int32_t* rel_index, float* dtable, float* dq_bias,
+                      float* dv_bias, float* dcq_bias, float* dcv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
+                      float scale, float p_drop, void* dqkv_mean, void* dqkv_cov, void* stream);
 /* The Philox keep mask of b200vit_attn_fwd as uint8 [BH, N, N] (parity tests inject it into the CPU oracle). */
 int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 

@@ -260,6 +260,25 @@ def test_dist_cyclical_forward_against_reference_golden(pkg, cuda, golden_dir):
     model.train()
     n = gold["noise"]
     model.inject_noise(drop_path_keep=n["keep"], attn_keep=n["attn_keep"])
-    with torch.no_grad():
-        om, oc = model(x, mask)
-    assert rel(om.cpu(), gold["outputs"]) < 2e-2 and rel(oc.cpu(), gold["cov_outputs"]) < 2e-2
+    om, oc = model(x, mask)
+    assert rel(om.detach().cpu(), gold["outputs"]) < 2e-2 and rel(oc.detach().cpu(), gold["cov_outputs"]) < 2e-2
+    # loss of the --stochastic engine (engine_for_cyclical.py:145-158): smooth-L1 + WassersteinLoss, torch autograd on top of the CUDA network
+    tg, ctg = gold["targets"].to(cuda), gold["cov_targets"].to(cuda)
+    loss = torch.nn.functional.smooth_l1_loss(om.float(), tg, beta=2.0)
+    a, b_, g_, h_ = (torch.sigmoid(t) for t in (om.float(), oc.float(), tg, ctg))
+    w = ((a - g_) ** 2).sum(-1) + ((torch.sqrt(torch.clamp(b_, min=1e-24)) - torch.sqrt(torch.clamp(h_, min=1e-24))) ** 2).sum(-1)
+    w = w / w.abs().max()
+    l2 = -torch.log(torch.sigmoid(-w + 1e-24))
+    wl = (l2 / l2.abs().max()).sum() * gold["lam"]
+    assert abs(float(wl) - gold["wloss"]) / abs(gold["wloss"]) < 3e-2
+    (loss + wl).backward()
+    bad = []
+    for name, p in model.named_parameters():
+        dig = gold["grads"][name]
+        if dig is None:
+            assert p.grad is None and name.endswith("cov_qkv.weight")        # the only parameter without a gradient
+            continue
+        e = abs(float(p.grad.double().norm()) - dig["norm"]) / max(dig["norm"], 1e-12)
+        if e > 5e-2:
+            bad.append((name, round(e, 4), dig["norm"]))
+    assert not bad, bad

@@ -472,3 +472,79 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
         ops.gemm(fb[:B], w, B, Kp, C, epilogue=EPI_F32, bias=hb, out_f32=logits)
         return (feat[:B], feat[B:], logits[:, :cfg.num_classes]), ctx
     raise B200VitError(f"unknown forward mode {mode!r}")
+
+
+def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.Tensor], dx: torch.Tensor, B: int, bias_t: torch.Tensor,
+                        grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor]):
+    """dx: fp32 [2*B*T, C] (mean rows then cov rows), updated IN PLACE. Shared weights (qkv, fc1, fc2, norms, gammas) receive the sum of
+    both streams' gradients simply because the GEMMs / reductions run over the stacked rows."""
+    T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
+    M = B * T
+    M2 = 2 * M
+    p = f"blocks.{i}."
+    g = lambda n: grads.get(p + n)
+    dt, dpre, dh, dqkv = ws["dt"], ws["dpre"], ws["dh"], ws["dqkv"]
+    g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
+    g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
+    # ---- shared MLP over the stacked rows
+    ops.scale_residual_bwd(dx, s["t2"], s["dp_mlp"], T, g2, M2, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
+    ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M2, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
+    ops.colsum_bf16(dpre, M2, Hd, g("mlp.fc1.bias"))
+    ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
+    ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M2, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
+    ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M2, C, dx, g("norm2.weight"), g("norm2.bias"))
+    # ---- attention branch: mean rows through proj, cov rows through cov_proj (shared gamma_1)
+    gg1 = g("gamma_1") if cfg.has_gamma else None
+    ops.scale_residual_bwd(dx[:M], s["t1"][:M], s["dp_attn_m"], T, g1, M, C, dt[:M], gg1, g("attn.proj.bias"))
+    ops.scale_residual_bwd(dx[M:], s["t1"][M:], s["dp_attn_c"], T, g1, M, C, dt[M:], gg1, g("attn.cov_proj.bias"))
+    att = s["att"]
+    ops.linear_wgrad(dt[:M], att[:M], g("attn.proj.weight"))
+    ops.linear_wgrad(dt[M:], att[M:], g("attn.cov_proj.weight"))
+    ops.gemm(dt[:M], ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh[:M])
+    ops.gemm(dt[M:], ps.bf16(p + "attn.cov_proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh[M:])
+    qkv = s["qkv"]
+    ops.wattn_bwd(qkv[:M], qkv[M:], att[:M], att[M:], dh[:M], dh[M:], s["lse"], bias_t, s["keep_bits"],
+                  ps.rel_index_i32() if dtable is not None else None, dtable, B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv[:M], dqkv[M:],
+                  ws["ds"], ws["ds2"] if dtable is not None else None, dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"),
+                  dcq_bias=g("attn.cov_q_bias"), dcv_bias=g("attn.cov_v_bias"))
+    ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))        # both streams multiply by qkv.weight (cov_qkv.weight stays unused, §A.2-1)
+    ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M2, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
+    ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"))
+
+
+def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, dout_c: torch.Tensor, grads: Dict[str, torch.Tensor]):
+    """Backward of dist_forward in the 'masked' / 'all' modes: gradients of (mean output, cov output) -> parameter gradients."""
+    B = ctx["B"]
+    T, C = cfg.tokens, cfg.embed_dim
+    M = B * T
+    dev = dout_m.device
+    if ctx["mode"] not in ("masked", "all"):
+        raise B200VitError("dual-stream backward is implemented for the data2vec modes ('masked', 'all')")
+    row_index, rows2 = ctx["row_index"], ctx["rows2"]
+    R = row_index.numel()
+    dx = torch.zeros((2 * M, C), dtype=torch.float32, device=dev)
+    if R > 0:
+        dym = ops.cast_bf16(dout_m.reshape(R, C).float().contiguous())
+        dyc = ops.cast_bf16(dout_c.reshape(R, C).float().contiguous())
+        hn = ctx["hn"]
+        ops.linear_wgrad(dym, hn[:R], grads["lm_head.weight"])
+        ops.linear_wgrad(dyc, hn[R:], grads["cov_lm_head.weight"])
+        ops.colsum_bf16(dym, R, C, grads["lm_head.bias"])
+        ops.colsum_bf16(dyc, R, C, grads["cov_lm_head.bias"])
+        dhn = _empty((2 * R, C), torch.bfloat16, dev)
+        ops.gemm(dym, ps.bf16("lm_head.weight"), R, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dhn[:R])
+        ops.gemm(dyc, ps.bf16("cov_lm_head.weight"), R, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dhn[R:])
+        ops.layernorm_bwd(dhn, ctx["x_final"], ps.f32("norm.weight"), ctx["hmean"], ctx["hrstd"], 2 * R, C, dx, grads["norm.weight"],
+                          grads["norm.bias"], row_index=rows2)
+    M2, Hd = 2 * M, cfg.hidden
+    bf = torch.bfloat16
+    ld = (T + 15) // 16 * 16
+    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
+              ds=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev), ds2=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev))
+    dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    for i in reversed(range(cfg.depth)):
+        dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
+        ctx["saved"][i] = None
+    stem_backward(ps, cfg, ctx["patches"], dx[:M], B, ctx["mask_u8"], grads)
+    stem_backward(ps, cfg, ctx["patches"], dx[M:], B, ctx["mask_u8"], grads, prefix="cov_")

@@ -584,6 +584,14 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   return 0;
 }
 
+// internal (not part of the public ABI): shared by the dual-stream backward in wattention.cu
+int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld_ds, const int32_t* rel_index, float* dtable, void* stream) {
+  const int sms = b200vit_num_sms();
+  relbias_grad_kernel<<<sms * 8, 256, 0, STREAM>>>(static_cast<const bf16*>(ds_work), B, H, N, ld_ds, rel_index, dtable);
+  B200_CHECK_LAUNCH("relbias_grad");
+  return 0;
+}
+
 extern "C" int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
   B200_CHECK_ARG(out != nullptr && BH > 0 && N > 0, "dropout_mask: bad arguments");
   const int sms = b200vit_num_sms();

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld_ds, const int32_t* rel_index, float* dtable, void* stream);
+
 namespace attn {
 
 constexpr int HD = 64;            // head dim

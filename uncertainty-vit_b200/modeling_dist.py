@@ -34,6 +34,27 @@ def _dist_common_init(self, img_size, patch_size, in_chans, embed_dim, depth, nu
                                  for i in range(depth)])
 
 
+class _DistFunction(torch.autograd.Function):
+    """Whole dual-stream network as one autograd node: outputs (mean, cov); backward = core.dist_backward."""
+
+    @staticmethod
+    def forward(ctx, model, images, mask_u8, row_index, mode, noise, names, *params):
+        (om, oc), saved = core.dist_forward(model._ps, model.cfg, images, mask_u8=mask_u8, row_index=row_index, mode=mode, train=model.training,
+                                            save=True, noise=noise)
+        ctx.model, ctx.saved, ctx.names, ctx.shapes = model, saved, names, [p.shape for p in params]
+        return om, oc
+
+    @staticmethod
+    def backward(ctx, dom, doc):
+        model = ctx.model
+        dev = dom.device
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(ctx.names, ctx.shapes)}
+        core.dist_backward(model._ps, model.cfg, ctx.saved, dom.contiguous(), doc.contiguous(), grads)
+        ctx.saved = None
+        unused = model._unused_param_names()
+        return (None,) * 7 + tuple(None if n in unused else grads[n] for n in ctx.names)
+
+
 class _DistBase(_VitBase):
     def _unused_param_names(self):
         # cov_qkv.weight is allocated, saved and EMA-ed but never used: the cov stream multiplies by qkv.weight (§A.2-1)
@@ -42,7 +63,10 @@ class _DistBase(_VitBase):
     def _run_dist(self, x, mask_u8, row_index, mode, collect=None):
         noise = self._noise()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("dual-stream training backward is the next SURVEY §8 row; wrap inference in torch.no_grad()")
+            if mode not in ("masked", "all"):
+                raise NotImplementedError("dual-stream fine-tune training backward is the next SURVEY §8 row; wrap inference in torch.no_grad()")
+            named = list(self.named_parameters())
+            return _DistFunction.apply(self, x, mask_u8, row_index, mode, noise, [n for n, _ in named], *[p for _, p in named])
         out, _ = core.dist_forward(self._ps, self.cfg, x, mask_u8=mask_u8, row_index=row_index, mode=mode, train=self.training, save=False,
                                    noise=noise, collect=collect)
         return out

@@ -125,6 +125,15 @@ def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, strea
     _count()
 
 
+def wattn_bwd(qkv_mean, qkv_cov, out_mean, out_cov, dout_mean, dout_cov, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p_drop,
+              dqkv_mean, dqkv_cov, work_dD, work_dA=None, dq_bias=None, dv_bias=None, dcq_bias=None, dcv_bias=None):
+    check(_lib.lib().b200vit_wattn_bwd(_p(qkv_mean), _p(qkv_cov), _p(out_mean), _p(out_cov), _p(dout_mean), _p(dout_cov), _p(lse), _p(bias_t),
+                                       bias_t.stride(1), _p(keep_bits), _p(work_dD), _p(work_dA), work_dD.shape[-1], _p(rel_index), _p(dtable),
+                                       _p(dq_bias), _p(dv_bias), _p(dcq_bias), _p(dcv_bias), B, H, N, 64, scale, p_drop, _p(dqkv_mean),
+                                       _p(dqkv_cov), _stream()), "wattn_bwd")
+    _count(3 if dtable is not None else 2)
+
+
 def dropout_mask(BH, N, p_drop, seed, stream_id, device) -> torch.Tensor:
     out = torch.empty(BH, N, N, dtype=torch.uint8, device=device)
     check(_lib.lib().b200vit_dropout_mask(_p(out), BH, N, p_drop, seed, stream_id, _stream()), "dropout_mask")
