@@ -159,6 +159,8 @@ int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, in
                          float* out_bwd_t, void* stream);
 /* x[:, 1:].mean(1) (modeling_finetune.py:512-514) */
 int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int32_t C, float* out, void* stream);
+/* backward of the mean pooling: dx[b, t>=1, :] += dpool[b, :] / (T-1) */
+int b200vit_meanpool_tokens_bwd(const float* dpool, int32_t B, int32_t T, int32_t C, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * data2vec step kernels

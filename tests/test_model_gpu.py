@@ -282,3 +282,52 @@ def test_dist_cyclical_forward_against_reference_golden(pkg, cuda, golden_dir):
         if e > 5e-2:
             bad.append((name, round(e, 4), dig["norm"]))
     assert not bad, bad
+
+
+def test_finetune_training_backward_vs_oracle(pkg, cuda, golden_dir):
+    """Fine-tune TRAIN step (cross-entropy on the classifier; + WassersteinLossFineTuning on the dual-stream features) against the
+    oracle's autograd on the same weights, inputs and injected noise: det and dual-stream."""
+    from oracle import vit_oracle as O
+    for name, builder in (("tiny_det_finetune", _build_from_gold), ("tiny_dist_finetune", lambda p, g, c: _build_dist(p, g, c))):
+        gold = dict(torch.load(os.path.join(golden_dir, name + ".pt")), dpr=0.2, attn_drop=0.1)
+        model, arch, sd = builder(pkg, gold, cuda)
+        B = gold["B"]
+        g = torch.Generator().manual_seed(5)
+        probs = [float(x) for x in torch.linspace(0, 0.2, arch.depth)]
+        draws = 4 if arch.dist else 2
+        keeps = [(torch.rand(draws, B, generator=g) >= p).float() for p in probs]
+        akeep = [(torch.rand(B, arch.num_heads, arch.tokens, arch.tokens, generator=g) >= 0.1).to(torch.uint8) for _ in range(arch.depth)]
+        labels = torch.tensor([1, 3, 5])
+        noise = O.Noise(drop_path_keep=keeps, drop_path_prob=probs, attn_keep=[k.float() for k in akeep], attn_drop=0.1)
+        sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+        out = O.finetune_forward(sdg, arch, gold["x"], noise=noise)
+        model.train()
+        model.inject_noise(drop_path_keep=keeps, attn_keep=akeep)
+        mine = model(gold["x"].to(cuda))
+        if arch.dist:
+            fm, fc, logits = out
+            loss_o = torch.nn.functional.cross_entropy(logits, labels) + O.wasserstein_loss(fm, fc, fm.detach().roll(1, 0), fc.detach().roll(1, 0), 1e-2)
+            mfm, mfc, mlog = mine
+            assert rel(mlog.detach().cpu(), logits.detach()) < 2e-2 and rel(mfc.detach().cpu(), fc.detach()) < 2e-2
+            a, b_, g_, h_ = (torch.sigmoid(t) for t in (mfm.float(), mfc.float(), mfm.detach().roll(1, 0).float(), mfc.detach().roll(1, 0).float()))
+            w = ((a - g_) ** 2).sum(-1) + ((torch.sqrt(torch.clamp(b_, min=1e-24)) - torch.sqrt(torch.clamp(h_, min=1e-24))) ** 2).sum(-1)
+            w = w / w.abs().max()
+            l2 = -torch.log(torch.sigmoid(-w + 1e-24))
+            loss_m = torch.nn.functional.cross_entropy(mlog.float(), labels.to(cuda)) + (l2 / l2.abs().max()).sum() * 1e-2
+        else:
+            loss_o = torch.nn.functional.cross_entropy(out, labels)
+            assert rel(mine.detach().cpu(), out.detach()) < 2e-2
+            loss_m = torch.nn.functional.cross_entropy(mine.float(), labels.to(cuda))
+        assert abs(float(loss_m) - float(loss_o)) / abs(float(loss_o)) < 2e-2
+        loss_o.backward()
+        loss_m.backward()
+        bad = []
+        for pname, p in model.named_parameters():
+            go = sdg[pname].grad
+            if go is None:
+                assert p.grad is None and pname.endswith("cov_qkv.weight")
+                continue
+            e = rel(p.grad.cpu(), go)
+            if e > 8e-2 and float(go.norm()) > 1e-6:
+                bad.append((pname, round(e, 4)))
+        assert not bad, (name, bad)

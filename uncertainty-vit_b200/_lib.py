@@ -50,6 +50,7 @@ _PROTOS = {
     "b200vit_drop_path_scales": (i32, [C.POINTER(f32), i32, i32, i32, u64, vp, vp]),
     "b200vit_rel_pos_bias": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "b200vit_meanpool_tokens": (i32, [vp, i32, i32, i32, vp, vp]),
+    "b200vit_meanpool_tokens_bwd": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "b200vit_ema_update": (i32, [vp, vp, i64, C.c_double, vp, vp]),
     "b200vit_sumsq": (i32, [vp, i64, vp, vp]),

@@ -293,7 +293,11 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
         ops.meanpool_tokens(x, B, T, C, pooled)
         feat = _empty((B, C), torch.float32, dev)
         fb = _empty((B, C), torch.bfloat16, dev)
-        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, B, C, y_bf16=fb, y_f32=feat)
+        fmean = _empty((B,), torch.float32, dev)
+        frstd = _empty((B,), torch.float32, dev)
+        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, B, C, y_bf16=fb, y_f32=feat, mean=fmean, rstd=frstd)
+        if save:
+            ctx.update(pooled=pooled, fb=fb, fmean=fmean, frstd=frstd)
         if mode == "features":
             return feat, ctx
         K = cfg.num_classes
@@ -465,7 +469,11 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
         ops.meanpool_tokens(x, 2 * B, T, C, pooled)
         feat = _empty((2 * B, C), torch.float32, dev)
         fb = _empty((2 * B, C), torch.bfloat16, dev)
-        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, 2 * B, C, y_bf16=fb, y_f32=feat)
+        fmean = _empty((2 * B,), torch.float32, dev)
+        frstd = _empty((2 * B,), torch.float32, dev)
+        ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, 2 * B, C, y_bf16=fb, y_f32=feat, mean=fmean, rstd=frstd)
+        if save:
+            ctx.update(pooled=pooled, fb=fb, fmean=fmean, frstd=frstd)
         w, hb = ps.head_padded()
         Kp = w.shape[0]
         logits = _empty((B, Kp), torch.float32, dev)
@@ -548,3 +556,76 @@ def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, do
         ctx["saved"][i] = None
     stem_backward(ps, cfg, ctx["patches"], dx[:M], B, ctx["mask_u8"], grads)
     stem_backward(ps, cfg, ctx["patches"], dx[M:], B, ctx["mask_u8"], grads, prefix="cov_")
+
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# classifier (fine-tune) backward: logits = head(fc_norm(mean_{t>=1} x_L))   (modeling_finetune.py:512-523, modeling_finetune_dist.py:311-326)
+# ------------------------------------------------------------------------------------------------------------------
+def _head_backward(ps: ParamSource, cfg: VitConfig, ctx, dlogits: torch.Tensor, dfeat_extra: Optional[torch.Tensor], grads, streams: int) -> torch.Tensor:
+    """Returns dx [streams*B*T, C] fp32 (gradient of the final residual stream). dfeat_extra: optional fp32 [streams*B, C] gradient
+    flowing directly into the fc_norm outputs (the W-loss of the dual-stream fine-tune step)."""
+    B = ctx["B"]
+    T, C, K = cfg.tokens, cfg.embed_dim, cfg.num_classes
+    dev = dlogits.device
+    SB = streams * B
+    w, _ = ps.head_padded()
+    Kp = w.shape[0]
+    dl = torch.zeros((B, Kp), dtype=torch.float32, device=dev)
+    dl[:, :K].copy_(dlogits)
+    dl16 = ops.cast_bf16(dl)
+    fb = ctx["fb"]
+    gw = grads["head.weight"]
+    if Kp == K:
+        ops.linear_wgrad(dl16, fb[:B], gw)
+    else:
+        tmp = torch.zeros((Kp, C), dtype=torch.float32, device=dev)
+        ops.linear_wgrad(dl16, fb[:B], tmp)
+        gw.add_(tmp[:K])
+    grads["head.bias"].add_(dlogits.sum(0))                                # [K] column sum of a [B, K] matrix: negligible
+    dfeat16 = torch.zeros((SB, C), dtype=torch.bfloat16, device=dev)
+    ops.gemm(dl16, w, B, C, Kp, b_mn=True, epilogue=EPI_BF16, out_bf16=dfeat16[:B])
+    dfeat = dfeat16.float()
+    if dfeat_extra is not None:
+        dfeat = dfeat + dfeat_extra
+    dpool = torch.zeros((SB, C), dtype=torch.float32, device=dev)
+    ops.layernorm_bwd(dfeat.contiguous(), ctx["pooled"], ps.f32("fc_norm.weight"), ctx["fmean"], ctx["frstd"], SB, C, dpool, grads["fc_norm.weight"],
+                      grads["fc_norm.bias"])
+    dx = torch.zeros((SB * T, C), dtype=torch.float32, device=dev)
+    ops.meanpool_tokens_bwd(dpool, SB, T, C, dx)
+    return dx
+
+
+def vit_backward_logits(ps: ParamSource, cfg: VitConfig, ctx, dlogits: torch.Tensor, grads: Dict[str, torch.Tensor]):
+    B = ctx["B"]
+    dx = _head_backward(ps, cfg, ctx, dlogits, None, grads, 1)
+    ws = backward_workspace(cfg, B, dlogits.device)
+    dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    for i in reversed(range(cfg.depth)):
+        block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
+        ctx["saved"][i] = None
+    stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)
+
+
+def dist_backward_logits(ps: ParamSource, cfg: VitConfig, ctx, dmean_feat, dcov_feat, dlogits, grads: Dict[str, torch.Tensor]):
+    B = ctx["B"]
+    T, C = cfg.tokens, cfg.embed_dim
+    M = B * T
+    dev = dlogits.device
+    extra = torch.zeros((2 * B, C), dtype=torch.float32, device=dev)
+    if dmean_feat is not None:
+        extra[:B].copy_(dmean_feat)
+    if dcov_feat is not None:
+        extra[B:].copy_(dcov_feat)
+    dx = _head_backward(ps, cfg, ctx, dlogits, extra, grads, 2)
+    M2, Hd = 2 * M, cfg.hidden
+    bf = torch.bfloat16
+    ld = (T + 15) // 16 * 16
+    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
+              ds=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev), ds2=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev))
+    dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    for i in reversed(range(cfg.depth)):
+        dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
+        ctx["saved"][i] = None
+    stem_backward(ps, cfg, ctx["patches"], dx[:M], B, None, grads)
+    stem_backward(ps, cfg, ctx["patches"], dx[M:], B, None, grads, prefix="cov_")

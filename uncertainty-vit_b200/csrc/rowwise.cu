@@ -319,6 +319,24 @@ __global__ void meanpool_kernel(const float* __restrict__ x, int B, int T, int C
   st4(out + (long long)b * C + c, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
 }
 
+// backward of meanpool: dx[b, 0, :] += 0 ; dx[b, t >= 1, :] += dpool[b, :] / (T - 1)
+__global__ void meanpool_bwd_kernel(const float* __restrict__ dpool, int B, int T, int C, float* __restrict__ dx) {
+  const int c4 = C >> 2;
+  const long long total = (long long)B * (T - 1) * c4;
+  const float inv = 1.0f / (T - 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const long long row = i / c4;
+    const int t = (int)(row % (T - 1)) + 1;
+    const int b = (int)(row / (T - 1));
+    const float4 d = ld4(dpool + (long long)b * C + c);
+    float* q = dx + ((long long)b * T + t) * C + c;
+    float4 v = ld4(q);
+    v.x += d.x * inv; v.y += d.y * inv; v.z += d.z * inv; v.w += d.w * inv;
+    st4(q, v);
+  }
+}
+
 int grid_for(long long work_items, int threads, int sms, int per_sm) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = (long long)sms * per_sm;
@@ -455,6 +473,14 @@ __global__ void drop_path_scales_kernel(DropPathProbs probs, int L, int draws, i
     const float u = (r.x >> 8) * (1.0f / 16777216.0f);    // [0,1)
     out[i] = (p <= 0.f) ? 1.0f : (u >= p ? 1.0f / (1.0f - p) : 0.0f);
   }
+}
+
+extern "C" int b200vit_meanpool_tokens_bwd(const float* dpool, int32_t B, int32_t T, int32_t C, float* dx, void* stream) {
+  B200_CHECK_ARG(dpool != nullptr && dx != nullptr && T > 1 && C % 4 == 0, "meanpool_tokens_bwd: bad arguments");
+  const int sms = b200vit_num_sms();
+  meanpool_bwd_kernel<<<grid_for((long long)B * (T - 1) * (C / 4), 256, sms, 8), 256, 0, STREAM>>>(dpool, B, T, C, dx);
+  B200_CHECK_LAUNCH("meanpool_tokens_bwd");
+  return 0;
 }
 
 extern "C" int b200vit_drop_path_scales(const float* probs_host, int32_t L, int32_t draws, int32_t B, uint64_t seed, float* out, void* stream) {

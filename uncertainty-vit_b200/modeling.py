@@ -198,7 +198,10 @@ class _VitFunction(torch.autograd.Function):
         model = ctx.model
         dev = dout.device
         grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(ctx.names, ctx.shapes)}
-        core.vit_backward(model._ps, model.cfg, ctx.saved, dout.contiguous(), grads)
+        if ctx.saved["mode"] == "logits":
+            core.vit_backward_logits(model._ps, model.cfg, ctx.saved, dout.float().contiguous(), grads)
+        else:
+            core.vit_backward(model._ps, model.cfg, ctx.saved, dout.contiguous(), grads)
         ctx.saved = None
         unused = model._unused_param_names()
         return (None, None, None, None, None, None, None) + tuple(None if n in unused else grads[n] for n in ctx.names)
@@ -282,7 +285,7 @@ class _VitBase(nn.Module):
     def _run(self, x, mask_u8, row_index, mode, collect=None, collect_what="end"):
         noise = self._noise()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if needs_grad and mode in ("masked", "all"):
+        if needs_grad and mode in ("masked", "all", "logits"):
             named = list(self.named_parameters())
             names = [n for n, _ in named]
             return _VitFunction.apply(self, x, mask_u8, row_index, mode, noise, names, *[p for _, p in named])
@@ -441,8 +444,6 @@ class VisionTransformer(_VitBase):
 
     def forward(self, x, bool_masked_pos=None):
         self._check_input(x)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("fine-tune training backward is the next SURVEY §8 row; call under torch.no_grad() for inference / MC eval")
         return self._run(x, None, None, "logits")
 
 

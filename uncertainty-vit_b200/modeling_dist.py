@@ -55,6 +55,29 @@ class _DistFunction(torch.autograd.Function):
         return (None,) * 7 + tuple(None if n in unused else grads[n] for n in ctx.names)
 
 
+class _DistLogitsFunction(torch.autograd.Function):
+    """Dual-stream classifier: outputs (mean_feat, cov_feat, logits) — the triple train_class_batch unpacks
+    (engine_for_finetuning_dist.py:288); all three receive gradients (CE on logits + WassersteinLossFineTuning on the features)."""
+
+    @staticmethod
+    def forward(ctx, model, images, noise, names, *params):
+        (fm, fc, logits), saved = core.dist_forward(model._ps, model.cfg, images, mode="logits", train=model.training, save=True, noise=noise)
+        ctx.model, ctx.saved, ctx.names, ctx.shapes = model, saved, names, [p.shape for p in params]
+        return fm.clone(), fc.clone(), logits.clone()
+
+    @staticmethod
+    def backward(ctx, dfm, dfc, dlogits):
+        model = ctx.model
+        dev = dlogits.device if dlogits is not None else dfm.device
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(ctx.names, ctx.shapes)}
+        if dlogits is None:
+            dlogits = torch.zeros((ctx.saved["B"], model.cfg.num_classes), dtype=torch.float32, device=dev)
+        core.dist_backward_logits(model._ps, model.cfg, ctx.saved, dfm, dfc, dlogits.float().contiguous(), grads)
+        ctx.saved = None
+        unused = model._unused_param_names()
+        return (None,) * 4 + tuple(None if n in unused else grads[n] for n in ctx.names)
+
+
 class _DistBase(_VitBase):
     def _unused_param_names(self):
         # cov_qkv.weight is allocated, saved and EMA-ed but never used: the cov stream multiplies by qkv.weight (§A.2-1)
@@ -63,9 +86,11 @@ class _DistBase(_VitBase):
     def _run_dist(self, x, mask_u8, row_index, mode, collect=None):
         noise = self._noise()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            if mode not in ("masked", "all"):
-                raise NotImplementedError("dual-stream fine-tune training backward is the next SURVEY §8 row; wrap inference in torch.no_grad()")
             named = list(self.named_parameters())
+            if mode == "logits":
+                return _DistLogitsFunction.apply(self, x, noise, [n for n, _ in named], *[p for _, p in named])
+            if mode not in ("masked", "all"):
+                raise NotImplementedError(f"no backward for mode {mode!r}")
             return _DistFunction.apply(self, x, mask_u8, row_index, mode, noise, [n for n, _ in named], *[p for _, p in named])
         out, _ = core.dist_forward(self._ps, self.cfg, x, mask_u8=mask_u8, row_index=row_index, mode=mode, train=self.training, save=False,
                                    noise=noise, collect=collect)

@@ -237,6 +237,11 @@ def meanpool_tokens(x, B, T, C_, out):
     _count()
 
 
+def meanpool_tokens_bwd(dpool, B, T, C_, dx):
+    check(_lib.lib().b200vit_meanpool_tokens_bwd(_p(dpool), B, T, C_, _p(dx), _stream()), "meanpool_tokens_bwd")
+    _count()
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # data2vec step
 # ----------------------------------------------------------------------------------------------------------------
