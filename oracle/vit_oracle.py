@@ -596,19 +596,28 @@ def mc_reduce(logits_snk: torch.Tensor, labels: torch.Tensor) -> Dict[str, objec
 # --------------------------------------------------------------------------------------------------------------
 def d2v_step(sd: Dict[str, torch.Tensor], ema: Dict[str, torch.Tensor], opt: Dict[str, Dict[str, torch.Tensor]], arch: Arch, x, mask,
              step: int, noise: Optional[Noise] = None, target_layers=(6, 7, 8, 9, 10, 11), lr=2e-3, wd=0.05, clip=3.0, ema_decay=0.9998,
-             l1_beta=2.0, return_grads: bool = False):
+             l1_beta=2.0, return_grads: bool = False, lam: float = 1e-5):
     """sd / ema: float state dicts (updated IN PLACE); opt: {'m': {...}, 'v': {...}}. Returns (loss, grad_norm[, grads])."""
     with torch.no_grad():
         t = cyclical_forward(ema, arch, x, None, return_all_tokens=True, layer_results="end")
+    if arch.dist:
+        t, tc = t
+        ctgt = build_targets(tc, list(target_layers), mask, post_target_layer_norm=True)      # engine_for_cyclical.py:74-86
     tgt = build_targets(t, list(target_layers), mask, post_target_layer_norm=True)
     names = [k for k, v in sd.items() if v.is_floating_point()]
     leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
     out = cyclical_forward(leaf, arch, x, mask, noise=noise)
+    if arch.dist:
+        out, cout = out
     loss, _ = d2v_loss(out.float(), tgt, l1_beta)
+    if arch.dist:
+        loss = loss + wasserstein_loss(out.float(), cout.float(), tgt, ctgt, lam)               # :152-158
     loss.backward()
     grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(sd[k])) for k in names}
     total, coef = clip_grad_norm(list(grads.values()), clip)
     for k in names:
+        if leaf[k].grad is None:
+            continue                      # torch.optim.AdamW skips parameters without a gradient (cov_qkv.weight, §A.2-1)
         decay = 0.0 if is_no_decay(k, sd[k].shape) else wd
         adamw_step(sd[k], grads[k] * coef, opt["m"][k], opt["v"][k], step, lr, decay)
     ema_update({k: ema[k] for k in names}, sd, ema_decay)

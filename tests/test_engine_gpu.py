@@ -82,3 +82,39 @@ def test_train_one_epoch_loop_and_schedules(cuda, golden_dir):
     loader = [((gold["x"], gold["mask"]), None)] * 3
     stats = E.train_one_epoch(eng, loader, epoch=0, start_steps=0, lr_schedule_values=lr, wd_schedule_values=wd, log=lambda s: None)
     assert np.isfinite(stats["loss"]) and abs(stats["cur_decay"] - (0.999 + 2 * (0.9998 - 0.999) / 4)) < 1e-9
+
+
+def test_dist_engine_step_matches_oracle_step(cuda, golden_dir):
+    """--stochastic data2vec step (dual-stream teacher/student, smooth-L1 + WassersteinLoss) through the fused engine vs the oracle step."""
+    import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import engine as E
+    from oracle import vit_oracle as O
+    from tests.test_model_gpu import _build_dist
+    gold = torch.load(os.path.join(golden_dir, "tiny_dist_cyclical.pt"))
+    model, arch, sd = _build_dist(pkg, gold, cuda)
+    lam = 1e-2          # larger than the README's 1e-5 so that the W-loss gradients matter in the comparison
+    eng = E.D2VEngine(model, lr=1e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.99, target_layers=gold["target_layers"], lambda_pretraining=lam)
+    n = gold["noise"]
+    noise = pkg.core.Noise(seed=1)
+    noise.drop_path_scale = torch.stack([k.float() / (1.0 - p) for k, p in zip(n["keep"], n["prob"])]).to(cuda).contiguous()
+    noise.attn_keep = [k.to(cuda).contiguous() for k in n["attn_keep"]]
+    m = gold["mask"].reshape(gold["mask"].shape[0], -1).numpy().astype(np.uint8)
+    rows = torch.from_numpy(eng.rows_from_host_mask(m, arch.tokens)).to(cuda)
+    w_before = model.state_dict()["blocks.0.attn.cov_qkv.weight"].clone()
+    loss = eng.step(gold["x"].to(cuda), torch.from_numpy(m.reshape(-1)).to(cuda), rows, noise=noise)
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    ema_o = {k: v.clone() for k, v in sd.items()}
+    onoise = O.Noise(drop_path_keep=n["keep"], drop_path_prob=n["prob"], attn_keep=[k.float() for k in n["attn_keep"]], attn_drop=n["attn_drop"])
+    loss_o, gnorm_o, grads_o = O.d2v_step(sd_o, ema_o, O.new_opt_state(sd_o), arch, gold["x"], gold["mask"], 1, onoise, gold["target_layers"],
+                                          lr=1e-3, wd=0.05, clip=3.0, ema_decay=0.99, return_grads=True, lam=lam)
+    assert abs(loss.item() - loss_o) / loss_o < 2e-2
+    assert abs(eng.grad_norm().item() - gnorm_o) / gnorm_o < 4e-2
+    bad = []
+    for k, g in grads_o.items():
+        if float(g.norm()) > 1e-7:
+            e = rel(eng.grads[k].cpu(), g)
+            if e > 1e-1:
+                bad.append((k, round(e, 3)))
+    assert not bad, bad
+    # the unused cov_qkv.weight is neither updated nor decayed (torch AdamW skips grad-less parameters)
+    assert torch.equal(model.state_dict()["blocks.0.attn.cov_qkv.weight"], w_before)

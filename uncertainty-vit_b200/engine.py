@@ -89,11 +89,10 @@ class D2VEngine:
     def __init__(self, model, *, lr=2e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, clip_grad=3.0, ema_decay=0.9998,
                  ema_decay_init=0.999, ema_start_at=0, target_layers: Sequence[int] = (6, 7, 8, 9, 10, 11), l1_beta=2.0, l2_loss=False,
                  target_layer_norm_last=True, post_target_layer_norm=True, layer_decay: Optional[float] = None, loss_scale=-1.0,
-                 skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0):
+                 skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0,
+                 lambda_pretraining: float = 1e-5):
         self.model = model
         self.cfg: VitConfig = model.cfg
-        if self.cfg.dist:
-            raise NotImplementedError("the fused engine covers the deterministic data2vec step; the dual-stream model trains through autograd")
         dev = model.cls_token.device
         if dev.type != "cuda":
             raise B200VitError("D2VEngine needs the model on a CUDA (B200) device")
@@ -103,6 +102,7 @@ class D2VEngine:
         self.target_layers = list(target_layers)
         self.l1_beta, self.l2_loss, self.ln_each, self.ln_post = l1_beta, l2_loss, target_layer_norm_last, post_target_layer_norm
         self.loss_scale = loss_scale
+        self.lam = lambda_pretraining
         self.world_size, self.pg = world_size, process_group
         self.seed = seed
         self.it = 0
@@ -130,14 +130,20 @@ class D2VEngine:
             layer_id = get_num_layer_for_vit(name, L)
             lr_scale = 1.0 if layer_decay is None else layer_decay ** (L - 1 - layer_id)
             no_decay = p.dim() == 1 or name.endswith(".bias") or name in skip            # optim_factory.py:66-67
-            if name.endswith("attn.q_bias"):
-                prefix = name[: -len("q_bias")]
+            if name.endswith("attn.q_bias") or name.endswith("attn.cov_q_bias"):
+                cov = "cov_" if name.endswith("cov_q_bias") else ""
+                prefix = name[: -len(cov + "q_bias")]
                 C = p.numel()
-                add(prefix + "__qkv_bias", (3 * C,), lr_scale, 0.0)
-                base = layout[prefix + "__qkv_bias"][0]
-                layout[prefix + "q_bias"] = (base, (C,))
-                layout[prefix + "v_bias"] = (base + 2 * C, (C,))
-                done.update({prefix + "q_bias", prefix + "v_bias"})
+                add(prefix + f"__{cov}qkv_bias", (3 * C,), lr_scale, 0.0)
+                base = layout[prefix + f"__{cov}qkv_bias"][0]
+                layout[prefix + cov + "q_bias"] = (base, (C,))
+                layout[prefix + cov + "v_bias"] = (base + 2 * C, (C,))
+                done.update({prefix + cov + "q_bias", prefix + cov + "v_bias"})
+                continue
+            if name.endswith("attn.cov_qkv.weight"):
+                # never receives a gradient in the reference (the cov stream multiplies by qkv.weight, §A.2-1): torch's AdamW skips
+                # grad-less parameters entirely (no update, no weight decay) -> lr_scale = wd_scale = 0
+                add(name, p.shape, 0.0, 0.0)
                 continue
             add(name, p.shape, lr_scale, 0.0 if no_decay else 1.0)
         self.layout, self.n = layout, off
@@ -195,6 +201,8 @@ class D2VEngine:
         self.cur_decay = self.decay_at(self.it)
         if noise is None:
             noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
+        if cfg.dist:
+            return self._step_dist(images, mask_u8, rows, lr, wd, noise)
         patches = core.patches_bf16(cfg, images)
         # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88
         layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers, patches=patches)
@@ -210,6 +218,40 @@ class D2VEngine:
         del layers
         self.g32.zero_()
         core.vit_backward(self.student, cfg, ctx, dy, self.grads)
+        return self._optimizer_step(lr, wd)
+
+    def _step_dist(self, images, mask_u8, rows, lr, wd, noise):
+        """--stochastic step (engine_for_cyclical.py:69-86,125-126,152-158): dual-stream teacher/student, targets for both streams,
+        smooth-L1 on the mean stream + WassersteinLoss(lambda) on (mean, cov) outputs vs (mean, cov) targets."""
+        cfg = self.cfg
+        B = images.shape[0]
+        C, T = cfg.embed_dim, cfg.tokens
+        M = B * T
+        R = rows.numel()
+        dev = self.dev
+        (lm, lc), _ = core.dist_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers)
+        (om, oc), ctx = core.dist_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise)
+        ls = self.loss_scale if self.loss_scale != -1 else 1.0
+        tgt_m = torch.empty((R, C), dtype=torch.float32, device=dev)
+        tgt_c = torch.empty((R, C), dtype=torch.float32, device=dev)
+        d_m = torch.empty((R, C), dtype=torch.float32, device=dev)
+        d_c = torch.zeros((R, C), dtype=torch.float32, device=dev)
+        row_loss = torch.empty((R,), dtype=torch.float32, device=dev)
+        ops.d2v_target_loss([lm[i].view(M, C) for i in self.target_layers], C, rows, om, R, C, self.ln_each, self.ln_post, self.l1_beta, self.l2_loss,
+                            ls / (R * C), tgt_m, None, d_m, row_loss, self.loss_dev)
+        ops.d2v_target_loss([lc[i].view(M, C) for i in self.target_layers], C, rows, None, R, C, self.ln_each, self.ln_post, self.l1_beta, False,
+                            1.0, tgt_c, None, None, None, None)
+        del lm, lc
+        work = torch.empty((2 * R + 8,), dtype=torch.float32, device=dev)
+        if not hasattr(self, "wloss_dev"):
+            self.wloss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev)
+        self.loss_dev.add_(self.wloss_dev, alpha=ls)          # loss = (loss_cyc + loss_stochastic) * loss_scale  (:160-163)
+        self.g32.zero_()
+        core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads)
+        return self._optimizer_step(lr, wd)
+
+    def _optimizer_step(self, lr, wd):
         if self.world_size > 1:
             torch.distributed.all_reduce(self.g32, group=self.pg)       # DDP gradient mean = sum / world (folded into grad_div)
         self.gnorm_sq.zero_()
