@@ -58,28 +58,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // erf-GELU (torch.nn.GELU(), reference modeling_finetune.py:65-82) and its derivative. erfc(|u|) by Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the bf16 resolution of the tensors it feeds): 2 MUFU + ~10 FMA per element instead of
-// erff()'s branchy ~25 — the GEMM epilogue that applies it is instruction-issue bound otherwise.
-__device__ __forceinline__ float erfc_abs_as(float a /* >= 0 */, float& e /* out: exp(-a^2) */) {
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  e = __expf(-a * a);
+// (|abs err| <= 1.5e-7, far below the bf16 resolution of the tensors it feeds) with raw MUFU rcp / ex2: ~13 issue slots per
+// element instead of erff()'s branchy ~25+ — the GEMM epilogue that applies it is instruction-issue bound.
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// q = 0.5 * erfc(|x| / sqrt(2)) = upper-tail probability of |x| ; e = exp(-x^2 / 2)
+__device__ __forceinline__ float half_erfc_abs(float x, float& e) {
+  const float t = mufu_rcp(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  e = mufu_ex2(x * (x * -0.72134752044448170f));        // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
   return p * t * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
-  const float q = 0.5f * erfc_abs_as(fabsf(x) * 0.70710678118654752f, e);   // 0.5 * erfc(|x|/sqrt2)
-  const float cdf = x >= 0.f ? 1.0f - q : q;
-  return x * cdf;
+  const float q = half_erfc_abs(x, e);
+  return fmaf(-fabsf(x), q, fmaxf(x, 0.f));             // x * Phi(x) = relu(x) - |x| * Q(|x|)
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float e;                                                                    // e = exp(-x^2/2)
-  const float q = 0.5f * erfc_abs_as(fabsf(x) * 0.70710678118654752f, e);
-  const float cdf = x >= 0.f ? 1.0f - q : q;
-  return fmaf(x * 0.39894228040143268f, e, cdf);
+  float e;
+  const float q = half_erfc_abs(x, e);
+  const float cdf = 0.5f + copysignf(0.5f - q, x);      // Phi(x)
+  return fmaf(x * 0.39894228040143268f, e, cdf);        // Phi(x) + x * phi(x)
 }
 
 // Philox4x32-10 (counter-based; Salmon et al. 2011). Same constants as cuRAND / torch.
