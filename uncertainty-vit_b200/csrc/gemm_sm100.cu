@@ -10,8 +10,10 @@
 //   QKV, proj (modeling_finetune.py:149,186), fc1/fc2 (modeling_finetune.py:76-81), lm_head (modeling_cyclical.py:219-225),
 //   patch-embed conv-as-GEMM (modeling_finetune.py:324), head (modeling_finetune.py:522).
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
-// warps 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4 of the 256-column accumulator).
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle (together one
+// warpgroup that shrinks to 40 registers), warps 4..19 = epilogue (four warpgroups grown to 104 registers; warp w owns TMEM lanes
+// 32*(w%4).. and the 64-column quarter (w-4)/4 of the 256-column accumulator) — 4 epilogue warps per scheduler hide the
+// TMEM/LDS/MUFU latencies that 2 per scheduler could not.
 #include <mutex>
 
 #include "../../include/b200vit.h"
@@ -25,9 +27,12 @@ constexpr int BLOCK_N = 256;   // tile width; each CTA of the pair stages HALF_N
 constexpr int HALF_N = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int ACC_STAGES = 2;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;   // 4 warpgroups: warp w drains TMEM lanes 32*(w%4).. and 64 accumulator columns ((w-4)/4)
+constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);   // 64 columns per epilogue warp
+constexpr int REGS_PRODUCER = 40;   // setmaxnreg budget of warpgroup 0 (TMA / MMA / TMEM-alloc / idle warps)
+constexpr int REGS_EPILOGUE = 104;  // setmaxnreg budget of the epilogue warpgroups: 128*40 + 512*104 <= 640*96
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -192,6 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_units = num_tiles * p.split_k;
 
+  if (warp < FIRST_EPI_WARP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
   if (warp == 0) {
     // ===================== TMA producer (one lane per CTA; both CTAs credit the leader's full barrier) =====================
     if (lane == 0) {
@@ -261,20 +267,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
     const int ew = warp - FIRST_EPI_WARP;
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                // column half of the accumulator
+    const int half = ew >> 2;                // 64-column quarter of the accumulator
     float* stage = reinterpret_cast<float*>(smem_raw + (stage_base - ptx::smem_u32(smem_raw))) + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int cg = lane & 7, sub = lane >> 3;      // coalesced view: 4-column group and row-within-4 of this lane
-    constexpr int CHUNKS = BLOCK_N / 2 / 32;       // 4 chunks of 32 columns per warp
+    constexpr int CHUNKS = EPI_COLS / 32;          // 2 chunks of 32 columns per warp
     const bool io = !p.epi.debug_skip_io;
     for (int u = pair; u < num_units; u += num_pairs) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
-      const int n_base = n_blk * BLOCK_N + half * (BLOCK_N / 2) + cg * 4;
+      const int n_base = n_blk * BLOCK_N + half * EPI_COLS + cg * 4;
       // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for the MMAs of this tile,
       // and for chunk c+1 while chunk c is being processed (no global-load latency on the TMEM-drain critical path)
       auto load_cols = [&](int n, float4& b4, float4& c4) {
@@ -298,7 +305,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * EPI_COLS;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_base + c * 32;
