@@ -500,8 +500,16 @@ __global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restric
     float s0 = 0.f, s1 = 0.f;
     const bf16* src = ds + ((long long)h * N + j) * ld + i;
     const long long bstride = (long long)H * N * ld;
-    for (int b = 0; b < B; ++b) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + b * bstride));
+    int b = 0;
+    for (; b + 8 <= B; b += 8) {     // 8 independent loads in flight
+      uint32_t w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const uint32_t*>(src + (long long)(b + u) * bstride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float2 v = unpack_bf16x2(w[u]); s0 += v.x; s1 += v.y; }
+    }
+    for (; b < B; ++b) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + (long long)b * bstride));
       s0 += v.x; s1 += v.y;
     }
     atomicAdd(dtable + (long long)rel_index[i * N + j] * H + h, s0);

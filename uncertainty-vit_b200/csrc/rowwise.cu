@@ -149,70 +149,83 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
 //   dt = rowscale*gamma*dx (bf16) ; dgamma += sum rowscale*t*dx ; dbias += sum dt      (dbias = grad of the branch's
 //   last Linear bias, i.e. column sum of dt)
 // ------------------------------------------------------------------------------------------------
-constexpr int CR_MAXG = 4;  // float4 groups per thread: C <= 4 * 4 * 256 = 4096
+// Column-reducing row kernels: blockDim = (column groups, ROWL row lanes), ONE CTA per SM-slot, RB_UNROLL rows in flight per thread
+// (enough bytes in flight for HBM), the row lanes are combined in shared memory and each CTA issues ONE atomic per column —
+// same-address atomics from many small CTAs were the bottleneck of the first version.
+constexpr int RB_UNROLL = 4;
 
-__global__ void __launch_bounds__(256) scale_residual_bwd_kernel(const float* __restrict__ dx, long long lddx, const bf16* __restrict__ t,
-                                                                 const float* __restrict__ rowscale, int rows_per_scale,
-                                                                 const float* __restrict__ gamma, int rows, int C,
-                                                                 bf16* __restrict__ dt, float* __restrict__ dgamma, float* __restrict__ dbias) {
-  const int ngroups = C >> 2;
-  float4 ag[CR_MAXG], ab[CR_MAXG], gm[CR_MAXG];
+__global__ void scale_residual_bwd_kernel(const float* __restrict__ dx, long long lddx, const bf16* __restrict__ t,
+                                          const float* __restrict__ rowscale, int rows_per_scale, const float* __restrict__ gamma, int rows, int C,
+                                          bf16* __restrict__ dt, float* __restrict__ dgamma, float* __restrict__ dbias) {
+  extern __shared__ float red[];   // [2][C]
+  const int c = threadIdx.x * 4;
+  const int rowl = blockDim.y;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) red[i] = 0.f;
+  __syncthreads();
+  const float4 gm = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int step = gridDim.x * rowl * RB_UNROLL;
+  for (int r0 = (blockIdx.x * rowl + threadIdx.y) * RB_UNROLL; r0 < rows; r0 += step) {
+    float4 d[RB_UNROLL], tv[RB_UNROLL];
+    float rs[RB_UNROLL];
 #pragma unroll
-  for (int i = 0; i < CR_MAXG; ++i) {
-    ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int gidx = threadIdx.x + i * 256;
-    gm[i] = (gidx < ngroups && gamma != nullptr) ? __ldg(reinterpret_cast<const float4*>(gamma) + gidx) : make_float4(1.f, 1.f, 1.f, 1.f);
-  }
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const float rs = rowscale != nullptr ? __ldg(rowscale + r / rows_per_scale) : 1.0f;
+    for (int u = 0; u < RB_UNROLL; ++u) {
+      const int r = r0 + u;
+      if (r < rows) {
+        d[u] = ld4(dx + (long long)r * lddx + c);
+        tv[u] = t != nullptr ? ld_bf16x4(t + (long long)r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rs[u] = rowscale != nullptr ? __ldg(rowscale + r / rows_per_scale) : 1.0f;
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < CR_MAXG; ++i) {
-      const int gidx = threadIdx.x + i * 256;
-      if (gidx < ngroups) {
-        const float4 d = ld4(dx + (long long)r * lddx + gidx * 4);
-        const float4 tv = t != nullptr ? ld_bf16x4(t + (long long)r * C + gidx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 o = make_float4(rs * gm[i].x * d.x, rs * gm[i].y * d.y, rs * gm[i].z * d.z, rs * gm[i].w * d.w);
-        st_bf16x4(dt + (long long)r * C + gidx * 4, o);
-        ag[i].x += rs * tv.x * d.x; ag[i].y += rs * tv.y * d.y; ag[i].z += rs * tv.z * d.z; ag[i].w += rs * tv.w * d.w;
-        ab[i].x += o.x; ab[i].y += o.y; ab[i].z += o.z; ab[i].w += o.w;
+    for (int u = 0; u < RB_UNROLL; ++u) {
+      const int r = r0 + u;
+      if (r < rows) {
+        const float4 o = make_float4(rs[u] * gm.x * d[u].x, rs[u] * gm.y * d[u].y, rs[u] * gm.z * d[u].z, rs[u] * gm.w * d[u].w);
+        st_bf16x4(dt + (long long)r * C + c, o);
+        ag.x += rs[u] * tv[u].x * d[u].x; ag.y += rs[u] * tv[u].y * d[u].y; ag.z += rs[u] * tv[u].z * d[u].z; ag.w += rs[u] * tv[u].w * d[u].w;
+        ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < CR_MAXG; ++i) {
-    const int gidx = threadIdx.x + i * 256;
-    if (gidx < ngroups) {
-      const int c = gidx * 4;
-      if (dgamma != nullptr) { atomicAdd(dgamma + c, ag[i].x); atomicAdd(dgamma + c + 1, ag[i].y); atomicAdd(dgamma + c + 2, ag[i].z); atomicAdd(dgamma + c + 3, ag[i].w); }
-      if (dbias != nullptr) { atomicAdd(dbias + c, ab[i].x); atomicAdd(dbias + c + 1, ab[i].y); atomicAdd(dbias + c + 2, ab[i].z); atomicAdd(dbias + c + 3, ab[i].w); }
-    }
+  atomicAdd(&red[c], ag.x); atomicAdd(&red[c + 1], ag.y); atomicAdd(&red[c + 2], ag.z); atomicAdd(&red[c + 3], ag.w);
+  atomicAdd(&red[C + c], ab.x); atomicAdd(&red[C + c + 1], ab.y); atomicAdd(&red[C + c + 2], ab.z); atomicAdd(&red[C + c + 3], ab.w);
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C; i += blockDim.x * blockDim.y) {
+    if (dgamma != nullptr) atomicAdd(dgamma + i, red[i]);
+    if (dbias != nullptr) atomicAdd(dbias + i, red[C + i]);
   }
 }
 
-// out[c] += sum_r x[r, c]   (bias gradients: fc1.bias from dpre, q_bias / v_bias from dqkv)
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ out) {
-  const int ngroups = C >> 2;
-  float4 acc[CR_MAXG];
+// out[c] += sum_r x[r, c]   (bias gradients, e.g. fc1.bias from dpre). One thread owns one 8-column group (16-byte loads).
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ out) {
+  extern __shared__ float red[];   // [C]
+  const int c = threadIdx.x * 8;
+  const int rowl = blockDim.y;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C; i += blockDim.x * blockDim.y) red[i] = 0.f;
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int step = gridDim.x * rowl * RB_UNROLL;
+  for (int r0 = (blockIdx.x * rowl + threadIdx.y) * RB_UNROLL; r0 < rows; r0 += step) {
+    uint4 v[RB_UNROLL];
 #pragma unroll
-  for (int i = 0; i < CR_MAXG; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    for (int u = 0; u < RB_UNROLL; ++u)
+      if (r0 + u < rows) v[u] = *reinterpret_cast<const uint4*>(x + (long long)(r0 + u) * ldx + c);
 #pragma unroll
-    for (int i = 0; i < CR_MAXG; ++i) {
-      const int gidx = threadIdx.x + i * 256;
-      if (gidx < ngroups) {
-        const float4 v = ld_bf16x4(x + (long long)r * ldx + gidx * 4);
-        acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+    for (int u = 0; u < RB_UNROLL; ++u)
+      if (r0 + u < rows) {
+        const uint32_t* w = &v[u].x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+        }
       }
-    }
   }
 #pragma unroll
-  for (int i = 0; i < CR_MAXG; ++i) {
-    const int gidx = threadIdx.x + i * 256;
-    if (gidx < ngroups) {
-      const int c = gidx * 4;
-      atomicAdd(out + c, acc[i].x); atomicAdd(out + c + 1, acc[i].y); atomicAdd(out + c + 2, acc[i].z); atomicAdd(out + c + 3, acc[i].w);
-    }
-  }
+  for (int k = 0; k < 8; ++k) atomicAdd(&red[c + k], acc[k]);
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < C; i += blockDim.x * blockDim.y) atomicAdd(out + i, red[i]);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n4, long long n) {
@@ -372,7 +385,7 @@ extern "C" int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const fl
   if (rows == 0) return 0;
   const int sms = b200vit_num_sms();
   int grid = (rows + 7) / 8;
-  if (grid > sms * 4) grid = sms * 4;
+  if (grid > sms * 2) grid = sms * 2;
   const size_t smem = 2 * C * sizeof(float);
 #define LN_BWD(NV)                                                                                                              \
   if (dy_is_f32) ln_bwd_kernel<NV, float><<<grid, 256, smem, STREAM>>>(static_cast<const float*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta); \
@@ -390,23 +403,34 @@ extern "C" int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const v
                                           const float* gamma, int32_t rows, int32_t C, void* dt_bf16, float* dgamma, float* dbias,
                                           void* stream) {
   B200_CHECK_ARG(dx != nullptr && dt_bf16 != nullptr, "scale_residual_bwd: null pointer");
-  B200_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 4 * 256 * CR_MAXG, "scale_residual_bwd: bad C=%d", C);
+  B200_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 4096, "scale_residual_bwd: C=%d must be a multiple of 4, <= 4096", C);
   B200_CHECK_ARG(rowscale == nullptr || rows_per_scale > 0, "scale_residual_bwd: rows_per_scale must be > 0");
   if (rows == 0) return 0;
   const int sms = b200vit_num_sms();
-  int grid = rows < sms * 4 ? rows : sms * 4;
-  scale_residual_bwd_kernel<<<grid, 256, 0, STREAM>>>(dx, lddx, static_cast<const bf16*>(t_bf16), rowscale, rows_per_scale > 0 ? rows_per_scale : 1, gamma, rows, C,
-                                                       static_cast<bf16*>(dt_bf16), dgamma, dbias);
+  const int tx = C / 4;
+  int ty = 768 / tx;                       // ~768 threads per CTA
+  if (ty < 1) ty = 1;
+  if (ty > 8) ty = 8;
+  int grid = (rows + ty * RB_UNROLL - 1) / (ty * RB_UNROLL);
+  if (grid > sms * 2) grid = sms * 2;
+  scale_residual_bwd_kernel<<<grid, dim3(tx, ty), 2 * C * sizeof(float), STREAM>>>(dx, lddx, static_cast<const bf16*>(t_bf16), rowscale, rows_per_scale > 0 ? rows_per_scale : 1,
+                                                          gamma, rows, C, static_cast<bf16*>(dt_bf16), dgamma, dbias);
   B200_CHECK_LAUNCH("scale_residual_bwd");
   return 0;
 }
 
 extern "C" int b200vit_colsum_bf16(const void* x, int64_t ldx, int32_t rows, int32_t C, float* out, void* stream) {
-  B200_CHECK_ARG(x != nullptr && out != nullptr && C > 0 && C % 4 == 0 && C <= 4 * 256 * CR_MAXG && ldx % 4 == 0, "colsum_bf16: bad arguments (C=%d)", C);
+  B200_CHECK_ARG(x != nullptr && out != nullptr && C > 0 && C % 8 == 0 && C <= 8192 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "colsum_bf16: C and ldx must be multiples of 8 (16-byte rows), C <= 8192 (C=%d)", C);
   if (rows == 0) return 0;
   const int sms = b200vit_num_sms();
-  int grid = rows < sms * 4 ? rows : sms * 4;
-  colsum_bf16_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const bf16*>(x), ldx, rows, C, out);
+  const int tx = C / 8;
+  int ty = 768 / tx;
+  if (ty < 1) ty = 1;
+  if (ty > 8) ty = 8;
+  int grid = (rows + ty * RB_UNROLL - 1) / (ty * RB_UNROLL);
+  if (grid > sms * 2) grid = sms * 2;
+  colsum_bf16_kernel<<<grid, dim3(tx, ty), C * sizeof(float), STREAM>>>(static_cast<const bf16*>(x), ldx, rows, C, out);
   B200_CHECK_LAUNCH("colsum_bf16");
   return 0;
 }
