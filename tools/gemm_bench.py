@@ -66,3 +66,10 @@ if __name__ == "__main__":
         run("fc1 wgrad atomic" + tag, 3072, 768, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, **kw)
         run("fc2 wgrad atomic" + tag, 768, 3072, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, **kw)
         run("square 8192 bf16" + tag, 8192, 8192, 8192, reps=5, nbuf=1, **kw)
+        if not skip:
+            for sk in (1, 2, 3, 4, 6, 8, 12):
+                run(f"fc1 wgrad split_k={sk}", 3072, 768, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, split_k=sk)
+            for sk in (2, 4, 6, 8, 12, 16):
+                run(f"proj wgrad split_k={sk}", 768, 768, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, split_k=sk)
+            for sk in (1, 2, 3, 4, 6, 8):
+                run(f"qkv wgrad split_k={sk}", 2304, 768, M, a_mn=True, b_mn=True, epi=ops.EPI_F32_ATOMIC, split_k=sk)

@@ -27,20 +27,27 @@ constexpr int BLOCK_N = 256;   // tile width; each CTA of the pair stages HALF_N
 constexpr int HALF_N = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 5;
 constexpr int ACC_STAGES = 2;
-constexpr int NUM_EPI_WARPS = 16;   // 4 warpgroups: warp w drains TMEM lanes 32*(w%4).. and 64 accumulator columns ((w-4)/4)
-constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);   // 64 columns per epilogue warp
-constexpr int REGS_PRODUCER = 40;   // setmaxnreg budget of warpgroup 0 (TMA / MMA / TMEM-alloc / idle warps)
-constexpr int REGS_EPILOGUE = 104;  // setmaxnreg budget of the epilogue warpgroups: 128*40 + 512*104 <= 640*96
+// Two launch shapes, chosen per epilogue (measured, profiles/r1_gemm_shapes.log):
+//   math-heavy epilogues (GELU, dGELU): 16 epilogue warps (4 per scheduler, 64 columns each), 5-stage ring, setmaxnreg 40 / 104
+//   I/O epilogues (bf16, residual, fp32, split-K atomics, ELU+1): 8 epilogue warps (128 columns each), 6-stage ring
+template <int MODE>
+struct Cfg {
+  static constexpr bool kWide = (MODE == B200VIT_EPI_GELU || MODE == B200VIT_EPI_DGELU);
+  static constexpr int STAGES = kWide ? 5 : 6;
+  static constexpr int NUM_EPI_WARPS = kWide ? 16 : 8;
+  static constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);
+  static constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int SMEM_BYTES = STAGES * (BLOCK_M * BLOCK_K * 2 + HALF_N * BLOCK_K * 2) + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+  static constexpr int REGS_PRODUCER = 40;    // setmaxnreg budget of warpgroup 0 (TMA / MMA / TMEM-alloc / idle warps)
+  static constexpr int REGS_EPILOGUE = kWide ? 104 : 208;   // 128*40 + 512*104 <= 640*96 ; 128*40 + 256*208 <= 384*168
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+};
 constexpr int FIRST_EPI_WARP = 4;
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // 32 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
-static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 
 struct EpiParams {
@@ -147,9 +154,14 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
 }
 
 template <bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<MODE>::NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
+  constexpr int STAGES = Cfg<MODE>::STAGES;
+  constexpr int NUM_EPI_WARPS = Cfg<MODE>::NUM_EPI_WARPS;
+  constexpr int EPI_COLS = Cfg<MODE>::EPI_COLS;
+  constexpr int REGS_PRODUCER = Cfg<MODE>::REGS_PRODUCER;
+  constexpr int REGS_EPILOGUE = Cfg<MODE>::REGS_EPILOGUE;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned stage bases
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -275,7 +287,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const int cg = lane & 7, sub = lane >> 3;      // coalesced view: 4-column group and row-within-4 of this lane
-    constexpr int CHUNKS = EPI_COLS / 32;          // 2 chunks of 32 columns per warp
+    constexpr int CHUNKS = EPI_COLS / 32;          // 2 or 4 chunks of 32 columns per warp
     const bool io = !p.epi.debug_skip_io;
     for (int u = pair; u < num_units; u += num_pairs) {
       const int tile = u / p.split_k;
@@ -412,17 +424,18 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-// split-K factor maximising wave efficiency on `sms` SMs (fewest splits on ties), >= 8 k-blocks per split.
-int pick_split_k(int tiles, int num_kb, int sms) {
-  if (tiles >= sms) return 1;
+// split-K factor for the fp32-atomic (wgrad) epilogue. Cost model in units of one k-block (512 tensor cycles), fitted to
+// profiles/r1_gemm_shapes.log: every wave of work units costs its k-blocks plus a small turnaround; only the LAST epilogue is
+// exposed (earlier ones overlap the next unit's mainloop through the double-buffered TMEM accumulator).
+int pick_split_k(int tiles, int num_kb, int pairs) {
   int best = 1;
-  double best_eff = 0.0;
+  double best_cost = 1e30;
   const int max_split = num_kb / 8 > 0 ? num_kb / 8 : 1;
   for (int s = 1; s <= max_split && s <= 64; ++s) {
-    const int units = tiles * s;
-    const int waves = (units + sms - 1) / sms;
-    const double eff = (double)units / ((double)waves * sms);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    const int kbs = (num_kb + s - 1) / s;
+    const int waves = (tiles * s + pairs - 1) / pairs;
+    const double cost = (double)waves * (kbs + 4) + 16.0;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
 }
@@ -431,7 +444,7 @@ template <bool A_MN, bool B_MN, int MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::SMEM_BYTES);
     if (e != cudaSuccess) {
       b200vit_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
@@ -440,8 +453,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.blockDim = dim3(Cfg<MODE>::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<MODE>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
