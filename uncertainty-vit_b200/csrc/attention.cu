@@ -37,21 +37,26 @@ struct FwdRowState {
   float m[2], l[2];
 };
 
-// One chunk of NTS 8-key tiles starting at key j0 for the 16-query tile of this warp.
+// Bias values of one chunk of up to 4 8-key tiles for the two query rows of this thread.
+struct BiasRegs {
+  float2 r0[4], r1[4];
+};
+template <int NTS>
+__device__ __forceinline__ void load_bias(BiasRegs& b, const float* brow0, const float* brow1, int j0, int quad) {
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) {
+    b.r0[nt] = __ldg(reinterpret_cast<const float2*>(brow0 + j0 + nt * 8 + quad * 2));
+    b.r1[nt] = __ldg(reinterpret_cast<const float2*>(brow1 + j0 + nt * 8 + quad * 2));
+  }
+}
+
+// One chunk of NTS (<= 4) 8-key tiles starting at key j0 for the 16-query tile of this warp. `cur` holds this chunk's bias
+// (fetched while the previous chunk was being processed).
 template <int NTS, bool DROP, bool HAS_BIAS>
 __device__ __forceinline__ void fwd_chunk(const AttnFwdParams& p, const bf16* sK, const bf16* sV, const uint32_t (&qa)[4][4], FwdRowState& st,
-                                          int j0, int i0, int i1, const float* brow0, const float* brow1, int bh, int lane, float sl2,
-                                          uint32_t thresh) {
+                                          int j0, int i0, int i1, const BiasRegs& cur, int bh, int lane, float sl2, uint32_t thresh) {
   const int quad = lane & 3;
   const int N = p.N;
-  float2 bv0[NTS], bv1[NTS];
-  if (HAS_BIAS) {   // requested first: the L2 latency overlaps the QK^T tensor work
-#pragma unroll
-    for (int nt = 0; nt < NTS; ++nt) {
-      bv0[nt] = __ldg(reinterpret_cast<const float2*>(brow0 + j0 + nt * 8 + quad * 2));
-      bv1[nt] = __ldg(reinterpret_cast<const float2*>(brow1 + j0 + nt * 8 + quad * 2));
-    }
-  }
   float s[NTS][4];
 #pragma unroll
   for (int nt = 0; nt < NTS; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -69,8 +74,8 @@ __device__ __forceinline__ void fwd_chunk(const AttnFwdParams& p, const bf16* sK
 #pragma unroll
   for (int nt = 0; nt < NTS; ++nt) {
     if (HAS_BIAS) {   // bias is pre-multiplied by log2(e); padding columns hold -inf (key mask)
-      s[nt][0] = fmaf(s[nt][0], sl2, bv0[nt].x); s[nt][1] = fmaf(s[nt][1], sl2, bv0[nt].y);
-      s[nt][2] = fmaf(s[nt][2], sl2, bv1[nt].x); s[nt][3] = fmaf(s[nt][3], sl2, bv1[nt].y);
+      s[nt][0] = fmaf(s[nt][0], sl2, cur.r0[nt].x); s[nt][1] = fmaf(s[nt][1], sl2, cur.r0[nt].y);
+      s[nt][2] = fmaf(s[nt][2], sl2, cur.r1[nt].x); s[nt][3] = fmaf(s[nt][3], sl2, cur.r1[nt].y);
     } else {
       const int j = j0 + nt * 8 + quad * 2;
       s[nt][0] = j < N ? s[nt][0] * sl2 : -INFINITY; s[nt][1] = j + 1 < N ? s[nt][1] * sl2 : -INFINITY;
@@ -95,52 +100,43 @@ __device__ __forceinline__ void fwd_chunk(const AttnFwdParams& p, const bf16* sK
     l1 += s[nt][2] + s[nt][3];
   }
   st.l[0] += l0; st.l[1] += l1;
-  if (DROP) {
+  if (DROP) {   // NTS <= 4: one 32-key Philox group per chunk (j0 is a multiple of 32)
+    uint32_t w0 = 0u, w1 = 0u;   // keep bits of rows i0 / i1 for keys j0 .. j0+31 (this thread: 2 bits per 8-key tile)
+    if (p.keep_in == nullptr) {
+      const Philox4 r0 = dropout_group(p.seed, p.stream_id, bh, i0, quad, j0 >> 5);
+      const Philox4 r1 = dropout_group(p.seed, p.stream_id, bh, i1, quad, j0 >> 5);
 #pragma unroll
-    for (int g = 0; g < (NTS + 3) / 4; ++g) {
-      uint32_t w0 = 0u, w1 = 0u;   // keep bits of rows i0 / i1 for keys j0 + g*32 .. +31 (this thread: 2 bits per 8-key tile)
-      if (p.keep_in == nullptr) {
-        const Philox4 r0 = dropout_group(p.seed, p.stream_id, bh, i0, quad, (j0 >> 5) + g);
-        const Philox4 r1 = dropout_group(p.seed, p.stream_id, bh, i1, quad, (j0 >> 5) + g);
-#pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) {
-          if (g * 4 + n4 < NTS) {
-            const int sh = n4 * 8 + quad * 2;
-            w0 |= (dropout_u16(r0, n4 * 2) >= thresh ? 1u : 0u) << sh;
-            w0 |= (dropout_u16(r0, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
-            w1 |= (dropout_u16(r1, n4 * 2) >= thresh ? 1u : 0u) << sh;
-            w1 |= (dropout_u16(r1, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) {
-          if (g * 4 + n4 < NTS) {
-            const int j = j0 + (g * 4 + n4) * 8 + quad * 2;
-            const int sh = n4 * 8 + quad * 2;
-            if (i0 < N && j < N && p.keep_in[((long long)bh * N + i0) * N + j]) w0 |= 1u << sh;
-            if (i0 < N && j + 1 < N && p.keep_in[((long long)bh * N + i0) * N + j + 1]) w0 |= 2u << sh;
-            if (i1 < N && j < N && p.keep_in[((long long)bh * N + i1) * N + j]) w1 |= 1u << sh;
-            if (i1 < N && j + 1 < N && p.keep_in[((long long)bh * N + i1) * N + j + 1]) w1 |= 2u << sh;
-          }
-        }
+      for (int n4 = 0; n4 < NTS; ++n4) {
+        const int sh = n4 * 8 + quad * 2;
+        w0 |= (dropout_u16(r0, n4 * 2) >= thresh ? 1u : 0u) << sh;
+        w0 |= (dropout_u16(r0, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
+        w1 |= (dropout_u16(r1, n4 * 2) >= thresh ? 1u : 0u) << sh;
+        w1 |= (dropout_u16(r1, n4 * 2 + 1) >= thresh ? 2u : 0u) << sh;
       }
+    } else {
 #pragma unroll
-      for (int n4 = 0; n4 < 4; ++n4) {
-        if (g * 4 + n4 < NTS) {
-          const int nt = g * 4 + n4, sh = n4 * 8 + quad * 2;
-          if (!((w0 >> sh) & 1u)) s[nt][0] = 0.f;
-          if (!((w0 >> sh) & 2u)) s[nt][1] = 0.f;
-          if (!((w1 >> sh) & 1u)) s[nt][2] = 0.f;
-          if (!((w1 >> sh) & 2u)) s[nt][3] = 0.f;
-        }
+      for (int n4 = 0; n4 < NTS; ++n4) {
+        const int j = j0 + n4 * 8 + quad * 2;
+        const int sh = n4 * 8 + quad * 2;
+        if (i0 < N && j < N && p.keep_in[((long long)bh * N + i0) * N + j]) w0 |= 1u << sh;
+        if (i0 < N && j + 1 < N && p.keep_in[((long long)bh * N + i0) * N + j + 1]) w0 |= 2u << sh;
+        if (i1 < N && j < N && p.keep_in[((long long)bh * N + i1) * N + j]) w1 |= 1u << sh;
+        if (i1 < N && j + 1 < N && p.keep_in[((long long)bh * N + i1) * N + j + 1]) w1 |= 2u << sh;
       }
-      w0 |= __shfl_xor_sync(0xffffffffu, w0, 1); w0 |= __shfl_xor_sync(0xffffffffu, w0, 2);
-      w1 |= __shfl_xor_sync(0xffffffffu, w1, 1); w1 |= __shfl_xor_sync(0xffffffffu, w1, 2);
-      if (quad == 0) {
-        if (i0 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i0) * 32 + (j0 >> 3) + g * 4) = w0;
-        if (i1 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i1) * 32 + (j0 >> 3) + g * 4) = w1;
-      }
+    }
+#pragma unroll
+    for (int n4 = 0; n4 < NTS; ++n4) {
+      const int sh = n4 * 8 + quad * 2;
+      if (!((w0 >> sh) & 1u)) s[n4][0] = 0.f;
+      if (!((w0 >> sh) & 2u)) s[n4][1] = 0.f;
+      if (!((w1 >> sh) & 1u)) s[n4][2] = 0.f;
+      if (!((w1 >> sh) & 2u)) s[n4][3] = 0.f;
+    }
+    w0 |= __shfl_xor_sync(0xffffffffu, w0, 1); w0 |= __shfl_xor_sync(0xffffffffu, w0, 2);
+    w1 |= __shfl_xor_sync(0xffffffffu, w1, 1); w1 |= __shfl_xor_sync(0xffffffffu, w1, 2);
+    if (quad == 0) {
+      if (i0 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i0) * 32 + (j0 >> 3)) = w0;
+      if (i1 < N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * N + i1) * 32 + (j0 >> 3)) = w1;
     }
   }
   // O += P~ V   (the 1/(1-p) rescale of the kept probabilities is folded into the final normalisation)
@@ -196,14 +192,24 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 2) attn_fwd_kernel(const AttnF
     const int i0 = mt * 16 + qrow, i1 = i0 + 8;
     const float* brow0 = HAS_BIAS ? p.bias + ((long long)h * N + min(i0, N - 1)) * p.ld_bias : nullptr;
     const float* brow1 = HAS_BIAS ? p.bias + ((long long)h * N + min(i1, N - 1)) * p.ld_bias : nullptr;
-    int j0 = 0;
-    for (; j0 + 64 <= n_pad; j0 += 64) fwd_chunk<8, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh);
-    switch ((n_pad - j0) >> 3) {   // tail: only the 8-key tiles that exist
-      case 6: fwd_chunk<6, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
-      case 4: fwd_chunk<4, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
-      case 2: fwd_chunk<2, DROP, HAS_BIAS>(p, sK, sV, qa, st, j0, i0, i1, brow0, brow1, bh, lane, sl2, thresh); break;
-      default: break;
+    // 32-key chunks; the bias of chunk c+1 is requested before chunk c is processed (software pipeline over the L2 latency)
+    BiasRegs bcur, bnext;
+    const int nfull = n_pad >> 5;                 // full 32-key chunks; a 16-key tail remains when n_pad % 32 != 0
+    const bool tail = (n_pad & 31) != 0;
+    if (HAS_BIAS) {
+      if (nfull > 0) load_bias<4>(bcur, brow0, brow1, 0, quad);
+      else load_bias<2>(bcur, brow0, brow1, 0, quad);
     }
+#pragma unroll 1
+    for (int c = 0; c < nfull; ++c) {
+      if (HAS_BIAS) {
+        if (c + 1 < nfull) load_bias<4>(bnext, brow0, brow1, (c + 1) * 32, quad);
+        else if (tail) load_bias<2>(bnext, brow0, brow1, (c + 1) * 32, quad);
+      }
+      fwd_chunk<4, DROP, HAS_BIAS>(p, sK, sV, qa, st, c * 32, i0, i1, bcur, bh, lane, sl2, thresh);
+      bcur = bnext;
+    }
+    if (tail) fwd_chunk<2, DROP, HAS_BIAS>(p, sK, sV, qa, st, nfull * 32, i0, i1, bcur, bh, lane, sl2, thresh);
     // finalise: row sums across the quad, normalise (and apply the dropout rescale), store
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -341,22 +347,30 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 1) attn_bwd_kernel(const AttnB
     const float* btB = p.bias_t != nullptr ? p.bias_t + ((long long)h * N + min(jB, N - 1)) * p.ld_bias : nullptr;
     const uint8_t* kb_base = drop ? p.keep_bits + (long long)bh * N * 32 + jt * 2 : nullptr;
 
+    // operands of the element-wise phase (bias^T, packed keep bits) are fetched ONE STEP AHEAD: their L2 latency is covered by a
+    // whole step of tensor + element-wise work instead of sitting on the critical path of a 13-warp CTA
+    float2 nbA[2], nbB[2];
+    uint32_t nkw[2][2];
+    auto fetch = [&](int it_, float2 (&fa)[2], float2 (&fb)[2], uint32_t (&fk)[2][2]) {
+      const int ia_ = it_ * 16 + quad * 2;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        fa[n] = btA != nullptr ? __ldg(reinterpret_cast<const float2*>(btA + ia_ + n * 8)) : make_float2(0.f, 0.f);
+        fb[n] = btB != nullptr ? __ldg(reinterpret_cast<const float2*>(btB + ia_ + n * 8)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = ia_ + n * 8 + e;
+          fk[n][e] = (drop && i < N) ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(kb_base + (long long)i * 32)) : 0xffffu;
+        }
+      }
+    };
+    fetch(0, nbA, nbB, nkw);
 #pragma unroll 1
     for (int it = 0; it < ntile; ++it) {
       const int ia = it * 16 + quad * 2;   // queries ia, ia+1 (n-tile 0) and ia+8, ia+9 (n-tile 1)
-      // operands of the element-wise phase are requested before the MMAs so their latency overlaps the tensor work
-      float2 bA[2], bB[2];
-      uint32_t kw[2][2];
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        bA[n] = btA != nullptr ? __ldg(reinterpret_cast<const float2*>(btA + ia + n * 8)) : make_float2(0.f, 0.f);
-        bB[n] = btB != nullptr ? __ldg(reinterpret_cast<const float2*>(btB + ia + n * 8)) : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = ia + n * 8 + e;
-          kw[n][e] = (drop && i < N) ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(kb_base + (long long)i * 32)) : 0xffffu;
-        }
-      }
+      float2 bA[2] = {nbA[0], nbA[1]}, bB[2] = {nbB[0], nbB[1]};
+      uint32_t kw[2][2] = {{nkw[0][0], nkw[0][1]}, {nkw[1][0], nkw[1][1]}};
+      if (it + 1 < ntile) fetch(it + 1, nbA, nbB, nkw);
       // S^T = K_j Q_i^T and dP^T = V_j dO_i^T : [16 keys x 16 queries]
       float st[2][4], dp[2][4];
 #pragma unroll
