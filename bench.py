@@ -54,6 +54,13 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None          # host-time window of the timed regions (value + e2e)
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -65,14 +72,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t_begin is not None and (ts < self.t_begin or (self.t_end is not None and ts > self.t_end + 0.05)):
+                continue                       # keep only samples taken while the timed steps were running
             f = [c.strip() for c in r.split(",")]
             if len(f) < 7:
                 continue
@@ -173,16 +182,17 @@ def run_b200(args):
         return float(t.item())
 
     lr_at = lambda i: float(lr_sched[min(i + 50, len(lr_sched) - 1)])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         eng.step(*dev_batches[i % 2], lr=lr_at(i))
     barrier()
     # ---- value: K steps, inputs resident in HBM, CUDA events
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for i in range(args.steps):
         loss = eng.step(*dev_batches[i % 2], lr=lr_at(i))
@@ -190,7 +200,6 @@ def run_b200(args):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (ops.LAUNCHES - launches0)
-    clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss.item())
     # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs
     for i in range(2):
@@ -201,6 +210,8 @@ def run_b200(args):
         eng.step_host(*host[i % 2], lr=lr_at(i))
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     h2d = host[0][0].numel() * 4 + BATCH * 196 + BATCH * MASKED * 4
     # ---- roofline: CUDA events around every tcgen05 GEMM launch inside 2 instrumented steps
     roof = None
@@ -243,7 +254,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -550,7 +550,7 @@ cudaError_t launch_fwd(const AttnFwdParams& p, cudaStream_t stream) {
 
 #define STREAM static_cast<cudaStream_t>(stream)
 
-extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
+extern "C" int b200vit_attn_fwd_mma(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                                 float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
                                 uint8_t* keep_bits, void* stream) {
   B200_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_fwd: null pointer");
