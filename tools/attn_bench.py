@@ -86,7 +86,7 @@ def bench():
         dqkv = torch.empty(B, N, 3, H, 64, dtype=torch.bfloat16, device=dev)
         idx = torch.randint(0, 732, (N, N), dtype=torch.int32, device=dev)
         dtable = torch.zeros(732, H, device=dev)
-        ds_work = torch.empty(B, H, N, ops.attn_ld(N), dtype=torch.bfloat16, device=dev)
+        ds_work = ops.attn_bwd_workspace(B, H, N, dev)
         for p in (0.0, 0.05):
             ops.attn_fwd(qkvs[0], bias_f, B, H, N, scale, p, 1, 2, None, outs[0], lse, bits if p > 0 else None)
             us = timeit(lambda i: ops.attn_bwd(qkvs[0], outs[0], douts[i % R], lse, bias_t, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv,
@@ -94,6 +94,31 @@ def bench():
             print(f"attn_bwd (+relbias_grad) p={p}: {us:8.1f} us")
 
 
+def ncu_run():
+    """three launches per variant at the step's shape (for `ncu -k regex:attn`)"""
+    B, H, N = 128, 12, 197
+    qkv = torch.randn(B, N, 3, H, 64, device=dev).bfloat16()
+    out = torch.empty(B, N, H * 64, dtype=torch.bfloat16, device=dev)
+    bias_f, bias_t = ops.pad_attn_bias(torch.randn(H, N, N, device=dev) * 0.5)
+    lse = torch.empty(B, H, N, device=dev)
+    bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=dev)
+    for p in (0.0, 0.05):
+        for _ in range(3):
+            ops.attn_fwd(qkv, bias_f, B, H, N, 0.125, p, 1, 2, None, out, lse, bits if p > 0 else None)
+    if "--bwd" in sys.argv:
+        dout = torch.randn(B, N, H * 64, device=dev).bfloat16()
+        dqkv = torch.empty(B, N, 3, H, 64, dtype=torch.bfloat16, device=dev)
+        idx = torch.randint(0, 732, (N, N), dtype=torch.int32, device=dev)
+        dtable = torch.zeros(732, H, device=dev)
+        ds_work = ops.attn_bwd_workspace(B, H, N, dev)
+        for _ in range(2):
+            ops.attn_bwd(qkv, out, dout, lse, bias_t, bits, idx, dtable, B, H, N, 0.125, 0.05, dqkv, ds_work=ds_work)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
-    parity()
-    bench()
+    if "--ncu" in sys.argv:
+        ncu_run()
+    else:
+        parity()
+        bench()

@@ -165,7 +165,7 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
     ops.linear_wgrad(dt, s["attn_out"], g("attn.proj.weight"))
     ops.gemm(dt, ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.attn_bwd(s["qkv"], s["attn_out"], dh, s["lse"], bias, s["keep_bits"], ps.rel_index_i32() if dtable is not None else None, dtable,
-                 B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv, ds_work=ws.get("ds"), dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"))
+                 B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv, ds_work=ws.get("attn_ws"), dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"))
     ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))
     ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"))
@@ -176,7 +176,8 @@ def backward_workspace(cfg: VitConfig, B: int, dev) -> Dict[str, torch.Tensor]:
     bf = torch.bfloat16
     T = cfg.tokens
     return dict(dt=_empty((M, C), bf, dev), dpre=_empty((M, Hd), bf, dev), dh=_empty((M, C), bf, dev), dqkv=_empty((M, 3 * C), bf, dev),
-                ds=torch.zeros((B, cfg.num_heads, T, (T + 15) // 16 * 16), dtype=bf, device=dev))
+                ds=torch.zeros((B, cfg.num_heads, T, (T + 15) // 16 * 16), dtype=bf, device=dev),
+                attn_ws=ops.attn_bwd_workspace(B, cfg.num_heads, T, dev))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -571,7 +571,7 @@ extern "C" int b200vit_attn_fwd_mma(const void* qkv, const float* bias, int64_t 
   return 0;
 }
 
-extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
+extern "C" int b200vit_attn_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
                                 const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                                 float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                                 void* dqkv, void* stream) {

@@ -327,7 +327,568 @@ cudaError_t launch_fwd100(const CUtensorMap& tq, const CUtensorMap& tkv, const C
   return cudaGetLastError();
 }
 
+
+// =================================================================================================================
+// backward
+// =================================================================================================================
+//   P = 2^(s2 - lse2) ; dP~ = dO V^T ; dP = c M o dP~ ; dS = P o (dP - D) ; dV = P~^T dO ; dK = scale dS^T Q ; dQ = scale dS K
+// Three kernels:
+//   attn_bwd_prep_kernel  : D_i = sum_d dO[i,d] O[i,d] and the keep mask transposed to [key][query bits] (one pass over O, dO).
+//   attn_bwd_kv_kernel    : one CTA per (batch, head, 128-KEY tile), two CTAs per SM. TMEM lane == key row, one thread per key
+//                           row. Per 64-query quarter: S^T = K Q^T and dP~^T = V dO^T (tcgen05, 64 TMEM columns each), the
+//                           element-wise phase straight out of TMEM (bias^T tile through a TMA ring, lse / D broadcast from smem,
+//                           keep bits from registers), P~^T and dS^T written back to TMEM as bf16 and consumed in place as the
+//                           A operands of dV += P~^T dO and dK += dS^T Q (accumulators in TMEM columns [128, 256)); dS^T is also
+//                           streamed to the workspace for the dQ kernel and the relative-position-bias table gradient.
+//   attn_bwd_dq_kernel    : one CTA per (batch, head, 128-query tile): dQ = scale * dS K with dS^T read back through TMA as an
+//                           MN-major A operand, K as an MN-major B operand; q_bias gradient fused.
+constexpr int KV_SM_K = 0;                          // 128 key rows x 128 B
+constexpr int KV_SM_V = 16384;
+constexpr int KV_SM_Q = 32768;                      // 2 stages x (64 query rows x 128 B)
+constexpr int KV_SM_DO = 49152;                     // 2 stages x (64 query rows x 128 B)
+constexpr int KV_SM_BIAS = 65536;                   // 2 stages x (128 key rows x 32 fp32)
+constexpr int KV_SM_LSE = 98304;                    // NMAX fp32 (log2 domain; +inf past N)
+constexpr int KV_SM_D = KV_SM_LSE + 1024;           // NMAX fp32
+constexpr int KV_SM_BAR = KV_SM_D + 1024;
+constexpr int KV_SMEM = KV_SM_BAR + 128 + 1024;
+constexpr int KV_THREADS = 192;                     // warps 0-3 element-wise, warp 4 TMA + MMA, warp 5 bias ring
+constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns
+static_assert(2 * KV_SMEM + 2048 <= 232448, "two CTAs per SM");
+
+struct BwdKvParams {
+  const float* lse;          // [B, H, N]
+  const float* dvec;         // [B, H, N]   D_i
+  const uint32_t* keep_t;    // [B, H, N(key), 8]  bit (i % 32) of word i / 32 = keep(i, j)
+  bf16* ds_out;              // [B, H, N(key), ld_ds(query)]
+  int ld_ds;
+  bf16* dqkv;                // [B, N, 3, H, 64]
+  float* dv_bias;            // [H*64] += or null
+  int B, H, N, n_pad, k_tiles;
+  float scale, sl2, inv_keep;
+};
+
+// column sums over the 32 lanes of a warp of 64 per-lane values: recursive halving (62 shuffles); lane l ends with columns 2l, 2l+1
+__device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane, float& c0, float& c1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 32], keep = up ? v[i + 32] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 1;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  c0 = v[0]; c1 = v[1];
+}
+
+// D[b, h, i] = sum_d dO[b, i, h, d] * O[b, i, h, d] : one warp per token row, 8 lanes per head, 4 heads per pass.
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ dvec,
+                                                            int B, int H, int N) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * N;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int b = (int)(r / N), i = (int)(r - (long long)b * N);
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      const int h = h0 + (lane >> 3);
+      float acc = 0.f;
+      if (h < H) {
+        const long long off = (r * H + h) * HD + (lane & 7) * 8;
+        const uint4 ov = *reinterpret_cast<const uint4*>(out + off), dv = *reinterpret_cast<const uint4*>(dout + off);
+        const uint32_t* op = &ov.x; const uint32_t* dp = &dv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(op[k]), d = unpack_bf16x2(dp[k]);
+          acc += a.x * d.x + a.y * d.y;
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (h < H && (lane & 7) == 0) dvec[((long long)b * H + h) * N + i] = acc;
+    }
+  }
+}
+
+// keep_bits [BH, N(query i), 8 words over keys] -> keep_t [BH, N(key j), 8 words over queries]: 32x32 bit-block transposes by ballot
+__global__ void __launch_bounds__(256) keep_transpose_kernel(const uint32_t* __restrict__ keep_bits, uint32_t* __restrict__ keep_t, int BH, int N) {
+  const int lane = threadIdx.x & 31;
+  const int blocks = (N + 31) >> 5;
+  const long long total = (long long)BH * blocks * blocks;
+  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int jb = (int)(t % blocks), ib = (int)((t / blocks) % blocks);
+    const long long bh = t / ((long long)blocks * blocks);
+    const int i = ib * 32 + lane;
+    const uint32_t w = i < N ? keep_bits[(bh * N + i) * 8 + jb] : 0u;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const uint32_t col = __ballot_sync(0xffffffffu, (w >> e) & 1u);
+      if (lane == e) mine = col;
+    }
+    const int j = jb * 32 + lane;
+    if (j < N) keep_t[(bh * N + j) * 8 + ib] = mine;
+  }
+}
+
+template <int COLS, bool DROP, bool HAS_BIAS>
+__device__ __forceinline__ void bwd_half(const BwdKvParams& p, uint32_t trow, int hh, const uint8_t* bias_row, int row, const float* sl, const float* sd,
+                                         uint32_t kw, bool valid, bf16* ds_row) {
+  uint32_t x[COLS], y[COLS];
+  if constexpr (COLS == 32) {
+    ptx::tmem_ld_x32_sync(trow + KV_X + hh * 32, reinterpret_cast<uint32_t(&)[32]>(x));
+    ptx::tmem_ld_x32_sync(trow + KV_Y + hh * 32, reinterpret_cast<uint32_t(&)[32]>(y));
+  } else {
+    ptx::tmem_ld_x16_sync(trow + KV_X + hh * 32, reinterpret_cast<uint32_t(&)[16]>(x));
+    ptx::tmem_ld_x16_sync(trow + KV_Y + hh * 32, reinterpret_cast<uint32_t(&)[16]>(y));
+  }
+  uint32_t px[COLS / 2], dx[COLS / 2];
+#pragma unroll
+  for (int q = 0; q < COLS / 4; ++q) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_row + ((q ^ (row & 7)) << 4));
+    const float4 l4 = *reinterpret_cast<const float4*>(sl + 4 * q);
+    const float4 d4 = *reinterpret_cast<const float4*>(sd + 4 * q);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    float pt[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = 4 * q + e;
+      float pv = ex2(fmaf(__uint_as_float(x[idx]), p.sl2, bb[e]) - ll[e]);
+      if (!valid) pv = 0.f;
+      float dp = __uint_as_float(y[idx]);
+      if (DROP) {
+        const bool keep = (kw >> idx) & 1u;
+        pt[e] = keep ? pv * p.inv_keep : 0.f;
+        dp = keep ? dp * p.inv_keep : 0.f;
+      } else {
+        pt[e] = pv;
+      }
+      ds[e] = pv * (dp - dd[e]);
+    }
+    px[2 * q] = pack_bf16x2(pt[0], pt[1]); px[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
+    dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
+  }
+  if constexpr (COLS == 32) {
+    ptx::tmem_st_x16(trow + KV_X + hh * 16, reinterpret_cast<const uint32_t(&)[16]>(px));
+    ptx::tmem_st_x16(trow + KV_Y + hh * 16, reinterpret_cast<const uint32_t(&)[16]>(dx));
+  } else {
+    ptx::tmem_st_x8(trow + KV_X + hh * 16, reinterpret_cast<const uint32_t(&)[8]>(px));
+    ptx::tmem_st_x8(trow + KV_Y + hh * 16, reinterpret_cast<const uint32_t(&)[8]>(dx));
+  }
+  if (valid) {
+#pragma unroll
+    for (int q = 0; q < COLS / 8; ++q)
+      *reinterpret_cast<uint4*>(ds_row + 8 * q) = make_uint4(dx[4 * q], dx[4 * q + 1], dx[4 * q + 2], dx[4 * q + 3]);
+  }
+}
+
+template <bool DROP, bool HAS_BIAS>
+__global__ void __launch_bounds__(KV_THREADS, 2)
+attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_bias, const BwdKvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t bar0 = base + KV_SM_BAR;
+  const uint32_t kv_full = bar0, s_full = bar0 + 8, p_full = bar0 + 16, acc_full = bar0 + 24;
+  auto ld_full = [&](int s) { return bar0 + 32u + 8u * s; };
+  auto ld_empty = [&](int s) { return bar0 + 48u + 8u * s; };
+  auto bias_full = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto bias_empty = [&](int s) { return bar0 + 80u + 8u * s; };
+  const uint32_t tmem_slot = bar0 + 96u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x % p.k_tiles, bh = blockIdx.x / p.k_tiles;
+  const int b = bh / p.H, h = bh - b * p.H;
+  const int j0 = kt * TILE_M;
+  const int n_pad = p.n_pad;
+  const int nq = (n_pad + 63) >> 6;            // 64-query quarters
+  const int nboxes = (n_pad + 31) >> 5;        // 32-query bias boxes / element-wise halves
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_init(kv_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 128); ptx::mbar_init(acc_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(ld_full(s), 1); ptx::mbar_init(ld_empty(s), 1); ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), 4);
+      }
+      ptx::fence_barrier_init();
+      ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_do);
+      if (HAS_BIAS) ptx::prefetch_tmap(&tm_bias);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA (K, V tiles; Q / dO quarters through a 2-stage ring) + MMA issue ----------------
+      auto load_quarter = [&](int qq) {
+        const int st = qq & 1;
+        ptx::mbar_arrive_expect_tx(ld_full(st), 2 * 8192);
+        ptx::tma_load_3d(base + KV_SM_Q + st * 8192, &tm_q, ld_full(st), h * HD, qq * 64, b);
+        ptx::tma_load_3d(base + KV_SM_DO + st * 8192, &tm_do, ld_full(st), h * HD, qq * 64, b);
+      };
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
+      ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
+      ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
+      load_quarter(0);
+      if (nq > 1) load_quarter(1);
+      auto issue_scores = [&](int qq) {   // X = K Q_q^T, Y = V dO_q^T
+        const int st = qq & 1;
+        const int qc = min(64, n_pad - qq * 64);
+        const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, qc, false, false);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16(tmem_base + KV_X, ptx::make_smem_desc(base + KV_SM_K + k * 32, 16, 1024),
+                         ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16(tmem_base + KV_Y, ptx::make_smem_desc(base + KV_SM_V + k * 32, 16, 1024),
+                         ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      ptx::mbar_wait(ld_full(0), 0);
+      ptx::tc_fence_after();
+      issue_scores(0);
+      const uint32_t idesc_acc = ptx::make_idesc_bf16(TILE_M, HD, false, true);
+      for (int qq = 0; qq < nq; ++qq) {
+        const int st = qq & 1;
+        const int qc = min(64, n_pad - qq * 64);
+        ptx::mbar_wait(p_full, (uint32_t)(qq & 1));
+        ptx::tc_fence_after();
+        for (int kk = 0; kk < qc / 16; ++kk)     // dV += P~^T dO_q   (A: bf16 pairs in TMEM columns X.., B: dO_q as MN-major [query][d])
+          ptx::umma_bf16_ts(tmem_base + KV_DV, tmem_base + KV_X + kk * 8, ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + kk * 2048, 8192, 1024),
+                            idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < qc / 16; ++kk)     // dK += dS^T Q_q
+          ptx::umma_bf16_ts(tmem_base + KV_DK, tmem_base + KV_Y + kk * 8, ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + kk * 2048, 8192, 1024),
+                            idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
+        ptx::umma_commit(ld_empty(st));
+        if (qq + 1 < nq) {
+          ptx::mbar_wait(ld_full((qq + 1) & 1), (uint32_t)(((qq + 1) >> 1) & 1));
+          ptx::tc_fence_after();
+          issue_scores(qq + 1);                  // executes after the accumulate MMAs above (issue order): X / Y are free by then
+        }
+        if (qq + 2 < nq) {
+          ptx::mbar_wait(ld_empty(st), (uint32_t)((qq >> 1) & 1));
+          load_quarter(qq + 2);
+        }
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else if (warp == 5) {
+    // ---------------- bias^T ring: [128 keys x 32 queries] fp32 boxes ----------------
+    if (HAS_BIAS && lane == 0) {
+      for (int bi = 0; bi < nboxes; ++bi) {
+        const int st = bi & 1;
+        if (bi >= 2) ptx::mbar_wait(bias_empty(st), (uint32_t)(((bi >> 1) - 1) & 1));
+        ptx::mbar_arrive_expect_tx(bias_full(st), BIAS_STAGE_BYTES);
+        ptx::tma_load_3d(base + KV_SM_BIAS + st * BIAS_STAGE_BYTES, &tm_bias, bias_full(st), bi * 32, j0, h);
+      }
+    }
+  } else {
+    // ---------------- element-wise warps: one thread per key row ----------------
+    float* s_lse = reinterpret_cast<float*>(gbase + KV_SM_LSE);
+    float* s_d = reinterpret_cast<float*>(gbase + KV_SM_D);
+    for (int i = threadIdx.x; i < n_pad; i += 128) {
+      s_lse[i] = i < p.N ? p.lse[(long long)bh * p.N + i] * LOG2E : INFINITY;
+      s_d[i] = i < p.N ? p.dvec[(long long)bh * p.N + i] : 0.f;
+    }
+    ptx::named_bar_sync(1, 128);
+    const int row = warp * 32 + lane;
+    const int j = j0 + row;
+    const bool valid = j < p.N;
+    const bool active = j0 + warp * 32 < p.N;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t kwords[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) kwords[w] = 0xffffffffu;
+    if (DROP && valid) {
+      const uint4 a = *reinterpret_cast<const uint4*>(p.keep_t + ((long long)bh * p.N + j) * 8);
+      const uint4 c = *reinterpret_cast<const uint4*>(p.keep_t + ((long long)bh * p.N + j) * 8 + 4);
+      kwords[0] = a.x; kwords[1] = a.y; kwords[2] = a.z; kwords[3] = a.w; kwords[4] = c.x; kwords[5] = c.y; kwords[6] = c.z; kwords[7] = c.w;
+    }
+    bf16* ds_base = p.ds_out + ((long long)bh * p.N + (valid ? j : 0)) * p.ld_ds;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      if (qq < nq) {
+        ptx::mbar_wait(s_full, (uint32_t)(qq & 1));
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int bi = qq * 2 + hh;
+          if (bi < nboxes) {
+            const int st = bi & 1;
+            const int c0 = bi * 32;
+            if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((bi >> 1) & 1));
+            if (active) {
+              const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
+              if (n_pad - c0 >= 32) bwd_half<32, DROP, HAS_BIAS>(p, trow, hh, bias_row, row, s_lse + c0, s_d + c0, kwords[bi], valid, ds_base + c0);
+              else bwd_half<16, DROP, HAS_BIAS>(p, trow, hh, bias_row, row, s_lse + c0, s_d + c0, kwords[bi], valid, ds_base + c0);
+            }
+            if (HAS_BIAS) {
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(bias_empty(st));
+            }
+          }
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_full);
+      }
+    }
+    // ---------------- epilogue: dV, dK rows of this key tile ----------------
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    if (active) {
+      const long long row_stride = 3LL * p.H * HD;
+      bf16* gk = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)p.H * HD + h * HD;
+#pragma unroll
+      for (int mat = 0; mat < 2; ++mat) {     // 0: dV (columns KV_DV, qkv part 2) ; 1: dK (columns KV_DK, part 1, * scale)
+        float v[64];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          ptx::tmem_ld_x32_sync(trow + (mat == 0 ? KV_DV : KV_DK) + half * 32, o);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[half * 32 + e] = __uint_as_float(o[e]) * (mat == 0 ? 1.0f : p.scale);
+        }
+        if (valid) {
+          bf16* dst = gk + (mat == 0 ? (long long)p.H * HD : 0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                 pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
+        if (mat == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
+          float c0, c1;
+          warp_colsum64(v, lane, c0, c1);
+          atomicAdd(p.dv_bias + h * HD + 2 * lane, c0);
+          atomicAdd(p.dv_bias + h * HD + 2 * lane + 1, c1);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------- dQ = scale * dS K ----------------
+constexpr int DQ_SM_A = 0;                              // 2 chunks (64 queries each) x [NMAX key rows x 128 B]  (dS^T, MN-major A)
+constexpr int DQ_SM_K = 2 * NMAX * 128;                 // NMAX key rows x 128 B (MN-major B)
+constexpr int DQ_SM_O = DQ_SM_K + NMAX * 128;           // 128 x 128 B staging
+constexpr int DQ_SM_BAR = DQ_SM_O + TILE_M * 128;
+constexpr int DQ_SMEM = DQ_SM_BAR + 64 + 1024;
+static_assert(DQ_SM_K % 1024 == 0 && DQ_SM_O % 1024 == 0 && 2 * DQ_SMEM + 2048 <= 232448, "dq kernel smem layout");
+
+struct BwdDqParams {
+  float* dq_bias;   // [H*64] += or null
+  int B, H, N, n_pad, m_tiles;
+  float scale;
+};
+
+__global__ void __launch_bounds__(160, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_dq,
+                   const BwdDqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t bar_full = base + DQ_SM_BAR, bar_done = bar_full + 8, tmem_slot = bar_full + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x % p.m_tiles, bh = blockIdx.x / p.m_tiles;
+  const int b = bh / p.H, h = bh - b * p.H;
+  const int m0 = mt * TILE_M;
+  const int n_pad = p.n_pad;
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_init(bar_full, 1); ptx::mbar_init(bar_done, 1);
+      ptx::fence_barrier_init();
+      ptx::prefetch_tmap(&tm_ds); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_dq);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar_full, 3 * n_pad * 128);
+      ptx::tma_load_3d(base + DQ_SM_A, &tm_ds, bar_full, m0, 0, bh);
+      ptx::tma_load_3d(base + DQ_SM_A + NMAX * 128, &tm_ds, bar_full, m0 + 64, 0, bh);
+      ptx::tma_load_3d(base + DQ_SM_K, &tm_kv, bar_full, (p.H + h) * HD, 0, b);
+      ptx::mbar_wait(bar_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, HD, true, true);
+      for (int kk = 0; kk < n_pad / 16; ++kk)
+        ptx::umma_bf16(tmem_base, ptx::make_smem_desc(base + DQ_SM_A + kk * 2048, NMAX * 128, 1024),
+                       ptx::make_smem_desc(base + DQ_SM_K + kk * 2048, NMAX * 128, 1024), idesc, kk > 0 ? 1u : 0u);
+      ptx::umma_commit(bar_done);
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const bool active = m0 + warp * 32 < p.N;
+    ptx::mbar_wait(bar_done, 0);
+    ptx::tc_fence_after();
+    if (active) {
+      float v[64];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        ptx::tmem_ld_x32_sync(tmem_base + ((uint32_t)(warp * 32) << 16) + half * 32, o);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[half * 32 + e] = __uint_as_float(o[e]) * p.scale;
+      }
+      uint8_t* orow = gbase + DQ_SM_O + row * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(orow + ((q ^ (row & 7)) << 4)) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+      if (p.dq_bias != nullptr) {   // q_bias gradient: query rows past N are exactly zero (their dS columns are zero)
+        float c0, c1;
+        warp_colsum64(v, lane, c0, c1);
+        atomicAdd(p.dq_bias + h * HD + 2 * lane, c0);
+        atomicAdd(p.dq_bias + h * HD + 2 * lane + 1, c1);
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::named_bar_sync(1, 128);
+    if (warp == 0 && lane == 0) {
+      ptx::tma_store_3d(&tm_dq, base + DQ_SM_O, h * HD, m0, b);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read0();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 64);
+}
+
+template <bool DROP, bool HAS_BIAS>
+cudaError_t launch_bwd_kv(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tdo, const CUtensorMap& tb, const BwdKvParams& p,
+                          cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kv_kernel<DROP, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KV_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  attn_bwd_kv_kernel<DROP, HAS_BIAS><<<p.B * p.H * p.k_tiles, KV_THREADS, KV_SMEM, stream>>>(tq, tkv, tdo, tb, p);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld_ds, const int32_t* rel_index, float* dtable, void* stream);
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N) {
+  const size_t n_pad = (size_t)(N + 15) / 16 * 16;
+  const size_t rows = (size_t)B * H * N;
+  return align256(rows * n_pad * sizeof(bf16)) + align256(rows * sizeof(float)) + align256(rows * 8 * sizeof(uint32_t));
+}
+
+extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
+                                const uint8_t* keep_bits, void* work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
+                                float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
+                                void* dqkv, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(qkv && out && dout && lse && dqkv && work, "attn_bwd: null pointer (the workspace of b200vit_attn_bwd_workspace_bytes is required)");
+  B200_CHECK_ARG(B > 0 && H > 0, "attn_bwd: bad B=%d H=%d", B, H);
+  B200_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim %d unsupported (64 only)", head_dim);
+  B200_CHECK_ARG(N > 0 && N <= NMAX, "attn_bwd: N=%d unsupported (1..%d)", N, NMAX);
+  B200_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "attn_bwd: bad p_drop");
+  B200_CHECK_ARG(p_drop == 0.f || keep_bits != nullptr, "attn_bwd: dropout needs keep_bits from the forward");
+  const int n_pad = (N + 15) / 16 * 16;
+  B200_CHECK_ARG(ld_ds == n_pad, "attn_bwd: ld_ds must be N rounded up to 16 (%d)", n_pad);
+  B200_CHECK_ARG(bias_t == nullptr || (ld_bias >= n_pad && ld_bias % 4 == 0 && (reinterpret_cast<uintptr_t>(bias_t) & 15) == 0),
+                 "attn_bwd: bias_t must be the transposed padded layout of b200vit_rel_pos_bias ([H,N,ld], ld %% 4 == 0, >= %d, 16-byte aligned)", n_pad);
+  B200_CHECK_ARG(dtable == nullptr || rel_index != nullptr, "attn_bwd: dtable needs rel_index");
+  const uintptr_t addrs[] = {(uintptr_t)qkv, (uintptr_t)out, (uintptr_t)dout, (uintptr_t)dqkv, (uintptr_t)work, (uintptr_t)keep_bits};
+  for (uintptr_t a : addrs) B200_CHECK_ARG((a & 15) == 0, "attn_bwd: tensors must be 16-byte aligned");
+  const size_t rows = (size_t)B * H * N;
+  bf16* ds = static_cast<bf16*>(work);
+  float* dvec = reinterpret_cast<float*>(static_cast<uint8_t*>(work) + align256(rows * n_pad * sizeof(bf16)));
+  uint32_t* keep_t = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(dvec) + align256(rows * sizeof(float)));
+  const int sms = b200vit_num_sms();
+  const bool drop = p_drop > 0.f;
+
+  attn_bwd_prep_kernel<<<sms * 8, 256, 0, stream>>>(static_cast<const bf16*>(out), static_cast<const bf16*>(dout), dvec, B, H, N);
+  B200_CHECK_LAUNCH("attn_bwd_prep");
+  if (drop) {
+    keep_transpose_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(keep_bits), keep_t, B * H, N);
+    B200_CHECK_LAUNCH("keep_transpose");
+  }
+
+  BwdKvParams p;
+  p.lse = lse; p.dvec = dvec; p.keep_t = keep_t; p.ds_out = ds; p.ld_ds = ld_ds; p.dqkv = static_cast<bf16*>(dqkv); p.dv_bias = dv_bias;
+  p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.k_tiles = (N + TILE_M - 1) / TILE_M;
+  p.scale = scale; p.sl2 = scale * LOG2E; p.inv_keep = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const uint64_t row = 3ull * H * HD, orow = (uint64_t)H * HD;
+  CUtensorMap tq, tkv, tdo, tb, tds, tkfull, tdq;
+  int rc;
+  if ((rc = make_tmap3(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, 64))) return rc;
+  if ((rc = make_tmap3(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, TILE_M))) return rc;
+  if ((rc = make_tmap3(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dout, orow, N, B, orow, orow * N, HD, 64))) return rc;
+  if (bias_t != nullptr) {
+    if ((rc = make_tmap3(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bias_t, ld_bias, N, H, ld_bias, (uint64_t)ld_bias * N, 32, TILE_M))) return rc;
+  } else {
+    tb = tq;
+  }
+  cudaError_t e;
+  if (drop) e = bias_t != nullptr ? launch_bwd_kv<true, true>(tq, tkv, tdo, tb, p, stream) : launch_bwd_kv<true, false>(tq, tkv, tdo, tb, p, stream);
+  else e = bias_t != nullptr ? launch_bwd_kv<false, true>(tq, tkv, tdo, tb, p, stream) : launch_bwd_kv<false, false>(tq, tkv, tdo, tb, p, stream);
+  if (e != cudaSuccess) { b200vit_set_error("attn_bwd (kv): launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+
+  // dQ = scale * dS K
+  if ((rc = make_tmap3(&tds, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ds, ld_ds, N, (uint64_t)B * H, ld_ds, (uint64_t)ld_ds * N, 64, n_pad))) return rc;
+  if ((rc = make_tmap3(&tkfull, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, n_pad))) return rc;
+  if ((rc = make_tmap3(&tdq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dqkv, row, N, B, row, row * N, HD, TILE_M))) return rc;
+  BwdDqParams dp;
+  dp.dq_bias = dq_bias; dp.B = B; dp.H = H; dp.N = N; dp.n_pad = n_pad; dp.m_tiles = (N + TILE_M - 1) / TILE_M; dp.scale = scale;
+  static bool dq_configured = false;
+  if (!dq_configured) {
+    e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM);
+    if (e != cudaSuccess) { b200vit_set_error("attn_bwd (dq): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    dq_configured = true;
+  }
+  attn_bwd_dq_kernel<<<B * H * dp.m_tiles, 160, DQ_SMEM, stream>>>(tds, tkfull, tdq, dp);
+  B200_CHECK_LAUNCH("attn_bwd_dq");
+  if (dtable != nullptr) return b200vit_relbias_grad_launch(ds, B, H, N, ld_ds, rel_index, dtable, stream);
+  return 0;
+}
 
 extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                                 float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,

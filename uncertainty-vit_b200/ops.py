@@ -105,17 +105,20 @@ def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in
     _count()
 
 
+def attn_bwd_workspace(B, H, N, device):
+    """Workspace of b200vit_attn_bwd: dS^T bf16 [B,H,N,ld] | D fp32 [B,H,N] | transposed keep bits u32 [B,H,N,8]."""
+    return torch.empty(int(_lib.lib().b200vit_attn_bwd_workspace_bytes(B, H, N)), dtype=torch.uint8, device=device)
+
+
 def attn_bwd(qkv, out, dout, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p_drop, dqkv, ds_work=None, dq_bias=None, dv_bias=None):
     bias = bias_t
     ld_bias = bias.stride(1) if bias is not None else 0
-    ld_ds = 0
-    if dtable is not None:
-        ld_ds = (N + 15) // 16 * 16
-        if ds_work is None:
-            ds_work = torch.empty((B, H, N, ld_ds), dtype=torch.bfloat16, device=qkv.device)
+    ld_ds = attn_ld(N)
+    if ds_work is None:
+        ds_work = attn_bwd_workspace(B, H, N, qkv.device)
     check(_lib.lib().b200vit_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(bias), ld_bias, _p(keep_bits), _p(ds_work), ld_ds, _p(rel_index),
                                       _p(dtable), _p(dq_bias), _p(dv_bias), B, H, N, 64, scale, p_drop, _p(dqkv), _stream()), "attn_bwd")
-    _count(2 if dtable is not None else 1)
+    _count((4 if p_drop > 0 else 3) + (1 if dtable is not None else 0))
 
 
 def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out_mean=None, out_cov=None, lse=None,
