@@ -54,6 +54,38 @@ def parity():
         print(f"    no-bias rel(out)={rel(out2.float(), ref2):.2e}")
 
 
+def parity_bwd():
+    for (B, H, N, p) in [(2, 2, 17, 0.0), (2, 3, 197, 0.0), (3, 2, 197, 0.1), (1, 2, 64, 0.25), (2, 2, 208, 0.05), (20, 12, 197, 0.05)]:
+        g = torch.Generator().manual_seed(N + B)
+        qkv = torch.randn(B, N, 3, H, 64, generator=g).bfloat16().to(dev)
+        bias = (torch.randn(H, N, N, generator=g) * 0.5).to(dev)
+        scale = 64 ** -0.5
+        out = torch.empty((B, N, H * 64), dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, H, N, device=dev)
+        bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=dev)
+        bias_f, bias_t = ops.pad_attn_bias(bias)
+        ops.attn_fwd(qkv, bias_f, B, H, N, scale, p, 1234, 7, None, out, lse, bits if p > 0 else None)
+        keep = ops.dropout_mask(B * H, N, p, 1234, 7, dev) if p > 0 else None
+        qr = qkv.float().requires_grad_(True)
+        br = bias.clone().requires_grad_(True)
+        ref, _ = ref_attn(qr, br, keep, p, scale)
+        dout = torch.randn(B, N, H * 64, generator=g).bfloat16().to(dev)
+        ref.backward(dout.float())
+        idx = torch.randint(0, 50, (N, N), generator=g).to(torch.int32).to(dev)
+        dtable = torch.zeros(50, H, device=dev)
+        dqkv = torch.full((B, N, 3, H, 64), float("nan"), dtype=torch.bfloat16, device=dev)
+        dqb = torch.zeros(H * 64, device=dev)
+        dvb = torch.zeros(H * 64, device=dev)
+        ops.attn_bwd(qkv, out, dout, lse, bias_t, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv, dq_bias=dqb, dv_bias=dvb)
+        torch.cuda.synchronize()
+        ref_tab = torch.zeros(50, H, device=dev)
+        ref_tab.index_add_(0, idx.long().flatten(), br.grad.permute(1, 2, 0).reshape(N * N, H))
+        gq = qr.grad
+        print(f"bwd B={B} H={H} N={N} p={p}: dq={rel(dqkv[:, :, 0].float(), gq[:, :, 0]):.2e} dk={rel(dqkv[:, :, 1].float(), gq[:, :, 1]):.2e} "
+              f"dv={rel(dqkv[:, :, 2].float(), gq[:, :, 2]):.2e} dqb={rel(dqb, gq[:, :, 0].sum((0, 1)).flatten()):.2e} "
+              f"dvb={rel(dvb, gq[:, :, 2].sum((0, 1)).flatten()):.2e} dtable={rel(dtable, ref_tab):.2e} finite={bool(torch.isfinite(dqkv.float()).all())}")
+
+
 def timeit(fn, n=20):
     for _ in range(3):
         fn(0)
@@ -119,6 +151,9 @@ def ncu_run():
 if __name__ == "__main__":
     if "--ncu" in sys.argv:
         ncu_run()
+    elif "--parity-bwd" in sys.argv:
+        parity_bwd()
     else:
         parity()
+        parity_bwd()
         bench()

@@ -342,18 +342,23 @@ cudaError_t launch_fwd100(const CUtensorMap& tq, const CUtensorMap& tkv, const C
 //                           streamed to the workspace for the dQ kernel and the relative-position-bias table gradient.
 //   attn_bwd_dq_kernel    : one CTA per (batch, head, 128-query tile): dQ = scale * dS K with dS^T read back through TMA as an
 //                           MN-major A operand, K as an MN-major B operand; q_bias gradient fused.
+// per-lane shared memory (a CTA holds KV_LANES independent lanes, each the size of a classic CTA)
 constexpr int KV_SM_K = 0;                          // 128 key rows x 128 B
 constexpr int KV_SM_V = 16384;
 constexpr int KV_SM_Q = 32768;                      // 2 stages x (64 query rows x 128 B)
 constexpr int KV_SM_DO = 49152;                     // 2 stages x (64 query rows x 128 B)
 constexpr int KV_SM_BIAS = 65536;                   // 2 stages x (128 key rows x 32 fp32)
-constexpr int KV_SM_LSE = 98304;                    // NMAX fp32 (log2 domain; +inf past N)
-constexpr int KV_SM_D = KV_SM_LSE + 1024;           // NMAX fp32
-constexpr int KV_SM_BAR = KV_SM_D + 1024;
-constexpr int KV_SMEM = KV_SM_BAR + 128 + 1024;
-constexpr int KV_THREADS = 192;                     // warps 0-3 element-wise, warp 4 TMA + MMA, warp 5 bias ring
-constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns
-static_assert(2 * KV_SMEM + 2048 <= 232448, "two CTAs per SM");
+constexpr int KV_SM_LSE = 98304;                    // 2 buffers x NMAX fp32 (log2 domain; +inf past N)
+constexpr int KV_SM_D = KV_SM_LSE + 2048;           // 2 buffers x NMAX fp32
+constexpr int KV_SM_BAR = KV_SM_D + 2048;
+constexpr int KV_LANE_BYTES = KV_SM_BAR + 1024;     // 103424 (multiple of 1024)
+constexpr int KV_LANES = 2;
+constexpr int KV_EW_WARPS = 8;                      // element-wise warps per lane: warp w owns TMEM lane quadrant w & 3, query half w >> 2
+constexpr int KV_LANE_WARPS = KV_EW_WARPS + 2;      // + TMA/MMA warp + bias-ring warp
+constexpr int KV_THREADS = KV_LANES * KV_LANE_WARPS * 32;
+constexpr int KV_SMEM = KV_LANES * KV_LANE_BYTES + 1024;
+constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns inside a lane's 256-column half
+static_assert(KV_LANE_BYTES % 1024 == 0 && KV_SMEM <= 232448, "kv kernel smem layout");
 
 struct BwdKvParams {
   const float* lse;          // [B, H, N]
@@ -363,9 +368,40 @@ struct BwdKvParams {
   int ld_ds;
   bf16* dqkv;                // [B, N, 3, H, 64]
   float* dv_bias;            // [H*64] += or null
-  int B, H, N, n_pad, k_tiles;
+  int B, H, N, n_pad, k_tiles, items;
   float scale, sl2, inv_keep;
 };
+
+// column sums over the 32 lanes of a warp of 32 per-lane values (recursive halving, 31 shuffles); lane l ends with column l
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const bool up = lane & 1;
+  const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
 
 // column sums over the 32 lanes of a warp of 64 per-lane values: recursive halving (62 shuffles); lane l ends with columns 2l, 2l+1
 __device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane, float& c0, float& c1) {
@@ -430,43 +466,53 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restri
   }
 }
 
-// keep_bits [BH, N(query i), 8 words over keys] -> keep_t [BH, N(key j), 8 words over queries]: 32x32 bit-block transposes by ballot
-__global__ void __launch_bounds__(256) keep_transpose_kernel(const uint32_t* __restrict__ keep_bits, uint32_t* __restrict__ keep_t, int BH, int N) {
-  const int lane = threadIdx.x & 31;
+// keep_bits [BH, N(query i), 8 words over keys] -> keep_t [BH, N(key j), 8 words over queries]. One CTA per (batch, head): the 6 KB
+// bit matrix is staged in shared memory (9-word pitch: conflict-free column reads), warp jb transposes the 32x32 bit blocks of its
+// 32 keys by ballot and writes whole 32-byte rows.
+__global__ void __launch_bounds__(256) keep_transpose_kernel(const uint32_t* __restrict__ keep_bits, uint32_t* __restrict__ keep_t, int N) {
+  __shared__ uint32_t tile[NMAX * 9];
+  const long long bh = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int blocks = (N + 31) >> 5;
-  const long long total = (long long)BH * blocks * blocks;
-  for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += (long long)gridDim.x * (blockDim.x >> 5)) {
-    const int jb = (int)(t % blocks), ib = (int)((t / blocks) % blocks);
-    const long long bh = t / ((long long)blocks * blocks);
-    const int i = ib * 32 + lane;
-    const uint32_t w = i < N ? keep_bits[(bh * N + i) * 8 + jb] : 0u;
-    uint32_t mine = 0u;
+  for (int idx = threadIdx.x; idx < N * 8; idx += blockDim.x) tile[(idx >> 3) * 9 + (idx & 7)] = keep_bits[bh * N * 8 + idx];
+  __syncthreads();
+  if (warp < blocks) {
+    const int jb = warp;
+    uint32_t mine[8];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const uint32_t col = __ballot_sync(0xffffffffu, (w >> e) & 1u);
-      if (lane == e) mine = col;
+    for (int ib = 0; ib < 8; ++ib) {
+      mine[ib] = 0u;
+      if (ib < blocks) {
+        const int i = ib * 32 + lane;
+        const uint32_t w = i < N ? tile[i * 9 + jb] : 0u;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const uint32_t col = __ballot_sync(0xffffffffu, (w >> e) & 1u);
+          if (lane == e) mine[ib] = col;
+        }
+      }
     }
     const int j = jb * 32 + lane;
-    if (j < N) keep_t[(bh * N + j) * 8 + ib] = mine;
+    if (j < N) {
+      uint4* dst = reinterpret_cast<uint4*>(keep_t + (bh * N + j) * 8);
+      dst[0] = make_uint4(mine[0], mine[1], mine[2], mine[3]);
+      dst[1] = make_uint4(mine[4], mine[5], mine[6], mine[7]);
+    }
   }
 }
 
-template <int COLS, bool DROP, bool HAS_BIAS>
-__device__ __forceinline__ void bwd_half(const BwdKvParams& p, uint32_t trow, int hh, const uint8_t* bias_row, int row, const float* sl, const float* sd,
-                                         uint32_t kw, bool valid, bf16* ds_row) {
-  uint32_t x[COLS], y[COLS];
-  if constexpr (COLS == 32) {
-    ptx::tmem_ld_x32_sync(trow + KV_X + hh * 32, reinterpret_cast<uint32_t(&)[32]>(x));
-    ptx::tmem_ld_x32_sync(trow + KV_Y + hh * 32, reinterpret_cast<uint32_t(&)[32]>(y));
-  } else {
-    ptx::tmem_ld_x16_sync(trow + KV_X + hh * 32, reinterpret_cast<uint32_t(&)[16]>(x));
-    ptx::tmem_ld_x16_sync(trow + KV_Y + hh * 32, reinterpret_cast<uint32_t(&)[16]>(y));
-  }
-  uint32_t px[COLS / 2], dx[COLS / 2];
+// 16 queries of one key row: P, dropout, dS out of TMEM; P~^T / dS^T written back as bf16 pairs (the A operands of the dV / dK MMAs)
+// at columns the same warp has already consumed, dS^T also to the workspace row.
+template <bool DROP, bool HAS_BIAS>
+__device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, uint32_t ty, uint32_t tpx, uint32_t tpy, const uint8_t* bias_row, int q0,
+                                           int row, const float* sl, const float* sd, uint32_t kw, bool valid, bf16* ds_row) {
+  uint32_t x[16], y[16];
+  ptx::tmem_ld_x16_pair_sync(tx, x, ty, y);
+  uint32_t px[8], dx[8];
 #pragma unroll
-  for (int q = 0; q < COLS / 4; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_row + ((q ^ (row & 7)) << 4));
+    if (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_row + (((q0 + q) ^ (row & 7)) << 4));
     const float4 l4 = *reinterpret_cast<const float4*>(sl + 4 * q);
     const float4 d4 = *reinterpret_cast<const float4*>(sd + 4 * q);
     const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
@@ -489,46 +535,55 @@ __device__ __forceinline__ void bwd_half(const BwdKvParams& p, uint32_t trow, in
     px[2 * q] = pack_bf16x2(pt[0], pt[1]); px[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
     dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
   }
-  if constexpr (COLS == 32) {
-    ptx::tmem_st_x16(trow + KV_X + hh * 16, reinterpret_cast<const uint32_t(&)[16]>(px));
-    ptx::tmem_st_x16(trow + KV_Y + hh * 16, reinterpret_cast<const uint32_t(&)[16]>(dx));
-  } else {
-    ptx::tmem_st_x8(trow + KV_X + hh * 16, reinterpret_cast<const uint32_t(&)[8]>(px));
-    ptx::tmem_st_x8(trow + KV_Y + hh * 16, reinterpret_cast<const uint32_t(&)[8]>(dx));
-  }
+  ptx::tmem_st_x8(tpx, px);
+  ptx::tmem_st_x8(tpy, dx);
   if (valid) {
-#pragma unroll
-    for (int q = 0; q < COLS / 8; ++q)
-      *reinterpret_cast<uint4*>(ds_row + 8 * q) = make_uint4(dx[4 * q], dx[4 * q + 1], dx[4 * q + 2], dx[4 * q + 3]);
+    *reinterpret_cast<uint4*>(ds_row) = make_uint4(dx[0], dx[1], dx[2], dx[3]);
+    *reinterpret_cast<uint4*>(ds_row + 8) = make_uint4(dx[4], dx[5], dx[6], dx[7]);
   }
 }
 
+// Persistent: one CTA per SM holds KV_LANES independent lanes; lane L of CTA c walks items (2c + L) + k * 2 * gridDim of the
+// (batch, head, key-tile) list. Inside a lane the K/V tiles of the NEXT item are requested as soon as the last score MMA of the
+// current item has read them and the Q / dO quarter ring simply runs on across item boundaries, so the load / launch latency that a
+// one-shot CTA exposes per item is paid once per lane.
 template <bool DROP, bool HAS_BIAS>
-__global__ void __launch_bounds__(KV_THREADS, 2)
+__global__ void __launch_bounds__(KV_THREADS, 1)
 attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_bias, const BwdKvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA warps 0..15: element-wise warps (lane L = warp >> 3; TMEM lane quadrant = CTA warp index & 3, a hardware rule), 16..19: the
+  // TMA+MMA warp and the bias-ring warp of lane 0, then of lane 1.  `warp` = role inside the lane: 0..7 element-wise, 8 TMA+MMA, 9 bias ring
+  const int L = warp_cta < KV_LANES * KV_EW_WARPS ? warp_cta / KV_EW_WARPS : (warp_cta - KV_LANES * KV_EW_WARPS) >> 1;
+  const int warp = warp_cta < KV_LANES * KV_EW_WARPS ? warp_cta % KV_EW_WARPS : KV_EW_WARPS + ((warp_cta - KV_LANES * KV_EW_WARPS) & 1);
+  const uint32_t cta_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = cta_base + L * KV_LANE_BYTES;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = base + KV_SM_BAR;
-  const uint32_t kv_full = bar0, s_full = bar0 + 8, p_full = bar0 + 16, acc_full = bar0 + 24;
-  auto ld_full = [&](int s) { return bar0 + 32u + 8u * s; };
-  auto ld_empty = [&](int s) { return bar0 + 48u + 8u * s; };
-  auto bias_full = [&](int s) { return bar0 + 64u + 8u * s; };
-  auto bias_empty = [&](int s) { return bar0 + 80u + 8u * s; };
-  const uint32_t tmem_slot = bar0 + 96u;
+  const uint32_t kv_full = bar0, kv_free = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, acc_full = bar0 + 32, acc_empty = bar0 + 40;
+  auto ld_full = [&](int s) { return bar0 + 48u + 8u * s; };
+  auto ld_empty = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto bias_full = [&](int s) { return bar0 + 80u + 8u * s; };
+  auto bias_empty = [&](int s) { return bar0 + 96u + 8u * s; };
+  const uint32_t tmem_slot = cta_base + KV_SM_BAR + 128u;    // lane 0's barrier page holds the CTA-wide TMEM slot
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x % p.k_tiles, bh = blockIdx.x / p.k_tiles;
-  const int b = bh / p.H, h = bh - b * p.H;
-  const int j0 = kt * TILE_M;
   const int n_pad = p.n_pad;
-  const int nq = (n_pad + 63) >> 6;            // 64-query quarters
-  const int nboxes = (n_pad + 31) >> 5;        // 32-query bias boxes / element-wise halves
+  const int nq = (n_pad + 63) >> 6;            // 64-query quarters per item
+  const int nboxes = (n_pad + 31) >> 5;        // 32-query bias boxes per item
+  const int first = blockIdx.x * KV_LANES + L, stride = gridDim.x * KV_LANES;
+  const int n_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
+  auto item_of = [&](int it, int& b, int& h, int& j0, int& bh) {
+    const int item = first + it * stride;
+    const int kt = item % p.k_tiles;
+    bh = item / p.k_tiles;
+    b = bh / p.H; h = bh - b * p.H; j0 = kt * TILE_M;
+  };
 
-  if (warp == 4) {
+  if (warp == KV_EW_WARPS) {
     if (lane == 0) {
-      ptx::mbar_init(kv_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 128); ptx::mbar_init(acc_full, 1);
+      ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_free, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, KV_EW_WARPS * 32);
+      ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, KV_EW_WARPS);
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(ld_full(s), 1); ptx::mbar_init(ld_empty(s), 1); ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), 4);
       }
@@ -537,31 +592,39 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (HAS_BIAS) ptx::prefetch_tmap(&tm_bias);
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 256);
-    ptx::tmem_relinquish();
+    if (L == 0) {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base += L * 256;
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (warp == KV_EW_WARPS) {
+    if (lane == 0 && n_items > 0) {
       // ---------------- TMA (K, V tiles; Q / dO quarters through a 2-stage ring) + MMA issue ----------------
-      auto load_quarter = [&](int qq) {
-        const int st = qq & 1;
+      const int total_q = n_items * nq;
+      auto load_quarter = [&](int gq) {           // gq: running quarter index of this lane
+        const int it = gq / nq, qq = gq - it * nq, st = gq & 1;
+        int b, h, j0, bh;
+        item_of(it, b, h, j0, bh);
         ptx::mbar_arrive_expect_tx(ld_full(st), 2 * 8192);
         ptx::tma_load_3d(base + KV_SM_Q + st * 8192, &tm_q, ld_full(st), h * HD, qq * 64, b);
         ptx::tma_load_3d(base + KV_SM_DO + st * 8192, &tm_do, ld_full(st), h * HD, qq * 64, b);
       };
-      ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
-      ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
-      ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
-      load_quarter(0);
-      if (nq > 1) load_quarter(1);
-      auto issue_scores = [&](int qq) {   // X = K Q_q^T, Y = V dO_q^T
-        const int st = qq & 1;
+      auto load_kv = [&](int it) {
+        int b, h, j0, bh;
+        item_of(it, b, h, j0, bh);
+        ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
+        ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
+        ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
+      };
+      auto issue_scores = [&](int gq, int it, int qq) {   // X = K Q_q^T, Y = V dO_q^T ; the last quarter of an item releases K / V
+        const int st = gq & 1;
         const int qc = min(64, n_pad - qq * 64);
         const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, qc, false, false);
 #pragma unroll
@@ -573,132 +636,152 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           ptx::umma_bf16(tmem_base + KV_Y, ptx::make_smem_desc(base + KV_SM_V + k * 32, 16, 1024),
                          ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
         ptx::umma_commit(s_full);
-      };
-      ptx::mbar_wait(kv_full, 0);
-      ptx::mbar_wait(ld_full(0), 0);
-      ptx::tc_fence_after();
-      issue_scores(0);
-      const uint32_t idesc_acc = ptx::make_idesc_bf16(TILE_M, HD, false, true);
-      for (int qq = 0; qq < nq; ++qq) {
-        const int st = qq & 1;
-        const int qc = min(64, n_pad - qq * 64);
-        ptx::mbar_wait(p_full, (uint32_t)(qq & 1));
-        ptx::tc_fence_after();
-        for (int kk = 0; kk < qc / 16; ++kk)     // dV += P~^T dO_q   (A: bf16 pairs in TMEM columns X.., B: dO_q as MN-major [query][d])
-          ptx::umma_bf16_ts(tmem_base + KV_DV, tmem_base + KV_X + kk * 8, ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + kk * 2048, 8192, 1024),
-                            idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
-        for (int kk = 0; kk < qc / 16; ++kk)     // dK += dS^T Q_q
-          ptx::umma_bf16_ts(tmem_base + KV_DK, tmem_base + KV_Y + kk * 8, ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + kk * 2048, 8192, 1024),
-                            idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
-        ptx::umma_commit(ld_empty(st));
-        if (qq + 1 < nq) {
-          ptx::mbar_wait(ld_full((qq + 1) & 1), (uint32_t)(((qq + 1) >> 1) & 1));
-          ptx::tc_fence_after();
-          issue_scores(qq + 1);                  // executes after the accumulate MMAs above (issue order): X / Y are free by then
+        if (qq == nq - 1) {
+          ptx::umma_commit(kv_free);
+          if (it + 1 < n_items) {
+            ptx::mbar_wait(kv_free, (uint32_t)(it & 1));
+            load_kv(it + 1);
+          }
         }
-        if (qq + 2 < nq) {
-          ptx::mbar_wait(ld_empty(st), (uint32_t)((qq >> 1) & 1));
-          load_quarter(qq + 2);
+      };
+      load_kv(0);
+      load_quarter(0);
+      if (total_q > 1) load_quarter(1);
+      const uint32_t idesc_acc = ptx::make_idesc_bf16(TILE_M, HD, false, true);
+      int gq = 0;
+      for (int it = 0; it < n_items; ++it) {
+        ptx::mbar_wait(kv_full, (uint32_t)(it & 1));
+        ptx::mbar_wait(ld_full(gq & 1), (uint32_t)((gq >> 1) & 1));
+        ptx::tc_fence_after();
+        issue_scores(gq, it, 0);
+        for (int qq = 0; qq < nq; ++qq, ++gq) {
+          const int st = gq & 1;
+          const int qc = min(64, n_pad - qq * 64);
+          ptx::mbar_wait(p_full, (uint32_t)(gq & 1));
+          if (qq == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
+          ptx::tc_fence_after();
+          // A operands: bf16 pairs of query half hh at TMEM columns 32*hh .. (written in place by the warps that own that half)
+          for (int kk = 0; kk < qc / 16; ++kk)     // dV += P~^T dO_q   (B: dO_q as MN-major [query][d])
+            ptx::umma_bf16_ts(tmem_base + KV_DV, tmem_base + KV_X + (kk >> 1) * 32 + (kk & 1) * 8,
+                              ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + kk * 2048, 8192, 1024), idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < qc / 16; ++kk)     // dK += dS^T Q_q
+            ptx::umma_bf16_ts(tmem_base + KV_DK, tmem_base + KV_Y + (kk >> 1) * 32 + (kk & 1) * 8,
+                              ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + kk * 2048, 8192, 1024), idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_commit(ld_empty(st));
+          if (qq + 1 < nq) {
+            ptx::mbar_wait(ld_full((gq + 1) & 1), (uint32_t)(((gq + 1) >> 1) & 1));
+            ptx::tc_fence_after();
+            issue_scores(gq + 1, it, qq + 1);      // executes after the accumulate MMAs above (issue order): X / Y are free by then
+          } else {
+            ptx::umma_commit(acc_full);
+          }
+          if (gq + 2 < total_q) {                  // refill this stage with the quarter two ahead (possibly of the next item)
+            ptx::mbar_wait(ld_empty(st), (uint32_t)((gq >> 1) & 1));
+            load_quarter(gq + 2);
+          }
         }
       }
-      ptx::umma_commit(acc_full);
     }
-  } else if (warp == 5) {
+  } else if (warp == KV_EW_WARPS + 1) {
     // ---------------- bias^T ring: [128 keys x 32 queries] fp32 boxes ----------------
     if (HAS_BIAS && lane == 0) {
-      for (int bi = 0; bi < nboxes; ++bi) {
-        const int st = bi & 1;
-        if (bi >= 2) ptx::mbar_wait(bias_empty(st), (uint32_t)(((bi >> 1) - 1) & 1));
-        ptx::mbar_arrive_expect_tx(bias_full(st), BIAS_STAGE_BYTES);
-        ptx::tma_load_3d(base + KV_SM_BIAS + st * BIAS_STAGE_BYTES, &tm_bias, bias_full(st), bi * 32, j0, h);
+      int gb = 0;
+      for (int it = 0; it < n_items; ++it) {
+        int b, h, j0, bh;
+        item_of(it, b, h, j0, bh);
+        for (int bi = 0; bi < nboxes; ++bi, ++gb) {
+          const int st = gb & 1;
+          if (gb >= 2) ptx::mbar_wait(bias_empty(st), (uint32_t)(((gb >> 1) - 1) & 1));
+          ptx::mbar_arrive_expect_tx(bias_full(st), BIAS_STAGE_BYTES);
+          ptx::tma_load_3d(base + KV_SM_BIAS + st * BIAS_STAGE_BYTES, &tm_bias, bias_full(st), bi * 32, j0, h);
+        }
       }
     }
   } else {
-    // ---------------- element-wise warps: one thread per key row ----------------
-    float* s_lse = reinterpret_cast<float*>(gbase + KV_SM_LSE);
-    float* s_d = reinterpret_cast<float*>(gbase + KV_SM_D);
-    for (int i = threadIdx.x; i < n_pad; i += 128) {
-      s_lse[i] = i < p.N ? p.lse[(long long)bh * p.N + i] * LOG2E : INFINITY;
-      s_d[i] = i < p.N ? p.dvec[(long long)bh * p.N + i] : 0.f;
-    }
-    ptx::named_bar_sync(1, 128);
-    const int row = warp * 32 + lane;
-    const int j = j0 + row;
-    const bool valid = j < p.N;
-    const bool active = j0 + warp * 32 < p.N;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t kwords[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) kwords[w] = 0xffffffffu;
-    if (DROP && valid) {
-      const uint4 a = *reinterpret_cast<const uint4*>(p.keep_t + ((long long)bh * p.N + j) * 8);
-      const uint4 c = *reinterpret_cast<const uint4*>(p.keep_t + ((long long)bh * p.N + j) * 8 + 4);
-      kwords[0] = a.x; kwords[1] = a.y; kwords[2] = a.z; kwords[3] = a.w; kwords[4] = c.x; kwords[5] = c.y; kwords[6] = c.z; kwords[7] = c.w;
-    }
-    bf16* ds_base = p.ds_out + ((long long)bh * p.N + (valid ? j : 0)) * p.ld_ds;
-#pragma unroll
-    for (int qq = 0; qq < 4; ++qq) {
-      if (qq < nq) {
-        ptx::mbar_wait(s_full, (uint32_t)(qq & 1));
+    // ---------------- element-wise warps: one thread per (key row, query half) ----------------
+    const int quad = warp & 3, hh = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int tid = warp * 32 + lane;                       // 0..255 inside the lane
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int gq = 0;
+    for (int it = 0; it < n_items; ++it) {
+      int b, h, j0, bh;
+      item_of(it, b, h, j0, bh);
+      float* s_lse = reinterpret_cast<float*>(gbase + KV_SM_LSE) + (it & 1) * NMAX;
+      float* s_d = reinterpret_cast<float*>(gbase + KV_SM_D) + (it & 1) * NMAX;
+      if (tid < n_pad) {
+        s_lse[tid] = tid < p.N ? p.lse[(long long)bh * p.N + tid] * LOG2E : INFINITY;
+        s_d[tid] = tid < p.N ? p.dvec[(long long)bh * p.N + tid] : 0.f;
+      }
+      ptx::named_bar_sync(1 + L, KV_EW_WARPS * 32);
+      const int j = j0 + row;
+      const bool valid = j < p.N;
+      const bool active = j0 + quad * 32 < p.N;
+      bf16* ds_base = p.ds_out + ((long long)bh * p.N + (valid ? j : 0)) * p.ld_ds;
+      const uint32_t* kt_row = p.keep_t + ((long long)bh * p.N + (valid ? j : 0)) * 8;
+      for (int qq = 0; qq < nq; ++qq, ++gq) {
+        const int bi = qq * 2 + hh;
+        const int c0 = bi * 32;
+        const bool has_box = bi < nboxes;
+        uint32_t kw = 0xffffffffu;
+        if (DROP && has_box && valid) kw = __ldg(kt_row + bi);
+        ptx::mbar_wait(s_full, (uint32_t)(gq & 1));
         ptx::tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int bi = qq * 2 + hh;
-          if (bi < nboxes) {
-            const int st = bi & 1;
-            const int c0 = bi * 32;
-            if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((bi >> 1) & 1));
-            if (active) {
-              const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
-              if (n_pad - c0 >= 32) bwd_half<32, DROP, HAS_BIAS>(p, trow, hh, bias_row, row, s_lse + c0, s_d + c0, kwords[bi], valid, ds_base + c0);
-              else bwd_half<16, DROP, HAS_BIAS>(p, trow, hh, bias_row, row, s_lse + c0, s_d + c0, kwords[bi], valid, ds_base + c0);
-            }
-            if (HAS_BIAS) {
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(bias_empty(st));
-            }
+        if (has_box) {
+          const int gb = it * nboxes + bi;
+          const int st = gb & 1;
+          if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((gb >> 1) & 1));
+          if (active) {
+            const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
+            const uint32_t cx = trow + KV_X + hh * 32, cy = trow + KV_Y + hh * 32;
+            bwd_step16<DROP, HAS_BIAS>(p, cx, cy, cx, cy, bias_row, 0, row, s_lse + c0, s_d + c0, kw, valid, ds_base + c0);
+            if (n_pad - c0 >= 32)
+              bwd_step16<DROP, HAS_BIAS>(p, cx + 16, cy + 16, cx + 8, cy + 8, bias_row, 4, row, s_lse + c0 + 16, s_d + c0 + 16, kw >> 16, valid,
+                                         ds_base + c0 + 16);
+          }
+          if (HAS_BIAS) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bias_empty(st));
           }
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full);
       }
-    }
-    // ---------------- epilogue: dV, dK rows of this key tile ----------------
-    ptx::mbar_wait(acc_full, 0);
-    ptx::tc_fence_after();
-    if (active) {
-      const long long row_stride = 3LL * p.H * HD;
-      bf16* gk = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)p.H * HD + h * HD;
-#pragma unroll
-      for (int mat = 0; mat < 2; ++mat) {     // 0: dV (columns KV_DV, qkv part 2) ; 1: dK (columns KV_DK, part 1, * scale)
-        float v[64];
+      // ---------------- epilogue: dV rows (warps of half 0) / dK rows (half 1) of this key tile ----------------
+      ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
+      ptx::tc_fence_after();
+      if (active) {
+        const long long row_stride = 3LL * p.H * HD;
+        bf16* dst = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)(hh == 0 ? 2 : 1) * p.H * HD + h * HD;
+        const float mul = hh == 0 ? 1.0f : p.scale;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t o[32];
-          ptx::tmem_ld_x32_sync(trow + (mat == 0 ? KV_DV : KV_DK) + half * 32, o);
+          ptx::tmem_ld_x32_sync(trow + (hh == 0 ? KV_DV : KV_DK) + half * 32, o);
+          float v[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[half * 32 + e] = __uint_as_float(o[e]) * (mat == 0 ? 1.0f : p.scale);
-        }
-        if (valid) {
-          bf16* dst = gk + (mat == 0 ? (long long)p.H * HD : 0);
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(o[e]) * mul;
+          if (valid) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                                                 pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-        }
-        if (mat == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
-          float c0, c1;
-          warp_colsum64(v, lane, c0, c1);
-          atomicAdd(p.dv_bias + h * HD + 2 * lane, c0);
-          atomicAdd(p.dv_bias + h * HD + 2 * lane + 1, c1);
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(dst + half * 32 + 8 * q) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          }
+          if (hh == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
+            const float c = warp_colsum32(v, lane);
+            atomicAdd(p.dv_bias + h * HD + half * 32 + lane, c);
+          }
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == KV_EW_WARPS && L == 0) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------- dQ = scale * dS K ----------------
@@ -804,7 +887,8 @@ cudaError_t launch_bwd_kv(const CUtensorMap& tq, const CUtensorMap& tkv, const C
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  attn_bwd_kv_kernel<DROP, HAS_BIAS><<<p.B * p.H * p.k_tiles, KV_THREADS, KV_SMEM, stream>>>(tq, tkv, tdo, tb, p);
+  const int ctas = min(b200vit_num_sms(), (p.items + KV_LANES - 1) / KV_LANES);
+  attn_bwd_kv_kernel<DROP, HAS_BIAS><<<ctas, KV_THREADS, KV_SMEM, stream>>>(tq, tkv, tdo, tb, p);
   return cudaGetLastError();
 }
 
@@ -848,13 +932,13 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   attn_bwd_prep_kernel<<<sms * 8, 256, 0, stream>>>(static_cast<const bf16*>(out), static_cast<const bf16*>(dout), dvec, B, H, N);
   B200_CHECK_LAUNCH("attn_bwd_prep");
   if (drop) {
-    keep_transpose_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(keep_bits), keep_t, B * H, N);
+    keep_transpose_kernel<<<B * H, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(keep_bits), keep_t, N);
     B200_CHECK_LAUNCH("keep_transpose");
   }
 
   BwdKvParams p;
   p.lse = lse; p.dvec = dvec; p.keep_t = keep_t; p.ds_out = ds; p.ld_ds = ld_ds; p.dqkv = static_cast<bf16*>(dqkv); p.dv_bias = dv_bias;
-  p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.k_tiles = (N + TILE_M - 1) / TILE_M;
+  p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.k_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.k_tiles;
   p.scale = scale; p.sl2 = scale * LOG2E; p.inv_keep = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
   const uint64_t row = 3ull * H * HD, orow = (uint64_t)H * HD;
   CUtensorMap tq, tkv, tdo, tb, tds, tkfull, tdq;
