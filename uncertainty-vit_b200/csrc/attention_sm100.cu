@@ -13,6 +13,7 @@
 //                      backward, bf16 pairs stored to TMEM columns [0, n_pad/2);
 //                      epilogue: O (TMEM columns [128, 192)) * 1/((1-p) * rowsum) -> bf16 -> swizzled smem tile -> TMA store
 //                      (rows past N clipped by the tensor map), log-sum-exp to global.
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/b200vit.h"
@@ -345,8 +346,8 @@ cudaError_t launch_fwd100(const CUtensorMap& tq, const CUtensorMap& tkv, const C
 // per-lane shared memory (a CTA holds KV_LANES independent lanes, each the size of a classic CTA)
 constexpr int KV_SM_K = 0;                          // 128 key rows x 128 B
 constexpr int KV_SM_V = 16384;
-constexpr int KV_SM_Q = 32768;                      // 2 stages x (64 query rows x 128 B)
-constexpr int KV_SM_DO = 49152;                     // 2 stages x (64 query rows x 128 B)
+constexpr int KV_SM_Q = 32768;                      // 4 slots x (32 query rows x 128 B)
+constexpr int KV_SM_DO = 49152;                     // 4 slots x (32 query rows x 128 B)
 constexpr int KV_SM_BIAS = 65536;                   // 2 stages x (128 key rows x 32 fp32)
 constexpr int KV_SM_LSE = 98304;                    // 2 buffers x NMAX fp32 (log2 domain; +inf past N)
 constexpr int KV_SM_D = KV_SM_LSE + 2048;           // 2 buffers x NMAX fp32
@@ -357,8 +358,18 @@ constexpr int KV_EW_WARPS = 8;                      // element-wise warps per la
 constexpr int KV_LANE_WARPS = KV_EW_WARPS + 2;      // + TMA/MMA warp + bias-ring warp
 constexpr int KV_THREADS = KV_LANES * KV_LANE_WARPS * 32;
 constexpr int KV_SMEM = KV_LANES * KV_LANE_BYTES + 1024;
-constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns inside a lane's 256-column half
+constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns inside a lane's 256-column half (X_g = KV_X + 32 g)
 static_assert(KV_LANE_BYTES % 1024 == 0 && KV_SMEM <= 232448, "kv kernel smem layout");
+
+// profiling experiment (B200VIT_ATTN_DEBUG & 8): clock64 timeline of lane 0 of CTA 0
+__device__ long long g_kv_trace[3 * 512 * 4];
+__device__ __forceinline__ void kv_trace(int debug, int L, int role, int& n, int code, int it, int bi) {   // fire-and-forget stores, no atomics
+  if ((debug & 8) && blockIdx.x == 0 && L == 0 && n < 512) {
+    long long* e = g_kv_trace + (role * 512 + n) * 4;
+    e[0] = code; e[1] = it; e[2] = bi; e[3] = clock64();
+    ++n;
+  }
+}
 
 struct BwdKvParams {
   const float* lse;          // [B, H, N]
@@ -370,6 +381,7 @@ struct BwdKvParams {
   float* dv_bias;            // [H*64] += or null
   int B, H, N, n_pad, k_tiles, items;
   float scale, sl2, inv_keep;
+  int debug;   // profiling experiments only (B200VIT_ATTN_DEBUG): 1 = no dS^T global store, 2 = no MUFU, 4 = no bf16 packs
 };
 
 // column sums over the 32 lanes of a warp of 32 per-lane values (recursive halving, 31 shuffles); lane l ends with column l
@@ -509,44 +521,54 @@ __device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, ui
   uint32_t x[16], y[16];
   ptx::tmem_ld_x16_pair_sync(tx, x, ty, y);
   uint32_t px[8], dx[8];
+  if (valid) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_row + (((q0 + q) ^ (row & 7)) << 4));
-    const float4 l4 = *reinterpret_cast<const float4*>(sl + 4 * q);
-    const float4 d4 = *reinterpret_cast<const float4*>(sd + 4 * q);
-    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    float pt[4], ds[4];
+    for (int q = 0; q < 4; ++q) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_row + (((q0 + q) ^ (row & 7)) << 4));
+      const float4 l4 = *reinterpret_cast<const float4*>(sl + 4 * q);
+      const float4 d4 = *reinterpret_cast<const float4*>(sd + 4 * q);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      float pt[4], ds[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = 4 * q + e;
-      float pv = ex2(fmaf(__uint_as_float(x[idx]), p.sl2, bb[e]) - ll[e]);
-      if (!valid) pv = 0.f;
-      float dp = __uint_as_float(y[idx]);
-      if (DROP) {
-        const bool keep = (kw >> idx) & 1u;
-        pt[e] = keep ? pv * p.inv_keep : 0.f;
-        dp = keep ? dp * p.inv_keep : 0.f;
-      } else {
-        pt[e] = pv;
+      for (int e = 0; e < 4; ++e) {
+        const int idx = 4 * q + e;
+        float pv = fmaf(__uint_as_float(x[idx]), p.sl2, bb[e]) - ll[e];
+        pv = (p.debug & 2) ? pv * 0.001f : ex2(pv);
+        if (DROP) {   // P~ = f P, dP = f dP~ with f = keep / (1 - p)
+          const float f = (kw & (1u << idx)) ? p.inv_keep : 0.f;
+          pt[e] = f * pv;
+          ds[e] = pv * fmaf(f, __uint_as_float(y[idx]), -dd[e]);
+        } else {
+          pt[e] = pv;
+          ds[e] = pv * (__uint_as_float(y[idx]) - dd[e]);
+        }
       }
-      ds[e] = pv * (dp - dd[e]);
+      if (p.debug & 4) {
+        px[2 * q] = __float_as_uint(pt[0]) ^ __float_as_uint(pt[1]); px[2 * q + 1] = __float_as_uint(pt[2]) ^ __float_as_uint(pt[3]);
+        dx[2 * q] = __float_as_uint(ds[0]) ^ __float_as_uint(ds[1]); dx[2 * q + 1] = __float_as_uint(ds[2]) ^ __float_as_uint(ds[3]);
+      } else {
+      px[2 * q] = pack_bf16x2(pt[0], pt[1]); px[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
+      dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
     }
-    px[2 * q] = pack_bf16x2(pt[0], pt[1]); px[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
-    dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
+    if (!(p.debug & 1)) {
+    *reinterpret_cast<uint4*>(ds_row) = make_uint4(dx[0], dx[1], dx[2], dx[3]);
+    *reinterpret_cast<uint4*>(ds_row + 8) = make_uint4(dx[4], dx[5], dx[6], dx[7]);
+    }
+  } else {      // key rows past N: P = dS = 0 (their K / V rows are TMA zero fill, not -inf scores)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) px[q] = dx[q] = 0u;
   }
   ptx::tmem_st_x8(tpx, px);
   ptx::tmem_st_x8(tpy, dx);
-  if (valid) {
-    *reinterpret_cast<uint4*>(ds_row) = make_uint4(dx[0], dx[1], dx[2], dx[3]);
-    *reinterpret_cast<uint4*>(ds_row + 8) = make_uint4(dx[4], dx[5], dx[6], dx[7]);
-  }
 }
 
 // Persistent: one CTA per SM holds KV_LANES independent lanes; lane L of CTA c walks items (2c + L) + k * 2 * gridDim of the
-// (batch, head, key-tile) list. Inside a lane the K/V tiles of the NEXT item are requested as soon as the last score MMA of the
-// current item has read them and the Q / dO quarter ring simply runs on across item boundaries, so the load / launch latency that a
-// one-shot CTA exposes per item is paid once per lane.
+// (batch, head, key-tile) list. Inside a lane the 8 element-wise warps form two groups that ping-pong over the 32-query boxes of an
+// item (group g owns TMEM columns X_g / Y_g): while group g computes box b, the tensor core runs dV/dK += of group 1-g's box and the
+// score MMAs of its next one, so the MMA round trip hides behind the other group's arithmetic. K / V of the NEXT item are requested
+// as soon as the last score MMA of the current item has read them and the Q / dO box ring runs on across item boundaries.
 template <bool DROP, bool HAS_BIAS>
 __global__ void __launch_bounds__(KV_THREADS, 1)
 attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_do,
@@ -561,16 +583,17 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const uint32_t base = cta_base + L * KV_LANE_BYTES;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = base + KV_SM_BAR;
-  const uint32_t kv_full = bar0, kv_free = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, acc_full = bar0 + 32, acc_empty = bar0 + 40;
-  auto ld_full = [&](int s) { return bar0 + 48u + 8u * s; };
-  auto ld_empty = [&](int s) { return bar0 + 64u + 8u * s; };
-  auto bias_full = [&](int s) { return bar0 + 80u + 8u * s; };
-  auto bias_empty = [&](int s) { return bar0 + 96u + 8u * s; };
-  const uint32_t tmem_slot = cta_base + KV_SM_BAR + 128u;    // lane 0's barrier page holds the CTA-wide TMEM slot
+  const uint32_t kv_full = bar0, kv_free = bar0 + 8, acc_full = bar0 + 16, acc_empty = bar0 + 24;
+  auto s_full = [&](int g) { return bar0 + 32u + 8u * g; };
+  auto p_full = [&](int g) { return bar0 + 48u + 8u * g; };
+  auto bias_full = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto bias_empty = [&](int s) { return bar0 + 80u + 8u * s; };
+  auto ld_full = [&](int s) { return bar0 + 96u + 8u * s; };     // 4 Q/dO box slots
+  auto ld_empty = [&](int s) { return bar0 + 128u + 8u * s; };
+  const uint32_t tmem_slot = cta_base + KV_SM_BAR + 192u;         // lane 0's barrier page holds the CTA-wide TMEM slot
 
   const int n_pad = p.n_pad;
-  const int nq = (n_pad + 63) >> 6;            // 64-query quarters per item
-  const int nboxes = (n_pad + 31) >> 5;        // 32-query bias boxes per item
+  const int nboxes = (n_pad + 31) >> 5;        // 32-query boxes per item; group g owns boxes bi = g, g + 2, ...
   const int first = blockIdx.x * KV_LANES + L, stride = gridDim.x * KV_LANES;
   const int n_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
   auto item_of = [&](int it, int& b, int& h, int& j0, int& bh) {
@@ -579,14 +602,16 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     bh = item / p.k_tiles;
     b = bh / p.H; h = bh - b * p.H; j0 = kt * TILE_M;
   };
+  // boxes of group g per item, and the running per-group box counter (barrier phases)
+  auto group_count = [&](int it, int bi) { const int g = bi & 1; return it * ((nboxes + 1 - g) >> 1) + (bi >> 1); };
 
   if (warp == KV_EW_WARPS) {
     if (lane == 0) {
-      ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_free, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, KV_EW_WARPS * 32);
-      ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, KV_EW_WARPS);
+      ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_free, 2); ptx::mbar_init(acc_full, 2); ptx::mbar_init(acc_empty, KV_EW_WARPS);
       for (int s = 0; s < 2; ++s) {
-        ptx::mbar_init(ld_full(s), 1); ptx::mbar_init(ld_empty(s), 1); ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), 4);
+        ptx::mbar_init(s_full(s), 2); ptx::mbar_init(p_full(s), 128); ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), 4);
       }
+      for (int s = 0; s < 4; ++s) { ptx::mbar_init(ld_full(s), 1); ptx::mbar_init(ld_empty(s), 2); }
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_do);
       if (HAS_BIAS) ptx::prefetch_tmap(&tm_bias);
@@ -605,86 +630,89 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tmem_base += L * 256;
 
   if (warp == KV_EW_WARPS) {
-    if (lane == 0 && n_items > 0) {
-      // ---------------- TMA (K, V tiles; Q / dO quarters through a 2-stage ring) + MMA issue ----------------
-      const int total_q = n_items * nq;
-      auto load_quarter = [&](int gq) {           // gq: running quarter index of this lane
-        const int it = gq / nq, qq = gq - it * nq, st = gq & 1;
-        int b, h, j0, bh;
-        item_of(it, b, h, j0, bh);
-        ptx::mbar_arrive_expect_tx(ld_full(st), 2 * 8192);
-        ptx::tma_load_3d(base + KV_SM_Q + st * 8192, &tm_q, ld_full(st), h * HD, qq * 64, b);
-        ptx::tma_load_3d(base + KV_SM_DO + st * 8192, &tm_do, ld_full(st), h * HD, qq * 64, b);
-      };
-      auto load_kv = [&](int it) {
-        int b, h, j0, bh;
-        item_of(it, b, h, j0, bh);
-        ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
-        ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
-        ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
-      };
-      auto issue_scores = [&](int gq, int it, int qq) {   // X = K Q_q^T, Y = V dO_q^T ; the last quarter of an item releases K / V
-        const int st = gq & 1;
-        const int qc = min(64, n_pad - qq * 64);
-        const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, qc, false, false);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16(tmem_base + KV_X, ptx::make_smem_desc(base + KV_SM_K + k * 32, 16, 1024),
-                         ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16(tmem_base + KV_Y, ptx::make_smem_desc(base + KV_SM_V + k * 32, 16, 1024),
-                         ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-        ptx::umma_commit(s_full);
-        if (qq == nq - 1) {
-          ptx::umma_commit(kv_free);
-          if (it + 1 < n_items) {
-            ptx::mbar_wait(kv_free, (uint32_t)(it & 1));
-            load_kv(it + 1);
-          }
-        }
-      };
-      load_kv(0);
-      load_quarter(0);
-      if (total_q > 1) load_quarter(1);
+    if (lane < 2 && n_items > 0) {
+      // ---------------- MMA issue only: this code paces the whole lane, so it is lean and issued SIMT from TWO threads ----------------
+      // thread m = 0 owns the S^T / dV chain (X = K Q^T, dV += P~^T dO), thread m = 1 the dP^T / dK chain (Y = V dO^T, dK += dS^T Q):
+      // one warp instruction issues both MMAs; every completion barrier therefore expects two commits.
+      // descriptor arithmetic: +2 in the encoded start address = +32 bytes (one K-major k-step), +128 = +2048 bytes (one MN-major k-step),
+      // +256 = one 4 KB box slot
+      const int m = lane;
+      const uint64_t dA = ptx::make_smem_desc(base + (m == 0 ? KV_SM_K : KV_SM_V), 16, 1024);
+      const uint64_t dBk = ptx::make_smem_desc(base + (m == 0 ? KV_SM_Q : KV_SM_DO), 16, 1024);      // score B operand, K-major
+      const uint64_t dBm = ptx::make_smem_desc(base + (m == 0 ? KV_SM_DO : KV_SM_Q), 4096, 1024);    // accumulate B operand, MN-major
+      const uint32_t t_score = tmem_base + (m == 0 ? KV_X : KV_Y), t_acc = tmem_base + (m == 0 ? KV_DV : KV_DK);
       const uint32_t idesc_acc = ptx::make_idesc_bf16(TILE_M, HD, false, true);
-      int gq = 0;
+      const uint32_t idesc_s32 = ptx::make_idesc_bf16(TILE_M, 32, false, false);
+      const uint32_t idesc_tail = ptx::make_idesc_bf16(TILE_M, n_pad - (nboxes - 1) * 32, false, false);
+      const int tail_ksteps = (n_pad - (nboxes - 1) * 32) >> 4;
+      int trn = 0;
+      int cnt[2] = {0, 0};      // boxes accumulated so far per group
+      int gb_s = 0;             // running box index of the NEXT score issue
+      auto issue_scores = [&](int bi) {   // X_g = K Q_box^T | Y_g = V dO_box^T ; the last box of an item releases K / V
+        const int sl = gb_s & 3, g = bi & 1;
+        ptx::mbar_wait(ld_full(sl), (uint32_t)((gb_s >> 2) & 1));      // TMA data: no tcgen05 fence needed
+        const uint32_t idesc = bi == nboxes - 1 ? idesc_tail : idesc_s32;
+        const uint64_t db = dBk + (uint64_t)(sl * 256);
+        const uint32_t d = t_score + g * 32;
+        ptx::umma_bf16(d, dA, db, idesc, 0u);
+        ptx::umma_bf16(d, dA + 2, db + 2, idesc, 1u);
+        ptx::umma_bf16(d, dA + 4, db + 4, idesc, 1u);
+        ptx::umma_bf16(d, dA + 6, db + 6, idesc, 1u);
+        ptx::umma_commit(s_full(g));
+        if (bi == nboxes - 1) ptx::umma_commit(kv_free);
+        ++gb_s;
+      };
+      int gb = 0;
       for (int it = 0; it < n_items; ++it) {
         ptx::mbar_wait(kv_full, (uint32_t)(it & 1));
-        ptx::mbar_wait(ld_full(gq & 1), (uint32_t)((gq >> 1) & 1));
-        ptx::tc_fence_after();
-        issue_scores(gq, it, 0);
-        for (int qq = 0; qq < nq; ++qq, ++gq) {
-          const int st = gq & 1;
-          const int qc = min(64, n_pad - qq * 64);
-          ptx::mbar_wait(p_full, (uint32_t)(gq & 1));
-          if (qq == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
+        issue_scores(0);
+        if (nboxes > 1) issue_scores(1);
+        for (int bi = 0; bi < nboxes; ++bi, ++gb) {
+          const int sl = gb & 3, g = bi & 1;
+          ptx::mbar_wait(p_full(g), (uint32_t)(cnt[g] & 1));
+          ++cnt[g];
+          if (m == 0) kv_trace(p.debug, L, 2, trn, 10, it, bi);
+          if (bi == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
           ptx::tc_fence_after();
-          // A operands: bf16 pairs of query half hh at TMEM columns 32*hh .. (written in place by the warps that own that half)
-          for (int kk = 0; kk < qc / 16; ++kk)     // dV += P~^T dO_q   (B: dO_q as MN-major [query][d])
-            ptx::umma_bf16_ts(tmem_base + KV_DV, tmem_base + KV_X + (kk >> 1) * 32 + (kk & 1) * 8,
-                              ptx::make_smem_desc(base + KV_SM_DO + st * 8192 + kk * 2048, 8192, 1024), idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
-          for (int kk = 0; kk < qc / 16; ++kk)     // dK += dS^T Q_q
-            ptx::umma_bf16_ts(tmem_base + KV_DK, tmem_base + KV_Y + (kk >> 1) * 32 + (kk & 1) * 8,
-                              ptx::make_smem_desc(base + KV_SM_Q + st * 8192 + kk * 2048, 8192, 1024), idesc_acc, (qq > 0 || kk > 0) ? 1u : 0u);
-          ptx::umma_commit(ld_empty(st));
-          if (qq + 1 < nq) {
-            ptx::mbar_wait(ld_full((gq + 1) & 1), (uint32_t)(((gq + 1) >> 1) & 1));
-            ptx::tc_fence_after();
-            issue_scores(gq + 1, it, qq + 1);      // executes after the accumulate MMAs above (issue order): X / Y are free by then
-          } else {
-            ptx::umma_commit(acc_full);
-          }
-          if (gq + 2 < total_q) {                  // refill this stage with the quarter two ahead (possibly of the next item)
-            ptx::mbar_wait(ld_empty(st), (uint32_t)((gq >> 1) & 1));
-            load_quarter(gq + 2);
-          }
+          const uint64_t db = dBm + (uint64_t)(sl * 256);
+          const uint32_t a = t_score + g * 32;     // bf16 pairs written in place by the element-wise warps
+          ptx::umma_bf16_ts(t_acc, a, db, idesc_acc, bi > 0 ? 1u : 0u);
+          if (bi < nboxes - 1 || tail_ksteps > 1) ptx::umma_bf16_ts(t_acc, a + 8, db + 128, idesc_acc, 1u);
+          ptx::umma_commit(ld_empty(sl));
+          if (bi == nboxes - 1) ptx::umma_commit(acc_full);
+          if (m == 0) kv_trace(p.debug, L, 2, trn, 11, it, bi);
+          if (bi + 2 < nboxes) issue_scores(bi + 2);   // same group's next box: runs after the MMAs above (issue order)
+          if (m == 0) kv_trace(p.debug, L, 2, trn, 12, it, bi);
         }
       }
     }
   } else if (warp == KV_EW_WARPS + 1) {
-    // ---------------- bias^T ring: [128 keys x 32 queries] fp32 boxes ----------------
-    if (HAS_BIAS && lane == 0) {
+    if (lane == 0 && n_items > 0) {
+      // ---------------- TMA: K / V tiles (one item ahead) and the Q / dO box ring (4 slots, runs on across items) ----------------
+      int b, h, j0, bh;
+      item_of(0, b, h, j0, bh);
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
+      ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
+      ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
+      int gb = 0;
+      for (int it = 0; it < n_items; ++it) {
+        for (int bi = 0; bi < nboxes; ++bi, ++gb) {
+          const int sl = gb & 3;
+          if (gb >= 4) ptx::mbar_wait(ld_empty(sl), (uint32_t)(((gb >> 2) - 1) & 1));
+          ptx::mbar_arrive_expect_tx(ld_full(sl), 2 * 4096);
+          ptx::tma_load_3d(base + KV_SM_Q + sl * 4096, &tm_q, ld_full(sl), h * HD, bi * 32, b);
+          ptx::tma_load_3d(base + KV_SM_DO + sl * 4096, &tm_do, ld_full(sl), h * HD, bi * 32, b);
+        }
+        if (it + 1 < n_items) {     // the boxes above were requested for item `it`; now K / V of item it + 1 once item it has released them
+          item_of(it + 1, b, h, j0, bh);
+          ptx::mbar_wait(kv_free, (uint32_t)(it & 1));
+          ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
+          ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
+          ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
+        }
+      }
+    } else if (HAS_BIAS && lane == 1 && n_items > 0) {
+      // ---------------- TMA: bias^T ring, [128 keys x 32 queries] fp32 boxes in box order ----------------
       int gb = 0;
       for (int it = 0; it < n_items; ++it) {
         int b, h, j0, bh;
@@ -698,12 +726,13 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else {
-    // ---------------- element-wise warps: one thread per (key row, query half) ----------------
-    const int quad = warp & 3, hh = warp >> 2;
+    // ---------------- element-wise warps: one thread per key row; group g = warp >> 2 owns boxes g, g + 2, ... ----------------
+    const int quad = warp & 3, g = warp >> 2;
     const int row = quad * 32 + lane;
     const int tid = warp * 32 + lane;                       // 0..255 inside the lane
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    int gq = 0;
+    const uint32_t cx = trow + KV_X + g * 32, cy = trow + KV_Y + g * 32;
+    int trn = 0;
     for (int it = 0; it < n_items; ++it) {
       int b, h, j0, bh;
       item_of(it, b, h, j0, bh);
@@ -714,51 +743,49 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         s_d[tid] = tid < p.N ? p.dvec[(long long)bh * p.N + tid] : 0.f;
       }
       ptx::named_bar_sync(1 + L, KV_EW_WARPS * 32);
+      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 5 + 100 * g, it, 0);
       const int j = j0 + row;
       const bool valid = j < p.N;
       const bool active = j0 + quad * 32 < p.N;
       bf16* ds_base = p.ds_out + ((long long)bh * p.N + (valid ? j : 0)) * p.ld_ds;
       const uint32_t* kt_row = p.keep_t + ((long long)bh * p.N + (valid ? j : 0)) * 8;
-      for (int qq = 0; qq < nq; ++qq, ++gq) {
-        const int bi = qq * 2 + hh;
+      for (int bi = g; bi < nboxes; bi += 2) {
         const int c0 = bi * 32;
-        const bool has_box = bi < nboxes;
+        const int gb = it * nboxes + bi, st = gb & 1;
         uint32_t kw = 0xffffffffu;
-        if (DROP && has_box && valid) kw = __ldg(kt_row + bi);
-        ptx::mbar_wait(s_full, (uint32_t)(gq & 1));
+        if (DROP && valid) kw = __ldg(kt_row + bi);
+        if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((gb >> 1) & 1));
+        ptx::mbar_wait(s_full(g), (uint32_t)(group_count(it, bi) & 1));
         ptx::tc_fence_after();
-        if (has_box) {
-          const int gb = it * nboxes + bi;
-          const int st = gb & 1;
-          if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((gb >> 1) & 1));
-          if (active) {
-            const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
-            const uint32_t cx = trow + KV_X + hh * 32, cy = trow + KV_Y + hh * 32;
-            bwd_step16<DROP, HAS_BIAS>(p, cx, cy, cx, cy, bias_row, 0, row, s_lse + c0, s_d + c0, kw, valid, ds_base + c0);
-            if (n_pad - c0 >= 32)
-              bwd_step16<DROP, HAS_BIAS>(p, cx + 16, cy + 16, cx + 8, cy + 8, bias_row, 4, row, s_lse + c0 + 16, s_d + c0 + 16, kw >> 16, valid,
-                                         ds_base + c0 + 16);
-          }
-          if (HAS_BIAS) {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bias_empty(st));
-          }
+        if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 1 + 100 * g, it, bi);
+        if (active) {
+          const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
+          bwd_step16<DROP, HAS_BIAS>(p, cx, cy, cx, cy, bias_row, 0, row, s_lse + c0, s_d + c0, kw, valid, ds_base + c0);
+          if (n_pad - c0 >= 32)
+            bwd_step16<DROP, HAS_BIAS>(p, cx + 16, cy + 16, cx + 8, cy + 8, bias_row, 4, row, s_lse + c0 + 16, s_d + c0 + 16, kw >> 16, valid,
+                                       ds_base + c0 + 16);
+        }
+        if (HAS_BIAS) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bias_empty(st));
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(p_full);
+        ptx::mbar_arrive(p_full(g));
+        if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 2 + 100 * g, it, bi);
       }
-      // ---------------- epilogue: dV rows (warps of half 0) / dK rows (half 1) of this key tile ----------------
+      // ---------------- epilogue: dV rows (group 0) / dK rows (group 1) of this key tile ----------------
       ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
       ptx::tc_fence_after();
+      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 3 + 100 * g, it, 0);
       if (active) {
         const long long row_stride = 3LL * p.H * HD;
-        bf16* dst = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)(hh == 0 ? 2 : 1) * p.H * HD + h * HD;
-        const float mul = hh == 0 ? 1.0f : p.scale;
+        bf16* dst = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)(g == 0 ? 2 : 1) * p.H * HD + h * HD;
+        const float mul = g == 0 ? 1.0f : p.scale;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t o[32];
-          ptx::tmem_ld_x32_sync(trow + (hh == 0 ? KV_DV : KV_DK) + half * 32, o);
+          ptx::tmem_ld_x32_sync(trow + (g == 0 ? KV_DV : KV_DK) + half * 32, o);
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(o[e]) * mul;
@@ -768,7 +795,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               *reinterpret_cast<uint4*>(dst + half * 32 + 8 * q) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                                                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
           }
-          if (hh == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
+          if (g == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
             const float c = warp_colsum32(v, lane);
             atomicAdd(p.dv_bias + h * HD + half * 32 + lane, c);
           }
@@ -777,6 +804,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(acc_empty);
+      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 4 + 100 * g, it, 0);
     }
   }
   ptx::tc_fence_before();
@@ -898,6 +926,12 @@ int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+extern "C" int b200vit_debug_kv_trace(long long* host_out, int max_events) {   // tools only (not in the public header)
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_out, g_kv_trace, sizeof(long long) * 3 * 512 * 4);
+  return 3 * 512;
+}
+
 extern "C" size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N) {
   const size_t n_pad = (size_t)(N + 15) / 16 * 16;
   const size_t rows = (size_t)B * H * N;
@@ -940,12 +974,13 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   p.lse = lse; p.dvec = dvec; p.keep_t = keep_t; p.ds_out = ds; p.ld_ds = ld_ds; p.dqkv = static_cast<bf16*>(dqkv); p.dv_bias = dv_bias;
   p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.k_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.k_tiles;
   p.scale = scale; p.sl2 = scale * LOG2E; p.inv_keep = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
+  { const char* dbg = getenv("B200VIT_ATTN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   const uint64_t row = 3ull * H * HD, orow = (uint64_t)H * HD;
   CUtensorMap tq, tkv, tdo, tb, tds, tkfull, tdq;
   int rc;
-  if ((rc = make_tmap3(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, 64))) return rc;
+  if ((rc = make_tmap3(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, 32))) return rc;
   if ((rc = make_tmap3(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, TILE_M))) return rc;
-  if ((rc = make_tmap3(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dout, orow, N, B, orow, orow * N, HD, 64))) return rc;
+  if ((rc = make_tmap3(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dout, orow, N, B, orow, orow * N, HD, 32))) return rc;
   if (bias_t != nullptr) {
     if ((rc = make_tmap3(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bias_t, ld_bias, N, H, ld_bias, (uint64_t)ld_bias * N, 32, TILE_M))) return rc;
   } else {
