@@ -8,7 +8,8 @@ One "step" = EMA-teacher forward + target builder / smooth-L1 + student forward/
 EMA on one batch of 128 synthetic 224x224 images per GPU with exactly 120 masked patches per image (README recipe:
 drop_path 0.25, attn_drop 0.05, layer-scale 1e-4, target_layers 6-11, post LayerNorm targets, l1_beta 2, EMA 0.9998, clip 3, wd 0.05).
 `value`   : device-timed (CUDA events) with the batch already resident in HBM.
-`e2e`     : the same step through D2VEngine.step_host(): pinned host batch -> device copy and loss read-back inside the timed region.
+`e2e`     : the same step through D2VEngine.stage_host()/step_staged() (what engine.train_one_epoch calls): every step's pinned host batch is
+            copied to the device (one batch ahead, on a copy stream) and its loss read back inside the timed region.
 `roofline`: all launches of the tcgen05 GEMM kernel inside instrumented steps: algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
 """
 from __future__ import annotations
@@ -201,13 +202,19 @@ def run_b200(args):
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (ops.LAUNCHES - launches0)
     final_loss = float(loss.item())
-    # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs
-    for i in range(2):
-        eng.step_host(*host[i % 2], lr=lr_at(i))
+    # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs. Every step's inputs are copied from
+    # pinned host memory inside the timed region; as in engine.train_one_epoch the copy of batch i+1 is enqueued on the copy stream
+    # before step i is launched (a one-batch look-ahead data loader), and the loss of every step is read back.
+    def e2e_loop(n):
+        nxt = eng.stage_host(*host[0])
+        for i in range(n):
+            cur, nxt = nxt, (eng.stage_host(*host[(i + 1) % 2]) if i + 1 < n else None)
+            eng.step_staged(cur, lr=lr_at(i))
+
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.step_host(*host[i % 2], lr=lr_at(i))
+    e2e_loop(args.steps)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     sampler.mark_end()

@@ -496,12 +496,16 @@ __global__ void __launch_bounds__(256) keep_transpose_kernel(const uint32_t* __r
       mine[ib] = 0u;
       if (ib < blocks) {
         const int i = ib * 32 + lane;
-        const uint32_t w = i < N ? tile[i * 9 + jb] : 0u;
+        uint32_t x = i < N ? tile[i * 9 + jb] : 0u;      // lane = query row, bit = key
+        // 32x32 bit-matrix transpose: five butterfly steps (swap the off-diagonal s x s blocks between lanes l and l ^ s)
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const uint32_t col = __ballot_sync(0xffffffffu, (w >> e) & 1u);
-          if (lane == e) mine[ib] = col;
+        for (int step = 0; step < 5; ++step) {
+          const int s_ = 16 >> step;
+          const uint32_t m = step == 0 ? 0x0000ffffu : step == 1 ? 0x00ff00ffu : step == 2 ? 0x0f0f0f0fu : step == 3 ? 0x33333333u : 0x55555555u;
+          const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s_);
+          x = (lane & s_) ? (((y >> s_) & m) | (x & ~m)) : ((x & m) | ((y << s_) & ~m));
         }
+        mine[ib] = x;                                     // lane = key, bit = query
       }
     }
     const int j = jb * 32 + lane;
@@ -813,39 +817,44 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 // ---------------- dQ = scale * dS K ----------------
-constexpr int DQ_SM_A = 0;                              // 2 chunks (64 queries each) x [NMAX key rows x 128 B]  (dS^T, MN-major A)
-constexpr int DQ_SM_K = 2 * NMAX * 128;                 // NMAX key rows x 128 B (MN-major B)
-constexpr int DQ_SM_O = DQ_SM_K + NMAX * 128;           // 128 x 128 B staging
+// Persistent (one CTA per SM): a TMA thread runs one item ahead through a 2-buffer operand ring, an MMA thread alternates between two
+// 64-column TMEM accumulators, four epilogue warps drain accumulator a while the MMAs of the next item fill accumulator 1 - a.
+constexpr int DQ_BUF_BYTES = 3 * NMAX * 128;            // 2 chunks (64 queries each) of dS^T [NMAX key rows x 128 B] (MN-major A) + K (MN-major B)
+constexpr int DQ_SM_O = 2 * DQ_BUF_BYTES;               // 128 x 128 B staging
 constexpr int DQ_SM_BAR = DQ_SM_O + TILE_M * 128;
-constexpr int DQ_SMEM = DQ_SM_BAR + 64 + 1024;
-static_assert(DQ_SM_K % 1024 == 0 && DQ_SM_O % 1024 == 0 && 2 * DQ_SMEM + 2048 <= 232448, "dq kernel smem layout");
+constexpr int DQ_SMEM = DQ_SM_BAR + 128 + 1024;
+constexpr int DQ_THREADS = 192;
+static_assert(DQ_BUF_BYTES % 1024 == 0 && DQ_SM_O % 1024 == 0 && DQ_SMEM <= 232448, "dq kernel smem layout");
 
 struct BwdDqParams {
   float* dq_bias;   // [H*64] += or null
-  int B, H, N, n_pad, m_tiles;
+  int B, H, N, n_pad, m_tiles, items;
   float scale;
 };
 
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(DQ_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_dq,
                    const BwdDqParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const uint32_t bar_full = base + DQ_SM_BAR, bar_done = bar_full + 8, tmem_slot = bar_full + 16;
+  const uint32_t bar0 = base + DQ_SM_BAR;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 16u + 8u * s; };
+  auto done = [&](int a) { return bar0 + 32u + 8u * a; };
+  auto tfree = [&](int a) { return bar0 + 48u + 8u * a; };
+  const uint32_t tmem_slot = bar0 + 64u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x % p.m_tiles, bh = blockIdx.x / p.m_tiles;
-  const int b = bh / p.H, h = bh - b * p.H;
-  const int m0 = mt * TILE_M;
   const int n_pad = p.n_pad;
+  const int n_items = (int)blockIdx.x < p.items ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (warp == 4) {
     if (lane == 0) {
-      ptx::mbar_init(bar_full, 1); ptx::mbar_init(bar_done, 1);
+      for (int s = 0; s < 2; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); ptx::mbar_init(done(s), 1); ptx::mbar_init(tfree(s), 4); }
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_ds); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_dq);
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_alloc(tmem_slot, 128);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -854,56 +863,86 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (warp == 4) {
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(bar_full, 3 * n_pad * 128);
-      ptx::tma_load_3d(base + DQ_SM_A, &tm_ds, bar_full, m0, 0, bh);
-      ptx::tma_load_3d(base + DQ_SM_A + NMAX * 128, &tm_ds, bar_full, m0 + 64, 0, bh);
-      ptx::tma_load_3d(base + DQ_SM_K, &tm_kv, bar_full, (p.H + h) * HD, 0, b);
-      ptx::mbar_wait(bar_full, 0);
-      ptx::tc_fence_after();
+    if (lane == 0) {       // ---------------- TMA ----------------
+      for (int it = 0; it < n_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int mt = item % p.m_tiles, bh = item / p.m_tiles;
+        const int b = bh / p.H, h = bh - b * p.H, m0 = mt * TILE_M, s = it & 1;
+        if (it >= 2) ptx::mbar_wait(empty(s), (uint32_t)(((it >> 1) - 1) & 1));
+        const uint32_t buf = base + s * DQ_BUF_BYTES;
+        ptx::mbar_arrive_expect_tx(full(s), 3 * n_pad * 128);
+        ptx::tma_load_3d(buf, &tm_ds, full(s), m0, 0, bh);
+        ptx::tma_load_3d(buf + NMAX * 128, &tm_ds, full(s), m0 + 64, 0, bh);
+        ptx::tma_load_3d(buf + 2 * NMAX * 128, &tm_kv, full(s), (p.H + h) * HD, 0, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {       // ---------------- MMA ----------------
       const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, HD, true, true);
-      for (int kk = 0; kk < n_pad / 16; ++kk)
-        ptx::umma_bf16(tmem_base, ptx::make_smem_desc(base + DQ_SM_A + kk * 2048, NMAX * 128, 1024),
-                       ptx::make_smem_desc(base + DQ_SM_K + kk * 2048, NMAX * 128, 1024), idesc, kk > 0 ? 1u : 0u);
-      ptx::umma_commit(bar_done);
+      for (int it = 0; it < n_items; ++it) {
+        const int s = it & 1;
+        const uint32_t buf = base + s * DQ_BUF_BYTES;
+        const uint64_t da = ptx::make_smem_desc(buf, NMAX * 128, 1024), db = ptx::make_smem_desc(buf + 2 * NMAX * 128, NMAX * 128, 1024);
+        ptx::mbar_wait(full(s), (uint32_t)((it >> 1) & 1));
+        if (it >= 2) ptx::mbar_wait(tfree(s), (uint32_t)(((it >> 1) - 1) & 1));
+        ptx::tc_fence_after();
+        for (int kk = 0; kk < n_pad / 16; ++kk) ptx::umma_bf16(tmem_base + s * 64, da + 128 * kk, db + 128 * kk, idesc, kk > 0 ? 1u : 0u);
+        ptx::umma_commit(empty(s));
+        ptx::umma_commit(done(s));
+      }
     }
   } else {
+    // ---------------- epilogue warps ----------------
     const int row = warp * 32 + lane;
-    const bool active = m0 + warp * 32 < p.N;
-    ptx::mbar_wait(bar_done, 0);
-    ptx::tc_fence_after();
-    if (active) {
+    for (int it = 0; it < n_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int mt = item % p.m_tiles, bh = item / p.m_tiles;
+      const int b = bh / p.H, h = bh - b * p.H, m0 = mt * TILE_M, s = it & 1;
+      const bool active = m0 + warp * 32 < p.N;
+      ptx::mbar_wait(done(s), (uint32_t)((it >> 1) & 1));
+      ptx::tc_fence_after();
       float v[64];
+      if (active) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t o[32];
-        ptx::tmem_ld_x32_sync(tmem_base + ((uint32_t)(warp * 32) << 16) + half * 32, o);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          ptx::tmem_ld_x32_sync(tmem_base + ((uint32_t)(warp * 32) << 16) + s * 64 + half * 32, o);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[half * 32 + e] = __uint_as_float(o[e]) * p.scale;
+          for (int e = 0; e < 32; ++e) v[half * 32 + e] = __uint_as_float(o[e]) * p.scale;
+        }
       }
-      uint8_t* orow = gbase + DQ_SM_O + row * 128;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tfree(s));
+      if (it > 0) {                         // the TMA store of the previous item must have read the staging tile
+        if (warp == 0 && lane == 0) ptx::bulk_wait_read0();
+        ptx::named_bar_sync(1, 128);
+      }
+      if (active) {
+        uint8_t* orow = gbase + DQ_SM_O + row * 128;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(orow + ((q ^ (row & 7)) << 4)) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                                                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-      if (p.dq_bias != nullptr) {   // q_bias gradient: query rows past N are exactly zero (their dS columns are zero)
-        float c0, c1;
-        warp_colsum64(v, lane, c0, c1);
-        atomicAdd(p.dq_bias + h * HD + 2 * lane, c0);
-        atomicAdd(p.dq_bias + h * HD + 2 * lane + 1, c1);
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(orow + ((q ^ (row & 7)) << 4)) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                                 pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        if (p.dq_bias != nullptr) {   // q_bias gradient: query rows past N are exactly zero (their dS columns are zero)
+          float c0, c1;
+          warp_colsum64(v, lane, c0, c1);
+          atomicAdd(p.dq_bias + h * HD + 2 * lane, c0);
+          atomicAdd(p.dq_bias + h * HD + 2 * lane + 1, c1);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(2, 128);
+      if (warp == 0 && lane == 0) {
+        ptx::tma_store_3d(&tm_dq, base + DQ_SM_O, h * HD, m0, b);
+        ptx::bulk_commit();
       }
     }
-    ptx::fence_proxy_async();
-    ptx::named_bar_sync(1, 128);
-    if (warp == 0 && lane == 0) {
-      ptx::tma_store_3d(&tm_dq, base + DQ_SM_O, h * HD, m0, b);
-      ptx::bulk_commit();
-      ptx::bulk_wait_read0();
-    }
+    if (warp == 0 && lane == 0) ptx::bulk_wait0();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, 64);
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 128);
 }
 
 template <bool DROP, bool HAS_BIAS>
@@ -997,13 +1036,14 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   if ((rc = make_tmap3(&tdq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dqkv, row, N, B, row, row * N, HD, TILE_M))) return rc;
   BwdDqParams dp;
   dp.dq_bias = dq_bias; dp.B = B; dp.H = H; dp.N = N; dp.n_pad = n_pad; dp.m_tiles = (N + TILE_M - 1) / TILE_M; dp.scale = scale;
+  dp.items = B * H * dp.m_tiles;
   static bool dq_configured = false;
   if (!dq_configured) {
     e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM);
     if (e != cudaSuccess) { b200vit_set_error("attn_bwd (dq): smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     dq_configured = true;
   }
-  attn_bwd_dq_kernel<<<B * H * dp.m_tiles, 160, DQ_SMEM, stream>>>(tds, tkfull, tdq, dp);
+  attn_bwd_dq_kernel<<<dp.items < sms ? dp.items : sms, DQ_THREADS, DQ_SMEM, stream>>>(tds, tkfull, tdq, dp);
   B200_CHECK_LAUNCH("attn_bwd_dq");
   if (dtable != nullptr) return b200vit_relbias_grad_launch(ds, B, H, N, ld_ds, rel_index, dtable, stream);
   return 0;

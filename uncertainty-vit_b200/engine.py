@@ -97,6 +97,7 @@ class D2VEngine:
         if dev.type != "cuda":
             raise B200VitError("D2VEngine needs the model on a CUDA (B200) device")
         self.dev = dev
+        self._copy_stream = None
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad
         self.ema_decay, self.ema_decay_init, self.ema_start_at = ema_decay, ema_decay_init, ema_start_at
         self.target_layers = list(target_layers)
@@ -267,17 +268,38 @@ class D2VEngine:
     def grad_norm(self) -> torch.Tensor:
         return torch.sqrt(self.gnorm_sq) / self.world_size
 
+    def stage_host(self, images_pinned: torch.Tensor, mask_host: np.ndarray):
+        """Enqueues the host->device copies of ONE batch on the engine's copy stream (so the next batch travels while the current
+        step computes) and returns the staged batch for step_staged(). Inputs as the data loader yields them
+        (engine_for_cyclical.py:58-60): pinned fp32 images + integer mask."""
+        B = images_pinned.shape[0]
+        m = np.ascontiguousarray(mask_host.reshape(B, -1).astype(np.uint8))
+        rows = torch.from_numpy(self.rows_from_host_mask(m, self.cfg.tokens)).pin_memory()
+        mask_pinned = torch.from_numpy(m.reshape(-1)).pin_memory()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.stream(self._copy_stream):
+            images = images_pinned.to(self.dev, non_blocking=True)
+            mask_u8 = mask_pinned.to(self.dev, non_blocking=True)
+            rows_d = rows.to(self.dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return images, mask_u8, rows_d, ev, (mask_pinned, rows)
+
+    def step_staged(self, staged, **kw) -> float:
+        """One step on a batch returned by stage_host(); reads the loss back (engine_for_cyclical.py:164)."""
+        images, mask_u8, rows, ev, _keepalive = staged
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        for t in (images, mask_u8, rows):
+            t.record_stream(cur)
+        loss = self.step(images, mask_u8, rows, **kw)
+        return float(loss.item())
+
     def step_host(self, images_pinned: torch.Tensor, mask_host: np.ndarray, **kw) -> float:
         """The reference-facing call: HOST batch in (pinned images + integer mask as the data loader yields them,
         engine_for_cyclical.py:58-60), loss value out (:164). Host->device copies and the loss read-back are inside."""
-        B = images_pinned.shape[0]
-        m = np.ascontiguousarray(mask_host.reshape(B, -1).astype(np.uint8))
-        rows = torch.from_numpy(self.rows_from_host_mask(m, self.cfg.tokens))
-        images = images_pinned.to(self.dev, non_blocking=True)
-        mask_u8 = torch.from_numpy(m.reshape(-1)).to(self.dev, non_blocking=True)
-        rows = rows.to(self.dev, non_blocking=True)
-        loss = self.step(images, mask_u8, rows, **kw)
-        return float(loss.item())
+        return self.step_staged(self.stage_host(images_pinned, mask_host), **kw)
 
 
 def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,
@@ -285,19 +307,29 @@ def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, st
     """Loop of engine_for_cyclical.train_one_epoch (:45-225) over the fused engine: per-step lr/wd from the schedule tables,
     EMA-decay anneal, non-finite loss aborts (:166-168)."""
     total, n = 0.0, 0
-    for step, (batch, _) in enumerate(data_loader):
+
+    def staged_batches():
+        for batch, _ in data_loader:
+            samples, bool_masked_pos = batch
+            if not samples.is_pinned():
+                samples = samples.pin_memory()
+            yield engine.stage_host(samples, np.asarray(bool_masked_pos))
+
+    it_batches = staged_batches()
+    nxt = next(it_batches, None)
+    step = 0
+    while nxt is not None:
+        cur, nxt = nxt, next(it_batches, None)      # batch step+1 is copied host->device while step `step` computes
         it = start_steps + step
-        samples, bool_masked_pos = batch
         lr = float(lr_schedule_values[it]) if lr_schedule_values is not None else None
         wd = float(wd_schedule_values[it]) if wd_schedule_values is not None else None
         engine.it = it
-        if not samples.is_pinned():
-            samples = samples.pin_memory()
-        loss = engine.step_host(samples, np.asarray(bool_masked_pos), lr=lr, weight_decay=wd)
+        loss = engine.step_staged(cur, lr=lr, weight_decay=wd)
         if not math.isfinite(loss):
             raise FloatingPointError(f"Loss is {loss}, stopping training")
         total += loss
         n += 1
         if step % print_freq == 0:
             log(f"Epoch: [{epoch}] step {step} loss {loss:.4f} ema_decay {engine.cur_decay:.6f}")
+        step += 1
     return {"loss": total / max(n, 1), "cur_decay": engine.cur_decay}
