@@ -142,6 +142,48 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
+MC_PASSES, MC_BATCH = 30, 192          # BASELINE.json configs[3]: S = 30 passes; eval batch int(1.5 * 128) (run_class_finetuning.py:329-331)
+
+
+def run_mc_inference(dev, rank, world, M, barrier, max_over_ranks):
+    """Second half of the BASELINE metric ("MC-inference img/s"): evaluate_MC_dropout (uncertainty_evaluations.py:42-89) — S stochastic
+    passes (eval mode, Dropout re-enabled: attn_drop 0.05) over one eval batch of 192 synthetic images, the S passes sharded across ranks,
+    logits all-gathered and reduced on device (mean logits, acc@1/5, 15-bin ECE, NLL, entropy / variance / mutual information).
+    Timed with CUDA events, max over ranks; `img_per_s` = images whose S-pass predictive statistics are produced per second (whole job),
+    `forward_img_per_s` = S * images / time."""
+    import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import mc
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(MC_BATCH, 3, 224, 224, generator=g).to(dev)
+    y = torch.randint(0, 1000, (MC_BATCH,), generator=g).to(dev)
+    out = {}
+    for key, kwargs in (("det", {}), ("stochastic", {"stochastic": True})):
+        torch.manual_seed(3)
+        model = M.create_model("beit_base_patch16_224", pretrained=False, num_classes=1000, drop_rate=0.0, drop_path_rate=0.1, attn_drop_rate=0.05,
+                               use_mean_pooling=True, init_scale=0.001, use_rel_pos_bias=False, use_shared_rel_pos_bias=True, use_abs_pos_emb=False,
+                               init_values=0.1, **kwargs).to(dev)
+        if world > 1:
+            import torch.distributed as dist
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        res = mc.evaluate_mc_dropout(model, [(x, y)], MC_PASSES, rank, world)        # warm-up (also allocates)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        e0.record()
+        for _ in range(reps):
+            res = mc.evaluate_mc_dropout(model, [(x, y)], MC_PASSES, rank, world)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+        out[key] = {"img_per_s": MC_BATCH / (ms * 1e-3), "forward_img_per_s": MC_PASSES * MC_BATCH / (ms * 1e-3), "ms_per_eval": ms,
+                    "ece": res["ece"], "nll": res["nll"], "entropy": res["entropy"]}
+        del model
+    out["config"] = {"workload": "beit_base_patch16_224 fine-tune model, MC-sample uncertainty eval", "passes": MC_PASSES, "eval_batch": MC_BATCH,
+                     "attn_drop": 0.05, "sharding": f"{MC_PASSES} passes over {world} rank(s), logits all-gathered", "scaling": "strong"}
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,6 +280,7 @@ def run_b200(args):
                 "gemm_ms_per_step": t_ms / 2, "gemm_share_of_step": (t_ms / 2) / ms, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / pk["bf16_burst"]}
     barrier()
+    mc_res = None if args.no_mc else run_mc_inference(dev, rank, world, M, barrier, max_over_ranks)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_steps(2, 1)
@@ -252,7 +295,7 @@ def run_b200(args):
                                    "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
                        "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"},
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mc_inference": mc_res, "final_loss": final_loss,
             "step_tflops_algorithmic": 140.93e9 * BATCH / (ms * 1e-3) / 1e12}))
     if world > 1:
         dist.destroy_process_group()
@@ -265,6 +308,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mc", action="store_true", help="skip the MC-sample uncertainty-inference measurement (BASELINE.json configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -82,27 +82,32 @@ typedef struct b200vit_gemm_desc {
 int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Attention (flash-style, one CTA per (batch, head), mma.sync bf16 tiles, online softmax, Philox dropout).
+ * Attention on tcgen05 / TMEM (scores and probabilities never leave tensor memory between the two GEMMs; TMA 3-D boxes of the
+ * un-permuted QKV GEMM output; one thread per score row, no shuffles; Philox4x32-7 dropout).
  * Replaces Attention.forward lines 155-185 (modeling_finetune.py): q*scale, q k^T, + rel_pos_bias, softmax,
  * attn_drop, attn @ v, transpose/reshape — and its autograd backward.
- *   qkv   : bf16 [B, N, 3, H, 64] (the QKV GEMM output, no permute copy)
- *   bias  : fp32 [H, N, ld_bias] = log2(e) * rel_pos_bias, -inf in columns [N, ld_bias) (b200vit_rel_pos_bias out_fwd), or NULL
+ *   qkv   : bf16 [B, N, 3, H, 64] (the QKV GEMM output, no permute copy), 16-byte aligned
+ *   bias  : fp32 [H, N, ld_bias] = log2(e) * rel_pos_bias, -inf in columns [N, ld_bias) (b200vit_rel_pos_bias out_fwd), or NULL;
+ *           ld_bias % 4 == 0, 16-byte aligned (it is read through a TMA tensor map)
  *   out : bf16 [B, N, H*64]      lse : fp32 [B, H, N]
  *   keep_bits : packed dropout keep mask [B, H, N, 32] bytes (bit j%8 of byte j/8), written by fwd, read by bwd
- *   keep_in   : optional injected keep mask uint8 [B, H, N, N]; NULL = Philox4x32-10 keyed on (seed, stream_id)
+ *   keep_in   : optional injected keep mask uint8 [B, H, N, N]; NULL = Philox4x32-7 keyed on (seed, stream_id)
  * N <= 208, head_dim == 64.
  * ---------------------------------------------------------------------------------------------- */
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                      float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
                      uint8_t* keep_bits, void* stream);
+/* Bytes of the caller-owned workspace of b200vit_attn_bwd: dS^T bf16 [B, H, N, ld_ds] | D fp32 [B, H, N] | transposed keep bits. */
+size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N);
 /* bias_t: the TRANSPOSED padded bias (b200vit_rel_pos_bias out_bwd_t) or NULL.
- * dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). dtable (optional, +=) is the gradient of
- * relative_position_bias_table [num_bins, H]: the kernel stores dS^T as bf16 into ds_work [B, H, N, ld_ds] (ld_ds % 8 == 0,
- * >= N rounded up to 16) and a second kernel reduces it over the batch and scatter-adds through rel_index int32 [N, N]
- * (the reference's relative_position_index, modeling_finetune.py:339-353). dq_bias / dv_bias (optional, +=, [H*64]) are the
- * q_bias / v_bias gradients (column sums of dQ / dV; modeling_finetune.py:148). */
+ * dqkv: bf16 [B, N, 3, H, 64] (fully overwritten). work: 256-byte aligned workspace of b200vit_attn_bwd_workspace_bytes() bytes;
+ * ld_ds = N rounded up to 16. The key-tile kernel leaves dS^T as bf16 [B, H, N(key), ld_ds(query)] at the start of `work`; the dQ
+ * kernel reads it back, and when dtable != NULL (the gradient of relative_position_bias_table [num_bins, H], +=) a reduction kernel
+ * sums it over the batch and scatter-adds through rel_index int32 [N, N] (the reference's relative_position_index,
+ * modeling_finetune.py:339-353). dq_bias / dv_bias (optional, +=, [H*64]) are the q_bias / v_bias gradients (column sums of
+ * dQ / dV; modeling_finetune.py:148). */
 int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_t, int64_t ld_bias,
-                     const uint8_t* keep_bits, void* ds_work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
+                     const uint8_t* keep_bits, void* work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                      float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                      void* dqkv, void* stream);
 /* Wasserstein-distance attention of the dual-stream (--stochastic) model: dist Attention.forward (modeling_finetune_dist.py:111-179)

@@ -655,6 +655,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto issue_scores = [&](int bi) {   // X_g = K Q_box^T | Y_g = V dO_box^T ; the last box of an item releases K / V
         const int sl = gb_s & 3, g = bi & 1;
         ptx::mbar_wait(ld_full(sl), (uint32_t)((gb_s >> 2) & 1));      // TMA data: no tcgen05 fence needed
+        if (m == 0) kv_trace(p.debug, L, 2, trn, 20, 0, bi);
         const uint32_t idesc = bi == nboxes - 1 ? idesc_tail : idesc_s32;
         const uint64_t db = dBk + (uint64_t)(sl * 256);
         const uint32_t d = t_score + g * 32;
@@ -662,6 +663,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::umma_bf16(d, dA + 2, db + 2, idesc, 1u);
         ptx::umma_bf16(d, dA + 4, db + 4, idesc, 1u);
         ptx::umma_bf16(d, dA + 6, db + 6, idesc, 1u);
+        if (m == 0) kv_trace(p.debug, L, 2, trn, 21, 0, bi);
         ptx::umma_commit(s_full(g));
         if (bi == nboxes - 1) ptx::umma_commit(kv_free);
         ++gb_s;
@@ -678,10 +680,12 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (m == 0) kv_trace(p.debug, L, 2, trn, 10, it, bi);
           if (bi == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
           ptx::tc_fence_after();
+          if (m == 0) kv_trace(p.debug, L, 2, trn, 13, it, bi);
           const uint64_t db = dBm + (uint64_t)(sl * 256);
           const uint32_t a = t_score + g * 32;     // bf16 pairs written in place by the element-wise warps
           ptx::umma_bf16_ts(t_acc, a, db, idesc_acc, bi > 0 ? 1u : 0u);
           if (bi < nboxes - 1 || tail_ksteps > 1) ptx::umma_bf16_ts(t_acc, a + 8, db + 128, idesc_acc, 1u);
+          if (m == 0) kv_trace(p.debug, L, 2, trn, 14, it, bi);
           ptx::umma_commit(ld_empty(sl));
           if (bi == nboxes - 1) ptx::umma_commit(acc_full);
           if (m == 0) kv_trace(p.debug, L, 2, trn, 11, it, bi);

@@ -55,7 +55,9 @@ def evaluate_mc_dropout(model, batches: Sequence[Tuple[torch.Tensor, torch.Tenso
     for _ in range(s0, s1):
         model.eval()
         enable_dropout(model)
-        outs.append(torch.cat([model(x).float() for x, _ in batches], 0))
+        # the dual-stream (--stochastic) model returns (mean_feat, cov_feat, logits): modeling_finetune_dist.py:311-326
+        fw = [model(x) for x, _ in batches]
+        outs.append(torch.cat([(o[-1] if isinstance(o, (tuple, list)) else o).float() for o in fw], 0))
     dev = batches[0][0].device
     K = model.cfg.num_classes
     N = sum(x.shape[0] for x, _ in batches)
