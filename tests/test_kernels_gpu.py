@@ -245,7 +245,8 @@ def _attn_ref(qkv, bias, keep, p, scale):
     return (pr @ v).transpose(1, 2).reshape(B, N, H * D)
 
 
-@pytest.mark.parametrize("B,H,N,p", [(2, 2, 17, 0.0), (2, 3, 197, 0.0), (3, 2, 197, 0.1), (1, 2, 64, 0.25), (2, 2, 208, 0.05)])
+@pytest.mark.parametrize("B,H,N,p", [(2, 2, 17, 0.0), (2, 3, 197, 0.0), (3, 2, 197, 0.1), (1, 2, 64, 0.25), (2, 2, 208, 0.05), (1, 1, 5, 0.0),
+                                      (2, 2, 129, 0.05), (40, 12, 197, 0.05)])
 def test_attention_fwd_bwd(ops, cuda, B, H, N, p):
     g = torch.Generator(device="cpu").manual_seed(N + B)
     qkv = _bf(torch.randn(B, N, 3, H, 64, generator=g)).to(cuda)

@@ -27,24 +27,26 @@ using namespace attn;
 constexpr int TILE_M = 128;
 constexpr int BIAS_STAGES = 2;
 constexpr int BIAS_STAGE_BYTES = TILE_M * 128;           // 128 rows x 32 fp32
-constexpr int SM_Q = 0;                                   // 128 rows x 128 B (re-used as the bf16 O staging tile)
+// per-lane shared memory of the forward kernel (a CTA holds FWD_LANES independent lanes)
+constexpr int SM_Q = 0;                                   // 128 rows x 128 B
 constexpr int SM_K = SM_Q + TILE_M * 128;                 // NMAX rows x 128 B
-constexpr int SM_V = SM_K + NMAX * 128;
+constexpr int SM_V = SM_K + NMAX * 128;                   // NMAX rows x 128 B; its first 16 KB double as the bf16 O staging tile of the epilogue
 constexpr int SM_BIAS = SM_V + NMAX * 128;
 constexpr int SM_BAR = SM_BIAS + BIAS_STAGES * BIAS_STAGE_BYTES;
-constexpr int FWD100_SMEM = SM_BAR + 128 + 1024;          // + barriers + 1024-byte alignment slack
-constexpr int TMEM_COLS = 256;
-constexpr int O_COL = 128;                                // O accumulator: TMEM columns [128, 192)
-constexpr int SOFTMAX_WARPS = 4;
-constexpr int FWD100_THREADS = (SOFTMAX_WARPS + 1) * 32;
-static_assert(SM_K % 1024 == 0 && SM_V % 1024 == 0 && SM_BIAS % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
-static_assert(2 * FWD100_SMEM + 2048 <= 232448, "two CTAs per SM");
+constexpr int FWD_LANE_BYTES = SM_BAR + 1024;             // 103424
+constexpr int FWD_LANES = 2;
+constexpr int FWD_EW_WARPS = 4;                           // softmax warps per lane (one thread per query row)
+constexpr int FWD100_THREADS = FWD_LANES * (FWD_EW_WARPS + 2) * 32;   // + MMA warp + TMA warp per lane
+constexpr int FWD100_SMEM = FWD_LANES * FWD_LANE_BYTES + 1024;
+constexpr int O_COL = 128;                                // O accumulator: TMEM columns [128, 192) of the lane's 256-column half
+static_assert(SM_K % 1024 == 0 && SM_V % 1024 == 0 && SM_BIAS % 1024 == 0 && FWD_LANE_BYTES % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+static_assert(FWD100_SMEM <= 232448, "forward kernel smem");
 
 struct Fwd100Params {
   float* lse;               // [B, H, N]
   uint8_t* keep_bits;       // [B, H, N, 32]
   const uint8_t* keep_in;   // [B, H, N, N] or null
-  int B, H, N, n_pad, m_tiles;
+  int B, H, N, n_pad, m_tiles, items;
   float sl2, inv_keep;
   uint32_t thresh;
   uint64_t seed;
@@ -100,178 +102,229 @@ __device__ __forceinline__ void pass1_chunk(const Fwd100Params& p, uint32_t tadd
   else ptx::tmem_st_x16(taddr, reinterpret_cast<const uint32_t(&)[16]>(s));
 }
 
-template <int COLS, bool DROP>
-__device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint32_t trow, int bh, int i, int c, float mx, float& l) {
-  uint32_t s[COLS];
-  if constexpr (COLS == 32) ptx::tmem_ld_x32_sync(trow + c * 32, reinterpret_cast<uint32_t(&)[32]>(s));
-  else ptx::tmem_ld_x16_sync(trow + c * 32, reinterpret_cast<uint32_t(&)[16]>(s));
-  float pr[COLS];
+// 16 probabilities of one row: p = 2^(s2 - max), row sum, dropout by the keep bits `w16` (bit e = key e of this step), bf16 pairs to TMEM
+template <bool DROP>
+__device__ __forceinline__ void pass2_step16(uint32_t t_src, uint32_t t_dst, float mx, float& l, uint32_t w16) {
+  uint32_t s[16];
+  ptx::tmem_ld_x16_sync(t_src, s);
+  float pr[16];
   float acc = 0.f;
 #pragma unroll
-  for (int e = 0; e < COLS; ++e) {
+  for (int e = 0; e < 16; ++e) {
     pr[e] = ex2(__uint_as_float(s[e]) - mx);
     acc += pr[e];
   }
   l += acc;
   if (DROP) {
-    const uint32_t w = keep_word<COLS>(p, bh, i, c);
 #pragma unroll
-    for (int e = 0; e < COLS; ++e)
-      if (!((w >> e) & 1u)) pr[e] = 0.f;
-    if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
+    for (int e = 0; e < 16; ++e)
+      if (!(w16 & (1u << e))) pr[e] = 0.f;
   }
-  uint32_t pk[COLS / 2];
+  uint32_t pk[8];
 #pragma unroll
-  for (int e = 0; e < COLS / 2; ++e) pk[e] = pack_bf16x2(pr[2 * e], pr[2 * e + 1]);
-  if constexpr (COLS == 32) ptx::tmem_st_x16(trow + c * 16, reinterpret_cast<const uint32_t(&)[16]>(pk));
-  else ptx::tmem_st_x8(trow + c * 16, reinterpret_cast<const uint32_t(&)[8]>(pk));
+  for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(pr[2 * e], pr[2 * e + 1]);
+  ptx::tmem_st_x8(t_dst, pk);
 }
 
+template <int COLS, bool DROP>
+__device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint32_t trow, int bh, int i, int c, float mx, float& l) {
+  uint32_t w = 0xffffffffu;
+  if (DROP) {
+    w = keep_word<COLS>(p, bh, i, c);
+    if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
+  }
+  pass2_step16<DROP>(trow + c * 32, trow + c * 16, mx, l, w);
+  if constexpr (COLS == 32) pass2_step16<DROP>(trow + c * 32 + 16, trow + c * 16 + 8, mx, l, w >> 16);
+}
+
+// Persistent: one CTA per SM holds FWD_LANES independent lanes (own smem, own 256-column TMEM half, own barriers); lane L of CTA c
+// walks items (2c + L) + k * 2 * gridDim of the (batch, head, query-tile) list. Q / K of the next item are requested as soon as the
+// S MMAs of the current one have read them, V once the epilogue's TMA store has drained the staging tile that aliases it, the bias
+// ring simply runs on: the load / launch latency a one-shot CTA exposes per item is paid once per lane.
 template <bool DROP, bool HAS_BIAS>
-__global__ void __launch_bounds__(FWD100_THREADS, 2)
+__global__ void __launch_bounds__(FWD100_THREADS, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                       const __grid_constant__ CUtensorMap tm_bias, const __grid_constant__ CUtensorMap tm_out, const Fwd100Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA warps 0..7: softmax warps (lane L = warp >> 2; TMEM lane quadrant = CTA warp index & 3, a hardware rule); 8, 9: MMA and TMA warp
+  // of lane 0; 10, 11: of lane 1.   `warp` = role inside the lane: 0..3 softmax, 4 MMA, 5 TMA
+  const int L = warp_cta < FWD_LANES * FWD_EW_WARPS ? warp_cta / FWD_EW_WARPS : (warp_cta - FWD_LANES * FWD_EW_WARPS) >> 1;
+  const int warp = warp_cta < FWD_LANES * FWD_EW_WARPS ? warp_cta % FWD_EW_WARPS : FWD_EW_WARPS + ((warp_cta - FWD_LANES * FWD_EW_WARPS) & 1);
+  const uint32_t cta_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = cta_base + L * FWD_LANE_BYTES;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
-  const uint32_t bar_qk = base + SM_BAR, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
-  auto bias_full = [&](int s) { return bar_qk + 40u + 8u * s; };
-  auto bias_empty = [&](int s) { return bar_qk + 40u + 8u * (BIAS_STAGES + s); };
-  const uint32_t tmem_slot = bar_qk + 40u + 16u * BIAS_STAGES;
+  const uint32_t bar0 = base + SM_BAR;
+  const uint32_t qk_full = bar0, v_full = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, o_full = bar0 + 32, qk_free = bar0 + 40,
+                 v_free = bar0 + 48, t_free = bar0 + 56;
+  auto bias_full = [&](int s) { return bar0 + 64u + 8u * s; };
+  auto bias_empty = [&](int s) { return bar0 + 80u + 8u * s; };
+  const uint32_t tmem_slot = cta_base + SM_BAR + 128u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x % p.m_tiles, bh = blockIdx.x / p.m_tiles;
-  const int b = bh / p.H, h = bh - b * p.H;
-  const int m0 = mt * TILE_M;
   const int n_pad = p.n_pad;
   const int nchunks = (n_pad + 31) >> 5;
   const int tail_cols = n_pad - (nchunks - 1) * 32;   // 16 or 32
+  const int first = blockIdx.x * FWD_LANES + L, stride = gridDim.x * FWD_LANES;
+  const int n_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
+  auto item_of = [&](int it, int& b, int& h, int& m0, int& bh) {
+    const int item = first + it * stride;
+    const int mt = item % p.m_tiles;
+    bh = item / p.m_tiles;
+    b = bh / p.H; h = bh - b * p.H; m0 = mt * TILE_M;
+  };
 
-  if (warp == SOFTMAX_WARPS) {
+  if (warp == FWD_EW_WARPS) {
     if (lane == 0) {
-      ptx::mbar_init(bar_qk, 1); ptx::mbar_init(bar_v, 1); ptx::mbar_init(bar_s, 1);
-      ptx::mbar_init(bar_p, SOFTMAX_WARPS * 32); ptx::mbar_init(bar_o, 1);
-      for (int s = 0; s < BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), SOFTMAX_WARPS); }
+      ptx::mbar_init(qk_full, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, FWD_EW_WARPS * 32);
+      ptx::mbar_init(o_full, 1); ptx::mbar_init(qk_free, 1); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, FWD_EW_WARPS);
+      for (int s = 0; s < BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), FWD_EW_WARPS); }
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_out);
       if (HAS_BIAS) ptx::prefetch_tmap(&tm_bias);
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (L == 0) {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base += L * 256;
 
-  if (warp == SOFTMAX_WARPS) {
-    if (lane == 0) {
-      // ---------------- TMA producer + MMA issuer ----------------
-      ptx::mbar_arrive_expect_tx(bar_qk, TILE_M * 128 + n_pad * 128);
-      ptx::tma_load_3d(base + SM_Q, &tm_q, bar_qk, h * HD, m0, b);
-      ptx::tma_load_3d(base + SM_K, &tm_kv, bar_qk, (p.H + h) * HD, 0, b);
-      ptx::mbar_arrive_expect_tx(bar_v, n_pad * 128);
-      ptx::tma_load_3d(base + SM_V, &tm_kv, bar_v, (2 * p.H + h) * HD, 0, b);
-      if (HAS_BIAS) {
-        for (int c = 0; c < nchunks && c < BIAS_STAGES; ++c) {
-          ptx::mbar_arrive_expect_tx(bias_full(c), BIAS_STAGE_BYTES);
-          ptx::tma_load_3d(base + SM_BIAS + c * BIAS_STAGE_BYTES, &tm_bias, bias_full(c), c * 32, m0, h);
-        }
+  if (warp == FWD_EW_WARPS) {
+    if (lane == 0 && n_items > 0) {
+      // ---------------- MMA issue ----------------
+      const uint64_t dQ = ptx::make_smem_desc(base + SM_Q, 16, 1024), dK = ptx::make_smem_desc(base + SM_K, 16, 1024);
+      const uint64_t dV = ptx::make_smem_desc(base + SM_V, NMAX * 128, 1024);                   // MN-major: key rows of 64 d-elements
+      const uint32_t idesc_s = ptx::make_idesc_bf16(TILE_M, n_pad, false, false), idesc_o = ptx::make_idesc_bf16(TILE_M, HD, false, true);
+      const int ksteps = n_pad >> 4;
+      for (int it = 0; it < n_items; ++it) {
+        const uint32_t ph = (uint32_t)(it & 1);
+        ptx::mbar_wait(qk_full, ph);
+        if (it > 0) { ptx::mbar_wait(t_free, ph ^ 1u); ptx::tc_fence_after(); }    // the epilogue has drained O of the previous item
+        ptx::umma_bf16(tmem_base, dQ, dK, idesc_s, 0u);
+        ptx::umma_bf16(tmem_base, dQ + 2, dK + 2, idesc_s, 1u);
+        ptx::umma_bf16(tmem_base, dQ + 4, dK + 4, idesc_s, 1u);
+        ptx::umma_bf16(tmem_base, dQ + 6, dK + 6, idesc_s, 1u);
+        ptx::umma_commit(s_full);
+        ptx::umma_commit(qk_free);
+        // O = P~ V : A = bf16 probabilities in TMEM columns [0, n_pad/2), B = V
+        ptx::mbar_wait(v_full, ph);
+        ptx::mbar_wait(p_full, ph);
+        ptx::tc_fence_after();
+        for (int kk = 0; kk < ksteps; ++kk) ptx::umma_bf16_ts(tmem_base + O_COL, tmem_base + kk * 8, dV + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
+        ptx::umma_commit(o_full);
       }
-      ptx::mbar_wait(bar_qk, 0);
-      ptx::tc_fence_after();
-      const uint32_t idesc_s = ptx::make_idesc_bf16(TILE_M, n_pad, false, false);
-#pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        ptx::umma_bf16(tmem_base, ptx::make_smem_desc(base + SM_Q + k * 32, 16, 1024), ptx::make_smem_desc(base + SM_K + k * 32, 16, 1024),
-                       idesc_s, k > 0 ? 1u : 0u);
-      ptx::umma_commit(bar_s);
-      if (HAS_BIAS) {
-        for (int c = BIAS_STAGES; c < nchunks; ++c) {
-          const int s = c % BIAS_STAGES, use = c / BIAS_STAGES;
-          ptx::mbar_wait(bias_empty(s), (uint32_t)((use - 1) & 1));
+    }
+  } else if (warp == FWD_EW_WARPS + 1) {
+    if (lane == 0 && n_items > 0) {
+      // ---------------- TMA: Q, K (freed by the S MMAs) and V (freed by the epilogue's TMA store) ----------------
+      for (int it = 0; it < n_items; ++it) {
+        int b, h, m0, bh;
+        item_of(it, b, h, m0, bh);
+        if (it > 0) ptx::mbar_wait(qk_free, (uint32_t)((it - 1) & 1));
+        ptx::mbar_arrive_expect_tx(qk_full, TILE_M * 128 + n_pad * 128);
+        ptx::tma_load_3d(base + SM_Q, &tm_q, qk_full, h * HD, m0, b);
+        ptx::tma_load_3d(base + SM_K, &tm_kv, qk_full, (p.H + h) * HD, 0, b);
+        if (it > 0) ptx::mbar_wait(v_free, (uint32_t)((it - 1) & 1));
+        ptx::mbar_arrive_expect_tx(v_full, n_pad * 128);
+        ptx::tma_load_3d(base + SM_V, &tm_kv, v_full, (2 * p.H + h) * HD, 0, b);
+      }
+    } else if (HAS_BIAS && lane == 1 && n_items > 0) {
+      // ---------------- TMA: bias ring, [128 queries x 32 keys] fp32 boxes ----------------
+      int gc = 0;
+      for (int it = 0; it < n_items; ++it) {
+        int b, h, m0, bh;
+        item_of(it, b, h, m0, bh);
+        for (int c = 0; c < nchunks; ++c, ++gc) {
+          const int s = gc % BIAS_STAGES;
+          if (gc >= BIAS_STAGES) ptx::mbar_wait(bias_empty(s), (uint32_t)(((gc / BIAS_STAGES) - 1) & 1));
           ptx::mbar_arrive_expect_tx(bias_full(s), BIAS_STAGE_BYTES);
           ptx::tma_load_3d(base + SM_BIAS + s * BIAS_STAGE_BYTES, &tm_bias, bias_full(s), c * 32, m0, h);
         }
       }
-      // O = P~ V : A = bf16 probabilities in TMEM columns [0, n_pad/2), B = V (MN-major: key rows of 64 d-elements)
-      ptx::mbar_wait(bar_p, 0);
-      ptx::mbar_wait(bar_v, 0);
-      ptx::tc_fence_after();
-      const uint32_t idesc_o = ptx::make_idesc_bf16(TILE_M, HD, false, true);
-      for (int kk = 0; kk < n_pad / 16; ++kk)
-        ptx::umma_bf16_ts(tmem_base + O_COL, tmem_base + kk * 8, ptx::make_smem_desc(base + SM_V + kk * 2048, NMAX * 128, 1024), idesc_o,
-                          kk > 0 ? 1u : 0u);
-      ptx::umma_commit(bar_o);
     }
   } else {
     // ---------------- softmax warps: one thread per query row ----------------
     const int row = warp * 32 + lane;
-    const int i = m0 + row;
-    const bool active = m0 + warp * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    ptx::mbar_wait(bar_s, 0);
-    ptx::tc_fence_after();
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % BIAS_STAGES;
-      if (HAS_BIAS) ptx::mbar_wait(bias_full(s), (uint32_t)((c / BIAS_STAGES) & 1));
-      if (active) {
-        const uint8_t* bias_row = gbase + SM_BIAS + s * BIAS_STAGE_BYTES + row * 128;
-        if (c + 1 < nchunks || tail_cols == 32) pass1_chunk<32, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
-        else pass1_chunk<16, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
-      }
-      if (HAS_BIAS) {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bias_empty(s));
-      }
-    }
-    ptx::tmem_st_wait();
-    float l = 0.f;
-    if (active) {
-      for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks || tail_cols == 32) pass2_chunk<32, DROP>(p, trow, bh, i, c, mx, l);
-        else pass2_chunk<16, DROP>(p, trow, bh, i, c, mx, l);
-      }
-    }
-    ptx::tmem_st_wait();
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(bar_p);
-    // ---------------- epilogue ----------------
-    ptx::mbar_wait(bar_o, 0);
-    ptx::tc_fence_after();
-    if (active) {
-      const float inv = p.inv_keep / l;
-      uint8_t* orow = gbase + SM_Q + row * 128;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t o[32];
-        ptx::tmem_ld_x32_sync(trow + O_COL + half * 32, o);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + (((half * 4 + q) ^ (row & 7)) << 4)) = u;
+    int gc = 0;
+    for (int it = 0; it < n_items; ++it) {
+      int b, h, m0, bh;
+      item_of(it, b, h, m0, bh);
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int i = m0 + row;
+      const bool active = m0 + warp * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
+      ptx::mbar_wait(s_full, ph);
+      ptx::tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunks; ++c, ++gc) {
+        const int s = gc % BIAS_STAGES;
+        if (HAS_BIAS) ptx::mbar_wait(bias_full(s), (uint32_t)((gc / BIAS_STAGES) & 1));
+        if (active) {
+          const uint8_t* bias_row = gbase + SM_BIAS + s * BIAS_STAGE_BYTES + row * 128;
+          if (c + 1 < nchunks || tail_cols == 32) pass1_chunk<32, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
+          else pass1_chunk<16, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
+        }
+        if (HAS_BIAS) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bias_empty(s));
         }
       }
-      if (i < p.N && p.lse != nullptr) p.lse[(long long)bh * p.N + i] = (mx + log2f(l)) / LOG2E;
+      ptx::tmem_st_wait();
+      float l = 0.f;
+      if (active) {
+        for (int c = 0; c < nchunks; ++c) {
+          if (c + 1 < nchunks || tail_cols == 32) pass2_chunk<32, DROP>(p, trow, bh, i, c, mx, l);
+          else pass2_chunk<16, DROP>(p, trow, bh, i, c, mx, l);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+      // ---------------- epilogue ----------------
+      ptx::mbar_wait(o_full, ph);
+      ptx::tc_fence_after();
+      if (active) {
+        const float inv = p.inv_keep / l;
+        uint8_t* orow = gbase + SM_V + row * 128;           // V is dead (o_full) and the previous store has drained the tile (v_free)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          ptx::tmem_ld_x32_sync(trow + O_COL + half * 32, o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + (((half * 4 + q) ^ (row & 7)) << 4)) = u;
+          }
+        }
+        if (i < p.N && p.lse != nullptr) p.lse[(long long)bh * p.N + i] = (mx + log2f(l)) / LOG2E;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(t_free);              // the next item's S MMAs may overwrite this lane's TMEM half
+      ptx::fence_proxy_async();
+      ptx::named_bar_sync(1 + L, FWD_EW_WARPS * 32);
+      if (warp == 0 && lane == 0) {
+        ptx::tma_store_3d(&tm_out, base + SM_V, h * HD, m0, b);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read0();
+        ptx::mbar_arrive(v_free);                           // the TMA warp may now overwrite V (and with it the staging tile)
+      }
     }
-    ptx::fence_proxy_async();
-    ptx::named_bar_sync(1, SOFTMAX_WARPS * 32);
-    if (warp == 0 && lane == 0) {
-      ptx::tma_store_3d(&tm_out, base + SM_Q, h * HD, m0, b);
-      ptx::bulk_commit();
-      ptx::bulk_wait_read0();
-    }
+    if (warp == 0 && lane == 0) ptx::bulk_wait0();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == SOFTMAX_WARPS) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == FWD_EW_WARPS && L == 0) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -324,7 +377,8 @@ cudaError_t launch_fwd100(const CUtensorMap& tq, const CUtensorMap& tkv, const C
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  attn_fwd_sm100_kernel<DROP, HAS_BIAS><<<p.B * p.H * p.m_tiles, FWD100_THREADS, FWD100_SMEM, stream>>>(tq, tkv, tb, to, p);
+  const int ctas = min(b200vit_num_sms(), (p.items + FWD_LANES - 1) / FWD_LANES);
+  attn_fwd_sm100_kernel<DROP, HAS_BIAS><<<ctas, FWD100_THREADS, FWD100_SMEM, stream>>>(tq, tkv, tb, to, p);
   return cudaGetLastError();
 }
 
@@ -1068,7 +1122,7 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
   B200_CHECK_ARG(bias == nullptr || (ld_bias >= n_pad && ld_bias % 4 == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                  "attn_fwd: bias must be the padded layout of b200vit_rel_pos_bias ([H,N,ld], ld %% 4 == 0, ld >= %d, 16-byte aligned)", n_pad);
   Fwd100Params p;
-  p.lse = lse; p.keep_bits = keep_bits; p.keep_in = keep_in; p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.m_tiles = (N + TILE_M - 1) / TILE_M;
+  p.lse = lse; p.keep_bits = keep_bits; p.keep_in = keep_in; p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.m_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.m_tiles;
   p.sl2 = scale * LOG2E; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   p.thresh = (uint32_t)(p_drop * 65536.0f + 0.5f); p.seed = seed; p.stream_id = stream_id;
   const uint64_t row = 3ull * H * HD;
