@@ -92,11 +92,13 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
  *   out : bf16 [B, N, H*64]      lse : fp32 [B, H, N]
  *   keep_bits : packed dropout keep mask [B, H, N, 32] bytes (bit j%8 of byte j/8), written by fwd, read by bwd
  *   keep_in   : optional injected keep mask uint8 [B, H, N, N]; NULL = Philox4x32-7 keyed on (seed, stream_id)
+ *   seed_dev  : optional DEVICE pointer to the 64-bit key; when non-NULL it replaces `seed` (a captured CUDA graph of the training
+ *               step stays valid across steps: the host rewrites *seed_dev before every replay)
  * N <= 208, head_dim == 64.
  * ---------------------------------------------------------------------------------------------- */
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
-                     float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
-                     uint8_t* keep_bits, void* stream);
+                     float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
+                     float* lse, uint8_t* keep_bits, void* stream);
 /* Bytes of the caller-owned workspace of b200vit_attn_bwd: dS^T bf16 [B, H, N, ld_ds] | D fp32 [B, H, N] | transposed keep bits. */
 size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N);
 /* bias_t: the TRANSPOSED padded bias (b200vit_rel_pos_bias out_bwd_t) or NULL.

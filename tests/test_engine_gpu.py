@@ -118,3 +118,30 @@ def test_dist_engine_step_matches_oracle_step(cuda, golden_dir):
     assert not bad, bad
     # the unused cov_qkv.weight is neither updated nor decayed (torch AdamW skips grad-less parameters)
     assert torch.equal(model.state_dict()["blocks.0.attn.cov_qkv.weight"], w_before)
+
+
+def test_graphed_step_matches_eager(cuda):
+    """The CUDA-graph replay of forward+backward (engine._fwd_bwd_graphed) and the eager launch sequence are the same computation:
+    same seeds -> same losses up to the fp32 atomic-order noise of the split-K / column-sum reductions."""
+    from functools import partial
+    from uncertainty_vit_b200 import engine as E, modeling as M
+    losses = {}
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        model = M.VisionTransformerForCyclicalTraining(img_size=224, patch_size=16, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                                                       norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), use_shared_rel_pos_bias=True,
+                                                       use_abs_pos_emb=False, init_values=0.1, drop_path_rate=0.1, attn_drop_rate=0.05).to(cuda)
+        eng = E.D2VEngine(model, lr=1e-3, target_layers=[0, 1], use_graph=use_graph, seed=5)
+        g = torch.Generator().manual_seed(1)
+        B = 4
+        x = torch.randn(B, 3, 224, 224, generator=g).to(cuda)
+        mask = np.zeros((B, 196), dtype=np.uint8)
+        for b in range(B):
+            mask[b, torch.randperm(196, generator=g)[:120].numpy()] = 1
+        rows = torch.from_numpy(eng.rows_from_host_mask(mask, 197)).to(cuda)
+        mu8 = torch.from_numpy(mask.reshape(-1)).to(cuda)
+        losses[use_graph] = [float(eng.step(x, mu8, rows).item()) for _ in range(6)]
+        if use_graph:
+            assert len(eng._graphs) == 1, "steps 3.. must have been replayed from the captured graph"
+    a, b = np.array(losses[False]), np.array(losses[True])
+    assert np.all(np.isfinite(b)) and np.max(np.abs(a - b) / np.abs(a)) < 5e-3, (a, b)

@@ -83,6 +83,7 @@ class ParamSource:
 class Noise:
     """Randomness of one training forward. Defaults = device Philox streams; any field may be injected (parity tests)."""
     seed: int = 0
+    seed_dev: Optional[torch.Tensor] = None             # int64 [1] on the device: overrides `seed` for attention dropout (CUDA-graph replays)
     drop_path_scale: Optional[torch.Tensor] = None      # fp32 [L, draws, B] = keep / (1 - p_l)
     attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
     drop_path_active: bool = True                       # applies only to training forwards
@@ -98,7 +99,7 @@ def _empty(shape, dtype, dev):
 # ------------------------------------------------------------------------------------------------------------------
 def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: Optional[torch.Tensor], *, save: bool,
                   dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
-                  x_mid: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                  x_mid: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None, seed_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """x_in: fp32 [B*T, C] residual stream. Returns the saved tensors (x_out under 'x_out')."""
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
@@ -114,7 +115,7 @@ def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B
     attn_out = _empty((M, C), bf, dev)
     lse = _empty((B, H, T), torch.float32, dev) if save else None
     keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
-    ops.attn_fwd(qkv, bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, attn_out, lse, keep_bits)
+    ops.attn_fwd(qkv, bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, attn_out, lse, keep_bits, seed_dev=seed_dev)
     if x_mid is None:
         x_mid = _empty((M, C), torch.float32, dev)
     t1 = _empty((M, C), bf, dev) if save else None
@@ -263,7 +264,7 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn, seed=noise.seed,
-                          keep_in=keep_in)
+                          keep_in=keep_in, seed_dev=noise.seed_dev)
         if i in collect:
             if collect_what == "fc":      # fc_feature = x_out - x_mid (modeling_cyclical.py:203-205); rarely used
                 layers[i] = (s["x_out"] - s["x_mid"]).view(B, T, C)

@@ -50,18 +50,19 @@ struct Fwd100Params {
   float sl2, inv_keep;
   uint32_t thresh;
   uint64_t seed;
+  const uint64_t* seed_dev;  // when non-null the Philox key is read from device memory (a captured CUDA graph re-keys every replay)
   uint32_t stream_id;
 };
 
 // Keep bits of the 32 (or 16) keys [32c, 32c + COLS) of query row i — bit e = key 32c + e. Same Philox stream layout as the
 // mma.sync kernels (dropout_group / dropout_u16 in attn_common.cuh), so b200vit_dropout_mask and the backward agree.
 template <int COLS>
-__device__ __forceinline__ uint32_t keep_word(const Fwd100Params& p, int bh, int i, int c) {
+__device__ __forceinline__ uint32_t keep_word(const Fwd100Params& p, uint64_t seed, int bh, int i, int c) {
   uint32_t w = 0u;
   if (p.keep_in == nullptr) {
 #pragma unroll
     for (int quad = 0; quad < 4; ++quad) {
-      const Philox4 r = dropout_group(p.seed, p.stream_id, bh, i, quad, c);
+      const Philox4 r = dropout_group(seed, p.stream_id, bh, i, quad, c);
 #pragma unroll
       for (int n4 = 0; n4 < COLS / 8; ++n4) {
         w |= (dropout_u16(r, n4 * 2) >= p.thresh ? 1u : 0u) << (n4 * 8 + quad * 2);
@@ -127,10 +128,10 @@ __device__ __forceinline__ void pass2_step16(uint32_t t_src, uint32_t t_dst, flo
 }
 
 template <int COLS, bool DROP>
-__device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint32_t trow, int bh, int i, int c, float mx, float& l) {
+__device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint64_t seed, uint32_t trow, int bh, int i, int c, float mx, float& l) {
   uint32_t w = 0xffffffffu;
   if (DROP) {
-    w = keep_word<COLS>(p, bh, i, c);
+    w = keep_word<COLS>(p, seed, bh, i, c);
     if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
   }
   pass2_step16<DROP>(trow + c * 32, trow + c * 16, mx, l, w);
@@ -252,6 +253,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ---------------- softmax warps: one thread per query row ----------------
     const int row = warp * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint64_t seed = (DROP && p.seed_dev != nullptr) ? __ldg(reinterpret_cast<const unsigned long long*>(p.seed_dev)) : p.seed;
     int gc = 0;
     for (int it = 0; it < n_items; ++it) {
       int b, h, m0, bh;
@@ -279,8 +281,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float l = 0.f;
       if (active) {
         for (int c = 0; c < nchunks; ++c) {
-          if (c + 1 < nchunks || tail_cols == 32) pass2_chunk<32, DROP>(p, trow, bh, i, c, mx, l);
-          else pass2_chunk<16, DROP>(p, trow, bh, i, c, mx, l);
+          if (c + 1 < nchunks || tail_cols == 32) pass2_chunk<32, DROP>(p, seed, trow, bh, i, c, mx, l);
+          else pass2_chunk<16, DROP>(p, seed, trow, bh, i, c, mx, l);
         }
       }
       ptx::tmem_st_wait();
@@ -1108,8 +1110,8 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
 }
 
 extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
-                                float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in, void* out, float* lse,
-                                uint8_t* keep_bits, void* stream_) {
+                                float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
+                                float* lse, uint8_t* keep_bits, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_fwd: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0, "attn_fwd: bad B=%d H=%d", B, H);
@@ -1124,7 +1126,7 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
   Fwd100Params p;
   p.lse = lse; p.keep_bits = keep_bits; p.keep_in = keep_in; p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.m_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.m_tiles;
   p.sl2 = scale * LOG2E; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-  p.thresh = (uint32_t)(p_drop * 65536.0f + 0.5f); p.seed = seed; p.stream_id = stream_id;
+  p.thresh = (uint32_t)(p_drop * 65536.0f + 0.5f); p.seed = seed; p.seed_dev = seed_dev; p.stream_id = stream_id;
   const uint64_t row = 3ull * H * HD;
   CUtensorMap tq, tkv, tb, to;
   int rc;

@@ -90,7 +90,7 @@ class D2VEngine:
                  ema_decay_init=0.999, ema_start_at=0, target_layers: Sequence[int] = (6, 7, 8, 9, 10, 11), l1_beta=2.0, l2_loss=False,
                  target_layer_norm_last=True, post_target_layer_norm=True, layer_decay: Optional[float] = None, loss_scale=-1.0,
                  skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0,
-                 lambda_pretraining: float = 1e-5):
+                 lambda_pretraining: float = 1e-5, use_graph: bool = True):
         self.model = model
         self.cfg: VitConfig = model.cfg
         dev = model.cls_token.device
@@ -98,6 +98,9 @@ class D2VEngine:
             raise B200VitError("D2VEngine needs the model on a CUDA (B200) device")
         self.dev = dev
         self._copy_stream = None
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._eager_steps = 0
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad
         self.ema_decay, self.ema_decay_init, self.ema_start_at = ema_decay, ema_decay_init, ema_start_at
         self.target_layers = list(target_layers)
@@ -190,7 +193,7 @@ class D2VEngine:
         return self.ema_decay
 
     def step(self, images: torch.Tensor, mask_u8: torch.Tensor, rows: torch.Tensor, *, lr: Optional[float] = None,
-             weight_decay: Optional[float] = None, noise: Optional[Noise] = None) -> torch.Tensor:
+             weight_decay: Optional[float] = None, noise: Optional[Noise] = None, graph: Optional[bool] = None) -> torch.Tensor:
         """One optimisation step on device-resident inputs. images fp32 [B,3,H,W]; mask_u8 uint8 [B*np]; rows int32 [R].
         Returns the device scalar loss (no sync)."""
         cfg = self.cfg
@@ -200,10 +203,26 @@ class D2VEngine:
         lr = self.lr if lr is None else lr
         wd = self.wd if weight_decay is None else weight_decay
         self.cur_decay = self.decay_at(self.it)
+        injected = noise
         if noise is None:
             noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
         if cfg.dist:
             return self._step_dist(images, mask_u8, rows, lr, wd, noise)
+        if graph is None:
+            graph = self.use_graph
+        if graph and injected is None and ops.GEMM_TIMING is None:
+            self._fwd_bwd_graphed(images, mask_u8, rows, noise.seed)
+        else:
+            self._fwd_bwd(images, mask_u8, rows, noise)
+            self._eager_steps += 1
+        return self._optimizer_step(lr, wd)
+
+    def _fwd_bwd(self, images, mask_u8, rows, noise):
+        """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser)."""
+        cfg = self.cfg
+        B = images.shape[0]
+        C, T = cfg.embed_dim, cfg.tokens
+        R = rows.numel()
         patches = core.patches_bf16(cfg, images)
         # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88
         layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers, patches=patches)
@@ -219,7 +238,41 @@ class D2VEngine:
         del layers
         self.g32.zero_()
         core.vit_backward(self.student, cfg, ctx, dy, self.grads)
-        return self._optimizer_step(lr, wd)
+
+    def _fwd_bwd_graphed(self, images, mask_u8, rows, seed: int):
+        """The same launch sequence replayed from a CUDA graph (one per (batch, masked-row count)): ~400 stream-ordered, allocation-free
+        launches whose Python issue time (~55 us each) exceeds the run time of the small row kernels. Inputs are copied into static
+        buffers; the per-step randomness enters through device memory (drop-path factors, the Philox key of attention dropout), so the
+        captured graph stays valid across steps. The first two steps of a shape run eagerly (lazy kernel attributes, allocator warm-up)."""
+        cfg = self.cfg
+        key = (tuple(images.shape), int(rows.numel()))
+        g = self._graphs.get(key)
+        if g is None and self._eager_steps < 2:
+            self._fwd_bwd(images, mask_u8, rows, Noise(seed=seed))
+            self._eager_steps += 1
+            return
+        if g is None:
+            st = dict(images=torch.empty_like(images), mask=torch.empty_like(mask_u8), rows=torch.empty_like(rows),
+                      seed=torch.zeros(1, dtype=torch.int64, device=self.dev),
+                      dps=torch.empty(cfg.depth, 2, images.shape[0], dtype=torch.float32, device=self.dev))
+            noise = Noise(seed=0, seed_dev=st["seed"], drop_path_scale=st["dps"] if cfg.drop_path_rate > 0 else None)
+            graph = torch.cuda.CUDAGraph()
+            launches0 = ops.LAUNCHES
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(graph):
+                self._fwd_bwd(st["images"], st["mask"], st["rows"], noise)
+            g = dict(graph=graph, st=st, launches=ops.LAUNCHES - launches0)
+            ops.LAUNCHES = launches0
+            self._graphs[key] = g
+        st = g["st"]
+        st["images"].copy_(images, non_blocking=True)
+        st["mask"].copy_(mask_u8, non_blocking=True)
+        st["rows"].copy_(rows, non_blocking=True)
+        st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+        if cfg.drop_path_rate > 0:
+            ops.drop_path_scales(cfg.drop_path_probs, 2, images.shape[0], seed, self.dev, out=st["dps"])
+        g["graph"].replay()
+        ops.LAUNCHES += g["launches"]
 
     def _step_dist(self, images, mask_u8, rows, lr, wd, noise):
         """--stochastic step (engine_for_cyclical.py:69-86,125-126,152-158): dual-stream teacher/student, targets for both streams,

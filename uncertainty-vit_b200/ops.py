@@ -98,9 +98,9 @@ def linear_wgrad(dy_bf16, x_bf16, dw_f32, alpha: float = 1.0):
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None):
+def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None, seed_dev=None):
     ld_bias = bias.stride(1) if bias is not None else 0
-    check(_lib.lib().b200vit_attn_fwd(_p(qkv), _p(bias), ld_bias, B, H, N, 64, scale, p_drop, seed, stream_id, _p(keep_in), _p(out),
+    check(_lib.lib().b200vit_attn_fwd(_p(qkv), _p(bias), ld_bias, B, H, N, 64, scale, p_drop, seed, _p(seed_dev), stream_id, _p(keep_in), _p(out),
                                       _p(lse), _p(keep_bits), _stream()), "attn_fwd")
     _count()
 
@@ -197,10 +197,11 @@ def assemble_tokens_bwd(dx, mask_u8, B, np_, C_, dpe_bf16, dcls, dmask_token, dp
     _count()
 
 
-def drop_path_scales(probs, draws, B, seed, device) -> torch.Tensor:
+def drop_path_scales(probs, draws, B, seed, device, out=None) -> torch.Tensor:
     """[L, draws, B] fp32 keep/(1-p) factors (device Philox; no torch RNG involved)."""
     L = len(probs)
-    out = torch.empty(L, draws, B, dtype=torch.float32, device=device)
+    if out is None:
+        out = torch.empty(L, draws, B, dtype=torch.float32, device=device)
     arr = (C.c_float * L)(*[float(p) for p in probs])
     check(_lib.lib().b200vit_drop_path_scales(arr, L, draws, B, seed, _p(out), _stream()), "drop_path_scales")
     _count()
