@@ -40,10 +40,10 @@ int b200vit_device_sm_count(void);
  * ---------------------------------------------------------------------------------------------- */
 enum b200vit_epilogue {
   B200VIT_EPI_BF16 = 0,       /* out_bf16 = (acc + bias[n]) * colscale[n]           (bias/colscale optional) */
-  B200VIT_EPI_GELU = 1,       /* t = acc + bias; out2_bf16 = t (optional); out_bf16 = gelu_erf(t)            */
+  B200VIT_EPI_GELU = 1,       /* t = acc + bias; out_bf16 = gelu_erf(t); out2_bf16 = gelu_erf'(t) (optional)  */
   B200VIT_EPI_RESIDUAL = 2,   /* t = acc + bias; out2_bf16 = t (optional);
                                  out_f32 = residual + rowscale[m / rows_per_scale] * colscale[n] * t         */
-  B200VIT_EPI_DGELU = 3,      /* out_bf16 = acc * gelu_erf'(aux[m,n])                                        */
+  B200VIT_EPI_DGELU = 3,      /* out_bf16 = acc * aux[m,n], aux = the gelu_erf'(t) saved by EPI_GELU's out2  */
   B200VIT_EPI_F32 = 4,        /* out_f32 = acc + bias                                                        */
   B200VIT_EPI_F32_ATOMIC = 5, /* out_f32 += alpha * acc  (red.global.add.v4; required with split_k)          */
   B200VIT_EPI_ELU1 = 6        /* out_bf16 = elu(acc + bias) + 1   (cov-stream QKV, modeling_finetune_dist.py:127)    */

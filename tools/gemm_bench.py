@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 M = 25216
 
 
-def run(name, m, n, k, a_mn=False, b_mn=False, epi=ops.EPI_BF16, reps=20, nbuf=3, **kw):
+def run(name, m, n, k, a_mn=False, b_mn=False, epi=ops.EPI_BF16, reps=20, nbuf=3, no_out2=False, **kw):
     bufs = []
     for _ in range(nbuf):
         a = torch.randn((k, m) if a_mn else (m, k), device=dev).to(torch.bfloat16)
@@ -32,7 +32,7 @@ def run(name, m, n, k, a_mn=False, b_mn=False, epi=ops.EPI_BF16, reps=20, nbuf=3
         if epi in (ops.EPI_BF16, ops.EPI_ELU1):
             ops.gemm(a, b, m, n, k, bias=bias, out_bf16=o16, **args)
         elif epi == ops.EPI_GELU:
-            ops.gemm(a, b, m, n, k, bias=bias, out_bf16=o16, out2_bf16=o16b, **args)
+            ops.gemm(a, b, m, n, k, bias=bias, out_bf16=o16, out2_bf16=None if no_out2 else o16b, **args)
         elif epi == ops.EPI_DGELU:
             ops.gemm(a, b, m, n, k, aux=o16b, out_bf16=o16, **args)
         elif epi == ops.EPI_RESIDUAL:
@@ -53,6 +53,12 @@ def run(name, m, n, k, a_mn=False, b_mn=False, epi=ops.EPI_BF16, reps=20, nbuf=3
 
 
 if __name__ == "__main__":
+    if "--quick" in sys.argv:
+        run("fc1 fwd gelu (teacher: no out2)", M, 3072, 768, epi=ops.EPI_GELU, no_out2=True)
+        run("fc1 fwd gelu + gelu' (student)", M, 3072, 768, epi=ops.EPI_GELU)
+        run("fc2 dgrad dgelu (acc * aux)", M, 3072, 768, b_mn=True, epi=ops.EPI_DGELU)
+        run("fc1 dgrad bf16", M, 768, 3072, b_mn=True)
+        sys.exit(0)
     for skip in (0, 1):
         tag = " [no epilogue I/O]" if skip else ""
         kw = dict(debug_flags=skip)

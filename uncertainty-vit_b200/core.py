@@ -130,7 +130,7 @@ def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B
     rstd2 = _empty((M,), torch.float32, dev)
     ops.layernorm_fwd(x_mid, ps.f32(p + "norm2.weight"), ps.f32(p + "norm2.bias"), cfg.ln_eps, M, C, y_bf16=h2, mean=mean2, rstd=rstd2)
     act = _empty((M, Hd), bf, dev)
-    pre = _empty((M, Hd), bf, dev) if save else None
+    pre = _empty((M, Hd), bf, dev) if save else None      # receives gelu'(fc1 output): the dGELU epilogue of the backward is one multiply
     ops.gemm(h2, ps.bf16(p + "mlp.fc1.weight"), M, Hd, C, epilogue=EPI_GELU, bias=ps.f32(p + "mlp.fc1.bias"), out_bf16=act, out2_bf16=pre)
     if x_out is None:
         x_out = _empty((M, C), torch.float32, dev)

@@ -33,7 +33,7 @@ constexpr int ACC_STAGES = 2;
 //   I/O epilogues (bf16, residual, fp32, split-K atomics, ELU+1): 8 epilogue warps (128 columns each), 6-stage ring
 template <int MODE>
 struct Cfg {
-  static constexpr bool kWide = (MODE == B200VIT_EPI_GELU || MODE == B200VIT_EPI_DGELU);
+  static constexpr bool kWide = (MODE == B200VIT_EPI_GELU || MODE == B200VIT_EPI_DGELU);   // dGELU: 16 warps hide the aux-load latency (8: 190 us, 16: 153 us)
   static constexpr int STAGES = kWide ? 5 : 6;
   static constexpr int NUM_EPI_WARPS = kWide ? 16 : 8;
   static constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);
@@ -116,6 +116,7 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
     return v;
   }
   v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+  const bool e_has_out2 = e.out2_bf16 != nullptr;
   switch (MODE) {
     case B200VIT_EPI_BF16: {
       v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
@@ -123,8 +124,22 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
       break;
     }
     case B200VIT_EPI_GELU: {
-      if (e.out2_bf16 != nullptr) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, v);
-      v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+      // out2 (training forward only) = gelu'(t) = Phi(t) + t phi(t): the backward GEMM epilogue then is one multiply per element
+      // instead of re-evaluating the polynomial + exp (the dGELU GEMM was epilogue-bound at 0.6 PFLOP/s).
+      float o[4], d[4];
+      const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float q = phi_minus_half(t[e]);
+        o[e] = fmaf(t[e], q, 0.5f * t[e]);                                            // t * Phi(t)
+        d[e] = 0.f;
+        if (e_has_out2) {
+          const float ex = mufu_ex2(t[e] * (t[e] * -0.72134752044448170f));            // exp(-t^2/2)
+          d[e] = fmaf(t[e] * 0.39894228040143268f, ex, 0.5f + q);
+        }
+      }
+      if (e_has_out2) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, make_float4(d[0], d[1], d[2], d[3]));
+      v = make_float4(o[0], o[1], o[2], o[3]);
       store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
@@ -135,7 +150,7 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
       break;
     }
     case B200VIT_EPI_DGELU: {
-      v = make_float4(v.x * gelu_erf_grad(pf.v.x), v.y * gelu_erf_grad(pf.v.y), v.z * gelu_erf_grad(pf.v.z), v.w * gelu_erf_grad(pf.v.w));
+      v = make_float4(v.x * pf.v.x, v.y * pf.v.y, v.z * pf.v.z, v.w * pf.v.w);     // aux = gelu'(pre) saved by the forward epilogue
       store_bf16x4(e.out_bf16 + (long long)m * e.ld_bf16 + n, v);
       break;
     }
