@@ -198,8 +198,9 @@ def run_b200(args):
     ops = pkg.ops
 
     torch.manual_seed(0 + rank)                                   # run_cyclical.py:315 seed + rank
+    extra = {"stochastic": True} if args.stochastic else {}      # --stochastic: the dual-stream (mean / cov) model + Wasserstein loss
     model = M.create_model("beit_base_patch16_224", pretrained=False, drop_path_rate=0.25, drop_rate=0.0, use_shared_rel_pos_bias=True,
-                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05).to(dev)
+                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05, **extra).to(dev)
     if world > 1:                                                 # DDP broadcasts rank 0's parameters at construction
         for p in model.parameters():
             dist.broadcast(p.data, 0)
@@ -275,8 +276,12 @@ def run_b200(args):
         t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
         pk = peaks()
         achieved = flops / (t_ms * 1e-3) / 1e12
+        traffic = None            # DRAM bytes per GEMM launch (ncu capture of the same step, committed under profiles/)
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("bytes_per_launch")
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05, all 4 operand-major instantiations)", "launches_timed": len(rec),
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_dram.json)", "kernel": "gemm_bf16_kernel (tcgen05, all 4 operand-major instantiations)", "launches_timed": len(rec),
                 "gemm_ms_per_step": t_ms / 2, "gemm_share_of_step": (t_ms / 2) / ms, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / pk["bf16_burst"]}
     barrier()
@@ -291,12 +296,13 @@ def run_b200(args):
             "metric": "data2vec ViT-B/16 pretrain throughput", "value": world * BATCH / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "beit_base_patch16_224 data2vec cyclical pretrain step (run_cyclical.py recipe), batch 128/GPU, 120 masked patches, "
+            "config": {"workload": ("beit_base_patch16_224 --stochastic (dual-stream mean/cov + Wasserstein loss) " if args.stochastic else "beit_base_patch16_224 ")
+                                   + "data2vec cyclical pretrain step (run_cyclical.py recipe), batch 128/GPU, 120 masked patches, "
                                    "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
                        "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"},
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mc_inference": mc_res, "final_loss": final_loss,
-            "step_tflops_algorithmic": 140.93e9 * BATCH / (ms * 1e-3) / 1e12}))
+            "step_tflops_algorithmic": (281.86e9 if args.stochastic else 140.93e9) * BATCH / (ms * 1e-3) / 1e12}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -308,6 +314,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stochastic", action="store_true",
+                    help="BASELINE.json configs[2] variant: the dual-stream --stochastic pre-training step (not the headline metric)")
     ap.add_argument("--no-mc", action="store_true", help="skip the MC-sample uncertainty-inference measurement (BASELINE.json configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
