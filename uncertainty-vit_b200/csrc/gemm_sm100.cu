@@ -129,13 +129,13 @@ __device__ __forceinline__ float4 epilogue4(const EpiParams& e, int m, int n, fl
       float o[4], d[4];
       const float t[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float q = phi_minus_half(t[e]);
-        o[e] = fmaf(t[e], q, 0.5f * t[e]);                                            // t * Phi(t)
-        d[e] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const float q = phi_minus_half(t[i]);
+        o[i] = fmaf(t[i], q, 0.5f * t[i]);                                            // t * Phi(t)
+        d[i] = 0.f;
         if (e_has_out2) {
-          const float ex = mufu_ex2(t[e] * (t[e] * -0.72134752044448170f));            // exp(-t^2/2)
-          d[e] = fmaf(t[e] * 0.39894228040143268f, ex, 0.5f + q);
+          const float ex = mufu_ex2(t[i] * (t[i] * -0.72134752044448170f));            // exp(-t^2/2)
+          d[i] = fmaf(t[i] * 0.39894228040143268f, ex, 0.5f + q);
         }
       }
       if (e_has_out2) store_bf16x4(e.out2_bf16 + (long long)m * e.ld2_bf16 + n, make_float4(d[0], d[1], d[2], d[3]));
