@@ -18,8 +18,8 @@ for rep in range(2):
     n = lib.b200vit_debug_kv_trace(buf, 1536)
 ev = sorted([(buf[4 * i + 3], buf[4 * i], buf[4 * i + 1], buf[4 * i + 2]) for i in range(n) if buf[4 * i + 3] > 0 and buf[4 * i] > 0])
 t0 = ev[0][0]
-names = {1: "g0 s_full seen", 2: "g0 box done", 3: "g0 acc_full seen", 4: "g0 epilogue done", 5: "g0 item start", 101: "g1 s_full seen", 102: "g1 box done",
+names = {1: "g0 s_full seen", 2: "g0 box done", 3: "g0 acc_full seen", 4: "g0 epilogue done", 5: "g0 item start", 6: "g0   epi tmem loaded", 7: "g0   epi stored", 8: "g0   epi colsum done", 106: "g1   epi tmem loaded", 107: "g1   epi stored", 108: "g1   epi colsum done", 101: "g1 s_full seen", 102: "g1 box done",
          103: "g1 acc_full seen", 104: "g1 epilogue done", 105: "g1 item start", 13: "MMA   fence done", 14: "MMA   acc mmas issued", 20: "MMA   ld_full seen", 21: "MMA   score mmas issued", 10: "MMA p_full seen", 11: "MMA acc issued", 12: "MMA scores issued"}
 for t, c, it, bi in ev:
-    if (1 <= it <= 1 or c in (20, 21)) and 26000 < t - t0 < 60000:
+    if it == 1 and c not in (10, 11, 12, 13, 14, 20, 21, 1, 2, 101, 102):
         print(f"{t - t0:8d} cyc  it={it} bi={bi}  {names.get(c, c)}")

@@ -427,6 +427,14 @@ __device__ __forceinline__ void kv_trace(int debug, int L, int role, int& n, int
   }
 }
 
+// 32-byte global store (sm_100: 256-bit vector stores): one LSU instruction per 32 bytes of a thread-private row segment
+__device__ __forceinline__ void st_global_32B(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
+                                              uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6),
+               "r"(a7)
+               : "memory");
+}
+
 struct BwdKvParams {
   const float* lse;          // [B, H, N]
   const float* dvec;         // [B, H, N]   D_i
@@ -612,10 +620,7 @@ __device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, ui
       dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
       }
     }
-    if (!(p.debug & 1)) {
-    *reinterpret_cast<uint4*>(ds_row) = make_uint4(dx[0], dx[1], dx[2], dx[3]);
-    *reinterpret_cast<uint4*>(ds_row + 8) = make_uint4(dx[4], dx[5], dx[6], dx[7]);
-    }
+    if (!(p.debug & 1)) st_global_32B(ds_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dx[6], dx[7]);
   } else {      // key rows past N: P = dS = 0 (their K / V rows are TMA zero fill, not -inf scores)
 #pragma unroll
     for (int q = 0; q < 8; ++q) px[q] = dx[q] = 0u;
@@ -797,22 +802,36 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t cx = trow + KV_X + g * 32, cy = trow + KV_Y + g * 32;
     int trn = 0;
+    // lse / D of the NEXT item are fetched into registers while the current item computes (no global-load latency at the item boundary)
+    float nx_lse = INFINITY, nx_d = 0.f;
+    auto fetch_row_stats = [&](int it) {
+      int b, h, j0, bh;
+      item_of(it, b, h, j0, bh);
+      nx_lse = tid < p.N ? __ldg(p.lse + (long long)bh * p.N + tid) * LOG2E : INFINITY;
+      nx_d = tid < p.N ? __ldg(p.dvec + (long long)bh * p.N + tid) : 0.f;
+    };
+    if (n_items > 0 && tid < n_pad) fetch_row_stats(0);
     for (int it = 0; it < n_items; ++it) {
       int b, h, j0, bh;
       item_of(it, b, h, j0, bh);
       float* s_lse = reinterpret_cast<float*>(gbase + KV_SM_LSE) + (it & 1) * NMAX;
       float* s_d = reinterpret_cast<float*>(gbase + KV_SM_D) + (it & 1) * NMAX;
       if (tid < n_pad) {
-        s_lse[tid] = tid < p.N ? p.lse[(long long)bh * p.N + tid] * LOG2E : INFINITY;
-        s_d[tid] = tid < p.N ? p.dvec[(long long)bh * p.N + tid] : 0.f;
+        s_lse[tid] = nx_lse;
+        s_d[tid] = nx_d;
       }
       ptx::named_bar_sync(1 + L, KV_EW_WARPS * 32);
+      if (it + 1 < n_items && tid < n_pad) fetch_row_stats(it + 1);
       if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 5 + 100 * g, it, 0);
       const int j = j0 + row;
       const bool valid = j < p.N;
       const bool active = j0 + quad * 32 < p.N;
       bf16* ds_base = p.ds_out + ((long long)bh * p.N + (valid ? j : 0)) * p.ld_ds;
       const uint32_t* kt_row = p.keep_t + ((long long)bh * p.N + (valid ? j : 0)) * 8;
+      // dV / dK row of this thread (written by the epilogue): touch it now so that the address translation and the L2 line are warm
+      // by then (the first store of an item otherwise stalls ~2500 cycles; clock64 trace in tools/micro/kv_trace.py)
+      bf16* dst = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * (3LL * p.H * HD) + (long long)(g == 0 ? 2 : 1) * p.H * HD + h * HD;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(dst));
       for (int bi = g; bi < nboxes; bi += 2) {
         const int c0 = bi * 32;
         const int gb = it * nboxes + bi, st = gb & 1;
@@ -843,8 +862,6 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ptx::tc_fence_after();
       if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 3 + 100 * g, it, 0);
       if (active) {
-        const long long row_stride = 3LL * p.H * HD;
-        bf16* dst = p.dqkv + ((long long)b * p.N + (valid ? j : 0)) * row_stride + (long long)(g == 0 ? 2 : 1) * p.H * HD + h * HD;
         const float mul = g == 0 ? 1.0f : p.scale;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -853,16 +870,21 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(o[e]) * mul;
+          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 6 + 100 * g, it, half);
           if (valid) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(dst + half * 32 + 8 * q) = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            for (int q = 0; q < 2; ++q)
+              st_global_32B(dst + half * 32 + 16 * q, pack_bf16x2(v[16 * q], v[16 * q + 1]), pack_bf16x2(v[16 * q + 2], v[16 * q + 3]),
+                            pack_bf16x2(v[16 * q + 4], v[16 * q + 5]), pack_bf16x2(v[16 * q + 6], v[16 * q + 7]),
+                            pack_bf16x2(v[16 * q + 8], v[16 * q + 9]), pack_bf16x2(v[16 * q + 10], v[16 * q + 11]),
+                            pack_bf16x2(v[16 * q + 12], v[16 * q + 13]), pack_bf16x2(v[16 * q + 14], v[16 * q + 15]));
           }
+          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 7 + 100 * g, it, half);
           if (g == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
             const float c = warp_colsum32(v, lane);
             atomicAdd(p.dv_bias + h * HD + half * 32 + lane, c);
           }
+          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 8 + 100 * g, it, half);
         }
       }
       ptx::tc_fence_before();
