@@ -192,6 +192,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT otherwise: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=120))
     import uncertainty_vit_b200 as pkg
     from uncertainty_vit_b200 import engine as E, modeling as M
