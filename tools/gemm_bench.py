@@ -58,6 +58,9 @@ if __name__ == "__main__":
         run("fc1 fwd gelu + gelu' (student)", M, 3072, 768, epi=ops.EPI_GELU)
         run("fc2 dgrad dgelu (acc * aux)", M, 3072, 768, b_mn=True, epi=ops.EPI_DGELU)
         run("fc1 dgrad bf16", M, 768, 3072, b_mn=True)
+        run("proj fwd residual", M, 768, 768, epi=ops.EPI_RESIDUAL)
+        run("fc2 fwd residual", M, 768, 3072, epi=ops.EPI_RESIDUAL)
+        run("qkv fwd bf16", M, 2304, 768)
         sys.exit(0)
     for skip in (0, 1):
         tag = " [no epilogue I/O]" if skip else ""
