@@ -44,9 +44,57 @@ def gather_passes(local: torch.Tensor, S: int, rank: int, world: int, group=None
     return torch.cat([bufs[r][: e - s] for r, (s, e) in enumerate(shards)], 0)
 
 
+class _GraphedForward:
+    """One stochastic forward pass of `model` on a fixed batch shape, replayed from a CUDA graph: ~200 launches whose Python issue time
+    (~55 us each) exceeds their run time at eval batch sizes. The per-pass randomness (attention dropout) is keyed from device memory
+    (`Noise.seed_dev`), so the captured graph is valid for every pass; it is re-captured when any parameter changes."""
+
+    def __init__(self, model, x):
+        from .core import Noise
+        self.model = model
+        self.sig = self._signature(model)
+        calls0 = model._seed_calls                 # warm-up and capture must not advance the model's noise counter
+        for _ in range(2):                         # lazy kernel attributes / bf16 weight shadows / allocator warm-up
+            model(x)
+        self.x = x.clone()
+        self.seed = torch.zeros(1, dtype=torch.int64, device=x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        model._injected = Noise(seed_dev=self.seed)
+        torch.cuda.synchronize(x.device)
+        with torch.cuda.graph(self.graph):
+            self.out = model(self.x)
+        model._seed_calls = calls0
+
+    @staticmethod
+    def _signature(model):
+        return tuple((p._version, p.data_ptr()) for p in model.parameters())
+
+    def valid_for(self, model, x):
+        return tuple(x.shape) == tuple(self.x.shape) and x.dtype == self.x.dtype and self._signature(model) == self.sig
+
+    def __call__(self, x):
+        self.model._seed_calls += 1                # the same key sequence as the eager forward (_VitBase._noise)
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * self.model._seed_calls) & 0xFFFFFFFFFFFFFFFF
+        self.x.copy_(x, non_blocking=True)
+        self.seed.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+        self.graph.replay()
+        return self.out
+
+
+def _forward_pass(model, x, use_graph: bool):
+    if not use_graph or model.cfg.dist:            # the Wasserstein attention kernels still take their Philox key by value
+        return model(x)
+    cache = model.__dict__.setdefault("_mc_graphs", {})
+    key = tuple(x.shape)
+    g = cache.get(key)
+    if g is None or not g.valid_for(model, x):
+        g = cache[key] = _GraphedForward(model, x)
+    return g(x)
+
+
 @torch.no_grad()
 def evaluate_mc_dropout(model, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]], forward_passes: int, rank: int = 0, world: int = 1,
-                        group=None) -> Dict[str, object]:
+                        group=None, use_graph: bool = True) -> Dict[str, object]:
     """batches: list of (images [b,3,H,W] on the device, labels [b]). Returns the reference's metrics (+ entropy / variance / MI)."""
     if forward_passes < 2:
         raise ValueError("the reference captures the labels at pass i == 1, so it needs forward_passes >= 2 (uncertainty_evaluations.py:69-70)")
@@ -56,8 +104,11 @@ def evaluate_mc_dropout(model, batches: Sequence[Tuple[torch.Tensor, torch.Tenso
         model.eval()
         enable_dropout(model)
         # the dual-stream (--stochastic) model returns (mean_feat, cov_feat, logits): modeling_finetune_dist.py:311-326
-        fw = [model(x) for x, _ in batches]
-        outs.append(torch.cat([(o[-1] if isinstance(o, (tuple, list)) else o).float() for o in fw], 0))
+        fw = []
+        for x, _ in batches:
+            o = _forward_pass(model, x, use_graph)
+            fw.append((o[-1] if isinstance(o, (tuple, list)) else o).float().clone())
+        outs.append(torch.cat(fw, 0))
     dev = batches[0][0].device
     K = model.cfg.num_classes
     N = sum(x.shape[0] for x, _ in batches)
