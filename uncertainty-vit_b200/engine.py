@@ -99,6 +99,7 @@ class D2VEngine:
         self.dev = dev
         self._copy_stream = None
         self.use_graph = use_graph
+        self.max_graphs = 2
         self._graphs = {}
         self._eager_steps = 0
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad
@@ -247,7 +248,9 @@ class D2VEngine:
         cfg = self.cfg
         key = (tuple(images.shape), int(rows.numel()))
         g = self._graphs.get(key)
-        if g is None and self._eager_steps < 2:
+        if g is None and (self._eager_steps < 2 or len(self._graphs) >= self.max_graphs):
+            # warm-up, or a workload whose masked-row count keeps changing (block-wise masking): launch eagerly instead of
+            # capturing one graph (and one private activation pool) per distinct count
             self._fwd_bwd(images, mask_u8, rows, Noise(seed=seed))
             self._eager_steps += 1
             return
