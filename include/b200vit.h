@@ -117,8 +117,8 @@ int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const f
  * elu(.)+1 already (GEMM epilogue B200VIT_EPI_ELU1). bias (required) in the padded layout of b200vit_rel_pos_bias.
  * out_mean = P~ v, out_cov = (P~)^2 cv, both bf16 [B, N, H*64]. */
 int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N,
-                      int32_t head_dim, float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in,
-                      void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
+                      int32_t head_dim, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                      const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
 /* Backward of b200vit_wattn_fwd (two kernels: key-tile owners -> dV, dCV, dK, dCK and dD^T; query-tile owners -> dQ, dCQ).
  * dqkv_cov is the gradient w.r.t. the PRE-activation of elu(.)+1, i.e. ready for the QKV wgrad / dgrad GEMMs.
  * work_dD / work_dA: bf16 workspaces [B, H, N, ld_ds] (dA only when dtable != NULL). Bias gradients (optional, +=, [H*64]):

@@ -20,8 +20,9 @@ def main():
     import uncertainty_vit_b200  # noqa: F401
     from uncertainty_vit_b200 import engine as E, modeling as M
     torch.manual_seed(0)
+    extra = {"stochastic": True} if os.environ.get("PROFILE_STOCHASTIC") else {}      # PROFILE_STOCHASTIC=1: the dual-stream step
     model = M.create_model("beit_base_patch16_224", pretrained=False, drop_path_rate=0.25, drop_rate=0.0, use_shared_rel_pos_bias=True,
-                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05).to(dev)
+                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05, **extra).to(dev)
     eng = E.D2VEngine(model, target_layers=[6, 7, 8, 9, 10, 11], use_graph=False)   # same kernels, launched eagerly (ncu sees plain launches)
     x, m = bench.synth_batch(B, 0)
     mu8 = np.ascontiguousarray(m.reshape(B, -1))

@@ -37,7 +37,7 @@ _PROTOS = {
     "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp]),
     "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp]),
     "b200vit_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
-    "b200vit_wattn_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, u32, vp, vp, vp, vp, vp, vp]),
+    "b200vit_wattn_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp, vp]),
     "b200vit_wattn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
     "b200vit_dropout_mask": (i32, [vp, i32, i32, f32, u64, u32, vp]),
     "b200vit_layernorm_fwd": (i32, [vp, i64, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]),

@@ -363,7 +363,8 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
 # DistVisionTransformerForCyclicalTraining.forward (modeling_cyclical_dist.py:108-165), DistVisionTransformer.forward (:280-326)
 # ------------------------------------------------------------------------------------------------------------------
 def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: torch.Tensor, *, save: bool,
-                       dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+                       dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
+                       seed_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
     M2 = 2 * M
@@ -381,7 +382,7 @@ def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tens
     att = _empty((M2, C), bf, dev)
     lse = _empty((B, H, T), torch.float32, dev) if save else None
     keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
-    ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits)
+    ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits, seed_dev=seed_dev)
     x_mid = _empty((M2, C), torch.float32, dev)
     t1 = _empty((M2, C), bf, dev) if save else None
     g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
@@ -437,7 +438,7 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = dist_block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn,
-                               seed=noise.seed, keep_in=keep_in)
+                               seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev)
         x = s["x_out"]
         if i in collect:
             lm[i] = x[:M].view(B, T, C)

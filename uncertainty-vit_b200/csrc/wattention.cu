@@ -30,6 +30,7 @@ struct WAttnFwdParams {
   int B, H, N;
   float scale, p_drop;
   uint64_t seed;
+  const uint64_t* seed_dev;   // when non-null: the Philox key is read from device memory (CUDA-graph replays)
   uint32_t stream_id;
 };
 
@@ -131,8 +132,9 @@ __device__ __forceinline__ void wfwd_chunk(const WAttnFwdParams& p, const bf16* 
     // NTS <= 4: one 32-key group per chunk (j0 is a multiple of 32)
     uint32_t w0 = 0u, w1 = 0u;
     if (p.keep_in == nullptr) {
-      const Philox4 r0 = dropout_group(p.seed, p.stream_id, bh, i0, quad, j0 >> 5);
-      const Philox4 r1 = dropout_group(p.seed, p.stream_id, bh, i1, quad, j0 >> 5);
+      const uint64_t seed = p.seed_dev != nullptr ? __ldg(reinterpret_cast<const unsigned long long*>(p.seed_dev)) : p.seed;
+      const Philox4 r0 = dropout_group(seed, p.stream_id, bh, i0, quad, j0 >> 5);
+      const Philox4 r1 = dropout_group(seed, p.stream_id, bh, i1, quad, j0 >> 5);
 #pragma unroll
       for (int n4 = 0; n4 < NTS; ++n4) {
         const int sh = n4 * 8 + quad * 2;
@@ -682,8 +684,8 @@ cudaError_t launch_wfwd(const WAttnFwdParams& p, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N,
-                                 int32_t head_dim, float scale, float p_drop, uint64_t seed, uint32_t stream_id, const uint8_t* keep_in,
-                                 void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream) {
+                                 int32_t head_dim, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                                 const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream) {
   B200_CHECK_ARG(qkv_mean && qkv_cov && out_mean && out_cov, "wattn_fwd: null pointer");
   B200_CHECK_ARG(head_dim == HD, "wattn_fwd: head_dim %d unsupported (64 only)", head_dim);
   B200_CHECK_ARG(N > 0 && N <= NMAX, "wattn_fwd: N=%d unsupported (1..%d)", N, NMAX);
@@ -695,7 +697,7 @@ extern "C" int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, cons
   WAttnFwdParams p;
   p.qkv_m = static_cast<const bf16*>(qkv_mean); p.qkv_c = static_cast<const bf16*>(qkv_cov); p.bias = bias; p.ld_bias = ld_bias;
   p.out_m = static_cast<bf16*>(out_mean); p.out_c = static_cast<bf16*>(out_cov); p.lse = lse; p.keep_bits = keep_bits; p.keep_in = keep_in;
-  p.B = B; p.H = H; p.N = N; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.stream_id = stream_id;
+  p.B = B; p.H = H; p.N = N; p.scale = scale; p.p_drop = p_drop; p.seed = seed; p.seed_dev = seed_dev; p.stream_id = stream_id;
   cudaError_t e = p_drop > 0.f ? launch_wfwd<true>(p, static_cast<cudaStream_t>(stream)) : launch_wfwd<false>(p, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { b200vit_set_error("wattn_fwd: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;

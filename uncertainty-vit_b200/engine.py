@@ -100,6 +100,7 @@ class D2VEngine:
         self._copy_stream = None
         self.use_graph = use_graph
         self.max_graphs = 2
+        self.wloss_dev = None
         self._graphs = {}
         self._eager_steps = 0
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad
@@ -207,8 +208,6 @@ class D2VEngine:
         injected = noise
         if noise is None:
             noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
-        if cfg.dist:
-            return self._step_dist(images, mask_u8, rows, lr, wd, noise)
         if graph is None:
             graph = self.use_graph
         if graph and injected is None and ops.GEMM_TIMING is None:
@@ -221,6 +220,8 @@ class D2VEngine:
     def _fwd_bwd(self, images, mask_u8, rows, noise):
         """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser)."""
         cfg = self.cfg
+        if cfg.dist:
+            return self._fwd_bwd_dist(images, mask_u8, rows, noise)
         B = images.shape[0]
         C, T = cfg.embed_dim, cfg.tokens
         R = rows.numel()
@@ -257,7 +258,7 @@ class D2VEngine:
         if g is None:
             st = dict(images=torch.empty_like(images), mask=torch.empty_like(mask_u8), rows=torch.empty_like(rows),
                       seed=torch.zeros(1, dtype=torch.int64, device=self.dev),
-                      dps=torch.empty(cfg.depth, 2, images.shape[0], dtype=torch.float32, device=self.dev))
+                      dps=torch.empty(cfg.depth, 4 if cfg.dist else 2, images.shape[0], dtype=torch.float32, device=self.dev))
             noise = Noise(seed=0, seed_dev=st["seed"], drop_path_scale=st["dps"] if cfg.drop_path_rate > 0 else None)
             graph = torch.cuda.CUDAGraph()
             launches0 = ops.LAUNCHES
@@ -273,13 +274,13 @@ class D2VEngine:
         st["rows"].copy_(rows, non_blocking=True)
         st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
         if cfg.drop_path_rate > 0:
-            ops.drop_path_scales(cfg.drop_path_probs, 2, images.shape[0], seed, self.dev, out=st["dps"])
+            ops.drop_path_scales(cfg.drop_path_probs, 4 if cfg.dist else 2, images.shape[0], seed, self.dev, out=st["dps"])
         g["graph"].replay()
         ops.LAUNCHES += g["launches"]
 
-    def _step_dist(self, images, mask_u8, rows, lr, wd, noise):
+    def _fwd_bwd_dist(self, images, mask_u8, rows, noise):
         """--stochastic step (engine_for_cyclical.py:69-86,125-126,152-158): dual-stream teacher/student, targets for both streams,
-        smooth-L1 on the mean stream + WassersteinLoss(lambda) on (mean, cov) outputs vs (mean, cov) targets."""
+        smooth-L1 on the mean stream + WassersteinLoss(lambda) on (mean, cov) outputs vs (mean, cov) targets (everything but the optimiser)."""
         cfg = self.cfg
         B = images.shape[0]
         C, T = cfg.embed_dim, cfg.tokens
@@ -300,13 +301,12 @@ class D2VEngine:
                             1.0, tgt_c, None, None, None, None)
         del lm, lc
         work = torch.empty((2 * R + 8,), dtype=torch.float32, device=dev)
-        if not hasattr(self, "wloss_dev"):
+        if self.wloss_dev is None:
             self.wloss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev)
         self.loss_dev.add_(self.wloss_dev, alpha=ls)          # loss = (loss_cyc + loss_stochastic) * loss_scale  (:160-163)
         self.g32.zero_()
         core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads)
-        return self._optimizer_step(lr, wd)
 
     def _optimizer_step(self, lr, wd):
         if self.world_size > 1:

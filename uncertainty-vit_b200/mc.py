@@ -82,7 +82,7 @@ class _GraphedForward:
 
 
 def _forward_pass(model, x, use_graph: bool):
-    if not use_graph or model.cfg.dist:            # the Wasserstein attention kernels still take their Philox key by value
+    if not use_graph:
         return model(x)
     cache = model.__dict__.setdefault("_mc_graphs", {})
     key = tuple(x.shape)

@@ -122,8 +122,8 @@ def attn_bwd(qkv, out, dout, lse, bias_t, keep_bits, rel_index, dtable, B, H, N,
 
 
 def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out_mean=None, out_cov=None, lse=None,
-              keep_bits=None):
-    check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), B, H, N, 64, scale, p_drop, seed, stream_id,
+              keep_bits=None, seed_dev=None):
+    check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), B, H, N, 64, scale, p_drop, seed, _p(seed_dev), stream_id,
                                        _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), _stream()), "wattn_fwd")
     _count()
 
