@@ -145,3 +145,44 @@ def test_graphed_step_matches_eager(cuda):
             assert len(eng._graphs) == 1, "steps 3.. must have been replayed from the captured graph"
     a, b = np.array(losses[False]), np.array(losses[True])
     assert np.all(np.isfinite(b)) and np.max(np.abs(a - b) / np.abs(a)) < 5e-3, (a, b)
+
+
+def test_finetune_engine_matches_module_autograd(cuda, golden_dir):
+    """FinetuneEngine.step (flat arenas, fused layer-decay AdamW) computes the same loss and parameter gradients as the nn.Module boundary
+    + torch autograd (which test_finetune_training_backward_vs_oracle pins to the oracle) on the same inputs and injected noise."""
+    import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import engine as E
+    from tests.test_model_gpu import _build_from_gold, _build_dist
+    for name, builder in (("tiny_det_finetune", _build_from_gold), ("tiny_dist_finetune", lambda p, g, c: _build_dist(p, g, c))):
+        gold = dict(torch.load(os.path.join(golden_dir, name + ".pt")), dpr=0.2, attn_drop=0.1)
+        model, arch, sd = builder(pkg, gold, cuda)
+        B = gold["B"]
+        g = torch.Generator().manual_seed(11)
+        probs = [float(x) for x in torch.linspace(0, 0.2, arch.depth)]
+        draws = 4 if arch.dist else 2
+        keeps = [(torch.rand(draws, B, generator=g) >= p).float() for p in probs]
+        akeep = [(torch.rand(B, arch.num_heads, arch.tokens, arch.tokens, generator=g) >= 0.1).to(torch.uint8) for _ in range(arch.depth)]
+        K = model.cfg.num_classes
+        targets = torch.softmax(torch.randn(B, K, generator=g), -1).to(cuda)
+        x = gold["x"].to(cuda)
+        eng = E.FinetuneEngine(model, lr=1e-3, weight_decay=0.05, layer_decay=0.65, clip_grad=None)
+        # module boundary + autograd (parameters alias the engine's arena)
+        model.train()
+        model.inject_noise(drop_path_keep=keeps, attn_keep=akeep)
+        out = model(x)
+        logits = out[-1] if isinstance(out, tuple) else out
+        loss_m = torch.sum(-targets * torch.log_softmax(logits.float(), -1), -1).mean()
+        loss_m.backward()
+        ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        before = eng.p32.clone()
+        noise = pkg.core.Noise(seed=1)
+        noise.drop_path_scale = torch.stack([k.float() / (1.0 - p) for k, p in zip(keeps, probs)]).to(cuda).contiguous()
+        noise.attn_keep = [k.to(cuda).contiguous() for k in akeep]
+        loss_e = float(eng.step(x, targets, noise=noise).item())
+        assert abs(loss_e - float(loss_m)) / abs(float(loss_m)) < 1e-3, (name, loss_e, float(loss_m))
+        bad = [(n, round(rel(eng.grads[n], gr), 4)) for n, gr in ref.items() if float(gr.norm()) > 1e-6 and rel(eng.grads[n], gr) > 2e-2]
+        assert not bad, (name, bad)
+        assert not torch.equal(before, eng.p32), "the fused AdamW must have updated the arena"
+        if arch.dist:      # triplet step: positive / negative forwards + WassersteinLossFineTuning on the features
+            l2 = float(eng.step(x, targets, x.roll(1, 0).contiguous(), x.flip(0).contiguous()).item())
+            assert np.isfinite(l2) and torch.isfinite(eng.g32).all()

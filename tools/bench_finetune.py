@@ -7,9 +7,9 @@ One step = anchor forward + backward through the dual-stream classifier (CUDA fo
 torch.autograd.Function), the positive / negative triplet forwards without gradients (engine_for_finetuning_dist.py:286-304 computes them on a
 per-batch deepcopy; the gradients are identical), soft-target cross-entropy (Mixup / CutMix targets, run_class_finetuning.py:339-347) +
 WassersteinLossFineTuning (distloss.py:39-70) on the [B, C] features, and AdamW over the reference's layer-decay parameter groups
-(optim_factory.py:33-97: lr_scale = 0.65^(25 - layer_id)). This is the nn.Module boundary (not the fused flat-arena engine of the
-pre-training step): loss and optimiser run as torch ops on [B, 1000] / per-parameter tensors — the reported number is a first measurement
-of the config, the fused fine-tune engine is a next row."""
+(optim_factory.py:33-97: lr_scale = 0.65^(25 - layer_id)). --path engine (default) runs the fused flat-arena
+FinetuneEngine (engine.py): forward / backward schedules without autograd, gradients in one arena, ONE all-reduce, clip + layer-decay AdamW in
+one kernel; --path module runs the nn.Module boundary with torch.optim.AdamW. The [B, 1000] / [B, C] loss terms are a few tiny torch ops."""
 import argparse
 import json
 import os
@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--model", default="beit_large_patch16_224")
+    ap.add_argument("--path", default="engine", choices=["engine", "module"],
+                    help="engine: fused flat-arena FinetuneEngine (default); module: nn.Module boundary + torch.optim.AdamW")
     args = ap.parse_args()
     import torch.distributed as dist
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -41,6 +43,12 @@ def main():
     model = M.create_model(args.model, pretrained=False, stochastic=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.2, attn_drop_rate=0.0,
                            use_mean_pooling=True, init_scale=0.001, use_rel_pos_bias=False, use_shared_rel_pos_bias=True, use_abs_pos_emb=False,
                            init_values=0.1).to(dev)
+    if args.path == "engine":
+        if world > 1:
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        eng = E.FinetuneEngine(model, lr=5e-4, weight_decay=0.05, layer_decay=0.65, clip_grad=3.0, lambda_finetuning=1e-2, lambda_pvn=1e-4,
+                               world_size=world, seed=rank)
     L = model.get_num_layers() + 2
     groups = {}
     for name, p in model.named_parameters():          # optim_factory.get_parameter_groups with LayerDecayValueAssigner(0.65)
@@ -65,6 +73,8 @@ def main():
         return lam * (l / l.abs().max().clamp_min(1e-30)).sum()
 
     def step():
+        if args.path == "engine":
+            return eng.step(x[0], tgt, x[1], x[2])
         model.train()
         am, ac, logits = model(x[0])
         with torch.no_grad():
@@ -105,7 +115,8 @@ def main():
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "dtype": "bf16", "data": "synthetic",
                           "config": {"workload": f"{args.model} --stochastic fine-tune train step (anchor fwd+bwd, pos/neg no-grad fwd, soft-target CE + "
                                                  "WassersteinLossFineTuning, AdamW with layer_decay 0.65 groups), drop_path 0.2, batch 64/GPU",
-                                     "path": "nn.Module boundary + torch.optim.AdamW(fused) (not the flat-arena engine)", "param_groups": len(groups)},
+                                     "path": "fused flat-arena FinetuneEngine (clip + layer-decay AdamW in one kernel)" if args.path == "engine"
+                                     else "nn.Module boundary + torch.optim.AdamW(fused)", "param_groups": len(groups)},
                           "final_loss": float(loss.item()), "params_M": sum(p.numel() for p in model.parameters()) / 1e6}))
     if world > 1:
         dist.destroy_process_group()

@@ -82,6 +82,13 @@ class ArenaParams(core.ParamSource):
     def rel_index_i32(self):
         return self._rel
 
+    def head_padded(self):
+        """(head.weight bf16 [Kp, C], head.bias fp32 [Kp]) straight from the arenas: the engine reserves Kp = K rounded up to 8 rows for
+        the classifier, rows >= K are zero and stay zero (zero gradient, zero weight)."""
+        (ow, (K, C)), (ob, _) = self.layout["head.weight"], self.layout["head.bias"]
+        kp = (K + 7) // 8 * 8
+        return self.a16[ow: ow + kp * C].view(kp, C), self.a32[ob: ob + kp]
+
 
 class D2VEngine:
     """Owns arenas + optimizer state for a data2vec student and its EMA teacher."""
@@ -90,7 +97,7 @@ class D2VEngine:
                  ema_decay_init=0.999, ema_start_at=0, target_layers: Sequence[int] = (6, 7, 8, 9, 10, 11), l1_beta=2.0, l2_loss=False,
                  target_layer_norm_last=True, post_target_layer_norm=True, layer_decay: Optional[float] = None, loss_scale=-1.0,
                  skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0,
-                 lambda_pretraining: float = 1e-5, use_graph: bool = True):
+                 lambda_pretraining: float = 1e-5, use_graph: bool = True, with_ema: bool = True):
         self.model = model
         self.cfg: VitConfig = model.cfg
         dev = model.cls_token.device
@@ -121,9 +128,9 @@ class D2VEngine:
         off = 0
         skip = set(skip_weight_decay)
 
-        def add(name, shape, lr_scale, wd_scale):
+        def add(name, shape, lr_scale, wd_scale, reserve=0):
             nonlocal off
-            n = int(np.prod(shape))
+            n = max(int(np.prod(shape)), reserve)
             layout[name] = (off, tuple(shape))
             nch = (n + CHUNK - 1) // CHUNK
             chunks_hp.extend([(lr_scale, wd_scale)] * nch)
@@ -151,12 +158,17 @@ class D2VEngine:
                 # grad-less parameters entirely (no update, no weight decay) -> lr_scale = wd_scale = 0
                 add(name, p.shape, 0.0, 0.0)
                 continue
-            add(name, p.shape, lr_scale, 0.0 if no_decay else 1.0)
+            reserve = 0
+            if name in ("head.weight", "head.bias"):      # classifier rows padded to a multiple of 8 (GEMM N); the padding stays zero
+                kp = (p.shape[0] + 7) // 8 * 8
+                reserve = kp * (p.numel() // p.shape[0])
+            add(name, p.shape, lr_scale, 0.0 if no_decay else 1.0, reserve)
         self.layout, self.n = layout, off
         f32 = lambda: torch.zeros(off, dtype=torch.float32, device=dev)
-        self.p32, self.g32, self.m32, self.v32, self.e32 = f32(), f32(), f32(), f32(), f32()
+        self.p32, self.g32, self.m32, self.v32 = f32(), f32(), f32(), f32()
+        self.e32 = f32() if with_ema else None
         self.p16 = torch.zeros(off, dtype=torch.bfloat16, device=dev)
-        self.e16 = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.e16 = torch.zeros(off, dtype=torch.bfloat16, device=dev) if with_ema else None
         self.hp = torch.tensor(chunks_hp, dtype=torch.float32, device=dev).contiguous()
         with torch.no_grad():
             for name, p in named.items():
@@ -164,12 +176,13 @@ class D2VEngine:
                 view = self.p32[o: o + p.numel()].view(shape)
                 view.copy_(p.detach())
                 p.data = view                     # the module now aliases the arena
-        self.e32.copy_(self.p32)                  # ModelEmaV2: deepcopy of the student at construction (run_cyclical.py:503)
         ops.cast_bf16(self.p32, self.p16)
-        ops.cast_bf16(self.e32, self.e16)
+        if with_ema:
+            self.e32.copy_(self.p32)              # ModelEmaV2: deepcopy of the student at construction (run_cyclical.py:503)
+            ops.cast_bf16(self.e32, self.e16)
         rel = model.rel_pos_bias.relative_position_index.to(torch.int32).contiguous() if model.rel_pos_bias is not None else None
         self.student = ArenaParams(layout, self.p32, self.p16, rel)
-        self.teacher = ArenaParams(layout, self.e32, self.e16, rel)
+        self.teacher = ArenaParams(layout, self.e32, self.e16, rel) if with_ema else None
         self.grads = {name: self.g32[o: o + int(np.prod(s))].view(s) for name, (o, s) in layout.items()}
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -314,7 +327,7 @@ class D2VEngine:
         self.gnorm_sq.zero_()
         ops.sumsq(self.g32, self.gnorm_sq)
         self.opt_step += 1
-        do_ema = self.cur_decay != 1
+        do_ema = self.cur_decay != 1 and self.e32 is not None
         ops.adamw_step(self.p32, self.g32, self.m32, self.v32, self.hp, self.opt_step, lr, wd, self.betas[0], self.betas[1], self.eps,
                        gnorm_sq=self.gnorm_sq, max_norm=self.clip if self.clip else 0.0, grad_div=float(self.world_size), p_bf16=self.p16,
                        ema=self.e32 if do_ema else None, ema_decay=self.cur_decay, ema_bf16=self.e16 if do_ema else None)
@@ -356,6 +369,87 @@ class D2VEngine:
         """The reference-facing call: HOST batch in (pinned images + integer mask as the data loader yields them,
         engine_for_cyclical.py:58-60), loss value out (:164). Host->device copies and the loss read-back are inside."""
         return self.step_staged(self.stage_host(images_pinned, mask_host), **kw)
+
+
+def soft_target_cross_entropy(logits: torch.Tensor, targets: torch.Tensor):
+    """SoftTargetCrossEntropy of timm (run_class_finetuning.py:619-621 after Mixup / CutMix): loss = mean_b sum_k -t log_softmax(z);
+    returns (loss, dLoss/dlogits). [B, K] tensors: a handful of tiny torch ops, not hot-path work."""
+    logp = torch.log_softmax(logits.float(), -1)
+    loss = -(targets * logp).sum(-1).mean()
+    dlogits = (torch.exp(logp) * targets.sum(-1, keepdim=True) - targets) / logits.shape[0]
+    return loss, dlogits
+
+
+def wasserstein_loss_finetuning(mean_out, cov_out, pos_mean, pos_cov, neg_mean, neg_cov, lambda_finetuning=1e-4, lambda_pvn=1e-4):
+    """WassersteinLossFineTuning.forward (distloss.py:39-70) on the [B, C] pooled features of anchor / positive / negative: every input goes
+    through a sigmoid; d(a, b) = |m_a - m_b|^2 + |sqrt(c_a) - sqrt(c_b)|^2 per row; the three distance vectors and the two loss vectors are
+    each divided by their max-abs (differentiated through, like autograd does in the reference)."""
+    mo, co, pm, pc, nm, nc = (torch.sigmoid(t.float()) for t in (mean_out, cov_out, pos_mean, pos_cov, neg_mean, neg_cov))
+
+    def dist(m1, c1, m2, c2):
+        return ((m1 - m2) ** 2).sum(-1) + ((torch.sqrt(c1.clamp_min(1e-24)) - torch.sqrt(c2.clamp_min(1e-24))) ** 2).sum(-1)
+    pos, neg, pvn = dist(mo, co, pm, pc), dist(mo, co, nm, nc), dist(pm, pc, nm, nc)
+    pos, neg, pvn = pos / pos.abs().max(), neg / neg.abs().max(), pvn / pvn.abs().max()
+    triplet = -torch.log(torch.sigmoid(neg - pos + 1e-24))
+    triplet = (triplet / triplet.abs().max() * lambda_finetuning).sum()
+    margin = torch.clamp(pos - pvn, 0)
+    margin = (margin / margin.abs().max() * lambda_pvn).sum()
+    return triplet + margin
+
+
+class FinetuneEngine(D2VEngine):
+    """Fused fine-tune TRAIN step (run_class_finetuning.py / engine_for_finetuning(_dist).py) over the same flat arenas as the pre-training
+    engine: classifier forward + backward on the CUDA schedules, the reference's layer-decay parameter groups as per-chunk lr scales of the
+    fused clip + AdamW kernel (optim_factory.py:33-97, LayerDecayValueAssigner), no EMA teacher.
+      det   : loss = SoftTargetCrossEntropy(model(x), targets)
+      dist  : loss = CE(logits) + WassersteinLossFineTuning(anchor, positive, negative features); the positive / negative forwards run
+              without gradients on the live weights (engine_for_finetuning_dist.py:286-304 uses a per-batch deepcopy: same gradients)."""
+
+    def __init__(self, model, *, lr=5e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, clip_grad=None, layer_decay: Optional[float] = 0.65,
+                 lambda_finetuning=1e-4, lambda_pvn=1e-4, world_size=1, process_group=None, seed=0):
+        if model.cfg.kind != "finetune":
+            raise B200VitError("FinetuneEngine needs a classifier (VisionTransformer / DistVisionTransformer)")
+        super().__init__(model, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, clip_grad=clip_grad, ema_decay=1.0, ema_decay_init=1.0,
+                         ema_start_at=0, layer_decay=layer_decay, world_size=world_size, process_group=process_group, seed=seed, use_graph=False,
+                         with_ema=False)
+        self.lam_ft, self.lam_pvn = lambda_finetuning, lambda_pvn
+
+    def step(self, images: torch.Tensor, targets: torch.Tensor, pos_images: Optional[torch.Tensor] = None, neg_images: Optional[torch.Tensor] = None,
+             *, lr: Optional[float] = None, weight_decay: Optional[float] = None, noise: Optional[Noise] = None) -> torch.Tensor:
+        """images fp32 [B,3,H,W]; targets: soft targets [B,K] (Mixup / CutMix) or class indices [B]. Returns the device scalar loss."""
+        cfg = self.cfg
+        lr = self.lr if lr is None else lr
+        wd = self.wd if weight_decay is None else weight_decay
+        self.cur_decay = 1.0
+        base_seed = (self.seed * 0x9E3779B97F4A7C15 + 3 * self.it + 1) & 0xFFFFFFFFFFFFFFFF
+        if noise is None:
+            noise = Noise(seed=base_seed)
+        if targets.dim() == 1:
+            targets = torch.nn.functional.one_hot(targets.long(), cfg.num_classes).float()
+        targets = targets.to(self.dev).float()
+        if cfg.dist:
+            (fm, fc, logits), ctx = core.dist_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
+            loss, dlogits = soft_target_cross_entropy(logits, targets)
+            dfm = dfc = None
+            if pos_images is not None and neg_images is not None:
+                (pm, pc, _), _ = core.dist_forward(self.student, cfg, pos_images, mode="logits", train=True, save=False,
+                                                   noise=Noise(seed=(base_seed + 1) & 0xFFFFFFFFFFFFFFFF))
+                (nm, nc, _), _ = core.dist_forward(self.student, cfg, neg_images, mode="logits", train=True, save=False,
+                                                   noise=Noise(seed=(base_seed + 2) & 0xFFFFFFFFFFFFFFFF))
+                with torch.enable_grad():
+                    a, b = fm.detach().float().requires_grad_(True), fc.detach().float().requires_grad_(True)
+                    wl = wasserstein_loss_finetuning(a, b, pm, pc, nm, nc, self.lam_ft, self.lam_pvn)
+                    dfm, dfc = torch.autograd.grad(wl, (a, b))
+                loss = loss + wl.detach()
+            self.g32.zero_()
+            core.dist_backward_logits(self.student, cfg, ctx, dfm, dfc, dlogits.contiguous(), self.grads)
+        else:
+            logits, ctx = core.vit_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
+            loss, dlogits = soft_target_cross_entropy(logits, targets)
+            self.g32.zero_()
+            core.vit_backward_logits(self.student, cfg, ctx, dlogits.contiguous(), self.grads)
+        self.loss_dev.copy_(loss.reshape(1))
+        return self._optimizer_step(lr, wd)
 
 
 def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,
