@@ -1,6 +1,6 @@
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-os.environ["B200VIT_ATTN_DEBUG"] = "8"
+# needs a trace build:  B200VIT_EXTRA_NVCC_FLAGS=-DB200VIT_KV_TRACE python uncertainty-vit_b200/build.py --force
 import uncertainty_vit_b200 as pkg
 ops = pkg.ops; dev = torch.device("cuda:0")
 B, H, N = 128, 12, 197

@@ -11,6 +11,7 @@ LIB = os.path.join(HERE, "libb200vit.so")
 SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "wattention.cu", "rowwise.cu", "d2v.cu", "mc_metrics.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "--use_fast_math=false" if False else "-Xptxas", "-v" if os.environ.get("B200VIT_PTXAS_V") else "-O3"]
+NVCC_FLAGS += os.environ.get("B200VIT_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DB200VIT_KV_TRACE for tools/micro/kv_trace.py
 
 
 def _newer(a: str, b: str) -> bool:

@@ -417,15 +417,21 @@ constexpr int KV_SMEM = KV_LANES * KV_LANE_BYTES + 1024;
 constexpr int KV_X = 0, KV_Y = 64, KV_DV = 128, KV_DK = 192;   // TMEM columns inside a lane's 256-column half (X_g = KV_X + 32 g)
 static_assert(KV_LANE_BYTES % 1024 == 0 && KV_SMEM <= 232448, "kv kernel smem layout");
 
-// profiling experiment (B200VIT_ATTN_DEBUG & 8): clock64 timeline of lane 0 of CTA 0
+// profiling experiment: clock64 timeline of lane 0 of CTA 0 — compiled in only with -DB200VIT_KV_TRACE (B200VIT_EXTRA_NVCC_FLAGS, see
+// tools/micro/kv_trace.py); a normal build has no trace code on the MMA-issuing thread that paces the kernel
+#ifdef B200VIT_KV_TRACE
 __device__ long long g_kv_trace[3 * 512 * 4];
 __device__ __forceinline__ void kv_trace(int debug, int L, int role, int& n, int code, int it, int bi) {   // fire-and-forget stores, no atomics
-  if ((debug & 8) && blockIdx.x == 0 && L == 0 && n < 512) {
+  if (blockIdx.x == 0 && L == 0 && n < 512) {
     long long* e = g_kv_trace + (role * 512 + n) * 4;
     e[0] = code; e[1] = it; e[2] = bi; e[3] = clock64();
     ++n;
   }
 }
+#define KV_TRACE(...) kv_trace(__VA_ARGS__)
+#else
+#define KV_TRACE(...) ((void)0)
+#endif
 
 // 32-byte global store (sm_100: 256-bit vector stores): one LSU instruction per 32 bytes of a thread-private row segment
 __device__ __forceinline__ void st_global_32B(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6,
@@ -445,7 +451,7 @@ struct BwdKvParams {
   float* dv_bias;            // [H*64] += or null
   int B, H, N, n_pad, k_tiles, items;
   float scale, sl2, inv_keep;
-  int debug;   // profiling experiments only (B200VIT_ATTN_DEBUG): 1 = no dS^T global store, 2 = no MUFU, 4 = no bf16 packs
+  int debug;   // unused in normal builds (trace builds: -DB200VIT_KV_TRACE)
 };
 
 // column sums over the 32 lanes of a warp of 32 per-lane values (recursive halving, 31 shuffles); lane l ends with column l
@@ -601,8 +607,7 @@ __device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, ui
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = 4 * q + e;
-        float pv = fmaf(__uint_as_float(x[idx]), p.sl2, bb[e]) - ll[e];
-        pv = (p.debug & 2) ? pv * 0.001f : ex2(pv);
+        const float pv = ex2(fmaf(__uint_as_float(x[idx]), p.sl2, bb[e]) - ll[e]);
         if (DROP) {   // P~ = f P, dP = f dP~ with f = keep / (1 - p)
           const float f = (kw & (1u << idx)) ? p.inv_keep : 0.f;
           pt[e] = f * pv;
@@ -612,15 +617,10 @@ __device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, ui
           ds[e] = pv * (__uint_as_float(y[idx]) - dd[e]);
         }
       }
-      if (p.debug & 4) {
-        px[2 * q] = __float_as_uint(pt[0]) ^ __float_as_uint(pt[1]); px[2 * q + 1] = __float_as_uint(pt[2]) ^ __float_as_uint(pt[3]);
-        dx[2 * q] = __float_as_uint(ds[0]) ^ __float_as_uint(ds[1]); dx[2 * q + 1] = __float_as_uint(ds[2]) ^ __float_as_uint(ds[3]);
-      } else {
       px[2 * q] = pack_bf16x2(pt[0], pt[1]); px[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
       dx[2 * q] = pack_bf16x2(ds[0], ds[1]); dx[2 * q + 1] = pack_bf16x2(ds[2], ds[3]);
-      }
     }
-    if (!(p.debug & 1)) st_global_32B(ds_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dx[6], dx[7]);
+    st_global_32B(ds_row, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dx[6], dx[7]);
   } else {      // key rows past N: P = dS = 0 (their K / V rows are TMA zero fill, not -inf scores)
 #pragma unroll
     for (int q = 0; q < 8; ++q) px[q] = dx[q] = 0u;
@@ -716,7 +716,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto issue_scores = [&](int bi) {   // X_g = K Q_box^T | Y_g = V dO_box^T ; the last box of an item releases K / V
         const int sl = gb_s & 3, g = bi & 1;
         ptx::mbar_wait(ld_full(sl), (uint32_t)((gb_s >> 2) & 1));      // TMA data: no tcgen05 fence needed
-        if (m == 0) kv_trace(p.debug, L, 2, trn, 20, 0, bi);
+        if (m == 0) KV_TRACE(p.debug, L, 2, trn, 20, 0, bi);
         const uint32_t idesc = bi == nboxes - 1 ? idesc_tail : idesc_s32;
         const uint64_t db = dBk + (uint64_t)(sl * 256);
         const uint32_t d = t_score + g * 32;
@@ -724,7 +724,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::umma_bf16(d, dA + 2, db + 2, idesc, 1u);
         ptx::umma_bf16(d, dA + 4, db + 4, idesc, 1u);
         ptx::umma_bf16(d, dA + 6, db + 6, idesc, 1u);
-        if (m == 0) kv_trace(p.debug, L, 2, trn, 21, 0, bi);
+        if (m == 0) KV_TRACE(p.debug, L, 2, trn, 21, 0, bi);
         ptx::umma_commit(s_full(g));
         if (bi == nboxes - 1) ptx::umma_commit(kv_free);
         ++gb_s;
@@ -738,20 +738,20 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const int sl = gb & 3, g = bi & 1;
           ptx::mbar_wait(p_full(g), (uint32_t)(cnt[g] & 1));
           ++cnt[g];
-          if (m == 0) kv_trace(p.debug, L, 2, trn, 10, it, bi);
+          if (m == 0) KV_TRACE(p.debug, L, 2, trn, 10, it, bi);
           if (bi == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
           ptx::tc_fence_after();
-          if (m == 0) kv_trace(p.debug, L, 2, trn, 13, it, bi);
+          if (m == 0) KV_TRACE(p.debug, L, 2, trn, 13, it, bi);
           const uint64_t db = dBm + (uint64_t)(sl * 256);
           const uint32_t a = t_score + g * 32;     // bf16 pairs written in place by the element-wise warps
           ptx::umma_bf16_ts(t_acc, a, db, idesc_acc, bi > 0 ? 1u : 0u);
           if (bi < nboxes - 1 || tail_ksteps > 1) ptx::umma_bf16_ts(t_acc, a + 8, db + 128, idesc_acc, 1u);
-          if (m == 0) kv_trace(p.debug, L, 2, trn, 14, it, bi);
+          if (m == 0) KV_TRACE(p.debug, L, 2, trn, 14, it, bi);
           ptx::umma_commit(ld_empty(sl));
           if (bi == nboxes - 1) ptx::umma_commit(acc_full);
-          if (m == 0) kv_trace(p.debug, L, 2, trn, 11, it, bi);
+          if (m == 0) KV_TRACE(p.debug, L, 2, trn, 11, it, bi);
           if (bi + 2 < nboxes) issue_scores(bi + 2);   // same group's next box: runs after the MMAs above (issue order)
-          if (m == 0) kv_trace(p.debug, L, 2, trn, 12, it, bi);
+          if (m == 0) KV_TRACE(p.debug, L, 2, trn, 12, it, bi);
         }
       }
     }
@@ -822,7 +822,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       ptx::named_bar_sync(1 + L, KV_EW_WARPS * 32);
       if (it + 1 < n_items && tid < n_pad) fetch_row_stats(it + 1);
-      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 5 + 100 * g, it, 0);
+      if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 5 + 100 * g, it, 0);
       const int j = j0 + row;
       const bool valid = j < p.N;
       const bool active = j0 + quad * 32 < p.N;
@@ -840,7 +840,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((gb >> 1) & 1));
         ptx::mbar_wait(s_full(g), (uint32_t)(group_count(it, bi) & 1));
         ptx::tc_fence_after();
-        if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 1 + 100 * g, it, bi);
+        if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 1 + 100 * g, it, bi);
         if (active) {
           const uint8_t* bias_row = gbase + KV_SM_BIAS + st * BIAS_STAGE_BYTES + row * 128;
           bwd_step16<DROP, HAS_BIAS>(p, cx, cy, cx, cy, bias_row, 0, row, s_lse + c0, s_d + c0, kw, valid, ds_base + c0);
@@ -855,12 +855,12 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(p_full(g));
-        if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 2 + 100 * g, it, bi);
+        if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 2 + 100 * g, it, bi);
       }
       // ---------------- epilogue: dV rows (group 0) / dK rows (group 1) of this key tile ----------------
       ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
       ptx::tc_fence_after();
-      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 3 + 100 * g, it, 0);
+      if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 3 + 100 * g, it, 0);
       if (active) {
         const float mul = g == 0 ? 1.0f : p.scale;
 #pragma unroll
@@ -870,7 +870,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(o[e]) * mul;
-          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 6 + 100 * g, it, half);
+          if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 6 + 100 * g, it, half);
           if (valid) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -879,18 +879,18 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                             pack_bf16x2(v[16 * q + 8], v[16 * q + 9]), pack_bf16x2(v[16 * q + 10], v[16 * q + 11]),
                             pack_bf16x2(v[16 * q + 12], v[16 * q + 13]), pack_bf16x2(v[16 * q + 14], v[16 * q + 15]));
           }
-          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 7 + 100 * g, it, half);
+          if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 7 + 100 * g, it, half);
           if (g == 0 && p.dv_bias != nullptr) {   // v_bias gradient: rows past N are exactly zero
             const float c = warp_colsum32(v, lane);
             atomicAdd(p.dv_bias + h * HD + half * 32 + lane, c);
           }
-          if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 8 + 100 * g, it, half);
+          if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 8 + 100 * g, it, half);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(acc_empty);
-      if (lane == 0 && quad == 0) kv_trace(p.debug, L, g, trn, 4 + 100 * g, it, 0);
+      if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 4 + 100 * g, it, 0);
     }
   }
   ptx::tc_fence_before();
@@ -1047,11 +1047,13 @@ int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+#ifdef B200VIT_KV_TRACE
 extern "C" int b200vit_debug_kv_trace(long long* host_out, int max_events) {   // tools only (not in the public header)
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(host_out, g_kv_trace, sizeof(long long) * 3 * 512 * 4);
   return 3 * 512;
 }
+#endif
 
 extern "C" size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N) {
   const size_t n_pad = (size_t)(N + 15) / 16 * 16;
@@ -1095,7 +1097,7 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
   p.lse = lse; p.dvec = dvec; p.keep_t = keep_t; p.ds_out = ds; p.ld_ds = ld_ds; p.dqkv = static_cast<bf16*>(dqkv); p.dv_bias = dv_bias;
   p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.k_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.k_tiles;
   p.scale = scale; p.sl2 = scale * LOG2E; p.inv_keep = drop ? 1.0f / (1.0f - p_drop) : 1.0f;
-  { const char* dbg = getenv("B200VIT_ATTN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  p.debug = 0;
   const uint64_t row = 3ull * H * HD, orow = (uint64_t)H * HD;
   CUtensorMap tq, tkv, tdo, tb, tds, tkfull, tdq;
   int rc;
