@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 1
+#define B200VIT_ABI_VERSION 2   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);

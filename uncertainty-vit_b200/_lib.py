@@ -80,7 +80,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 1:
+        if l.b200vit_abi_version() != 2:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

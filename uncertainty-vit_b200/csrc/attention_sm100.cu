@@ -211,8 +211,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ptx::umma_bf16(tmem_base, dQ + 2, dK + 2, idesc_s, 1u);
         ptx::umma_bf16(tmem_base, dQ + 4, dK + 4, idesc_s, 1u);
         ptx::umma_bf16(tmem_base, dQ + 6, dK + 6, idesc_s, 1u);
-        ptx::umma_commit(s_full);
-        ptx::umma_commit(qk_free);
+        ptx::umma_commit(s_full);                 // also tells the TMA thread that Q / K have been read (one completion per item)
         // O = P~ V : A = bf16 probabilities in TMEM columns [0, n_pad/2), B = V
         ptx::mbar_wait(v_full, ph);
         ptx::mbar_wait(p_full, ph);
@@ -227,7 +226,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       for (int it = 0; it < n_items; ++it) {
         int b, h, m0, bh;
         item_of(it, b, h, m0, bh);
-        if (it > 0) ptx::mbar_wait(qk_free, (uint32_t)((it - 1) & 1));
+        if (it > 0) ptx::mbar_wait(s_full, (uint32_t)((it - 1) & 1));      // S MMAs of the previous item complete: Q / K are free
         ptx::mbar_arrive_expect_tx(qk_full, TILE_M * 128 + n_pad * 128);
         ptx::tma_load_3d(base + SM_Q, &tm_q, qk_full, h * HD, m0, b);
         ptx::tma_load_3d(base + SM_K, &tm_kv, qk_full, (p.H + h) * HD, 0, b);
