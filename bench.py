@@ -8,7 +8,7 @@ One "step" = EMA-teacher forward + target builder / smooth-L1 + student forward/
 EMA on one batch of 128 synthetic 224x224 images per GPU with exactly 120 masked patches per image (README recipe:
 drop_path 0.25, attn_drop 0.05, layer-scale 1e-4, target_layers 6-11, post LayerNorm targets, l1_beta 2, EMA 0.9998, clip 3, wd 0.05).
 `value`   : device-timed (CUDA events) with the batch already resident in HBM.
-`e2e`     : the same step through D2VEngine.stage_host()/step_staged() (what engine.train_one_epoch calls): every step's pinned host batch is
+`e2e`     : the same step through D2VEngine.stage_host()/launch_staged() (what engine.train_one_epoch calls): every step's pinned host batch is
             copied to the device (one batch ahead, on a copy stream) and its loss read back inside the timed region.
 `roofline`: all launches of the tcgen05 GEMM kernel inside instrumented steps: algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
 """
@@ -253,8 +253,9 @@ def run_b200(args):
     def e2e_loop(n):
         nxt = eng.stage_host(*host[0])
         for i in range(n):
-            cur, nxt = nxt, (eng.stage_host(*host[(i + 1) % 2]) if i + 1 < n else None)
-            eng.step_staged(cur, lr=lr_at(i))
+            loss_dev = eng.launch_staged(nxt, lr=lr_at(i))                       # enqueue step i
+            nxt = eng.stage_host(*host[(i + 1) % 2]) if i + 1 < n else None      # stage batch i+1 (host work + H2D) while it runs
+            float(loss_dev.item())                                                # read the loss of step i back
 
     e2e_loop(2)
     barrier()

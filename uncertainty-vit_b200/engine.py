@@ -355,15 +355,19 @@ class D2VEngine:
             ev.record(self._copy_stream)
         return images, mask_u8, rows_d, ev, (mask_pinned, rows)
 
-    def step_staged(self, staged, **kw) -> float:
-        """One step on a batch returned by stage_host(); reads the loss back (engine_for_cyclical.py:164)."""
+    def launch_staged(self, staged, **kw) -> torch.Tensor:
+        """Enqueues one step on a batch returned by stage_host() and returns the DEVICE loss scalar without synchronising: the caller can
+        stage the next batch while the step runs and read the loss afterwards."""
         images, mask_u8, rows, ev, _keepalive = staged
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
         for t in (images, mask_u8, rows):
             t.record_stream(cur)
-        loss = self.step(images, mask_u8, rows, **kw)
-        return float(loss.item())
+        return self.step(images, mask_u8, rows, **kw)
+
+    def step_staged(self, staged, **kw) -> float:
+        """One step on a batch returned by stage_host(); reads the loss back (engine_for_cyclical.py:164)."""
+        return float(self.launch_staged(staged, **kw).item())
 
     def step_host(self, images_pinned: torch.Tensor, mask_host: np.ndarray, **kw) -> float:
         """The reference-facing call: HOST batch in (pinned images + integer mask as the data loader yields them,
@@ -469,12 +473,14 @@ def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, st
     nxt = next(it_batches, None)
     step = 0
     while nxt is not None:
-        cur, nxt = nxt, next(it_batches, None)      # batch step+1 is copied host->device while step `step` computes
+        cur = nxt
         it = start_steps + step
         lr = float(lr_schedule_values[it]) if lr_schedule_values is not None else None
         wd = float(wd_schedule_values[it]) if wd_schedule_values is not None else None
         engine.it = it
-        loss = engine.step_staged(cur, lr=lr, weight_decay=wd)
+        loss_dev = engine.launch_staged(cur, lr=lr, weight_decay=wd)      # enqueue step `step` ...
+        nxt = next(it_batches, None)                                       # ... stage batch step+1 (host work + H2D) while it runs ...
+        loss = float(loss_dev.item())                                      # ... and read the loss back (engine_for_cyclical.py:164)
         if not math.isfinite(loss):
             raise FloatingPointError(f"Loss is {loss}, stopping training")
         total += loss
