@@ -191,9 +191,13 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT otherwise: stdout carries ONE JSON line
+        # NCCL writes its version banner to file descriptor 1: stdout must carry ONE JSON line, so fd 1 is pointed at stderr for the
+        # whole run and the JSON line is written through a duplicate of the original stdout.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=120))
     import uncertainty_vit_b200 as pkg
     from uncertainty_vit_b200 import engine as E, modeling as M
@@ -295,7 +299,8 @@ def run_b200(args):
         cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
                "sample": f"2 full data2vec steps of {CPU_SAMPLE_BATCH} images after 1 warm-up ({sec:.2f} s/step), fp32 oracle port, {cores} threads"}
     if rank == 0:
-        print(json.dumps({
+        emit = (lambda line: os.write(json_fd, (line + "\n").encode())) if json_fd is not None else print
+        emit(json.dumps({
             "metric": "data2vec ViT-B/16 pretrain throughput", "value": world * BATCH / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
