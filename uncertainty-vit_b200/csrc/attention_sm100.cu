@@ -628,6 +628,28 @@ __device__ __forceinline__ void bwd_step16(const BwdKvParams& p, uint32_t tx, ui
   ptx::tmem_st_x8(tpy, dx);
 }
 
+// mbarrier wait whose slow path (spin loop + timeout trap) is ONE out-of-line function: the kv kernel waits at ~20 sites and the inlined
+// slow paths cost it instruction-cache misses ("no instruction" stalls); measured -14 us per launch. (The same change in the GEMM kernel
+// halves ITS throughput - a call in a setmaxnreg kernel - and slows the forward kernel, so it stays local to this kernel.)
+__device__ __noinline__ void wait_slow(uint32_t bar, uint32_t parity) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {
+        printf("b200vit: mbarrier timeout (kv kernel, block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void wait_ool(uint32_t bar, uint32_t parity) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  wait_slow(bar, parity);
+}
+
 // Persistent: one CTA per SM holds KV_LANES independent lanes; lane L of CTA c walks items (2c + L) + k * 2 * gridDim of the
 // (batch, head, key-tile) list. Inside a lane the 8 element-wise warps form two groups that ping-pong over the 32-query boxes of an
 // item (group g owns TMEM columns X_g / Y_g): while group g computes box b, the tensor core runs dV/dK += of group 1-g's box and the
@@ -714,7 +736,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       int gb_s = 0;             // running box index of the NEXT score issue
       auto issue_scores = [&](int bi) {   // X_g = K Q_box^T | Y_g = V dO_box^T ; the last box of an item releases K / V
         const int sl = gb_s & 3, g = bi & 1;
-        ptx::mbar_wait(ld_full(sl), (uint32_t)((gb_s >> 2) & 1));      // TMA data: no tcgen05 fence needed
+        wait_ool(ld_full(sl), (uint32_t)((gb_s >> 2) & 1));      // TMA data: no tcgen05 fence needed
         if (m == 0) KV_TRACE(p.debug, L, 2, trn, 20, 0, bi);
         const uint32_t idesc = bi == nboxes - 1 ? idesc_tail : idesc_s32;
         const uint64_t db = dBk + (uint64_t)(sl * 256);
@@ -730,15 +752,15 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       };
       int gb = 0;
       for (int it = 0; it < n_items; ++it) {
-        ptx::mbar_wait(kv_full, (uint32_t)(it & 1));
+        wait_ool(kv_full, (uint32_t)(it & 1));
         issue_scores(0);
         if (nboxes > 1) issue_scores(1);
         for (int bi = 0; bi < nboxes; ++bi, ++gb) {
           const int sl = gb & 3, g = bi & 1;
-          ptx::mbar_wait(p_full(g), (uint32_t)(cnt[g] & 1));
+          wait_ool(p_full(g), (uint32_t)(cnt[g] & 1));
           ++cnt[g];
           if (m == 0) KV_TRACE(p.debug, L, 2, trn, 10, it, bi);
-          if (bi == 0 && it > 0) ptx::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
+          if (bi == 0 && it > 0) wait_ool(acc_empty, (uint32_t)((it - 1) & 1));
           ptx::tc_fence_after();
           if (m == 0) KV_TRACE(p.debug, L, 2, trn, 13, it, bi);
           const uint64_t db = dBm + (uint64_t)(sl * 256);
@@ -766,14 +788,14 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int it = 0; it < n_items; ++it) {
         for (int bi = 0; bi < nboxes; ++bi, ++gb) {
           const int sl = gb & 3;
-          if (gb >= 4) ptx::mbar_wait(ld_empty(sl), (uint32_t)(((gb >> 2) - 1) & 1));
+          if (gb >= 4) wait_ool(ld_empty(sl), (uint32_t)(((gb >> 2) - 1) & 1));
           ptx::mbar_arrive_expect_tx(ld_full(sl), 2 * 4096);
           ptx::tma_load_3d(base + KV_SM_Q + sl * 4096, &tm_q, ld_full(sl), h * HD, bi * 32, b);
           ptx::tma_load_3d(base + KV_SM_DO + sl * 4096, &tm_do, ld_full(sl), h * HD, bi * 32, b);
         }
         if (it + 1 < n_items) {     // the boxes above were requested for item `it`; now K / V of item it + 1 once item it has released them
           item_of(it + 1, b, h, j0, bh);
-          ptx::mbar_wait(kv_free, (uint32_t)(it & 1));
+          wait_ool(kv_free, (uint32_t)(it & 1));
           ptx::mbar_arrive_expect_tx(kv_full, 2 * 16384);
           ptx::tma_load_3d(base + KV_SM_K, &tm_kv, kv_full, (p.H + h) * HD, j0, b);
           ptx::tma_load_3d(base + KV_SM_V, &tm_kv, kv_full, (2 * p.H + h) * HD, j0, b);
@@ -787,7 +809,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         item_of(it, b, h, j0, bh);
         for (int bi = 0; bi < nboxes; ++bi, ++gb) {
           const int st = gb & 1;
-          if (gb >= 2) ptx::mbar_wait(bias_empty(st), (uint32_t)(((gb >> 1) - 1) & 1));
+          if (gb >= 2) wait_ool(bias_empty(st), (uint32_t)(((gb >> 1) - 1) & 1));
           ptx::mbar_arrive_expect_tx(bias_full(st), BIAS_STAGE_BYTES);
           ptx::tma_load_3d(base + KV_SM_BIAS + st * BIAS_STAGE_BYTES, &tm_bias, bias_full(st), bi * 32, j0, h);
         }
@@ -836,8 +858,8 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int gb = it * nboxes + bi, st = gb & 1;
         uint32_t kw = 0xffffffffu;
         if (DROP && valid) kw = __ldg(kt_row + bi);
-        if (HAS_BIAS) ptx::mbar_wait(bias_full(st), (uint32_t)((gb >> 1) & 1));
-        ptx::mbar_wait(s_full(g), (uint32_t)(group_count(it, bi) & 1));
+        if (HAS_BIAS) wait_ool(bias_full(st), (uint32_t)((gb >> 1) & 1));
+        wait_ool(s_full(g), (uint32_t)(group_count(it, bi) & 1));
         ptx::tc_fence_after();
         if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 1 + 100 * g, it, bi);
         if (active) {
@@ -857,7 +879,7 @@ attn_bwd_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 2 + 100 * g, it, bi);
       }
       // ---------------- epilogue: dV rows (group 0) / dK rows (group 1) of this key tile ----------------
-      ptx::mbar_wait(acc_full, (uint32_t)(it & 1));
+      wait_ool(acc_full, (uint32_t)(it & 1));
       ptx::tc_fence_after();
       if (lane == 0 && quad == 0) KV_TRACE(p.debug, L, g, trn, 3 + 100 * g, it, 0);
       if (active) {
