@@ -1,0 +1,71 @@
+"""CPU: host-side logic of the engines against the oracle (which is pinned to the reference): the fine-tune loss front-end
+(SoftTargetCrossEntropy, WassersteinLossFineTuning), the layer-decay group assignment, the lr schedule and the pass sharding."""
+import math
+
+import numpy as np
+import torch
+
+
+def test_wasserstein_loss_finetuning_matches_oracle_value_and_gradients():
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import engine as E
+    g = torch.Generator().manual_seed(0)
+    B, C = 6, 32
+    args = [torch.randn(B, C, generator=g) for _ in range(6)]
+    a = [t.clone().requires_grad_(True) for t in args]
+    b = [t.clone().requires_grad_(True) for t in args]
+    lo = O.wasserstein_loss_finetune(*a, lam_ft=1e-2, lam_pvn=1e-3)
+    lm = E.wasserstein_loss_finetuning(*b, lambda_finetuning=1e-2, lambda_pvn=1e-3)
+    assert abs(float(lo) - float(lm)) <= 1e-6 * abs(float(lo))
+    lo.backward()
+    lm.backward()
+    for x, y in zip(a, b):
+        assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_soft_target_cross_entropy_loss_and_gradient():
+    from uncertainty_vit_b200 import engine as E
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(5, 17, generator=g, requires_grad=True)
+    t = torch.softmax(torch.randn(5, 17, generator=g), -1)
+    ref = torch.sum(-t * torch.log_softmax(z, -1), -1).mean()          # timm.loss.SoftTargetCrossEntropy
+    ref.backward()
+    loss, dz = E.soft_target_cross_entropy(z.detach(), t)
+    assert abs(float(loss) - float(ref)) < 1e-6 and torch.allclose(dz, z.grad, rtol=1e-5, atol=1e-8)
+    hard = torch.tensor([3, 0, 16, 7, 7])
+    loss_h, _ = E.soft_target_cross_entropy(z.detach(), torch.nn.functional.one_hot(hard, 17).float())
+    assert abs(float(loss_h) - float(torch.nn.functional.cross_entropy(z.detach(), hard))) < 1e-6
+
+
+def test_layer_ids_match_oracle_for_every_reference_parameter_name():
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import engine as E
+    arch = O.Arch(kind="finetune", dist=True, **O.VIT_B) if hasattr(O, "VIT_B") else None
+    names = list(O.make_state(arch, 0).keys()) if arch is not None else []
+    names += ["cls_token", "mask_token", "pos_embed", "patch_embed.proj.weight", "rel_pos_bias.relative_position_bias_table", "blocks.0.norm1.weight",
+              "blocks.11.mlp.fc2.bias", "fc_norm.weight", "head.weight", "cov_cls_token", "cov_patch_embed.proj.bias"]
+    L = 12 + 2
+    for n in names:
+        assert E.get_num_layer_for_vit(n, L) == O.get_num_layer_for_vit(n, L), n
+    # LayerDecayValueAssigner(0.65) of run_class_finetuning.py:569-573: scale = 0.65 ** (L - 1 - layer_id)
+    assert math.isclose(0.65 ** (L - 1 - E.get_num_layer_for_vit("blocks.0.attn.qkv.weight", L)), 0.65 ** 12)
+    assert E.get_num_layer_for_vit("head.bias", L) == L - 1
+
+
+def test_cosine_scheduler_shape_and_endpoints():
+    from uncertainty_vit_b200 import engine as E
+    s = E.cosine_scheduler(2e-3, 1e-5, 10, 7, warmup_epochs=2)
+    assert len(s) == 70 and s[0] == 0.0 and abs(s[14] - 2e-3) < 1e-12 and s[-1] > 1e-5 and np.all(np.diff(s[14:]) <= 1e-15)
+    s2 = E.cosine_scheduler(1.0, 0.0, 4, 5, warmup_steps=3)
+    assert len(s2) == 20 and abs(s2[2] - 1.0) < 1e-12
+
+
+def test_shard_passes_partitions_every_pass_once():
+    from uncertainty_vit_b200 import mc
+    for S in (2, 7, 30, 31):
+        for world in (1, 2, 3, 8):
+            sh = mc.shard_passes(S, world)
+            assert len(sh) == world and sh[0][0] == 0 and sh[-1][1] == S
+            assert all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+            sizes = [e - s for s, e in sh]
+            assert max(sizes) - min(sizes) <= 1
