@@ -156,7 +156,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t base = cta_base + L * FWD_LANE_BYTES;
   uint8_t* gbase = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t bar0 = base + SM_BAR;
-  const uint32_t qk_full = bar0, v_full = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, o_full = bar0 + 32, qk_free = bar0 + 40,
+  const uint32_t qk_full = bar0, v_full = bar0 + 8, s_full = bar0 + 16, p_full = bar0 + 24, o_full = bar0 + 32,
                  v_free = bar0 + 48, t_free = bar0 + 56;
   auto bias_full = [&](int s) { return bar0 + 64u + 8u * s; };
   auto bias_empty = [&](int s) { return bar0 + 80u + 8u * s; };
@@ -177,7 +177,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (warp == FWD_EW_WARPS) {
     if (lane == 0) {
       ptx::mbar_init(qk_full, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, FWD_EW_WARPS * 32);
-      ptx::mbar_init(o_full, 1); ptx::mbar_init(qk_free, 1); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, FWD_EW_WARPS);
+      ptx::mbar_init(o_full, 1); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, FWD_EW_WARPS);
       for (int s = 0; s < BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), FWD_EW_WARPS); }
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_out);
