@@ -270,6 +270,31 @@ def run_b200(args):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     h2d = host[0][0].numel() * 4 + BATCH * 196 + BATCH * MASKED * 4
+    # ---- the same e2e loop with the reference's BLOCK-WISE masks (masking_generator.py:29-92) drawn on the device: the masked-row count
+    # then differs from batch to batch (a third of the images end 1-10 patches short of 120); one captured graph must serve them all.
+    from uncertainty_vit_b200 import masking_generator as MG
+    gen = MG.MaskingGenerator(14, MASKED, min_num_patches=16, seed=rank, device=dev)
+    counts = []
+
+    def blockwise_loop(n):
+        nxt = eng.stage_device_masks(host[0][0], gen)
+        for i in range(n):
+            loss_dev = eng.launch_staged(nxt, lr=lr_at(i))
+            counts.append(nxt[5])
+            nxt = eng.stage_device_masks(host[(i + 1) % 2][0], gen) if i + 1 < n else None
+            float(loss_dev.item())
+
+    blockwise_loop(3)
+    barrier()
+    del counts[:]
+    t0 = time.perf_counter()
+    blockwise_loop(args.steps)
+    barrier()
+    bw_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    bw_rows = [int(c.item()) for c in counts]
+    blockwise = {"value": world * BATCH / (bw_ms * 1e-3), "unit": "img/s", "ms_per_step": bw_ms, "masked_rows_min": min(bw_rows),
+                 "masked_rows_max": max(bw_rows), "graphs": len(eng._graphs), "h2d_bytes_per_step": host[0][0].numel() * 4,
+                 "what": "e2e loop with device block-wise masks (variable masked-row count, padded row list, one CUDA graph)"}
     # ---- roofline: CUDA events around every tcgen05 GEMM launch inside 2 instrumented steps
     roof = None
     if rank == 0:
@@ -309,7 +334,8 @@ def run_b200(args):
                                    "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
                        "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"},
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mc_inference": mc_res, "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mc_inference": mc_res, "blockwise_masks_e2e": blockwise,
+            "final_loss": final_loss,
             "step_tflops_algorithmic": (281.86e9 if args.stochastic else 140.93e9) * BATCH / (ms * 1e-3) / 1e12}))
     if world > 1:
         dist.destroy_process_group()

@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 2   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace */
+#define B200VIT_ABI_VERSION 3   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -158,6 +159,19 @@ int b200vit_assemble_tokens_bwd(const float* dx, const uint8_t* mask, int32_t B,
 /* DropPath (timm drop_path, modeling_finetune.py:51-62): out[l, d, b] = keep / (1 - p_l), keep ~ Bernoulli(1 - p_l) from
  * Philox4x32-10 keyed on (seed; l, d, b). probs_host: HOST array of L drop probabilities (linspace(0, rate, L), :401). */
 int b200vit_drop_path_scales(const float* probs_host, int32_t L, int32_t draws, int32_t B, uint64_t seed, float* out, void* stream);
+/* Block-wise mask generator of the pre-training input pipeline (MaskingGenerator.__call__ / _mask, masking_generator.py:29-92; one call
+ * per image in DataAugmentationForBEiT.__call__, datasets.py:104-118) for a whole batch on the device, plus the masked-row list the
+ * student's head gathers (modeling_cyclical.py:221-225: row-major over (image, patch)).
+ *   mask  [B, height*width] uint8 {0,1};   count [B+1] int32: masked patches per image, count[B] = their sum R (-1: injected stream exhausted)
+ *   rows  [>= B*num_masking_patches] int32 or NULL: rows[k] = b*tokens + 1 + patch of the k-th masked patch (tokens = patches + cls)
+ *   log_aspect_lo/hi = log(min_aspect), log(max_aspect) as the reference computes them (:42-43); height, width <= 32.
+ * uniforms == NULL: draws come from Philox4x32-10 keyed on (seed; first_image + b, draw index) as 53-bit doubles.
+ * uniforms != NULL: [B, uniforms_per_image] doubles in [0,1) consumed in call order (uniform(a,b) = a + (b-a)*u, randint(0,n) =
+ * min(n, floor(u*(n+1)))): with the same stream fed to the reference generator the masks are bit-identical. */
+int b200vit_block_masks(uint8_t* mask, int32_t* count, int32_t* rows, int32_t B, int32_t height, int32_t width, int32_t tokens,
+                        int32_t num_masking_patches, int32_t min_num_patches, int32_t max_num_patches, double log_aspect_lo,
+                        double log_aspect_hi, uint64_t seed, uint64_t first_image, const double* uniforms, int32_t uniforms_per_image,
+                        void* stream);
 /* RelativePositionBias.forward (modeling_finetune.py:359-364) in the padded layouts the attention kernels read:
  *   out_fwd  [H, N, ld]: scale * table[index[i,j], h] for j < N, -inf for N <= j < ld  (key mask baked into the padding)
  *   out_bwd_t[H, N, ld]: the transpose (row = key j, column = query i), 0 in the padding.   Either may be NULL.
@@ -175,11 +189,15 @@ int b200vit_meanpool_tokens_bwd(const float* dpool, int32_t B, int32_t T, int32_
 /* Target builder + loss (engine_for_cyclical.py:90-150), masked rows only: per row r (source row row_index[r] of each
  * [*, ld_layer] fp32 teacher layer): t = LN?( mean_l LN?(layer_l[row]) ), eps 1e-5 no affine; loss = smooth_l1(y, t, beta)
  * (or MSE) mean over R*C; dy = dloss/dy * grad_scale. layers_host is a HOST array of device pointers.
- * Any of targets / dy_bf16 / dy_f32 / y may be NULL. row_loss: workspace of R floats; loss_out: device scalar. */
+ * Any of targets / dy_bf16 / dy_f32 / y may be NULL. row_loss: workspace of R floats; loss_out: device scalar.
+ * n_valid_dev (device int32, or NULL): the row list is PADDED to a fixed capacity R and only its first *n_valid_dev rows are masked
+ * patches (block-wise masking yields a slightly different count every batch, masking_generator.py:80-92; a fixed R keeps every launch
+ * shape of the step constant). Padded rows get zero loss, zero dy and zero targets; the mean and grad_scale are rescaled by
+ * R / *n_valid_dev, i.e. grad_scale is given as if all R rows were valid. Padded row_index entries must still be valid rows. */
 int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
                             const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
                             float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
-                            void* stream);
+                            const int32_t* n_valid_dev, void* stream);
 /* EMA teacher update e = d*e + (1-d)*m (engine_for_cyclical.py:182-185, timm ModelEmaV2._update) + bf16 shadow */
 int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, void* ema_bf16, void* stream);
 /* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
@@ -191,10 +209,11 @@ int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, 
                        float beta1, float beta2,
                        float eps, int32_t step, const float* gnorm_sq, float max_norm, float grad_div, void* p_bf16, float* ema,
                        double ema_decay, void* ema_bf16, void* stream);
-/* WassersteinLoss.forward + backward (distloss.py:13-30,73-79). work: 2R+8 floats. d_* are accumulated (+=). */
+/* WassersteinLoss.forward + backward (distloss.py:13-30,73-79). work: 2R+8 floats. d_* are accumulated (+=).
+ * n_valid_dev as in d2v_target_loss: rows >= *n_valid_dev of a padded list take no part in the normalisers, the sum or the gradient. */
 int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
                              int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,
-                             float* loss_out, void* stream);
+                             float* loss_out, const int32_t* n_valid_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MC-sample uncertainty reduction (uncertainty_evaluations.py:77-85,110-202,270-272)

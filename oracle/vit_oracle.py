@@ -529,6 +529,28 @@ def blockwise_mask(rng, height=14, width=14, num_masking_patches=120, min_num_pa
     return mask
 
 
+class InjectedUniformRng:
+    """`random`-module stand-in that replays a given sequence of uniforms in [0,1): uniform(a, b) = a + (b - a) * u exactly as
+    random.uniform computes it, randint(a, b) = a + min(b - a, floor(u * (b - a + 1))). Feeding the same sequence to the device
+    generator (b200vit_block_masks, uniforms != NULL) must give bit-identical masks."""
+
+    def __init__(self, uniforms):
+        self.u = uniforms
+        self.i = 0
+
+    def random(self):
+        v = float(self.u[self.i])
+        self.i += 1
+        return v
+
+    def uniform(self, a, b):
+        return a + (b - a) * self.random()
+
+    def randint(self, a, b):
+        n = b - a
+        return a + min(n, int(self.random() * (n + 1)))
+
+
 # --------------------------------------------------------------------------------------------------------------
 # MC-sample uncertainty metrics (uncertainty_evaluations.py)
 # --------------------------------------------------------------------------------------------------------------

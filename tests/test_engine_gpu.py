@@ -186,3 +186,91 @@ def test_finetune_engine_matches_module_autograd(cuda, golden_dir):
         if arch.dist:      # triplet step: positive / negative forwards + WassersteinLossFineTuning on the features
             l2 = float(eng.step(x, targets, x.roll(1, 0).contiguous(), x.flip(0).contiguous()).item())
             assert np.isfinite(l2) and torch.isfinite(eng.g32).all()
+
+
+def _gold_noise(pkg, gold, cuda):
+    n = gold["noise"]
+    noise = pkg.core.Noise(seed=1)
+    noise.drop_path_scale = torch.stack([k.float() / (1.0 - p) for k, p in zip(n["keep"], n["prob"])]).to(cuda).contiguous()
+    noise.attn_keep = [k.to(cuda).contiguous() for k in n["attn_keep"]]
+    return noise
+
+
+@pytest.mark.parametrize("name", ["tiny_det_cyclical.pt", "tiny_dist_cyclical.pt"])
+def test_padded_row_list_is_the_same_step(cuda, golden_dir, name):
+    """Block-wise masking gives a different masked-row count every batch; the engine keeps one launch shape by padding the row list to a
+    capacity and passing the true count in device memory. A step on the padded list (padding = stale but valid row numbers) must equal
+    the step on the exact list (itself pinned to the oracle above): same loss, same gradients, same updated weights."""
+    import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import engine as E
+    from tests.test_model_gpu import _build_dist, _build_from_gold
+    res = {}
+    for padded in (False, True):
+        gold = torch.load(os.path.join(golden_dir, name))
+        model, arch, sd = (_build_dist if "dist" in name else _build_from_gold)(pkg, gold, cuda)
+        eng = E.D2VEngine(model, lr=1e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.99, target_layers=gold["target_layers"],
+                          lambda_pretraining=1e-2)
+        m = gold["mask"].reshape(gold["mask"].shape[0], -1).numpy().astype(np.uint8)
+        rows = torch.from_numpy(eng.rows_from_host_mask(m, arch.tokens)).to(cuda)
+        R = rows.numel()
+        n_valid = None
+        if padded:
+            pad = torch.randint(0, m.shape[0] * arch.tokens, (13,), dtype=torch.int32, generator=torch.Generator().manual_seed(2)).to(cuda)
+            rows = torch.cat([rows, pad])
+            n_valid = torch.tensor([R], dtype=torch.int32, device=cuda)
+        loss = eng.step(gold["x"].to(cuda), torch.from_numpy(m.reshape(-1)).to(cuda), rows, noise=_gold_noise(pkg, gold, cuda), n_valid=n_valid)
+        res[padded] = (float(loss.item()), eng.g32.clone(), eng.p32.clone(), float(eng.grad_norm().item()))
+    (l0, g0, p0, n0), (l1, g1, p1, n1) = res[False], res[True]
+    assert abs(l0 - l1) / abs(l0) < 1e-5, (l0, l1)
+    assert abs(n0 - n1) / n0 < 1e-3
+    assert rel(g1, g0) < 2e-3, rel(g1, g0)                 # bf16 dy rounding of the rescaled grad_scale + fp32 atomic order
+    assert rel(p1, p0) < 1e-2                               # (Adam's first step is sign-like: only a loose check on the weights)
+
+
+def test_graph_serves_changing_masked_row_counts(cuda):
+    """One captured graph replays batches whose masked-row counts differ (device block-wise masks, no read-back): the loss of each
+    replayed step equals the eager step on the exact row list with the same seed."""
+    from functools import partial
+    from uncertainty_vit_b200 import engine as E, masking_generator as MG, modeling as M
+    losses = {}
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        model = M.VisionTransformerForCyclicalTraining(img_size=224, patch_size=16, embed_dim=768, depth=2, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                                                       norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), use_shared_rel_pos_bias=True,
+                                                       use_abs_pos_emb=False, init_values=0.1, drop_path_rate=0.1, attn_drop_rate=0.05).to(cuda)
+        eng = E.D2VEngine(model, lr=1e-3, target_layers=[0, 1], use_graph=use_graph, seed=5)
+        gen = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=9, device=cuda)
+        g = torch.Generator().manual_seed(1)
+        B = 8
+        out, counts = [], []
+        for i in range(7):
+            x = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+            if use_graph:
+                staged = eng.stage_device_masks(x, gen)
+                staged[3].synchronize()             # (the count lives on the copy stream; the engine itself never reads it back)
+                counts.append(int(staged[5].item()))
+                out.append(float(eng.launch_staged(staged).item()))
+            else:                                   # exact row list on the host from the same device masks
+                mask, count, _ = gen.batch(B)
+                counts.append(int(count[B].item()))
+                out.append(eng.step_host(x, mask.cpu().numpy()))
+        losses[use_graph] = out
+        if use_graph:
+            assert len(eng._graphs) == 1 and eng._eager_steps == 2, "steps 3.. must replay ONE graph whatever the count"
+            assert len(set(counts)) > 1, counts      # the counts did change
+        else:
+            ref_counts = counts
+    assert counts == ref_counts
+    a, b = np.array(losses[False]), np.array(losses[True])
+    assert np.all(np.isfinite(b)) and np.max(np.abs(a - b) / np.abs(a)) < 5e-3, (a, b)
+
+
+def test_train_one_epoch_with_device_masks(cuda, golden_dir):
+    pkg, E, gold, model, arch, sd = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+    from uncertainty_vit_b200 import masking_generator as MG
+    eng = E.D2VEngine(model, target_layers=gold["target_layers"])
+    side = int(round((arch.tokens - 1) ** 0.5))
+    gen = MG.MaskingGenerator(side, max(2, (arch.tokens - 1) * 6 // 10), min_num_patches=2, seed=1, device=cuda)
+    loader = [(gold["x"], None)] * 5
+    stats = E.train_one_epoch(eng, loader, log=lambda s: None, mask_generator=gen)
+    assert np.isfinite(stats["loss"]) and gen.images_drawn == 5 * gold["x"].shape[0]

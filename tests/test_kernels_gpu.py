@@ -2,6 +2,7 @@
 of the same op on identical seeded inputs. Tolerances: fp32 paths 1e-4 relative, bf16 paths 2e-2 (BASELINE.json north_star)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -410,3 +411,71 @@ def test_mc_reduce_vs_oracle_and_golden(ops, cuda, golden_dir):
     mean_logits, rows, hist, summary = ops.mc_reduce(gold["logits"].to(cuda), gold["labels"].to(torch.int32).to(cuda))
     assert abs(summary[3].item() - gold["ece_reference"]) < 1e-5 and abs(summary[4].item() - gold["nll"]) < 1e-5
     assert abs(summary[0].item() - gold["acc1"]) < 1e-3 and abs(summary[1].item() - gold["acc5"]) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device block-wise mask generator (masking_generator.py:29-92) — bit-exact against the oracle under an injected uniform stream
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grid,num,minp,maxp,min_aspect", [
+    ((14, 14), 120, 16, None, 0.3),      # run_cyclical.py defaults (--num_mask_patches 120, --min_mask_patches_per_block 16)
+    ((14, 14), 75, 16, None, 0.3),       # BEiT's 40 %
+    ((14, 14), 120, 4, None, 0.3),       # the class's own default min_num_patches
+    ((12, 16), 80, 4, 20, 0.3),          # non-square grid, capped block size
+    ((14, 14), 190, 16, None, 0.3),      # nearly full: ends through the "10 rejected proposals" break
+    ((31, 32), 400, 16, 100, 0.2),       # largest supported grid
+    ((14, 14), 0, 16, None, 0.3),        # nothing to mask
+])
+def test_block_masks_bit_exact_under_injected_uniforms(cuda, grid, num, minp, maxp, min_aspect):
+    import math
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import masking_generator as MG
+    from uncertainty_vit_b200.engine import D2VEngine
+    B, n_u = 70, 4096
+    rng = np.random.default_rng(grid[0] * 1000 + num + minp)
+    u = rng.random((B, n_u))
+    gen = MG.MaskingGenerator(grid, num, min_num_patches=minp, max_num_patches=maxp, min_aspect=min_aspect, device=cuda)
+    mask, count, rows = gen.batch(B, uniforms=torch.from_numpy(u).to(cuda))
+    torch.cuda.synchronize()
+    mask, count, rows = mask.cpu().numpy(), count.cpu().numpy(), rows.cpu().numpy()
+    ref = np.stack([O.blockwise_mask(O.InjectedUniformRng(u[b]), grid[0], grid[1], num, minp, maxp, min_aspect).reshape(-1) for b in range(B)])
+    assert np.array_equal(mask, ref.astype(np.uint8))
+    assert np.array_equal(count[:B], ref.sum(1)) and count[B] == ref.sum()
+    assert np.array_equal(rows[:count[B]], D2VEngine.rows_from_host_mask(ref, grid[0] * grid[1] + 1))
+    assert gen.log_aspect_ratio == (math.log(min_aspect), math.log(1 / min_aspect))
+
+
+def test_block_masks_philox_stream(cuda):
+    """Without injected uniforms: reproducible per (seed, image number), fresh masks on every call, the reference's invariants
+    (never more than num_masking_patches; about two thirds of the images reach it, the rest stop a few patches short), injected-stream exhaustion is reported, bad grids refused."""
+    from uncertainty_vit_b200 import masking_generator as MG, _lib
+    gen = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=3, device=cuda)
+    assert repr(gen) == "Generator(14, 14 -> [16 ~ 120], max = 120, -1.204 ~ 1.204)" and gen.get_shape() == (14, 14)
+    m1, c1, r1 = gen.batch(256)
+    m2, c2, _ = gen.batch(256)
+    again = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=3, device=cuda)
+    m1b, c1b, r1b = again.batch(256)
+    assert torch.equal(m1, m1b) and torch.equal(c1, c1b) and torch.equal(r1[:int(c1[256])], r1b[:int(c1b[256])])
+    assert not torch.equal(m1, m2)
+    other = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=4, device=cuda).batch(256)[0]
+    assert not torch.equal(m1, other)
+    c = c1[:256].cpu().numpy()
+    assert c.max() <= 120 and c.min() >= 100 and 0.5 < (c == 120).mean() < 0.85 and int(c1[256]) == c.sum()   # the reference generator: 68 % reach 120
+    assert np.array_equal(m1.sum(1).cpu().numpy(), c)
+    assert len({bytes(r) for r in m1.cpu().numpy()}) > 250                       # images get different masks
+    # same distribution as the reference generator driven by Python's `random`: per-cell masking frequency (corners ~0.09, centre ~0.95)
+    # and the histogram of per-image counts, 4096 device images against 4000 oracle masks (4 sigma of the sampling noise = 0.045)
+    import random
+    from oracle import vit_oracle as O
+    big = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=11, device=cuda)
+    mb, cb, _ = big.batch(4096)
+    r = random.Random(0)
+    ref = np.stack([O.blockwise_mask(r, 14, 14, 120, 16, None, 0.3) for _ in range(4000)]).reshape(4000, 196)
+    assert np.abs(mb.float().mean(0).cpu().numpy() - ref.mean(0)).max() < 0.05
+    cd = cb[:4096].cpu().numpy()
+    assert abs((cd == 120).mean() - (ref.sum(1) == 120).mean()) < 0.04 and abs(cd.mean() - ref.sum(1).mean()) < 0.1
+    one = gen()
+    assert one.shape == (14, 14) and one.dtype == np.int64 and 0 < one.sum() <= 120
+    short = torch.rand(4, 3, dtype=torch.float64, device=cuda)
+    assert int(gen.batch(4, uniforms=short)[1][4]) == -1
+    with pytest.raises(_lib.B200VitError):
+        MG.MaskingGenerator(33, 120, device=cuda).batch(2)

@@ -49,14 +49,15 @@ _PROTOS = {
     "b200vit_assemble_tokens": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "b200vit_assemble_tokens_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "b200vit_drop_path_scales": (i32, [C.POINTER(f32), i32, i32, i32, u64, vp, vp]),
+    "b200vit_block_masks": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, C.c_double, C.c_double, u64, u64, vp, i32, vp]),
     "b200vit_rel_pos_bias": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "b200vit_meanpool_tokens": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_meanpool_tokens_bwd": (i32, [vp, i32, i32, i32, vp, vp]),
-    "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "b200vit_ema_update": (i32, [vp, vp, i64, C.c_double, vp, vp]),
     "b200vit_sumsq": (i32, [vp, i64, vp, vp]),
     "b200vit_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, C.c_double, vp, vp]),
-    "b200vit_wasserstein_loss": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
+    "b200vit_wasserstein_loss": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "b200vit_mc_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "b200vit_mc_finalize": (i32, [vp, vp, i32, i32, vp, vp]),
 }
@@ -80,7 +81,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 2:
+        if l.b200vit_abi_version() != 3:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

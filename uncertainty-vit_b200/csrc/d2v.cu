@@ -48,10 +48,26 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
                                                               int R, int C, int ln_each, int ln_post, float beta, int l2_loss,
                                                               float grad_scale, float* __restrict__ targets,
                                                               bf16* __restrict__ dy_bf16, float* __restrict__ dy_f32,
-                                                              float* __restrict__ row_loss) {
+                                                              float* __restrict__ row_loss, const int* __restrict__ n_valid) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
+  if (n_valid != nullptr) {
+    // R is the capacity of a padded row list: rows >= *n_valid carry no loss and no gradient, the mean runs over *n_valid rows
+    const int rv = *n_valid;
+    if (r >= rv) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (targets != nullptr) *reinterpret_cast<float4*>(targets + (long long)r * C + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dy_bf16 != nullptr) *reinterpret_cast<uint2*>(dy_bf16 + (long long)r * C + c) = make_uint2(0u, 0u);
+        if (dy_f32 != nullptr) *reinterpret_cast<float4*>(dy_f32 + (long long)r * C + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (lane == 0 && row_loss != nullptr) row_loss[r] = 0.f;
+      return;
+    }
+    grad_scale *= (float)R / (float)rv;
+  }
   const long long src = row_index[r];
   float4 acc[NV];
 #pragma unroll
@@ -103,9 +119,11 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
   if (lane == 0 && row_loss != nullptr) row_loss[r] = loss;
 }
 
-// deterministic single-CTA sum: out[0] = scale * sum(v[0..n))
-__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out) {
+// deterministic single-CTA sum: out[0] = scale * sum(v[0..n)); with n_valid, scale is rescaled by n / *n_valid (mean over the valid rows)
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out,
+                                                          const int* __restrict__ n_valid) {
   __shared__ double sh[32];
+  if (n_valid != nullptr) scale *= (float)n / (float)*n_valid;
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
 #pragma unroll
@@ -246,8 +264,11 @@ __global__ void __launch_bounds__(256) wloss_rowdist_kernel(const float* __restr
 // pass 2 (single CTA): wmax = max|w| ; l_r = -log(sigmoid(-w_r/wmax + 1e-24)) ; lmax = max|l| ; loss = lam * sum l_r / lmax
 // and the row coefficients of dloss/dw_r INCLUDING the two max-normalisers (autograd differentiates through torch.max):
 //   stats[0]=loss, stats[1]=wmax, stats[2]=lmax, stats[3]=argmax_w, stats[4]=argmax_l ; coef[r] = dloss/dw_r
-__global__ void __launch_bounds__(1024) wloss_finalize_kernel(const float* __restrict__ w, int R, float lam, float* __restrict__ stats,
-                                                              float* __restrict__ coef) {
+__global__ void __launch_bounds__(1024) wloss_finalize_kernel(const float* __restrict__ w, int R_cap, float lam, float* __restrict__ stats,
+                                                              float* __restrict__ coef, const int* __restrict__ n_valid) {
+  // padded row list: only the first *n_valid rows take part in the normalisers and the sum; the rest get a zero coefficient
+  const int R = n_valid != nullptr ? min(*n_valid, R_cap) : R_cap;
+  for (int r = R + threadIdx.x; r < R_cap; r += blockDim.x) coef[r] = 0.f;
   __shared__ float sh_v[32];
   __shared__ int sh_i[32];
   __shared__ float bc[4];
@@ -351,7 +372,7 @@ __global__ void __launch_bounds__(256) wloss_bwd_kernel(const float* __restrict_
 extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
                                        const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
                                        float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
-                                       void* stream) {
+                                       const int32_t* n_valid_dev, void* stream) {
   B200_CHECK_ARG(layers_host != nullptr && num_layers > 0 && num_layers <= MAX_LAYERS, "d2v_target_loss: 1..%d layers", MAX_LAYERS);
   B200_CHECK_ARG(row_index != nullptr && C % 128 == 0 && C <= 128 * MAXV, "d2v_target_loss: C=%d must be a multiple of 128, <= %d", C, 128 * MAXV);
   B200_CHECK_ARG(loss_out == nullptr || (row_loss != nullptr && y != nullptr), "d2v_target_loss: loss_out needs y and a row_loss workspace of R floats");
@@ -362,7 +383,7 @@ extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t 
     lp.p[i] = layers_host[i];
   }
   const int grid = (R + 7) / 8;
-#define TL(NV) d2v_target_loss_kernel<NV><<<grid, 256, 0, STREAM>>>(lp, num_layers, ld_layer, row_index, y, R, C, ln_each, ln_post, beta, l2_loss, grad_scale, targets, static_cast<bf16*>(dy_bf16), dy_f32, row_loss)
+#define TL(NV) d2v_target_loss_kernel<NV><<<grid, 256, 0, STREAM>>>(lp, num_layers, ld_layer, row_index, y, R, C, ln_each, ln_post, beta, l2_loss, grad_scale, targets, static_cast<bf16*>(dy_bf16), dy_f32, row_loss, n_valid_dev)
   switch (C / 128) {
     case 1: TL(1); break; case 2: TL(2); break; case 3: TL(3); break; case 4: TL(4); break;
     case 5: TL(5); break; case 6: TL(6); break; case 7: TL(7); break; default: TL(8); break;
@@ -370,7 +391,7 @@ extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t 
 #undef TL
   B200_CHECK_LAUNCH("d2v_target_loss");
   if (loss_out != nullptr) {
-    reduce_sum_kernel<<<1, 1024, 0, STREAM>>>(row_loss, R, 1.0f / ((float)R * (float)C), loss_out);
+    reduce_sum_kernel<<<1, 1024, 0, STREAM>>>(row_loss, R, 1.0f / ((float)R * (float)C), loss_out, n_valid_dev);
     B200_CHECK_LAUNCH("d2v_loss_reduce");
   }
   return 0;
@@ -419,7 +440,7 @@ extern "C" int b200vit_adamw_step(float* p, const float* g, float* m, float* v, 
 
 extern "C" int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
                                         int32_t C, float lam, float grad_scale, float* work /* 2R+8 floats */, float* d_mean_out,
-                                        float* d_cov_out, float* loss_out, void* stream) {
+                                        float* d_cov_out, float* loss_out, const int32_t* n_valid_dev, void* stream) {
   B200_CHECK_ARG(mean_out && cov_out && pos_mean && pos_cov && work && loss_out, "wasserstein_loss: null pointer");
   B200_CHECK_ARG(R > 0 && C % 4 == 0, "wasserstein_loss: bad shape R=%d C=%d", R, C);
   float* w = work;
@@ -427,7 +448,7 @@ extern "C" int b200vit_wasserstein_loss(const float* mean_out, const float* cov_
   float* stats = work + 2 * R;
   wloss_rowdist_kernel<<<(R + 7) / 8, 256, 0, STREAM>>>(mean_out, cov_out, pos_mean, pos_cov, R, C, w);
   B200_CHECK_LAUNCH("wloss_rowdist");
-  wloss_finalize_kernel<<<1, 1024, 0, STREAM>>>(w, R, lam, stats, coef);
+  wloss_finalize_kernel<<<1, 1024, 0, STREAM>>>(w, R, lam, stats, coef, n_valid_dev);
   B200_CHECK_LAUNCH("wloss_finalize");
   cudaMemcpyAsync(loss_out, stats, sizeof(float), cudaMemcpyDeviceToDevice, STREAM);
   if (d_mean_out != nullptr && d_cov_out != nullptr) {

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
     const float mean = mean_in[r], rstd = rstd_in[r];
     float4 xh[NV], d[NV];
     float s1 = 0.f, s2 = 0.f;
+    bool live = false;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
       float4 dv;
       if constexpr (sizeof(DY) == 2) dv = ld_bf16x4(reinterpret_cast<const bf16*>(dy) + (long long)r * C + c);
       else dv = ld4(reinterpret_cast<const float*>(dy) + (long long)r * C + c);
+      live |= (dv.x != 0.f) | (dv.y != 0.f) | (dv.z != 0.f) | (dv.w != 0.f);
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
       ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
@@ -115,6 +117,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
       s1 += d[i].x + d[i].y + d[i].z + d[i].w;
       s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
     }
+    // A row whose dy is all zero adds nothing. It is skipped rather than added as zeros because dx[src] is updated with a plain
+    // read-modify-write: the padding entries of a fixed-capacity row list (b200vit_d2v_target_loss, n_valid_dev) may repeat a row
+    // number that a live row of another warp is updating at the same time.
+    if (!__any_sync(0xffffffffu, live)) continue;
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
     float* dxr = dx + src * lddx;

@@ -208,8 +208,11 @@ class D2VEngine:
         return self.ema_decay
 
     def step(self, images: torch.Tensor, mask_u8: torch.Tensor, rows: torch.Tensor, *, lr: Optional[float] = None,
-             weight_decay: Optional[float] = None, noise: Optional[Noise] = None, graph: Optional[bool] = None) -> torch.Tensor:
+             weight_decay: Optional[float] = None, noise: Optional[Noise] = None, graph: Optional[bool] = None,
+             n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step on device-resident inputs. images fp32 [B,3,H,W]; mask_u8 uint8 [B*np]; rows int32 [R].
+        n_valid (device int32 [1]): `rows` is padded to a fixed capacity and only its first n_valid entries are masked patches (the
+        padding must hold valid row numbers, e.g. 0); the step then has the same launch shapes whatever the block-wise generator drew.
         Returns the device scalar loss (no sync)."""
         cfg = self.cfg
         B = images.shape[0]
@@ -223,18 +226,19 @@ class D2VEngine:
             noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
         if graph is None:
             graph = self.use_graph
-        if graph and injected is None and ops.GEMM_TIMING is None:
-            self._fwd_bwd_graphed(images, mask_u8, rows, noise.seed)
+        if graph and injected is None and ops.GEMM_TIMING is None and R > 0:
+            self._fwd_bwd_graphed(images, mask_u8, rows, noise.seed, n_valid)
         else:
-            self._fwd_bwd(images, mask_u8, rows, noise)
+            self._fwd_bwd(images, mask_u8, rows, noise, n_valid)
             self._eager_steps += 1
         return self._optimizer_step(lr, wd)
 
-    def _fwd_bwd(self, images, mask_u8, rows, noise):
-        """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser)."""
+    def _fwd_bwd(self, images, mask_u8, rows, noise, n_valid=None):
+        """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser).
+        With n_valid the padded rows of `rows` get dy = 0 from the loss kernel, so they add nothing to any gradient."""
         cfg = self.cfg
         if cfg.dist:
-            return self._fwd_bwd_dist(images, mask_u8, rows, noise)
+            return self._fwd_bwd_dist(images, mask_u8, rows, noise, n_valid)
         B = images.shape[0]
         C, T = cfg.embed_dim, cfg.tokens
         R = rows.numel()
@@ -249,49 +253,66 @@ class D2VEngine:
         row_loss = torch.empty((R,), dtype=torch.float32, device=self.dev)
         ls = self.loss_scale if self.loss_scale != -1 else 1.0
         ops.d2v_target_loss([layers[i].view(B * T, C) for i in self.target_layers], C, rows, out, R, C, self.ln_each, self.ln_post, self.l1_beta,
-                            self.l2_loss, ls / (R * C), None, dy, None, row_loss, self.loss_dev)
+                            self.l2_loss, ls / (R * C), None, dy, None, row_loss, self.loss_dev, n_valid=n_valid)
         del layers
         self.g32.zero_()
         core.vit_backward(self.student, cfg, ctx, dy, self.grads)
 
-    def _fwd_bwd_graphed(self, images, mask_u8, rows, seed: int):
-        """The same launch sequence replayed from a CUDA graph (one per (batch, masked-row count)): ~400 stream-ordered, allocation-free
-        launches whose Python issue time (~55 us each) exceeds the run time of the small row kernels. Inputs are copied into static
-        buffers; the per-step randomness enters through device memory (drop-path factors, the Philox key of attention dropout), so the
-        captured graph stays valid across steps. The first two steps of a shape run eagerly (lazy kernel attributes, allocator warm-up)."""
+    def _fwd_bwd_graphed(self, images, mask_u8, rows, seed: int, n_valid=None):
+        """The same launch sequence replayed from a CUDA graph: ~400 stream-ordered, allocation-free launches whose Python issue time
+        (~55 us each) exceeds the run time of the small row kernels. Inputs are copied into static buffers; the per-step randomness
+        enters through device memory (drop-path factors, the Philox key of attention dropout), so the captured graph stays valid across
+        steps. The first two steps of a shape run eagerly (lazy kernel attributes, allocator warm-up).
+
+        The masked-row count of block-wise masking changes from batch to batch (masking_generator.py:80-92 stops a few patches short of
+        the target in a third of the images), so the graph is captured for a row CAPACITY — the count rounded up to a multiple of
+        4 x batch, or the length of a caller-padded list — and the true count travels in device memory (`n_valid`): the loss kernel
+        zeroes dy of the padding rows, which therefore contribute nothing downstream. One graph serves every batch of a shape."""
         cfg = self.cfg
-        key = (tuple(images.shape), int(rows.numel()))
+        R = int(rows.numel())
+        if n_valid is None:
+            bucket = 4 * int(images.shape[0])
+            cap = (R + bucket - 1) // bucket * bucket
+        else:
+            cap = R
+        key = (tuple(images.shape), cap)
         g = self._graphs.get(key)
         if g is None and (self._eager_steps < 2 or len(self._graphs) >= self.max_graphs):
-            # warm-up, or a workload whose masked-row count keeps changing (block-wise masking): launch eagerly instead of
-            # capturing one graph (and one private activation pool) per distinct count
-            self._fwd_bwd(images, mask_u8, rows, Noise(seed=seed))
+            # warm-up, or a workload that keeps changing shape: launch eagerly instead of capturing one graph (and one private
+            # activation pool) per shape
+            self._fwd_bwd(images, mask_u8, rows, Noise(seed=seed), n_valid)
             self._eager_steps += 1
             return
         if g is None:
-            st = dict(images=torch.empty_like(images), mask=torch.empty_like(mask_u8), rows=torch.empty_like(rows),
+            st = dict(images=torch.empty_like(images), mask=torch.empty_like(mask_u8),
+                      rows=torch.zeros(cap, dtype=torch.int32, device=self.dev), nvalid=torch.zeros(1, dtype=torch.int32, device=self.dev),
                       seed=torch.zeros(1, dtype=torch.int64, device=self.dev),
                       dps=torch.empty(cfg.depth, 4 if cfg.dist else 2, images.shape[0], dtype=torch.float32, device=self.dev))
+            st["nvalid"].fill_(cap)
             noise = Noise(seed=0, seed_dev=st["seed"], drop_path_scale=st["dps"] if cfg.drop_path_rate > 0 else None)
             graph = torch.cuda.CUDAGraph()
             launches0 = ops.LAUNCHES
             torch.cuda.synchronize(self.dev)
             with torch.cuda.graph(graph):
-                self._fwd_bwd(st["images"], st["mask"], st["rows"], noise)
+                self._fwd_bwd(st["images"], st["mask"], st["rows"], noise, st["nvalid"])
             g = dict(graph=graph, st=st, launches=ops.LAUNCHES - launches0)
             ops.LAUNCHES = launches0
             self._graphs[key] = g
         st = g["st"]
         st["images"].copy_(images, non_blocking=True)
         st["mask"].copy_(mask_u8, non_blocking=True)
-        st["rows"].copy_(rows, non_blocking=True)
+        st["rows"][:R].copy_(rows, non_blocking=True)       # entries beyond R keep earlier (valid) row numbers: they are padding
+        if n_valid is None:
+            st["nvalid"].fill_(R)
+        else:
+            st["nvalid"].copy_(n_valid, non_blocking=True)
         st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
         if cfg.drop_path_rate > 0:
             ops.drop_path_scales(cfg.drop_path_probs, 4 if cfg.dist else 2, images.shape[0], seed, self.dev, out=st["dps"])
         g["graph"].replay()
         ops.LAUNCHES += g["launches"]
 
-    def _fwd_bwd_dist(self, images, mask_u8, rows, noise):
+    def _fwd_bwd_dist(self, images, mask_u8, rows, noise, n_valid=None):
         """--stochastic step (engine_for_cyclical.py:69-86,125-126,152-158): dual-stream teacher/student, targets for both streams,
         smooth-L1 on the mean stream + WassersteinLoss(lambda) on (mean, cov) outputs vs (mean, cov) targets (everything but the optimiser)."""
         cfg = self.cfg
@@ -309,14 +330,14 @@ class D2VEngine:
         d_c = torch.zeros((R, C), dtype=torch.float32, device=dev)
         row_loss = torch.empty((R,), dtype=torch.float32, device=dev)
         ops.d2v_target_loss([lm[i].view(M, C) for i in self.target_layers], C, rows, om, R, C, self.ln_each, self.ln_post, self.l1_beta, self.l2_loss,
-                            ls / (R * C), tgt_m, None, d_m, row_loss, self.loss_dev)
+                            ls / (R * C), tgt_m, None, d_m, row_loss, self.loss_dev, n_valid=n_valid)
         ops.d2v_target_loss([lc[i].view(M, C) for i in self.target_layers], C, rows, None, R, C, self.ln_each, self.ln_post, self.l1_beta, False,
-                            1.0, tgt_c, None, None, None, None)
+                            1.0, tgt_c, None, None, None, None, n_valid=n_valid)
         del lm, lc
         work = torch.empty((2 * R + 8,), dtype=torch.float32, device=dev)
         if self.wloss_dev is None:
             self.wloss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev)
+        ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev, n_valid=n_valid)
         self.loss_dev.add_(self.wloss_dev, alpha=ls)          # loss = (loss_cyc + loss_stochastic) * loss_scale  (:160-163)
         self.g32.zero_()
         core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads)
@@ -355,15 +376,33 @@ class D2VEngine:
             ev.record(self._copy_stream)
         return images, mask_u8, rows_d, ev, (mask_pinned, rows)
 
+    def stage_device_masks(self, images_pinned: torch.Tensor, generator):
+        """stage_host() for a pipeline whose masks are drawn on the device (masking_generator.MaskingGenerator.batch): only the images
+        cross PCIe. The block masks, the masked-row list (padded to batch x num_masking_patches rows) and the masked-row count stay in
+        device memory — nothing is read back, and the step keeps one launch shape (see _fwd_bwd_graphed)."""
+        B = images_pinned.shape[0]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        if (generator.height * generator.width + 1) != self.cfg.tokens:
+            raise ValueError(f"mask grid {generator.get_shape()} does not match the model's {self.cfg.tokens - 1} patches")
+        with torch.cuda.stream(self._copy_stream):
+            rows = torch.zeros(B * generator.num_masking_patches, dtype=torch.int32, device=self.dev)   # padding = row 0 (a cls row)
+            mask_u8, count, rows = generator.batch(B, rows=rows)
+            images = images_pinned.to(self.dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return images, mask_u8.view(-1), rows, ev, (count,), count[B:B + 1]
+
     def launch_staged(self, staged, **kw) -> torch.Tensor:
         """Enqueues one step on a batch returned by stage_host() and returns the DEVICE loss scalar without synchronising: the caller can
         stage the next batch while the step runs and read the loss afterwards."""
-        images, mask_u8, rows, ev, _keepalive = staged
+        images, mask_u8, rows, ev, _keepalive, *rest = staged
+        n_valid = rest[0] if rest else None          # device masks: rows is padded, the true count lives on the device
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
-        for t in (images, mask_u8, rows):
+        for t in (images, mask_u8, rows) + ((n_valid,) if n_valid is not None else ()):
             t.record_stream(cur)
-        return self.step(images, mask_u8, rows, **kw)
+        return self.step(images, mask_u8, rows, n_valid=n_valid, **kw)
 
     def step_staged(self, staged, **kw) -> float:
         """One step on a batch returned by stage_host(); reads the loss back (engine_for_cyclical.py:164)."""
@@ -457,17 +496,21 @@ class FinetuneEngine(D2VEngine):
 
 
 def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,
-                    wd_schedule_values=None, print_freq: int = 10, log=print) -> Dict[str, float]:
+                    wd_schedule_values=None, print_freq: int = 10, log=print, mask_generator=None) -> Dict[str, float]:
     """Loop of engine_for_cyclical.train_one_epoch (:45-225) over the fused engine: per-step lr/wd from the schedule tables,
-    EMA-decay anneal, non-finite loss aborts (:166-168)."""
+    EMA-decay anneal, non-finite loss aborts (:166-168). With `mask_generator` (masking_generator.MaskingGenerator) the masks of each
+    batch are drawn on the device and whatever mask the loader yields is ignored (the loader may then yield bare image batches)."""
     total, n = 0.0, 0
 
     def staged_batches():
         for batch, _ in data_loader:
-            samples, bool_masked_pos = batch
+            samples, bool_masked_pos = batch if isinstance(batch, (tuple, list)) else (batch, None)
             if not samples.is_pinned():
                 samples = samples.pin_memory()
-            yield engine.stage_host(samples, np.asarray(bool_masked_pos))
+            if mask_generator is not None:
+                yield engine.stage_device_masks(samples, mask_generator)
+            else:
+                yield engine.stage_host(samples, np.asarray(bool_masked_pos))
 
     it_batches = staged_batches()
     nxt = next(it_batches, None)

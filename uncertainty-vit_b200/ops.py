@@ -208,6 +208,28 @@ def drop_path_scales(probs, draws, B, seed, device, out=None) -> torch.Tensor:
     return out
 
 
+def block_masks(B, height, width, tokens, num_masking_patches, min_num_patches, max_num_patches, log_aspect_lo, log_aspect_hi, seed,
+                first_image, device, uniforms: Optional[torch.Tensor] = None, want_rows: bool = True, rows: Optional[torch.Tensor] = None):
+    """Device block-wise masks for B images (masking_generator.py:29-92) -> (mask uint8 [B, height*width], count int32 [B+1] with
+    count[B] = total masked rows R, rows int32 [B*num_masking_patches] of which the first R are valid, or None)."""
+    mask = torch.empty(B, height * width, dtype=torch.uint8, device=device)
+    count = torch.empty(B + 1, dtype=torch.int32, device=device)
+    if rows is None:
+        rows = torch.empty(max(B * num_masking_patches, 1), dtype=torch.int32, device=device) if want_rows else None
+    elif rows.dtype != torch.int32 or rows.numel() < B * num_masking_patches or not rows.is_contiguous():
+        raise _lib.B200VitError("block_masks: rows must be a contiguous int32 buffer of at least B * num_masking_patches entries")
+    per_image = 0
+    if uniforms is not None:
+        if uniforms.dtype != torch.float64 or uniforms.dim() != 2 or uniforms.shape[0] != B or not uniforms.is_contiguous():
+            raise _lib.B200VitError("block_masks: injected uniforms must be a contiguous float64 [B, n] tensor")
+        per_image = uniforms.shape[1]
+    check(_lib.lib().b200vit_block_masks(_p(mask), _p(count), _p(rows), B, height, width, tokens, num_masking_patches, min_num_patches,
+                                         max_num_patches, float(log_aspect_lo), float(log_aspect_hi), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                         int(first_image) & 0xFFFFFFFFFFFFFFFF, _p(uniforms), per_image, _stream()), "block_masks")
+    _count(2)
+    return mask, count, rows
+
+
 LOG2E = 1.4426950408889634
 
 
@@ -250,11 +272,12 @@ def meanpool_tokens_bwd(dpool, B, T, C_, dx):
 # data2vec step
 # ----------------------------------------------------------------------------------------------------------------
 def d2v_target_loss(layers: Sequence[torch.Tensor], ld_layer, row_index, y, R, C_, ln_each=True, ln_post=True, beta=2.0, l2_loss=False,
-                    grad_scale=1.0, targets=None, dy_bf16=None, dy_f32=None, row_loss=None, loss_out=None):
+                    grad_scale=1.0, targets=None, dy_bf16=None, dy_f32=None, row_loss=None, loss_out=None, n_valid=None):
+    """n_valid: device int32 [1] when row_index is padded to the capacity R (rows >= n_valid: zero loss / dy / targets)."""
     arr = (C.c_void_p * len(layers))(*[_p(t) for t in layers])
     check(_lib.lib().b200vit_d2v_target_loss(arr, len(layers), ld_layer, _p(row_index), _p(y), R, C_, int(ln_each), int(ln_post), beta,
                                              int(l2_loss), grad_scale, _p(targets), _p(dy_bf16), _p(dy_f32), _p(row_loss), _p(loss_out),
-                                             _stream()), "d2v_target_loss")
+                                             _p(n_valid), _stream()), "d2v_target_loss")
     _count(2 if loss_out is not None else 1)
 
 
@@ -275,10 +298,10 @@ def adamw_step(p, g, m, v, hp, step, lr, weight_decay, beta1=0.9, beta2=0.999, e
     _count()
 
 
-def wasserstein_loss(mean_out, cov_out, pos_mean, pos_cov, lam, grad_scale, work, d_mean, d_cov, loss_out):
+def wasserstein_loss(mean_out, cov_out, pos_mean, pos_cov, lam, grad_scale, work, d_mean, d_cov, loss_out, n_valid=None):
     R, C_ = mean_out.shape
     check(_lib.lib().b200vit_wasserstein_loss(_p(mean_out), _p(cov_out), _p(pos_mean), _p(pos_cov), R, C_, lam, grad_scale, _p(work),
-                                              _p(d_mean), _p(d_cov), _p(loss_out), _stream()), "wasserstein_loss")
+                                              _p(d_mean), _p(d_cov), _p(loss_out), _p(n_valid), _stream()), "wasserstein_loss")
     _count(3 if d_mean is not None else 2)
 
 
