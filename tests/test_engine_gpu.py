@@ -274,3 +274,54 @@ def test_train_one_epoch_with_device_masks(cuda, golden_dir):
     loader = [(gold["x"], None)] * 5
     stats = E.train_one_epoch(eng, loader, log=lambda s: None, mask_generator=gen)
     assert np.isfinite(stats["loss"]) and gen.images_drawn == 5 * gold["x"].shape[0]
+
+
+def test_engine_checkpoint_resume_and_torch_adamw_interop(cuda, golden_dir, tmp_path):
+    """save_model / auto_load_model over the fused engine (utils.py:462-520): a run resumed from the checkpoint file continues exactly like
+    the uninterrupted run, and the stored optimizer entry loads into the torch.optim.AdamW the reference builds (same parameter numbering
+    and moments), so the reference runner can resume an engine checkpoint."""
+    from uncertainty_vit_b200 import checkpoint as CK
+    pkg, E, gold, model, arch, sd = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+    kw = dict(lr=1e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.99, ema_decay_init=0.9, ema_start_at=10, target_layers=gold["target_layers"],
+              use_graph=False, seed=4)
+    eng = E.D2VEngine(model, **kw)
+    x = gold["x"].pin_memory()
+    mask = gold["mask"].numpy()
+    for _ in range(3):
+        eng.step_host(x, mask)
+    path = CK.save_model(str(tmp_path), 0, eng)
+    assert path.endswith("checkpoint-0.pth") and CK.latest_checkpoint(str(tmp_path)) == path
+    cont = [eng.step_host(x, mask) for _ in range(2)]
+    # fresh process: new model (different init), new engine, resume
+    _, _, _, model2, _, _ = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+    with torch.no_grad():
+        for p in model2.parameters():
+            p.add_(0.1)
+    eng2 = E.D2VEngine(model2, **kw)
+    start_epoch = CK.auto_load_model(str(tmp_path), eng2)
+    assert start_epoch == 1 and eng2.it == 3 and eng2.opt_step == 3
+    resumed = [eng2.step_host(x, mask) for _ in range(2)]
+    assert np.allclose(cont, resumed, rtol=1e-4), (cont, resumed)             # fp32 atomic-order noise only
+    assert rel(eng2.p32, eng.p32) < 1e-5 and rel(eng2.e32, eng.e32) < 1e-6 and rel(eng2.m32, eng.m32) < 1e-3
+    # the reference side: torch AdamW over optim_factory's groups accepts the optimizer entry
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ckpt) >= {"model", "optimizer", "epoch", "model_ema"} and list(ckpt["model_ema"]) == list(ckpt["model"])
+    ref_model = {n: torch.nn.Parameter(p.detach().cpu().clone()) for n, p in model2.named_parameters()}
+    groups = CK.engine_parameter_groups(eng2)
+    opt = torch.optim.AdamW([{"params": [ref_model[n] for n in g["params"]], "weight_decay": g["weight_decay"], "lr_scale": g["lr_scale"]} for g in groups],
+                            lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt.load_state_dict(ckpt["optimizer"])
+    st = opt.state[ref_model["blocks.1.mlp.fc1.weight"]]
+    assert float(st["step"]) == 3.0
+    for p, s in opt.state.items():
+        assert torch.isfinite(s["exp_avg"]).all() and s["exp_avg"].shape == p.shape
+    names = [n for g in groups for n in g["params"]]
+    k = names.index("blocks.1.mlp.fc1.weight")
+    assert torch.equal(ckpt["optimizer"]["state"][k]["exp_avg"], st["exp_avg"])
+    # and back: an optimizer state dict produced by torch loads into a fresh engine
+    _, _, _, model3, _, _ = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+    eng3 = E.D2VEngine(model3, **kw)
+    CK.load_optimizer_state_dict(eng3, opt.state_dict())
+    assert eng3.opt_step == 3
+    ck3 = CK.optimizer_state_dict(eng3)
+    assert torch.equal(ck3["state"][k]["exp_avg_sq"], ckpt["optimizer"]["state"][k]["exp_avg_sq"])

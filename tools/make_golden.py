@@ -297,6 +297,48 @@ def case_ema_adamw():
     print("[ema_adamw] oracle AdamW+clip+EMA == torch.optim.AdamW + ModelEmaV2 over 5 steps")
 
 
+def case_host_logic():
+    """Pins the host-side checkpoint / optimizer-group logic (uncertainty-vit_b200/checkpoint.py) to the reference's own functions:
+    optim_factory.get_parameter_groups (+ LayerDecayValueAssigner) and utils.load_state_dict, run on the reference's modules."""
+    import contextlib
+    import io
+    import json
+    import optim_factory
+    import utils as ref_utils
+    tiny = lambda **kw: O.Arch(**{**O.TINY, **kw})
+    out = {"groups": {}, "load": {}}
+    for label, arch, layer_decay in (("det_cyclical", tiny(kind="cyclical"), None), ("dist_cyclical", tiny(kind="cyclical", dist=True), None),
+                                     ("det_finetune_ld", tiny(kind="finetune"), 0.65), ("dist_finetune_ld", tiny(kind="finetune", dist=True), 0.65)):
+        model = build_reference(arch, 0.0, 0.0)
+        names = {id(p): n for n, p in model.named_parameters()}
+        kw = {}
+        if layer_decay is not None:
+            L = arch.depth + 2
+            assigner = optim_factory.LayerDecayValueAssigner(list(layer_decay ** (L - 1 - i) for i in range(L)))
+            kw = dict(get_num_layer=assigner.get_layer_id, get_layer_scale=assigner.get_scale)
+        with contextlib.redirect_stdout(io.StringIO()):
+            groups = optim_factory.get_parameter_groups(model, 0.05, model.no_weight_decay(), **kw)
+        out["groups"][label] = [{"weight_decay": g["weight_decay"], "lr_scale": g["lr_scale"], "params": [names[id(p)] for p in g["params"]]} for g in groups]
+    # utils.load_state_dict: pre-training checkpoint (as run_class_finetuning.py sees it after the head/index surgery) into the classifier
+    pre = build_reference(tiny(kind="cyclical"), 0.0, 0.0)
+    ft = build_reference(tiny(kind="finetune"), 0.0, 0.0)
+    ckpt = {k: v.clone() for k, v in pre.state_dict().items() if "relative_position_index" not in k}
+    del ckpt["blocks.1.mlp.fc2.bias"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref_utils.load_state_dict(ft, ckpt, prefix="")
+    out["load"]["plain"] = buf.getvalue()
+    assert torch.equal(ft.state_dict()["blocks.0.attn.qkv.weight"], pre.state_dict()["blocks.0.attn.qkv.weight"])
+    ft2 = build_reference(tiny(kind="finetune"), 0.0, 0.0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref_utils.load_state_dict(ft2, {"module." + k: v for k, v in ckpt.items()}, prefix="module.")
+    out["load"]["prefix"] = buf.getvalue()
+    with open(os.path.join(GOLD, "host_logic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("[host_logic] parameter groups of 4 models + load_state_dict messages written")
+
+
 def main():
     assert ref_shim.reference_available(), "needs /root/reference"
     ref_shim.install()
@@ -306,6 +348,7 @@ def main():
     case_index_and_masks()
     case_metrics()
     case_ema_adamw()
+    case_host_logic()
     case_cyclical("tiny_det_cyclical", tiny(kind="cyclical"), B=3, dpr=0.2, attn_drop=0.1, seed=11, target_layers=[0, 1])
     case_cyclical("tiny_dist_cyclical", tiny(kind="cyclical", dist=True), B=3, dpr=0.2, attn_drop=0.1, seed=12, target_layers=[0, 1])
     case_finetune("tiny_det_finetune", tiny(kind="finetune"), B=3, seed=13)

@@ -119,6 +119,7 @@ class D2VEngine:
         self.world_size, self.pg = world_size, process_group
         self.seed = seed
         self.it = 0
+        self.layer_decay, self.skip_weight_decay = layer_decay, tuple(skip_weight_decay)
         # ---- layout: every segment starts on a CHUNK boundary; (q_bias | 0 | v_bias) of a block form ONE segment so that the
         # QKV GEMM bias cat(q_bias, zeros, v_bias) (modeling_finetune.py:148) is a plain arena view
         named = dict(model.named_parameters())
@@ -192,6 +193,15 @@ class D2VEngine:
             model._ps.invalidate()
 
     # ------------------------------------------------------------------------------------------------------------
+    def state_dict(self, epoch: Optional[int] = None) -> Dict[str, object]:
+        """Checkpoint in the layout utils.save_model writes (utils.py:462-485): see checkpoint.engine_state_dict."""
+        from . import checkpoint
+        return checkpoint.engine_state_dict(self, epoch)
+
+    def load_state_dict(self, ckpt: Dict[str, object], load_optimizer: bool = True) -> None:
+        from . import checkpoint
+        checkpoint.load_engine_state_dict(self, ckpt, load_optimizer=load_optimizer)
+
     def ema_state_dict(self) -> Dict[str, torch.Tensor]:
         return {name: self.e32[o: o + int(np.prod(s))].view(s) for name, (o, s) in self.layout.items() if "__" not in name}
 
