@@ -202,7 +202,7 @@ def test_padded_row_list_is_the_same_step(cuda, golden_dir, name):
     capacity and passing the true count in device memory. A step on the padded list (padding = stale but valid row numbers) must equal
     the step on the exact list (itself pinned to the oracle above): same loss, same gradients, same updated weights."""
     import uncertainty_vit_b200 as pkg
-    from uncertainty_vit_b200 import engine as E
+    from uncertainty_vit_b200 import engine as E, modeling  # noqa: F401  (pkg.modeling is used by _build_from_gold)
     from tests.test_model_gpu import _build_dist, _build_from_gold
     res = {}
     for padded in (False, True):
