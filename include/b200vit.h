@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define B200VIT_ABI_VERSION 3   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
-                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks */
+                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -214,6 +214,16 @@ int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, 
 int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
                              int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,
                              float* loss_out, const int32_t* n_valid_dev, void* stream);
+
+/* Mixup / CutMix of a fine-tune batch in place, "batch" mode (timm 0.3.2 Mixup._mix_batch + mixup_target, built at
+ * run_class_finetuning.py:339-347 and applied at engine_for_finetuning.py:87-88): image b is paired with image B-1-b.
+ *   use_cutmix == 0: x[b] = lam * x[b] + one_minus_lam * x[B-1-b] (two rounded products + one rounded sum, as the torch ops)
+ *   use_cutmix != 0: x[b][:, yl:yh, xl:xh] = x[B-1-b][:, yl:yh, xl:xh]                (lam is then the box-corrected lambda)
+ *   soft_targets[b, k] = lam * v(y[b], k) + one_minus_lam * v(y[B-1-b], k), v = on_value if k is the label else off_value
+ * x fp32 [B, C, H, W] (NULL: targets only); labels int64 [B] and soft_targets fp32 [B, K] (both NULL: images only); lam == 1 leaves x alone. */
+int b200vit_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, float lam, float one_minus_lam, int32_t use_cutmix,
+                        int32_t yl, int32_t yh, int32_t xl, int32_t xh, const int64_t* labels, int32_t K, float on_value, float off_value,
+                        float* soft_targets, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * MC-sample uncertainty reduction (uncertainty_evaluations.py:77-85,110-202,270-272)

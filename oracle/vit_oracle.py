@@ -529,6 +529,60 @@ def blockwise_mask(rng, height=14, width=14, num_masking_patches=120, min_num_pa
     return mask
 
 
+# --------------------------------------------------------------------------------------------------------------
+# Mixup / CutMix (timm.data.mixup, timm 0.3.2 pinned by the reference's requirements.txt:3; timm is NOT in this image, so this restates
+# its published algorithm: PARITY UNPINNED against timm itself, anchored on the reference's call sites run_class_finetuning.py:339-347 and
+# engine_for_finetuning.py:87-88). Plain torch CPU ops in timm's order, so the device kernel can be checked bit for bit.
+# --------------------------------------------------------------------------------------------------------------
+def mixup_images(x: torch.Tensor, lam: float, use_cutmix: bool, box) -> torch.Tensor:
+    """Mixup._mix_batch on a copy of x."""
+    x = x.clone()
+    if lam == 1.0:
+        return x
+    if use_cutmix:
+        yl, yh, xl, xh = box
+        x[:, :, yl:yh, xl:xh] = x.flip(0)[:, :, yl:yh, xl:xh]
+    else:
+        x_flipped = x.flip(0).mul_(1.0 - lam)
+        x.mul_(lam).add_(x_flipped)
+    return x
+
+
+def mixup_target(target: torch.Tensor, num_classes: int, lam: float = 1.0, smoothing: float = 0.0) -> torch.Tensor:
+    off_value = smoothing / num_classes
+    on_value = 1.0 - smoothing + off_value
+
+    def one_hot(t):
+        t = t.long().view(-1, 1)
+        return torch.full((t.size()[0], num_classes), off_value).scatter_(1, t, on_value)
+    return one_hot(target) * lam + one_hot(target.flip(0)) * (1.0 - lam)
+
+
+def mixup_draw(rng, img_shape, mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5, correct_lam=True):
+    """Mixup._params_per_batch + cutmix_bbox_and_lam / rand_bbox for mode='batch' with numpy's RandomState call order."""
+    lam, use_cutmix, box = 1.0, False, (0, 0, 0, 0)
+    if rng.rand() < prob:
+        if mixup_alpha > 0.0 and cutmix_alpha > 0.0:
+            use_cutmix = bool(rng.rand() < switch_prob)
+            lam = float(rng.beta(cutmix_alpha, cutmix_alpha) if use_cutmix else rng.beta(mixup_alpha, mixup_alpha))
+        elif mixup_alpha > 0.0:
+            lam = float(rng.beta(mixup_alpha, mixup_alpha))
+        else:
+            use_cutmix = True
+            lam = float(rng.beta(cutmix_alpha, cutmix_alpha))
+    if lam != 1.0 and use_cutmix:
+        img_h, img_w = img_shape[-2:]
+        ratio = np.sqrt(1 - lam)
+        cut_h, cut_w = int(img_h * ratio), int(img_w * ratio)
+        cy, cx = rng.randint(0, img_h), rng.randint(0, img_w)
+        yl, yh = int(np.clip(cy - cut_h // 2, 0, img_h)), int(np.clip(cy + cut_h // 2, 0, img_h))
+        xl, xh = int(np.clip(cx - cut_w // 2, 0, img_w)), int(np.clip(cx + cut_w // 2, 0, img_w))
+        box = (yl, yh, xl, xh)
+        if correct_lam:
+            lam = 1.0 - (yh - yl) * (xh - xl) / float(img_h * img_w)
+    return lam, use_cutmix, box
+
+
 class InjectedUniformRng:
     """`random`-module stand-in that replays a given sequence of uniforms in [0,1): uniform(a, b) = a + (b - a) * u exactly as
     random.uniform computes it, randint(a, b) = a + min(b - a, floor(u * (b - a + 1))). Feeding the same sequence to the device

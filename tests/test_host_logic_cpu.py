@@ -3,6 +3,7 @@
 import math
 
 import numpy as np
+import pytest
 import torch
 
 
@@ -69,3 +70,31 @@ def test_shard_passes_partitions_every_pass_once():
             assert all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
             sizes = [e - s for s, e in sh]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_mixup_parameter_draws_follow_timm_call_order():
+    """Host side of the device Mixup: (lam, cutmix?, box) per batch == the oracle's restatement of timm 0.3.2 Mixup._params_per_batch /
+    cutmix_bbox_and_lam on the same numpy RandomState, for the README recipe (--mixup 0.8 --cutmix 1.0) and the single-mode settings."""
+    import numpy as np
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import mixup as MX
+    shape = (8, 3, 224, 224)
+    for ma, ca, prob in ((0.8, 1.0, 1.0), (0.8, 0.0, 1.0), (0.0, 1.0, 0.7)):
+        mine = MX.Mixup(mixup_alpha=ma, cutmix_alpha=ca, prob=prob, num_classes=10, rng=np.random.RandomState(5))
+        r = np.random.RandomState(5)
+        seen_cut = seen_mix = seen_off = 0
+        for _ in range(300):
+            a = mine.draw(shape)
+            b = O.mixup_draw(r, shape, mixup_alpha=ma, cutmix_alpha=ca, prob=prob)
+            assert a == b
+            lam, cut, (yl, yh, xl, xh) = a
+            seen_cut += cut and lam != 1.0
+            seen_mix += (not cut) and lam != 1.0
+            seen_off += lam == 1.0
+            if cut and lam != 1.0:
+                assert 0 <= yl <= yh <= 224 and 0 <= xl <= xh <= 224 and abs(lam - (1 - (yh - yl) * (xh - xl) / 224 ** 2)) < 1e-12
+        assert (seen_cut > 0) == (ca > 0) and (seen_mix > 0) == (ma > 0) and (seen_off > 0) == (prob < 1)
+    with pytest.raises(NotImplementedError):
+        MX.Mixup(mode="elem")
+    t = O.mixup_target(torch.tensor([1, 3, 3, 0]), 5, 0.3, 0.1)
+    assert torch.allclose(t.sum(1), torch.ones(4)) and abs(float(t[0, 1]) - (0.3 * 0.92 + 0.7 * 0.02)) < 1e-6

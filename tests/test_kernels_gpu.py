@@ -479,3 +479,45 @@ def test_block_masks_philox_stream(cuda):
     assert int(gen.batch(4, uniforms=short)[1][4]) == -1
     with pytest.raises(_lib.B200VitError):
         MG.MaskingGenerator(33, 120, device=cuda).batch(2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device Mixup / CutMix (timm Mixup, batch mode) — bit-exact against the torch ops timm runs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,shape,lam,cut,box", [
+    (8, (3, 32, 32), 0.37, False, None),
+    (7, (3, 16, 20), 0.81234, False, None),          # odd batch: the middle image pairs with itself
+    (6, (3, 32, 32), 0.6, True, (5, 21, 0, 32)),
+    (4, (1, 9, 7), 0.5, True, (0, 9, 2, 3)),
+    (4, (3, 8, 8), 0.5, True, (3, 3, 1, 5)),         # empty box (clipped to nothing): images unchanged, targets still mixed
+    (6, (3, 32, 32), 1.0, False, None),              # lam == 1: no mixing, smoothed one-hot targets
+])
+def test_mixup_batch_bit_exact(ops, cuda, B, shape, lam, cut, box):
+    from oracle import vit_oracle as O
+    g = torch.Generator().manual_seed(B * 100 + shape[1])
+    x = torch.randn(B, *shape, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    xd = x.to(cuda)
+    soft = ops.mixup_batch(xd, lam, cut, box or (0, 0, 0, 0), y.to(cuda), 10, 1.0 - 0.1 + 0.1 / 10, 0.1 / 10)
+    assert torch.equal(xd.cpu(), O.mixup_images(x, lam, cut, box))
+    assert torch.equal(soft.cpu(), O.mixup_target(y, 10, lam, 0.1))
+
+
+def test_mixup_class_matches_oracle_run(cuda):
+    """timm's interface end to end: seeded numpy stream -> same lambdas / boxes -> identical images and soft targets over 12 batches."""
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import mixup as MX
+    fn = MX.Mixup(mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5, label_smoothing=0.1, num_classes=16, rng=np.random.RandomState(3))
+    r = np.random.RandomState(3)
+    g = torch.Generator().manual_seed(0)
+    kinds = set()
+    for _ in range(12):
+        x = torch.randn(6, 3, 64, 64, generator=g)
+        y = torch.randint(0, 16, (6,), generator=g)
+        xd, soft = fn(x.to(cuda), y.to(cuda))
+        lam, cut, box = O.mixup_draw(r, x.shape)
+        kinds.add(cut)
+        assert torch.equal(xd.cpu(), O.mixup_images(x, lam, cut, box)) and torch.equal(soft.cpu(), O.mixup_target(y, 16, lam, 0.1))
+    assert kinds == {True, False}
+    with pytest.raises(AssertionError):
+        fn(torch.zeros(3, 3, 8, 8, device=cuda), torch.zeros(3, dtype=torch.int64, device=cuda))

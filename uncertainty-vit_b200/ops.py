@@ -230,6 +230,26 @@ def block_masks(B, height, width, tokens, num_masking_patches, min_num_patches, 
     return mask, count, rows
 
 
+def mixup_batch(x: Optional[torch.Tensor], lam: float, use_cutmix: bool = False, box=(0, 0, 0, 0), labels: Optional[torch.Tensor] = None,
+                num_classes: int = 0, on_value: float = 1.0, off_value: float = 0.0) -> Optional[torch.Tensor]:
+    """In-place Mixup / CutMix of x fp32 [B,C,H,W] against x.flip(0) (timm Mixup, batch mode) and the mixed soft targets [B,K] (or None)."""
+    import numpy as np
+    soft = None
+    if labels is not None:
+        if labels.dtype != torch.int64 or not labels.is_contiguous():
+            raise _lib.B200VitError("mixup_batch: labels must be contiguous int64")
+        soft = torch.empty(labels.shape[0], num_classes, dtype=torch.float32, device=labels.device)
+    if x is not None and (x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous()):
+        raise _lib.B200VitError("mixup_batch: x must be a contiguous fp32 [B,C,H,W] tensor")
+    B, Cc, H, W = x.shape if x is not None else (labels.shape[0], 1, 1, 1)
+    yl, yh, xl, xh = (int(v) for v in box)
+    check(_lib.lib().b200vit_mixup_batch(_p(x), B, Cc, H, W, float(np.float32(lam)), float(np.float32(1.0 - lam)), int(use_cutmix), yl, yh, xl, xh,
+                                         _p(labels), num_classes, float(np.float32(on_value)), float(np.float32(off_value)), _p(soft), _stream()),
+          "mixup_batch")
+    _count((1 if x is not None and lam != 1.0 else 0) + (1 if labels is not None else 0))
+    return soft
+
+
 LOG2E = 1.4426950408889634
 
 
