@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--model", default="beit_large_patch16_224")
     ap.add_argument("--path", default="engine", choices=["engine", "module"],
                     help="engine: fused flat-arena FinetuneEngine (default); module: nn.Module boundary + torch.optim.AdamW")
+    ap.add_argument("--mixup", action="store_true",
+                    help="README recipe --mixup 0.8 --cutmix 1.0 --smoothing 0.1: device Mixup / CutMix of a fresh copy of the batch inside every step")
     args = ap.parse_args()
     import torch.distributed as dist
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -72,8 +74,19 @@ def main():
         l = -torch.log(torch.sigmoid(neg - pos + 1e-24))
         return lam * (l / l.abs().max().clamp_min(1e-30)).sum()
 
+    labels = torch.randint(0, 1000, (B,), generator=g).to(dev)
+    mixup_fn = None
+    if args.mixup:
+        import numpy as np
+        from uncertainty_vit_b200.mixup import Mixup
+        mixup_fn = Mixup(mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5, label_smoothing=0.1, num_classes=1000,
+                         rng=np.random.RandomState(rank))
+
     def step():
         if args.path == "engine":
+            if mixup_fn is not None:        # the loader hands over a fresh batch every step: mix a copy, as Mixup works in place
+                xa, t = mixup_fn(x[0].clone(), labels)
+                return eng.step(xa, t, x[1], x[2])
             return eng.step(x[0], tgt, x[1], x[2])
         model.train()
         am, ac, logits = model(x[0])
@@ -116,7 +129,7 @@ def main():
                           "config": {"workload": f"{args.model} --stochastic fine-tune train step (anchor fwd+bwd, pos/neg no-grad fwd, soft-target CE + "
                                                  "WassersteinLossFineTuning, AdamW with layer_decay 0.65 groups), drop_path 0.2, batch 64/GPU",
                                      "path": "fused flat-arena FinetuneEngine (clip + layer-decay AdamW in one kernel)" if args.path == "engine"
-                                     else "nn.Module boundary + torch.optim.AdamW(fused)", "param_groups": len(groups)},
+                                     else "nn.Module boundary + torch.optim.AdamW(fused)", "param_groups": len(groups), "mixup": bool(args.mixup)},
                           "final_loss": float(loss.item()), "params_M": sum(p.numel() for p in model.parameters()) / 1e6}))
     if world > 1:
         dist.destroy_process_group()
