@@ -139,7 +139,9 @@ int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint
  * row_index != NULL (final-norm + masked-row gather of modeling_cyclical.py:219-224). Outputs are compact [rows, C]. */
 int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index, const float* gamma, const float* beta, float eps,
                           int32_t rows, int32_t C, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
-/* dx[row_index[r]] += LN-backward(dy[r]) ; dgamma += ; dbeta += */
+/* dx[row_index[r]] += LN-backward(dy[r]) ; dgamma += ; dbeta +=
+ * The dx update is a plain read-modify-write: row_index entries of rows with a non-zero dy must be distinct. Rows whose dy is entirely
+ * zero are skipped, so the padding of a fixed-capacity row list (see b200vit_d2v_target_loss, n_valid_dev) may repeat any valid row. */
 int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
                           const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma,
                           float* dbeta, void* stream);
