@@ -325,3 +325,70 @@ def test_engine_checkpoint_resume_and_torch_adamw_interop(cuda, golden_dir, tmp_
     assert eng3.opt_step == 3
     ck3 = CK.optimizer_state_dict(eng3)
     assert torch.equal(ck3["state"][k]["exp_avg_sq"], ckpt["optimizer"]["state"][k]["exp_avg_sq"])
+
+
+def test_finetune_loop_and_evaluate(cuda, golden_dir):
+    """finetune_one_epoch (engine_for_finetuning.train_one_epoch / dist_train_one_epoch over the fused engine, with device Mixup) and evaluate
+    (engine_for_finetuning.evaluate): the loop learns a fixed batch, reports class_acc only without Mixup, and the evaluation metrics equal
+    the oracle's on the model's own logits."""
+    import uncertainty_vit_b200 as pkg
+    from oracle import vit_oracle as O
+    from uncertainty_vit_b200 import engine as E, mixup as MX, modeling  # noqa: F401
+    from tests.test_model_gpu import _build_dist, _build_from_gold
+    for name, builder in (("tiny_det_finetune", _build_from_gold), ("tiny_dist_finetune", _build_dist)):
+        gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+        model, arch, sd = builder(pkg, gold, cuda)
+        K = model.cfg.num_classes
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(4, 3, arch.img_size, arch.img_size, generator=g)
+        y = torch.randint(0, K, (4,), generator=g)
+        eng = E.FinetuneEngine(model, lr=2e-3, weight_decay=0.0, layer_decay=0.65, clip_grad=3.0)
+        model.eval()
+        with torch.no_grad():                      # builds the module's bf16 weight shadows on the arena views BEFORE any training
+            before = model(x.to(cuda))
+        before = (before[-1] if isinstance(before, tuple) else before).float().clone()
+        batch = (x, x.roll(1, 0), x.flip(0), y) if arch.dist else (x, y)
+        lr = E.cosine_scheduler(2e-3, 1e-4, 1, 25, warmup_epochs=0)
+        logs = []
+        st = E.finetune_one_epoch(eng, [batch] * 25, lr_schedule_values=lr, num_training_steps_per_epoch=25, log=logs.append)
+        first = float(logs[0].split("loss ")[1].split()[0])
+        assert np.isfinite(st["loss"]) and st["loss"] < first and st["class_acc"] is not None and 0 <= st["class_acc"] <= 1
+        assert st["min_lr"] < st["lr"] <= 2e-3 and np.isfinite(st["grad_norm"]) and len(logs) == 3
+        mix = MX.Mixup(mixup_alpha=0.8, cutmix_alpha=1.0, label_smoothing=0.1, num_classes=K, rng=np.random.RandomState(0))
+        st2 = E.finetune_one_epoch(eng, [batch] * 4, start_steps=20, lr_schedule_values=lr, mixup_fn=mix, log=lambda s: None)
+        assert np.isfinite(st2["loss"]) and st2["class_acc"] is None
+        with pytest.raises(NotImplementedError):
+            E.finetune_one_epoch(eng, [batch], update_freq=2)
+        # the module boundary sees the weights the engine's kernels wrote (its bf16 shadows are keyed on a version the engine bumps): a fresh
+        # module loaded from the state dict gives the same logits
+        model.eval()
+        with torch.no_grad():
+            live = model(x.to(cuda))
+        gold2 = torch.load(os.path.join(golden_dir, name + ".pt"))
+        fresh, _, _ = builder(pkg, gold2, cuda)
+        fresh.load_state_dict(model.state_dict())
+        fresh.eval()
+        with torch.no_grad():
+            ref = fresh(x.to(cuda))
+        pick = lambda o: (o[-1] if isinstance(o, tuple) else o).float()
+        assert rel(pick(live), pick(ref)) < 1e-6 and rel(pick(live), before) > 1e-2
+        # evaluation: two batches of different size
+        loader = [(x, y), (x[:3], y[:3])]
+        ev = E.evaluate(loader, model, cuda, K)
+        model.eval()
+        with torch.no_grad():
+            outs = [model(b.to(cuda)) for b, _ in loader]
+        outs = [(o[-1] if isinstance(o, tuple) else o).float().cpu() for o in outs]
+        exp = {"acc1": 0.0, "acc5": 0.0, "ECE": 0.0, "NLL": 0.0}
+        for o, (_, t) in zip(outs, loader):
+            p = torch.softmax(o, 1)
+            top5 = o.topk(5, 1).indices
+            b = o.shape[0]
+            exp["acc1"] += 100.0 * float((o.argmax(1) == t).float().mean()) * b
+            exp["acc5"] += 100.0 * float((top5 == t[:, None]).any(1).float().mean()) * b
+            exp["ECE"] += float(O.ece(p, t)) * b
+            exp["NLL"] += float(-torch.log(p[torch.arange(b), t]).mean()) * b
+        for k, v in exp.items():
+            assert abs(ev[k] - v / 7) < 2e-3 * max(1.0, abs(v / 7)), (name, k, ev[k], v / 7)
+        ce = np.mean([float(torch.nn.functional.cross_entropy(o, t)) for o, (_, t) in zip(outs, loader)])
+        assert abs(ev["loss"] - ce) < 1e-3

@@ -146,6 +146,7 @@ def load_engine_state_dict(engine, ckpt: dict, load_optimizer: bool = True) -> N
         engine.it = int(meta["it"])       # (the noise seed is per rank, args.seed + rank, and stays what the constructor was given)
         if load_optimizer:
             engine.opt_step = int(meta["opt_step"])
+    engine.model._weights_version = getattr(engine.model, "_weights_version", 0) + 1
     if hasattr(engine.model, "_ps"):
         engine.model._ps.invalidate()
 

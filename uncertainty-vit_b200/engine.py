@@ -363,6 +363,9 @@ class D2VEngine:
                        gnorm_sq=self.gnorm_sq, max_norm=self.clip if self.clip else 0.0, grad_div=float(self.world_size), p_bf16=self.p16,
                        ema=self.e32 if do_ema else None, ema_decay=self.cur_decay, ema_bf16=self.e16 if do_ema else None)
         self.it += 1
+        # the module aliases the arena, but its bf16 weight shadows / captured eval graphs are keyed on autograd version counters, which a
+        # raw-pointer kernel update does not touch: tell the module its weights moved
+        self.model._weights_version = getattr(self.model, "_weights_version", 0) + 1
         return self.loss_dev
 
     def grad_norm(self) -> torch.Tensor:
@@ -502,7 +505,87 @@ class FinetuneEngine(D2VEngine):
             self.g32.zero_()
             core.vit_backward_logits(self.student, cfg, ctx, dlogits.contiguous(), self.grads)
         self.loss_dev.copy_(loss.reshape(1))
+        self.last_logits = logits               # class_acc of the training log (engine_for_finetuning.py:132-133)
         return self._optimizer_step(lr, wd)
+
+
+def finetune_one_epoch(engine: "FinetuneEngine", data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,
+                       wd_schedule_values=None, mixup_fn=None, num_training_steps_per_epoch: Optional[int] = None, update_freq: int = 1,
+                       print_freq: int = 10, log=print) -> Dict[str, float]:
+    """Loop of engine_for_finetuning.train_one_epoch (:46-170) / engine_for_finetuning_dist.dist_train_one_epoch (:312-440) over the fused
+    FinetuneEngine. The loader yields (samples, targets) or, for the --stochastic triplet set, (samples, pos_samples, neg_samples, labels)
+    (dist_datasets.py:143-148). Per step: schedule lr (x the group's layer-decay scale inside the fused AdamW) and weight decay, host->device
+    copy, device Mixup / CutMix when `mixup_fn` is given (mixup.Mixup), one fused step, loss read back, non-finite loss aborts.
+    Gradient accumulation (update_freq > 1) is not implemented: the README recipes use --update_freq 1."""
+    if update_freq != 1:
+        raise NotImplementedError("update_freq > 1 (gradient accumulation) is outside the B200 hot path; the README recipes use 1")
+    engine.model.train(True)
+    dev = engine.dev
+    total = acc_sum = 0.0
+    n = n_acc = 0
+    lr = engine.lr
+    for data_iter_step, batch in enumerate(data_loader):
+        step = data_iter_step
+        if num_training_steps_per_epoch is not None and step >= num_training_steps_per_epoch:
+            continue
+        it = start_steps + step
+        lr = float(lr_schedule_values[it]) if lr_schedule_values is not None else None
+        wd = float(wd_schedule_values[it]) if wd_schedule_values is not None else None
+        if len(batch) == 4:
+            samples, pos, neg, labels = batch
+            pos, neg = pos.to(dev, non_blocking=True).float(), neg.to(dev, non_blocking=True).float()
+        else:
+            (samples, labels), pos, neg = batch, None, None
+        samples = samples.to(dev, non_blocking=True).float().contiguous()
+        labels = labels.to(dev, non_blocking=True)
+        targets = labels
+        if mixup_fn is not None:
+            samples, targets = mixup_fn(samples, labels)
+        engine.it = it
+        loss = float(engine.step(samples, targets, pos, neg, lr=lr, weight_decay=wd).item())
+        if not math.isfinite(loss):
+            raise FloatingPointError(f"Loss is {loss}, stopping training")
+        total += loss
+        n += 1
+        if mixup_fn is None and labels.dim() == 1:
+            acc_sum += float((engine.last_logits.argmax(-1) == labels).float().mean().item())
+            n_acc += 1
+        if data_iter_step % print_freq == 0:
+            log(f"Epoch: [{epoch}] step {data_iter_step} loss {loss:.4f} lr {lr if lr is not None else engine.lr:.6f}")
+    hp = engine.hp[:, 0]
+    cur = lr if lr is not None else engine.lr
+    stepped = hp[hp > 0]
+    return {"loss": total / max(n, 1), "class_acc": acc_sum / n_acc if n_acc else None, "lr": cur * float(hp.max().item()),
+            "min_lr": cur * float(stepped.min().item()) if stepped.numel() else cur, "grad_norm": float(engine.grad_norm().item())}
+
+
+@torch.no_grad()
+def evaluate(data_loader: Iterable, model, device=None, num_classes: Optional[int] = None) -> Dict[str, float]:
+    """engine_for_finetuning.evaluate (:175-222) / dist_evaluate: deterministic evaluation with the per-batch metrics of the reference,
+    averaged over the batches weighted by batch size (loss: plain mean over batches, as MetricLogger.update(loss=...) does): cross-entropy,
+    acc@1 / acc@5 (percent), 15-bin ECE and NLL, all reduced on the device by the MC-metrics kernel with one sample (S = 1).
+    TACE and AUROC of the reference's printout are not computed (outside the scoped hot path)."""
+    dev = device if device is not None else next(model.parameters()).device
+    sums = {"acc1": 0.0, "acc5": 0.0, "ECE": 0.0, "ECE_as_reference_computes_it": 0.0, "NLL": 0.0}
+    loss_sum, nb, ntot = 0.0, 0, 0
+    was_training = model.training
+    model.eval()
+    for batch in data_loader:
+        images, target = batch[0].to(dev).float().contiguous(), batch[-1].to(dev)
+        out = model(images)
+        logits = (out[-1] if isinstance(out, (tuple, list)) else out).float()
+        _, _, _, summary = ops.mc_reduce(logits.unsqueeze(0).contiguous(), target.to(torch.int32))
+        a1, a5, ece, ece_ref, nll = summary.tolist()[:5]
+        b = images.shape[0]
+        loss_sum += float(torch.nn.functional.cross_entropy(logits, target.long()).item())
+        nb += 1
+        ntot += b
+        for k, v in zip(sums, (a1, a5, ece, ece_ref, nll)):
+            sums[k] += v * b
+    model.train(was_training)
+    out = {k: v / max(ntot, 1) for k, v in sums.items()}
+    out["loss"] = loss_sum / max(nb, 1)
+    return out
 
 
 def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, start_steps: int = 0, lr_schedule_values=None,

@@ -67,7 +67,7 @@ class _GraphedForward:
 
     @staticmethod
     def _signature(model):
-        return tuple((p._version, p.data_ptr()) for p in model.parameters())
+        return (getattr(model, "_weights_version", 0),) + tuple((p._version, p.data_ptr()) for p in model.parameters())
 
     def valid_for(self, model, x):
         return tuple(x.shape) == tuple(self.x.shape) and x.dtype == self.x.dtype and self._signature(model) == self.sig

@@ -141,7 +141,7 @@ class ModuleParams(core.ParamSource):
         return None if t is None else t.detach()
 
     def _cached(self, key, src_tensors, build):
-        sig = tuple((t._version, t.data_ptr()) for t in src_tensors)
+        sig = (getattr(self.module, "_weights_version", 0),) + tuple((t._version, t.data_ptr()) for t in src_tensors)
         ent = self._cache.get(key)
         if ent is None or ent[0] != sig:
             ent = (sig, build())
@@ -220,6 +220,7 @@ class _VitBase(nn.Module):
 
     def _finish_init(self):
         self._ps = ModuleParams(self)
+        self._weights_version = 0        # bumped by the fused engines: their kernels update the parameter arena behind autograd's version counters
         self._seed_calls = 0
         self._injected: Optional[Noise] = None
 
