@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define B200VIT_ABI_VERSION 3   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
-                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch */
+                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8 */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -217,6 +217,11 @@ int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const 
                              int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,
                              float* loss_out, const int32_t* n_valid_dev, void* stream);
 
+/* patch_transform of the data pipeline on the device: transforms.ToTensor() + transforms.Normalize(mean, std) (datasets.py:80-85) from uint8
+ * pixels, so only 1 byte per element crosses PCIe. src uint8 [B,H,W,C] (hwc != 0: PIL / numpy layout) or [B,C,H,W]; C <= 4; mean_host / std_host:
+ * HOST arrays of C floats. out fp32 [B,C,H,W] = ((src / 255) - mean[c]) / std[c], three rounded fp32 operations (bit-identical to torchvision). */
+int b200vit_normalize_u8(const uint8_t* src, int32_t hwc, int32_t B, int32_t C, int32_t H, int32_t W, const float* mean_host,
+                         const float* std_host, float* out, void* stream);
 /* Mixup / CutMix of a fine-tune batch in place, "batch" mode (timm 0.3.2 Mixup._mix_batch + mixup_target, built at
  * run_class_finetuning.py:339-347 and applied at engine_for_finetuning.py:87-88): image b is paired with image B-1-b.
  *   use_cutmix == 0: x[b] = lam * x[b] + one_minus_lam * x[B-1-b] (two rounded products + one rounded sum, as the torch ops)

@@ -392,3 +392,22 @@ def test_finetune_loop_and_evaluate(cuda, golden_dir):
             assert abs(ev[k] - v / 7) < 2e-3 * max(1.0, abs(v / 7)), (name, k, ev[k], v / 7)
         ce = np.mean([float(torch.nn.functional.cross_entropy(o, t)) for o, (_, t) in zip(outs, loader)])
         assert abs(ev["loss"] - ce) < 1e-3
+
+
+def test_uint8_staging_is_the_same_step(cuda, golden_dir):
+    """A uint8 pixel batch normalised on the device gives the step of the fp32 batch torchvision's ToTensor + Normalize would have produced."""
+    losses = {}
+    g = torch.Generator().manual_seed(7)
+    pix = torch.randint(0, 256, (3, 64, 64, 3), dtype=torch.uint8, generator=g)
+    mean, std = (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)
+    f32 = pix.permute(0, 3, 1, 2).contiguous().float().div(255).sub_(torch.tensor(mean).view(-1, 1, 1)).div_(torch.tensor(std).view(-1, 1, 1))
+    for kind in ("f32", "u8"):
+        pkg, E, gold, model, arch, sd = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+        eng = E.D2VEngine(model, lr=1e-3, target_layers=gold["target_layers"], use_graph=False, seed=2)
+        eng.pixel_norm = (mean, std, True)
+        x = (pix if kind == "u8" else f32).pin_memory()
+        losses[kind] = [eng.step_host(x, gold["mask"].numpy()) for _ in range(3)]
+    assert np.allclose(losses["f32"], losses["u8"], rtol=1e-5), losses
+    pkg, E, gold, model, arch, sd = _setup(cuda, golden_dir, "tiny_det_cyclical.pt")
+    with pytest.raises(ValueError):
+        E.D2VEngine(model, target_layers=gold["target_layers"]).step_host(pix.pin_memory(), gold["mask"].numpy())

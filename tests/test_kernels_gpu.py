@@ -521,3 +521,19 @@ def test_mixup_class_matches_oracle_run(cuda):
     assert kinds == {True, False}
     with pytest.raises(AssertionError):
         fn(torch.zeros(3, 3, 8, 8, device=cuda), torch.zeros(3, dtype=torch.int64, device=cuda))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device ToTensor + Normalize from uint8 pixels (datasets.py:80-85) — bit-exact against the torch ops torchvision runs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,W,hwc", [(3, 3, 224, 224, True), (2, 3, 10, 6, True), (2, 3, 5, 7, True), (2, 3, 8, 8, False), (2, 1, 9, 5, True)])
+def test_normalize_u8_bit_exact(ops, cuda, B, C, H, W, hwc):
+    g = torch.Generator().manual_seed(H * W + C)
+    shape = (B, H, W, C) if hwc else (B, C, H, W)
+    src = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+    mean, std = [0.5, 0.485, 0.406][:C], [0.5, 0.229, 0.225][:C]        # IMAGENET_INCEPTION / IMAGENET_DEFAULT values
+    chw = src.permute(0, 3, 1, 2).contiguous() if hwc else src
+    ref = chw.to(torch.float32).div(255)                                  # transforms.ToTensor
+    ref = ref.sub_(torch.as_tensor(mean).view(-1, 1, 1)).div_(torch.as_tensor(std).view(-1, 1, 1))   # transforms.Normalize
+    out = ops.normalize_u8(src.to(cuda), mean, std, hwc)
+    assert torch.equal(out.cpu(), ref)

@@ -42,6 +42,9 @@ def main():
     us = timeit(lambda i: ops.mixup_batch(bufs[i % 4], 0.5, True, (32, 192, 40, 180), labels, 1000, 0.9001, 0.0001))
     box = 3 * 160 * 140 * 4 * B
     out["cutmix_b128_box160x140"] = {"us": us, "algorithmic_GBps": 2 * box / us * 1e-3, "bytes": 2 * box}
+    pix = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(4)]
+    us = timeit(lambda i: ops.normalize_u8(pix[i % 4], (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), True, out=bufs[i % 4]))
+    out["normalize_u8_b128"] = {"us": us, "algorithmic_GBps": (pix[0].numel() + nbytes) / us * 1e-3, "bytes": pix[0].numel() + nbytes}
     for nb in (128, 4096):
         gen = MG.MaskingGenerator(14, 120, min_num_patches=16, seed=1, device=dev)
         us = timeit(lambda i: gen.batch(nb))

@@ -50,6 +50,7 @@ _PROTOS = {
     "b200vit_assemble_tokens_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "b200vit_drop_path_scales": (i32, [C.POINTER(f32), i32, i32, i32, u64, vp, vp]),
     "b200vit_mixup_batch": (i32, [vp, i32, i32, i32, i32, f32, f32, i32, i32, i32, i32, i32, vp, i32, f32, f32, vp, vp]),
+    "b200vit_normalize_u8": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp]),
     "b200vit_block_masks": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, C.c_double, C.c_double, u64, u64, vp, i32, vp]),
     "b200vit_rel_pos_bias": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "b200vit_meanpool_tokens": (i32, [vp, i32, i32, i32, vp, vp]),

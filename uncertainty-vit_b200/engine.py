@@ -120,6 +120,8 @@ class D2VEngine:
         self.seed = seed
         self.it = 0
         self.layer_decay, self.skip_weight_decay = layer_decay, tuple(skip_weight_decay)
+        # (mean, std, hwc): set to accept uint8 pixel batches from the loader; ToTensor + Normalize (datasets.py:80-85) then run on the device
+        self.pixel_norm = None
         # ---- layout: every segment starts on a CHUNK boundary; (q_bias | 0 | v_bias) of a block form ONE segment so that the
         # QKV GEMM bias cat(q_bias, zeros, v_bias) (modeling_finetune.py:148) is a plain arena view
         named = dict(model.named_parameters())
@@ -371,6 +373,16 @@ class D2VEngine:
     def grad_norm(self) -> torch.Tensor:
         return torch.sqrt(self.gnorm_sq) / self.world_size
 
+    def _images_to_device(self, images_pinned: torch.Tensor) -> torch.Tensor:
+        """Host->device copy of one batch on the current (copy) stream. fp32 batches as the reference loader yields them, or uint8 pixels
+        ([B,H,W,3] / [B,3,H,W]) when `pixel_norm` is set: a quarter of the PCIe bytes, normalised by b200vit_normalize_u8."""
+        if images_pinned.dtype == torch.uint8:
+            if self.pixel_norm is None:
+                raise ValueError("uint8 image batch: set engine.pixel_norm = (mean, std, hwc) first")
+            mean, std, hwc = self.pixel_norm
+            return ops.normalize_u8(images_pinned.to(self.dev, non_blocking=True), mean, std, hwc)
+        return images_pinned.to(self.dev, non_blocking=True)
+
     def stage_host(self, images_pinned: torch.Tensor, mask_host: np.ndarray):
         """Enqueues the host->device copies of ONE batch on the engine's copy stream (so the next batch travels while the current
         step computes) and returns the staged batch for step_staged(). Inputs as the data loader yields them
@@ -382,7 +394,7 @@ class D2VEngine:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
         with torch.cuda.stream(self._copy_stream):
-            images = images_pinned.to(self.dev, non_blocking=True)
+            images = self._images_to_device(images_pinned)
             mask_u8 = mask_pinned.to(self.dev, non_blocking=True)
             rows_d = rows.to(self.dev, non_blocking=True)
             ev = torch.cuda.Event()
@@ -401,7 +413,7 @@ class D2VEngine:
         with torch.cuda.stream(self._copy_stream):
             rows = torch.zeros(B * generator.num_masking_patches, dtype=torch.int32, device=self.dev)   # padding = row 0 (a cls row)
             mask_u8, count, rows = generator.batch(B, rows=rows)
-            images = images_pinned.to(self.dev, non_blocking=True)
+            images = self._images_to_device(images_pinned)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return images, mask_u8.view(-1), rows, ev, (count,), count[B:B + 1]

@@ -230,6 +230,25 @@ def block_masks(B, height, width, tokens, num_masking_patches, min_num_patches, 
     return mask, count, rows
 
 
+def normalize_u8(src: torch.Tensor, mean, std, hwc: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ToTensor + Normalize (datasets.py:80-85) of uint8 pixels on the device: src [B,H,W,C] (hwc) or [B,C,H,W] -> fp32 [B,C,H,W]."""
+    if src.dtype != torch.uint8 or src.dim() != 4 or not src.is_contiguous():
+        raise _lib.B200VitError("normalize_u8: src must be a contiguous uint8 4-D tensor")
+    if hwc:
+        B, H, W, Cc = src.shape
+    else:
+        B, Cc, H, W = src.shape
+    if len(mean) != Cc or len(std) != Cc:
+        raise _lib.B200VitError("normalize_u8: mean / std need one value per channel")
+    if out is None:
+        out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=src.device)
+    m = (C.c_float * Cc)(*[float(v) for v in mean])
+    s = (C.c_float * Cc)(*[float(v) for v in std])
+    check(_lib.lib().b200vit_normalize_u8(_p(src), int(hwc), B, Cc, H, W, m, s, _p(out), _stream()), "normalize_u8")
+    _count()
+    return out
+
+
 def mixup_batch(x: Optional[torch.Tensor], lam: float, use_cutmix: bool = False, box=(0, 0, 0, 0), labels: Optional[torch.Tensor] = None,
                 num_classes: int = 0, on_value: float = 1.0, off_value: float = 0.0) -> Optional[torch.Tensor]:
     """In-place Mixup / CutMix of x fp32 [B,C,H,W] against x.flip(0) (timm Mixup, batch mode) and the mixed soft targets [B,K] (or None)."""
