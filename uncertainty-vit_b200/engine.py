@@ -572,8 +572,10 @@ def finetune_one_epoch(engine: "FinetuneEngine", data_loader: Iterable, epoch: i
 
 
 @torch.no_grad()
-def evaluate(data_loader: Iterable, model, device=None, num_classes: Optional[int] = None) -> Dict[str, float]:
-    """engine_for_finetuning.evaluate (:175-222) / dist_evaluate: deterministic evaluation with the per-batch metrics of the reference,
+def evaluate(data_loader: Iterable, model, device=None, num_classes: Optional[int] = None, dist_criterion=None) -> Dict[str, float]:
+    """engine_for_finetuning.evaluate (:175-222) / engine_for_finetuning_dist.dist_evaluate (:442-494; pass
+    dist_criterion=(lambda_finetuning, lambda_pvn) and a loader of (images, pos, neg, labels): the loss then includes
+    WassersteinLossFineTuning of the three forwards): deterministic evaluation with the per-batch metrics of the reference,
     averaged over the batches weighted by batch size (loss: plain mean over batches, as MetricLogger.update(loss=...) does): cross-entropy,
     acc@1 / acc@5 (percent), 15-bin ECE and NLL, all reduced on the device by the MC-metrics kernel with one sample (S = 1).
     TACE and AUROC of the reference's printout are not computed (outside the scoped hot path)."""
@@ -589,7 +591,12 @@ def evaluate(data_loader: Iterable, model, device=None, num_classes: Optional[in
         _, _, _, summary = ops.mc_reduce(logits.unsqueeze(0).contiguous(), target.to(torch.int32))
         a1, a5, ece, ece_ref, nll = summary.tolist()[:5]
         b = images.shape[0]
-        loss_sum += float(torch.nn.functional.cross_entropy(logits, target.long()).item())
+        loss = torch.nn.functional.cross_entropy(logits, target.long())
+        if dist_criterion is not None and len(batch) == 4 and isinstance(out, (tuple, list)):
+            pm, pc, _ = model(batch[1].to(dev).float().contiguous())
+            nm, nc, _ = model(batch[2].to(dev).float().contiguous())
+            loss = loss + wasserstein_loss_finetuning(out[0], out[1], pm, pc, nm, nc, dist_criterion[0], dist_criterion[1])
+        loss_sum += float(loss.item())
         nb += 1
         ntot += b
         for k, v in zip(sums, (a1, a5, ece, ece_ref, nll)):
