@@ -98,3 +98,21 @@ def test_mixup_parameter_draws_follow_timm_call_order():
         MX.Mixup(mode="elem")
     t = O.mixup_target(torch.tensor([1, 3, 3, 0]), 5, 0.3, 0.1)
     assert torch.allclose(t.sum(1), torch.ones(4)) and abs(float(t[0, 1]) - (0.3 * 0.92 + 0.7 * 0.02)) < 1e-6
+
+
+def test_masking_generator_host_interface():
+    """The device generator keeps the reference class's host-visible interface (masking_generator.py:29-53): constructor defaults, repr,
+    get_shape; plus the image counter that makes a resumed run continue its Philox stream."""
+    from uncertainty_vit_b200 import masking_generator as MG
+    g = MG.MaskingGenerator((14, 14), num_masking_patches=120, max_num_patches=None, min_num_patches=16, device="cpu")
+    assert repr(g) == "Generator(14, 14 -> [16 ~ 120], max = 120, -1.204 ~ 1.204)"
+    assert g.get_shape() == (14, 14) and g.num_patches == 196 and g.max_num_patches == 120
+    assert g.log_aspect_ratio == (math.log(0.3), math.log(1 / 0.3))
+    h = MG.MaskingGenerator(12, 75, min_num_patches=4, max_num_patches=40, min_aspect=0.5, max_aspect=3.0, seed=7, device="cpu")
+    assert h.get_shape() == (12, 12) and h.max_num_patches == 40 and h.log_aspect_ratio == (math.log(0.5), math.log(3.0))
+    h.images_drawn = 4096
+    k = MG.MaskingGenerator(12, 75, device="cpu")
+    k.load_state_dict(h.state_dict())
+    assert (k.seed, k.images_drawn) == (7, 4096)
+    with pytest.raises(Exception):        # no CPU path: drawing needs the CUDA library and CUDA tensors
+        g.batch(2)
