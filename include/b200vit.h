@@ -23,8 +23,9 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 3   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
-                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8 */
+#define B200VIT_ABI_VERSION 4   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+                                   3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8;
+                                   4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -200,6 +201,63 @@ int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers,
                             const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
                             float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
                             const int32_t* n_valid_dev, void* stream);
+/* The same kernel through a descriptor, with the optional pieces of engine_for_cyclical.train_one_epoch:
+ *   affine / rows_per_sample : instance / batch norm of the teacher layers (:94-104) or of the averaged target (:112-115) as one
+ *                              {shift, scale} pair per (image, channel) from b200vit_channel_stats: v = (v - shift) * scale before the
+ *                              per-row LayerNorm; image = source row / rows_per_sample. affine: HOST array of num_layers device pointers.
+ *   compact_tokens = T       : `layers` are compact [B, T-1, C] patch-row tensors (no cls row) while row_index still holds residual-stream
+ *                              rows b*T + 1 + p (second pass of post_target_instance_norm over the averaged target of ALL patch rows)
+ *   row_index == NULL        : rows 0..R-1 (first pass of post_target_instance_norm: targets for every patch row)
+ *   col_hinge                : device float2 [C] {mean_c, k_c} from b200vit_column_std: dy[r,c] += k_c * (y[r,c] - mean_c) (var_w0 hinge, :136-137)
+ *   loss_out = loss_mult * (mean loss + loss_add_weight * *loss_add)   (loss_add: device scalar or NULL; `loss * loss_scale`, :160-163) */
+typedef struct b200vit_d2v_desc {
+  const float* const* layers;
+  int32_t num_layers;
+  int64_t ld_layer;
+  const int32_t* row_index;
+  const float* y;
+  int32_t R, C;
+  int32_t ln_each, ln_post;
+  float beta;
+  int32_t l2_loss;
+  float grad_scale;
+  float* targets;
+  void* dy_bf16;
+  float* dy_f32;
+  float* row_loss;
+  float* loss_out;
+  const int32_t* n_valid_dev;
+  const float* const* affine;
+  int32_t rows_per_sample;
+  int32_t compact_tokens;
+  const float* col_hinge;
+  const float* loss_add;
+  float loss_add_weight;
+  float loss_mult;
+} b200vit_d2v_desc;
+int b200vit_d2v_target_loss_ex(const b200vit_d2v_desc* desc, void* stream);
+/* Statistics of target_batch_norm / target_instance_norm / post_target_instance_norm (engine_for_cyclical.py:94-104,112-115: F.batch_norm(training)
+ * and F.instance_norm over the patch tokens of each channel, biased variance, eps 1e-5). For every layer l, image b and channel c the mean and
+ * variance over rows [row0, row0 + nrows) of the image's `sample_rows` rows (row0 = 1 skips the cls row of a residual stream) are folded into
+ * affine_out float2 [num_layers, samples, C] = {shift, scale}: batch norm alone {mu_c, rsqrt(var_c + eps)}; instance norm
+ * {mean_bc, r_c * rsqrt(r_c^2 var_bc + eps)} with r_c the batch-norm scale in front of it (1 without). */
+int b200vit_channel_stats(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, int32_t samples, int32_t sample_rows,
+                          int32_t row0, int32_t nrows, int32_t C, int32_t batch_norm, int32_t instance_norm, float eps, float* affine_out,
+                          void* stream);
+/* z0 = sqrt(outputs.var(dim=0) + eps) over the (valid) student rows and the var_w0 hinge std_loss0 = sum relu(margin - z0) / C
+ * (engine_for_cyclical.py:130-139). y fp32 [R, C]; z0 [C] (optional); hinge_out device scalar (optional); col_hinge float2 [C] (optional) =
+ * {mean_c, k_c}, k_c = -k_scale / (C (n-1) z0_c) where the hinge is active: the dy term of k_scale * std_loss0 (k_scale = var_w0 * loss_scale).
+ * work: b200vit_column_std_workspace_bytes(C) bytes. */
+size_t b200vit_column_std_workspace_bytes(int32_t C);
+int b200vit_column_std(const float* y, int32_t R, int32_t C, const int32_t* n_valid_dev, float eps, float margin, float k_scale, float* work,
+                       float* z0, float* hinge_out, float* col_hinge, void* stream);
+/* out = wa * *a + wb * *b on device scalars (b may be NULL): (loss_cyc + loss_stochastic) * loss_scale, engine_for_cyclical.py:160-163 */
+int b200vit_scalar_fma(float* out, const float* a, float wa, const float* b, float wb, void* stream);
+/* mask_dropout_prob (engine_for_cyclical.py:62-66): mask = logical_and(bernoulli(1 - p_drop), mask) per patch, in place, then the per-image
+ * counts (count [B+1], count[B] = total) and the masked-row list as b200vit_block_masks builds them. keep_in (uint8 [B*num_patches], optional)
+ * injects the Bernoulli draws; otherwise Philox4x32-10 keyed on (seed; first_image + b, patch). */
+int b200vit_mask_dropout(uint8_t* mask, int32_t* count, int32_t* rows, int32_t B, int32_t num_patches, int32_t tokens, float p_drop, uint64_t seed,
+                         uint64_t first_image, const uint8_t* keep_in, void* stream);
 /* EMA teacher update e = d*e + (1-d)*m (engine_for_cyclical.py:182-185, timm ModelEmaV2._update) + bf16 shadow */
 int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, void* ema_bf16, void* stream);
 /* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
@@ -216,6 +274,27 @@ int b200vit_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, 
 int b200vit_wasserstein_loss(const float* mean_out, const float* cov_out, const float* pos_mean, const float* pos_cov, int32_t R,
                              int32_t C, float lam, float grad_scale, float* work, float* d_mean_out, float* d_cov_out,
                              float* loss_out, const int32_t* n_valid_dev, void* stream);
+
+/* Reparameterised Gaussian draw z = mean + sqrt(max(cov, 0)) * eps in front of the classifier head of the dual-stream model
+ * (modeling_finetune_dist.py:314-325: Normal(mean, sqrt(cov)).sample(), commented out in the reference — optional here, default off).
+ * eps_in != NULL injects the noise; otherwise eps ~ N(0,1) from Philox4x32-10 keyed on (seed; element / 4, stream_id) + Box-Muller.
+ * eps_out (optional) receives the noise used (the backward needs it). n % 4 == 0. */
+int b200vit_gaussian_sample(const float* mean, const float* cov, const float* eps_in, int64_t n, uint64_t seed, uint32_t stream_id,
+                            float* eps_out, float* out_f32, void* out_bf16, void* stream);
+/* dmean += dz ; dcov += dz * eps / (2 sqrt(cov)) where cov > 0 (either may be NULL) */
+int b200vit_gaussian_sample_bwd(const float* dz, const float* cov, const float* eps, int64_t n, float* dmean, float* dcov, void* stream);
+/* Fine-tune criterion (train_class_batch, engine_for_finetuning_dist.py:286-304): soft-target / label-smoothing cross-entropy of the logits
+ * (mean over the batch) + optionally WassersteinLossFineTuning (distloss.py:39-70) of the anchor features against the positive / negative
+ * features, with gradients w.r.t. logits and anchor features (through all max normalisers, like autograd). logits fp32 [B, ld_logits];
+ * targets fp32 [B, K]; features fp32 [B, C] (mean_feat == NULL: cross-entropy only). dlogits fp32 [B, ld_dlogits] and / or dlogits_bf16
+ * [B, ld_dlogits_bf16] with columns [K, K_padded) zeroed (the operand of the head's backward GEMMs). loss_out[3] = {total, ce, wloss}.
+ * work: b200vit_finetune_loss_workspace_floats(B) floats. */
+size_t b200vit_finetune_loss_workspace_floats(int32_t B);
+int b200vit_finetune_loss(const float* logits, int64_t ld_logits, const float* targets, int32_t B, int32_t K, const float* mean_feat,
+                          const float* cov_feat, const float* pos_mean, const float* pos_cov, const float* neg_mean, const float* neg_cov,
+                          int32_t C, float lambda_finetuning, float lambda_pvn, float grad_scale, float* work, float* dlogits,
+                          int64_t ld_dlogits, void* dlogits_bf16, int64_t ld_dlogits_bf16, int32_t K_padded, float* d_mean_feat,
+                          float* d_cov_feat, float* loss_out, void* stream);
 
 /* patch_transform of the data pipeline on the device: transforms.ToTensor() + transforms.Normalize(mean, std) (datasets.py:80-85) from uint8
  * pixels, so only 1 byte per element crosses PCIe. src uint8 [B,H,W,C] (hwc != 0: PIL / numpy layout) or [B,C,H,W]; C <= 4; mean_host / std_host:
@@ -242,6 +321,15 @@ int b200vit_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, fl
 int b200vit_mc_reduce(const float* logits, const int32_t* labels, int32_t S, int32_t N, int32_t K, int32_t n_bins, float* mean_logits,
                       float* row_stats, float* hist, void* stream);
 int b200vit_mc_finalize(const float* row_stats, const float* hist, int32_t N, int32_t n_bins, float* summary, void* stream);
+
+/* Class-wise calibration of the evaluation printout: TACELoss.loss (uncertainty_evaluations.py:241-261; threshold 0.01, 30 adaptive bins
+ * per class from the sorted class probabilities, :119-132,159-186) and torchmetrics' multiclass AUROC (:49,85; macro one-vs-rest, exact).
+ * logits fp32 [N, K] (is_prob != 0: already probabilities), labels int32 [N]; N >= n_bins, n_bins <= 64.
+ * out[3] = {TACE, TACE as the reference computes it (uint8 fancy-index quirk of compute_bins, :173-184), AUROC}.
+ * work: 256-byte aligned, b200vit_tace_auroc_workspace_bytes(N, K) bytes. */
+size_t b200vit_tace_auroc_workspace_bytes(int32_t N, int32_t K);
+int b200vit_tace_auroc(const float* logits, int32_t is_prob, const int32_t* labels, int32_t N, int32_t K, float threshold, int32_t n_bins,
+                       void* work, float* out, void* stream);
 
 #ifdef __cplusplus
 }

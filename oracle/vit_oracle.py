@@ -449,8 +449,8 @@ def ema_decay_at(it: int, decay_init: float, decay: float, ema_start_at: int) ->
 
 
 def ema_update(ema: Dict[str, torch.Tensor], model: Dict[str, torch.Tensor], d: float) -> None:
-    """engine_for_cyclical.py:182-185 + timm ModelEmaV2._update: e.copy_(d*e + (1-d)*m) over the state_dict
-    (the int64 relative_position_index buffer round-trips unchanged)."""
+    """engine_for_cyclical.py:182-185 + timm ModelEmaV2._update: e.copy_(d*e + (1-d)*m) over the state_dict, integer buffers included
+    (int64 * python float -> fp32 arithmetic, truncated by copy_: relative_position_index entries can come back one lower)."""
     with torch.no_grad():
         for k in ema:
             ema[k].copy_(d * ema[k] + (1.0 - d) * model[k])
@@ -650,6 +650,62 @@ def accuracy_topk(logits: torch.Tensor, labels: torch.Tensor, topk=(1, 5)):
     return [float(correct[:k].reshape(-1).float().sum() * 100.0 / labels.shape[0]) for k in topk]
 
 
+def tace(probs: torch.Tensor, labels: torch.Tensor, threshold: float = 0.01, n_bins: int = 30, reference_indexing: bool = False) -> float:
+    """TACELoss.loss(probs, labels, logits=False) (uncertainty_evaluations.py:241-261): probabilities below `threshold` are zeroed, then per
+    class the n_bins ADAPTIVE bin edges are sorted_p[i * int(N / n_bins)] (+ 1.0) (compute_bin_boundaries, :119-132) and
+    sum_bins prop * |mean conf - mean acc| over bins (lo, hi] (compute_bins, :159-186), averaged over the classes.
+    reference_indexing=True: as for ece(), compute_bins indexes the numpy `accuracies` with a uint8 array (:173-184), i.e.
+    bin_acc = ((N - n_b) * acc[0] + n_b * acc[1]) / N — what the reference actually prints (golden in tests/golden/metrics.pt)."""
+    p = probs.detach().clone().float().numpy()
+    p[p < threshold] = 0
+    lab = labels.numpy()
+    n, k = p.shape
+    bin_n = int(n / n_bins)
+    total = 0.0
+    for i in range(k):
+        col = p[:, i]
+        srt = np.sort(col)
+        bounds = np.append(np.array([srt[j * bin_n] for j in range(n_bins)], dtype=np.float64), 1.0)
+        acc = (lab == i).astype("float")
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            in_bin = np.greater(col, np.float32(lo)) * np.less_equal(col, np.float32(hi))
+            prop = np.mean(in_bin)
+            if prop > 0:
+                nb = int(in_bin.sum())
+                bin_acc = ((n - nb) * acc[0] + nb * acc[1]) / n if reference_indexing else np.mean(acc[in_bin])
+                total += prop * np.abs(np.mean(col[in_bin]) - bin_acc)
+    return float(total / k)
+
+
+def auroc_macro_ovr(probs: torch.Tensor, labels: torch.Tensor) -> float:
+    """torchmetrics AUROC(task="multiclass", num_classes=K) as called at uncertainty_evaluations.py:49,85 (defaults: average="macro",
+    thresholds=None -> exact curve). torchmetrics is NOT in this image (requirements.txt lists it unpinned): PARITY UNPINNED against the
+    package, restated from its published algorithm — softmax if the input is not already in [0,1], one-vs-rest ROC per class, area by the
+    trapezoid rule (= Mann-Whitney U with half credit for ties), a class without positives or without negatives contributes 0, plain mean
+    over the K classes. tests check it against sklearn.metrics.roc_auc_score(multi_class="ovr") where every class is present."""
+    p = probs.double()
+    if not bool(((p >= 0) & (p <= 1)).all()):
+        p = torch.softmax(p, 1)
+    n, k = p.shape
+    out = []
+    for c in range(k):
+        pos = p[labels == c, c]
+        neg = p[labels != c, c]
+        if pos.numel() == 0 or neg.numel() == 0:
+            out.append(0.0)
+            continue
+        less = (neg[None, :] < pos[:, None]).double().sum()
+        tie = (neg[None, :] == pos[:, None]).double().sum()
+        out.append(float((less + 0.5 * tie) / (pos.numel() * neg.numel())))
+    return float(np.mean(out))
+
+
+def gaussian_sample(mean: torch.Tensor, cov: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    """The reparameterised draw the reference sketches (and leaves commented out) in DistVisionTransformer.forward
+    (modeling_finetune_dist.py:314-324: Normal(mean, sqrt(cov)).sample()) with the noise injected: mean + sqrt(max(cov, 0)) * eps."""
+    return mean + torch.sqrt(torch.clamp(cov, min=0.0)) * eps
+
+
 def mc_reduce(logits_snk: torch.Tensor, labels: torch.Tensor) -> Dict[str, object]:
     """evaluate_MC_dropout reduction (uncertainty_evaluations.py:77-85): mean of LOGITS over S, then metrics.
     entropy / variance / mutual information are extensions (no reference function: parity unpinned)."""
@@ -672,22 +728,35 @@ def mc_reduce(logits_snk: torch.Tensor, labels: torch.Tensor) -> Dict[str, objec
 # --------------------------------------------------------------------------------------------------------------
 def d2v_step(sd: Dict[str, torch.Tensor], ema: Dict[str, torch.Tensor], opt: Dict[str, Dict[str, torch.Tensor]], arch: Arch, x, mask,
              step: int, noise: Optional[Noise] = None, target_layers=(6, 7, 8, 9, 10, 11), lr=2e-3, wd=0.05, clip=3.0, ema_decay=0.9998,
-             l1_beta=2.0, return_grads: bool = False, lam: float = 1e-5):
-    """sd / ema: float state dicts (updated IN PLACE); opt: {'m': {...}, 'v': {...}}. Returns (loss, grad_norm[, grads])."""
+             l1_beta=2.0, return_grads: bool = False, lam: float = 1e-5, l2_loss: bool = False, target_kwargs: Optional[dict] = None,
+             var_w0: float = 0.0, var_margin0: float = 0.5, loss_scale: float = -1, update_ema: bool = True, info: Optional[dict] = None):
+    """sd / ema: float state dicts (updated IN PLACE); opt: {'m': {...}, 'v': {...}}. Returns (loss, grad_norm[, grads]).
+    target_kwargs: the build_targets switches (target_layer_norm_last, target_batch_norm, target_instance_norm, post_target_instance_norm,
+    post_target_layer_norm; default = the README recipe, post layer norm). var_w0 / var_margin0: the column-std hinge (:130-139);
+    loss_scale (:162-163); update_ema=False: the `start_lr_decay_at_step` cut-off branch (:182-185). info (dict) receives z0 / std_loss0."""
+    tk = dict(post_target_layer_norm=True) if target_kwargs is None else dict(target_kwargs)
     with torch.no_grad():
         t = cyclical_forward(ema, arch, x, None, return_all_tokens=True, layer_results="end")
     if arch.dist:
         t, tc = t
-        ctgt = build_targets(tc, list(target_layers), mask, post_target_layer_norm=True)      # engine_for_cyclical.py:74-86
-    tgt = build_targets(t, list(target_layers), mask, post_target_layer_norm=True)
+        # the cov targets only ever get the per-layer LayerNorm, the mean and the post LayerNorm: engine_for_cyclical.py:74-86
+        ctgt = build_targets(tc, list(target_layers), mask, target_layer_norm_last=tk.get("target_layer_norm_last", True),
+                             post_target_layer_norm=tk.get("post_target_layer_norm", False))
+    tgt = build_targets(t, list(target_layers), mask, **tk)
     names = [k for k, v in sd.items() if v.is_floating_point()]
     leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
     out = cyclical_forward(leaf, arch, x, mask, noise=noise)
     if arch.dist:
         out, cout = out
-    loss, _ = d2v_loss(out.float(), tgt, l1_beta)
+    loss, z0 = d2v_loss(out.float(), tgt, l1_beta, l2_loss)
+    std_loss0 = torch.sum(F.relu(var_margin0 - z0)) / z0.size(0) if var_w0 > 0 else 0      # :136-139
+    loss = loss + std_loss0 * var_w0
+    if info is not None:
+        info.update(z0=z0.detach(), std_loss0=float(std_loss0))
     if arch.dist:
         loss = loss + wasserstein_loss(out.float(), cout.float(), tgt, ctgt, lam)               # :152-158
+    if loss_scale != -1:
+        loss = loss * loss_scale                                                                  # :162-163
     loss.backward()
     grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(sd[k])) for k in names}
     total, coef = clip_grad_norm(list(grads.values()), clip)
@@ -696,7 +765,11 @@ def d2v_step(sd: Dict[str, torch.Tensor], ema: Dict[str, torch.Tensor], opt: Dic
             continue                      # torch.optim.AdamW skips parameters without a gradient (cov_qkv.weight, §A.2-1)
         decay = 0.0 if is_no_decay(k, sd[k].shape) else wd
         adamw_step(sd[k], grads[k] * coef, opt["m"][k], opt["v"][k], step, lr, decay)
-    ema_update({k: ema[k] for k in names}, sd, ema_decay)
+    if update_ema:
+        # over the WHOLE state dict, like ModelEmaV2._update: the int64 relative_position_index buffer goes through
+        # `d * e + (1 - d) * m` in fp32 and is truncated back to int64 by copy_ — for many decays (0.9, and about half of the values on the
+        # 0.999 -> 0.9998 anneal) some entries come back as k - 1, so the TEACHER's index table drifts. Pinned by tests/golden/tiny_*_loop.pt.
+        ema_update(ema, sd, ema_decay)
     if return_grads:
         return float(loss), float(total), grads
     return float(loss), float(total)
@@ -705,3 +778,40 @@ def d2v_step(sd: Dict[str, torch.Tensor], ema: Dict[str, torch.Tensor], opt: Dic
 def new_opt_state(sd):
     return {"m": {k: torch.zeros_like(v) for k, v in sd.items() if v.is_floating_point()},
             "v": {k: torch.zeros_like(v) for k, v in sd.items() if v.is_floating_point()}}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fine-tune criterion + one fine-tune step (engine_for_finetuning_dist.train_class_batch, :286-304; engine_for_finetuning.py:30-43)
+# --------------------------------------------------------------------------------------------------------------
+def soft_target_cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """timm SoftTargetCrossEntropy / LabelSmoothingCrossEntropy on already-soft targets (run_class_finetuning.py:617-624):
+    mean_b sum_k -t_bk log_softmax(z)_bk."""
+    return torch.sum(-targets * F.log_softmax(logits.float(), dim=-1), dim=-1).mean()
+
+
+def smoothed_targets(labels: torch.Tensor, num_classes: int, smoothing: float) -> torch.Tensor:
+    """LabelSmoothingCrossEntropy(smoothing) of timm 0.3.2 == soft-target CE with t = (1 - s) onehot + s / K."""
+    t = torch.full((labels.shape[0], num_classes), smoothing / num_classes)
+    return t.scatter_(1, labels.long().view(-1, 1), 1.0 - smoothing + smoothing / num_classes)
+
+
+def finetune_loss_and_grads(sd: Dict[str, torch.Tensor], arch: Arch, x, targets, pos=None, neg=None, noise: Optional[Noise] = None,
+                            lam_ft=1e-4, lam_pvn=1e-4):
+    """train_class_batch: anchor forward in train mode (injected noise); for the dual-stream model the positive / negative forwards run on a
+    deep copy in eval() mode (:293-296), i.e. deterministic and without a gradient path into the model. Returns (loss, logits, grads)."""
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    leaf = {k: (sd[k].detach().clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
+    out = finetune_forward(leaf, arch, x, noise)
+    if arch.dist:
+        fm, fc, logits = out
+    else:
+        logits = out
+    loss = soft_target_cross_entropy(logits, targets)
+    if arch.dist and pos is not None:
+        with torch.no_grad():
+            pm, pc, _ = finetune_forward(sd, arch, pos, None)
+            nm, nc, _ = finetune_forward(sd, arch, neg, None)
+        loss = loss + wasserstein_loss_finetune(fm, fc, pm, pc, nm, nc, lam_ft, lam_pvn)
+    loss.backward()
+    grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(sd[k])) for k in names}
+    return float(loss), logits.detach(), grads

@@ -163,6 +163,7 @@ def case_cyclical(name, arch: O.Arch, B, dpr, attn_drop, seed, target_layers, la
                 teacher_layers=[t.clone() for t in t_ref] if arch.embed_dim <= 128 else None,
                 targets=tgt_ref, outputs=out_ref.detach(), loss=float(loss_ref), total_loss=float(total_ref),
                 grads=grad_digest(grads_ref), lam=lam,
+                grads_full={k: (None if g is None else g.detach().clone()) for k, g in grads_ref.items()} if arch.embed_dim <= 128 else None,
                 state_checksum=float(sum(v.double().sum() for k, v in sd.items() if v.is_floating_point())))
     if arch.dist:
         gold.update(cov_outputs=cout_ref.detach(), cov_targets=ctgt_ref, wloss=float(wl_ref))
@@ -232,6 +233,8 @@ def case_metrics():
     probs = torch.softmax(zbar, 1)
     ece_ref = float(U.ECELoss().loss(probs, labels, logits=False))           # default logits=True path raises (§8c)
     nll_ref = float(U.NLL(zbar, labels))
+    tace_ref = float(U.TACELoss().loss(probs.clone(), labels, logits=False))    # TACELoss zeroes sub-threshold entries of its input in place
+    assert abs(O.tace(probs, labels, reference_indexing=True) - tace_ref) < 1e-9, (O.tace(probs, labels, reference_indexing=True), tace_ref)
     from timm.utils import accuracy
     a1, a5 = [float(v) for v in accuracy(zbar, labels, topk=(1, 5))]
     r = O.mc_reduce(logits, labels)
@@ -245,9 +248,18 @@ def case_metrics():
     assert abs(float(O.wasserstein_loss_finetune(*t, 1e-4, 1e-4)) - wlf) < 1e-9
     wdm = U.wasserstein_distance_matmul(t[0][None], t[1][None], t[2][None], t[3][None])
     assert rel_err(O.wasserstein_distance_matmul(t[0][None], t[1][None], t[2][None], t[3][None]), wdm) < 1e-6
+    # a second, larger TACE case (adaptive bins with many sub-threshold zeros: 40 classes, 300 samples)
+    g2 = torch.Generator().manual_seed(17)
+    z2 = torch.randn(300, 40, generator=g2) * 3.0
+    y2 = torch.randint(0, 40, (300,), generator=g2)
+    y2 = torch.where(torch.rand(300, generator=g2) < 0.5, z2.argmax(1), y2)
+    p2 = torch.softmax(z2, 1)
+    tace2_ref = float(U.TACELoss().loss(p2.clone(), y2, logits=False))
+    assert abs(O.tace(p2, y2, reference_indexing=True) - tace2_ref) < 1e-9
     torch.save(dict(logits=logits, labels=labels, ece_reference=ece_ref, ece=r["ece"], nll=nll_ref, acc1=a1, acc5=a5, w_inputs=t, wloss=wl,
-                    wloss_ft=wlf, wdm=wdm), os.path.join(GOLD, "metrics.pt"))
-    print(f"[metrics] ece={ece_ref:.6f} nll={nll_ref:.6f} acc1={a1:.2f} wl={wl:.3e} wlf={wlf:.3e}")
+                    wloss_ft=wlf, wdm=wdm, tace_reference=tace_ref, tace=O.tace(probs, labels), tace2_logits=z2, tace2_labels=y2,
+                    tace2_reference=tace2_ref, tace2=O.tace(p2, y2)), os.path.join(GOLD, "metrics.pt"))
+    print(f"[metrics] ece={ece_ref:.6f} nll={nll_ref:.6f} acc1={a1:.2f} wl={wl:.3e} wlf={wlf:.3e} tace={tace_ref:.6f} tace2={tace2_ref:.6f}")
 
 
 def case_index_and_masks():
@@ -339,6 +351,186 @@ def case_host_logic():
     print("[host_logic] parameter groups of 4 models + load_state_dict messages written")
 
 
+class _PassThroughScaler:
+    """Stands in for utils.NativeScalerWithGradNormCount (utils.py:364-390) on a CPU-only host, where torch.cuda.amp.GradScaler is disabled
+    and its state_dict() is empty: backward, clip_grad_norm_ (same call), optimizer.step()."""
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        loss.backward(create_graph=create_graph)
+        norm = torch.nn.utils.clip_grad_norm_(parameters, clip_grad)
+        optimizer.step()
+        return norm
+
+    def state_dict(self):
+        return {"scale": 1.0}
+
+
+PIN_TENSORS = ("cls_token", "mask_token", "patch_embed.proj.bias", "rel_pos_bias.relative_position_bias_table", "blocks.0.gamma_1",
+               "blocks.0.attn.q_bias", "blocks.0.attn.qkv.weight", "blocks.1.attn.proj.weight", "blocks.1.mlp.fc2.weight", "blocks.1.norm2.weight",
+               "norm.bias", "lm_head.weight", "lm_head.bias", "blocks.1.attn.cov_proj.weight", "blocks.0.attn.cov_q_bias", "cov_lm_head.weight",
+               "blocks.0.attn.cov_qkv.weight", "cov_patch_embed.proj.bias")
+
+
+def case_train_loop(name, arch: O.Arch, B, dpr, attn_drop, seed, target_layers, steps=2, **loop_kw):
+    """Runs the reference's OWN engine_for_cyclical.train_one_epoch (:24-227) for `steps` steps on CPU (stub loader, torch.optim.AdamW over
+    optim_factory.get_parameter_groups, the shim's ModelEmaV2, a pass-through loss scaler) and pins oracle.d2v_step to it end to end:
+    per-step loss, final gradient norm, updated weights, EMA teacher."""
+    import contextlib
+    import io
+    import engine_for_cyclical
+    import optim_factory
+    from timm.utils import ModelEmaV2
+    torch.manual_seed(seed)
+    sd = O.make_state(arch, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    P = arch.num_patches
+    batches, noises = [], []
+    for s_ in range(steps):
+        x = torch.randn(B, 3, arch.img_size, arch.img_size, generator=g)
+        mask = torch.zeros(B, P, dtype=torch.int64)
+        for b in range(B):
+            mask[b, torch.randperm(P, generator=g)[: max(1, int(P * 0.6) - b - s_)]] = 1
+        batches.append((x, mask.reshape(B, arch.grid, arch.grid)))
+        noises.append(make_noise(arch, B, dpr, attn_drop, seed + 10 + s_))
+    ref = build_reference(arch, dpr, attn_drop)
+    load_state(ref, sd)
+    ema = ModelEmaV2(ref, 0.99)
+    lr, wd, clip = 1e-3, 0.05, 3.0
+    with contextlib.redirect_stdout(io.StringIO()):
+        groups = optim_factory.get_parameter_groups(ref, wd, ref.no_weight_decay())
+    opt = torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.999), eps=1e-8)
+    lr_sched = [lr * (0.5 + 0.5 * i) for i in range(steps)]
+    wd_sched = [wd * (1.0 + 0.1 * i) for i in range(steps)]
+    inj = Injector(arch, noises[0])
+    losses = []
+
+    class Loader:
+        def __iter__(self_inner):
+            for s_ in range(steps):
+                inj.noise = noises[s_]
+                inj.reset()
+                yield (batches[s_], None)
+
+        def __len__(self_inner):
+            return steps
+
+    kw = dict(ema_start_at=1, decay_init=0.9, decay=0.99, target_layers=target_layers, l1_beta=2.0, post_target_layer_norm=True,
+              stochastic=arch.dist, lambda_pretraining=1e-2)
+    kw.update(loop_kw)
+    real_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda *a, **k: None            # :186 on a CPU-only host
+    # record every step's loss: MetricLogger.update(loss=...) is the only place the loop exposes it
+    import utils as ref_utils
+    real_update = ref_utils.MetricLogger.update
+
+    def spy(self_inner, **kwargs):
+        if "loss" in kwargs:
+            losses.append(float(kwargs["loss"]))
+        return real_update(self_inner, **kwargs)
+    ref_utils.MetricLogger.update = spy
+    try:
+        with inj, contextlib.redirect_stdout(io.StringIO()), __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            stats = engine_for_cyclical.train_one_epoch(ref, ema, data_loader=Loader(), optimizer=opt, device=torch.device("cpu"), epoch=0,
+                                                        loss_scaler=_PassThroughScaler(), max_norm=clip, start_steps=0,
+                                                        lr_schedule_values=lr_sched, wd_schedule_values=wd_sched, **kw)
+    finally:
+        torch.cuda.synchronize = real_sync
+        ref_utils.MetricLogger.update = real_update
+    # ---- the oracle's loop on the same inputs
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    ema_o = {k: v.clone() for k, v in sd.items()}
+    opt_o = O.new_opt_state(sd_o)
+    tk = {k: kw[k] for k in ("target_layer_norm_last", "target_batch_norm", "target_instance_norm", "post_target_instance_norm",
+                             "post_target_layer_norm") if k in kw}
+    cur_decay = kw["decay"]
+    losses_o, gns = [], []
+    for it in range(steps):
+        if it < kw["ema_start_at"]:
+            cur_decay = kw["decay_init"] + it * (kw["decay"] - kw["decay_init"]) / kw["ema_start_at"]
+        sl = kw.get("start_lr_decay_at_step", -1)
+        upd = cur_decay != 1 and (sl == -1 or it <= sl)
+        info = {}
+        lo, gn_ = O.d2v_step(sd_o, ema_o, opt_o, arch, batches[it][0], batches[it][1], it + 1, noises[it], target_layers, lr=lr_sched[it],
+                            wd=wd_sched[it], clip=clip, ema_decay=cur_decay, l1_beta=kw["l1_beta"], lam=kw["lambda_pretraining"],
+                            l2_loss=kw.get("l2_loss", False), target_kwargs=tk, var_w0=kw.get("var_w0", 0), var_margin0=kw.get("var_margin0", 0.5),
+                            loss_scale=kw.get("loss_scale", -1), update_ema=upd, info=info)
+        if not upd:
+            cur_decay = 0
+        losses_o.append(lo)
+        gns.append(gn_)
+    gn = float(np.mean(gns))                       # the loop returns MetricLogger's global average of the per-step norms
+    ref_sd, ema_sd = ref.state_dict(), ema.module.state_dict()
+    errs = dict(loss=max(abs(a - b) / abs(b) for a, b in zip(losses_o, losses)),
+                gnorm=abs(gn - float(stats["grad_norm"])) / float(stats["grad_norm"]),
+                weights=max(rel_err(sd_o[k], ref_sd[k]) for k in sd_o if sd_o[k].is_floating_point()),
+                ema=max(rel_err(ema_o[k], ema_sd[k]) for k in ema_o if ema_o[k].is_floating_point()),
+                ema_index=float((ema_o["rel_pos_bias.relative_position_index"] != ema_sd["rel_pos_bias.relative_position_index"]).sum()))
+    print(f"[{name}] oracle loop vs engine_for_cyclical.train_one_epoch: {errs}   losses {losses}")
+    assert max(errs.values()) < 2e-5, errs
+    keep = [k for k in PIN_TENSORS if k in ref_sd]
+    torch.save(dict(arch=arch.__dict__.copy(), B=B, dpr=dpr, attn_drop=attn_drop, seed=seed, target_layers=list(target_layers), steps=steps,
+                    batches=batches, noises=[dict(keep=n.drop_path_keep, prob=n.drop_path_prob, attn_keep=[k.to(torch.uint8) for k in n.attn_keep],
+                                                  attn_drop=attn_drop) for n in noises],
+                    lr=lr_sched, wd=wd_sched, clip=clip, loop_kw=kw, losses=losses, grad_norm=float(stats["grad_norm"]),
+                    cur_decay=float(stats["cur_decay"]), loss_var0=float(stats.get("loss_var0", 0.0)),
+                    weights={k: ref_sd[k].clone() for k in keep}, ema={k: ema_sd[k].clone() for k in keep},
+                    ema_index=ema_sd["rel_pos_bias.relative_position_index"].to(torch.int16), grad_norms=gns,
+                    weight_norms={k: float(v.double().norm()) for k, v in ref_sd.items() if v.is_floating_point()},
+                    ema_norms={k: float(v.double().norm()) for k, v in ema_sd.items() if v.is_floating_point()}),
+               os.path.join(GOLD, name + ".pt"))
+
+
+def case_train_class_batch(name, arch: O.Arch, B, dpr, seed):
+    """engine_for_finetuning_dist.train_class_batch (:286-304) of the REAL reference on CPU: CE(SoftTarget) + WassersteinLossFineTuning of the
+    anchor (train mode, injected drop-path) against positive / negative forwards of an eval-mode deep copy; loss, logits and gradients."""
+    import ast
+    import types
+    import distloss
+    # engine_for_finetuning_dist.py imports the whole dataset stack at module level (torchvision, tin, cifar_semi.x_u_split, ...), most of
+    # it absent here: compile ONLY the unmodified `train_class_batch` function out of the reference file (:286-304)
+    src_path = os.path.join(ref_shim.REFERENCE_ROOT, "engine_for_finetuning_dist.py")
+    tree = ast.parse(open(src_path).read(), src_path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train_class_batch"]
+    assert len(fn) == 1
+    EFD = types.ModuleType("engine_for_finetuning_dist__train_class_batch")
+    EFD.__dict__.update(torch=torch, nn=nn, F=F)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), src_path, "exec"), EFD.__dict__)
+    sd = O.make_state(arch, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x, xp, xn = (torch.randn(B, 3, arch.img_size, arch.img_size, generator=g) for _ in range(3))
+    labels = torch.randint(0, arch.num_classes, (B,), generator=g)
+    targets = O.mixup_target(labels, arch.num_classes, lam=0.7, smoothing=0.1)
+    noise = make_noise(arch, B, dpr, 0.0, seed + 2)
+    ref = build_reference(arch, dpr, 0.0)
+    load_state(ref, sd)
+    ref.train()
+
+    class Wrap(nn.Module):                      # train_class_batch deep-copies `model.module` (the DDP wrapper's attribute)
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+        def forward(self, *a, **k):
+            return self.module(*a, **k)
+
+    crit = lambda out, tgt: torch.sum(-tgt * F.log_softmax(out, dim=-1), dim=-1).mean()       # timm SoftTargetCrossEntropy
+    lam_ft, lam_pvn = 1e-1, 1e-1        # larger than the README's 1e-4 so that the W-loss gradients matter in the comparison
+    with Injector(arch, noise):
+        loss, outputs = EFD.train_class_batch(Wrap(ref), x, xp, xn, targets, crit, distloss.WassersteinLossFineTuning(lam_ft, lam_pvn))
+    loss.backward()
+    grads_ref = {k: p.grad for k, p in ref.named_parameters()}
+    lo, logits_o, grads_o = O.finetune_loss_and_grads(sd, arch, x, targets, xp, xn, noise, lam_ft, lam_pvn)
+    worst = max(rel_err(grads_o[k], gr) for k, gr in grads_ref.items() if gr is not None)
+    errs = dict(loss=abs(lo - float(loss)) / abs(float(loss)), logits=rel_err(logits_o, outputs), grad_worst=worst)
+    print(f"[{name}] oracle vs engine_for_finetuning_dist.train_class_batch: {errs}")
+    assert max(errs.values()) < 5e-5, errs
+    torch.save(dict(arch=arch.__dict__.copy(), B=B, dpr=dpr, seed=seed, x=x, pos=xp, neg=xn, labels=labels, targets=targets,
+                    noise=dict(keep=noise.drop_path_keep, prob=noise.drop_path_prob), lam_ft=lam_ft, lam_pvn=lam_pvn, loss=float(loss),
+                    logits=outputs.detach(), grads=grad_digest(grads_ref),
+                    grads_full={k: (None if g_ is None else g_.detach().clone()) for k, g_ in grads_ref.items()}), os.path.join(GOLD, name + ".pt"))
+
+
 def main():
     assert ref_shim.reference_available(), "needs /root/reference"
     ref_shim.install()
@@ -351,6 +543,14 @@ def main():
     case_host_logic()
     case_cyclical("tiny_det_cyclical", tiny(kind="cyclical"), B=3, dpr=0.2, attn_drop=0.1, seed=11, target_layers=[0, 1])
     case_cyclical("tiny_dist_cyclical", tiny(kind="cyclical", dist=True), B=3, dpr=0.2, attn_drop=0.1, seed=12, target_layers=[0, 1])
+    case_train_loop("tiny_det_loop", tiny(kind="cyclical"), B=3, dpr=0.2, attn_drop=0.1, seed=21, target_layers=[0, 1])
+    case_train_loop("tiny_dist_loop", tiny(kind="cyclical", dist=True), B=3, dpr=0.2, attn_drop=0.1, seed=22, target_layers=[0, 1])
+    case_train_loop("tiny_det_loop_variants", tiny(kind="cyclical"), B=3, dpr=0.2, attn_drop=0.1, seed=23, target_layers=[0, 1], steps=3,
+                    target_instance_norm=True, post_target_instance_norm=True, post_target_layer_norm=False, var_w0=0.5, var_margin0=2.0,
+                    loss_scale=1.5, start_lr_decay_at_step=1)
+    case_train_loop("tiny_det_loop_bn", tiny(kind="cyclical"), B=3, dpr=0.0, attn_drop=0.0, seed=24, target_layers=[0, 1], steps=2,
+                    target_batch_norm=True, target_layer_norm_last=False, post_target_layer_norm=True, l2_loss=True)
+    case_train_class_batch("tiny_dist_train_class_batch", tiny(kind="finetune", dist=True), B=6, dpr=0.2, seed=28)   # seeds 25/26 give the 0/0 = NaN margin term of the reference
     case_finetune("tiny_det_finetune", tiny(kind="finetune"), B=3, seed=13)
     case_finetune("tiny_dist_finetune", tiny(kind="finetune", dist=True), B=3, seed=14)
     if "--fast" not in sys.argv:

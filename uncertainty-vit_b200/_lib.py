@@ -29,6 +29,13 @@ class GemmDesc(C.Structure):
                 ("alpha", f32), ("split_k", i32), ("max_ctas", i32), ("debug_flags", i32), ("colsum", vp)]
 
 
+class D2VDesc(C.Structure):
+    _fields_ = [("layers", C.POINTER(vp)), ("num_layers", i32), ("ld_layer", i64), ("row_index", vp), ("y", vp), ("R", i32), ("C", i32),
+                ("ln_each", i32), ("ln_post", i32), ("beta", f32), ("l2_loss", i32), ("grad_scale", f32), ("targets", vp), ("dy_bf16", vp),
+                ("dy_f32", vp), ("row_loss", vp), ("loss_out", vp), ("n_valid_dev", vp), ("affine", C.POINTER(vp)), ("rows_per_sample", i32),
+                ("compact_tokens", i32), ("col_hinge", vp), ("loss_add", vp), ("loss_add_weight", f32), ("loss_mult", f32)]
+
+
 _PROTOS = {
     "b200vit_last_error": (C.c_char_p, []),
     "b200vit_abi_version": (i32, []),
@@ -56,6 +63,18 @@ _PROTOS = {
     "b200vit_meanpool_tokens": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_meanpool_tokens_bwd": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "b200vit_d2v_target_loss_ex": (i32, [C.POINTER(D2VDesc), vp]),
+    "b200vit_channel_stats": (i32, [C.POINTER(vp), i32, i64, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp]),
+    "b200vit_column_std_workspace_bytes": (C.c_size_t, [i32]),
+    "b200vit_column_std": (i32, [vp, i32, i32, vp, f32, f32, f32, vp, vp, vp, vp, vp]),
+    "b200vit_scalar_fma": (i32, [vp, vp, f32, vp, f32, vp]),
+    "b200vit_mask_dropout": (i32, [vp, vp, vp, i32, i32, i32, f32, u64, u64, vp, vp]),
+    "b200vit_gaussian_sample": (i32, [vp, vp, vp, i64, u64, u32, vp, vp, vp, vp]),
+    "b200vit_gaussian_sample_bwd": (i32, [vp, vp, vp, i64, vp, vp, vp]),
+    "b200vit_finetune_loss_workspace_floats": (C.c_size_t, [i32]),
+    "b200vit_finetune_loss": (i32, [vp, i64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, vp, vp, i64, vp, i64, i32, vp, vp, vp, vp]),
+    "b200vit_tace_auroc_workspace_bytes": (C.c_size_t, [i32, i32]),
+    "b200vit_tace_auroc": (i32, [vp, i32, vp, i32, i32, f32, i32, vp, vp, vp]),
     "b200vit_ema_update": (i32, [vp, vp, i64, C.c_double, vp, vp]),
     "b200vit_sumsq": (i32, [vp, i64, vp, vp]),
     "b200vit_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, C.c_double, vp, vp]),
@@ -83,7 +102,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 3:
+        if l.b200vit_abi_version() != 4:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

@@ -8,9 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200vit.so")
-SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "wattention.cu", "rowwise.cu", "d2v.cu", "mc_metrics.cu", "maskgen.cu", "mixup.cu", "imgnorm.cu"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "--use_fast_math=false" if False else "-Xptxas", "-v" if os.environ.get("B200VIT_PTXAS_V") else "-O3"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "wattention.cu", "rowwise.cu", "d2v.cu", "mc_metrics.cu", "maskgen.cu", "mixup.cu", "imgnorm.cu", "d2v_extras.cu", "calibration.cu", "ft_loss.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas",
+              "-v" if os.environ.get("B200VIT_PTXAS_V") else "-O3"]
 NVCC_FLAGS += os.environ.get("B200VIT_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DB200VIT_KV_TRACE for tools/micro/kv_trace.py
 
 

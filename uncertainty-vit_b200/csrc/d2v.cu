@@ -15,6 +15,9 @@ constexpr int MAX_LAYERS = 24;
 struct LayerPtrs {
   const float* p[MAX_LAYERS];
 };
+struct AffinePtrs {
+  const float2* p[MAX_LAYERS];   // per layer: [samples, C] {shift, scale} of the instance / batch norm (b200vit_channel_stats), or all NULL
+};
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4_stream(const float* p) {
@@ -48,7 +51,9 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
                                                               int R, int C, int ln_each, int ln_post, float beta, int l2_loss,
                                                               float grad_scale, float* __restrict__ targets,
                                                               bf16* __restrict__ dy_bf16, float* __restrict__ dy_f32,
-                                                              float* __restrict__ row_loss, const int* __restrict__ n_valid) {
+                                                              float* __restrict__ row_loss, const int* __restrict__ n_valid,
+                                                              AffinePtrs aff, int rows_per_sample, int compact_tokens,
+                                                              const float2* __restrict__ col_hinge) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -68,7 +73,10 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
     }
     grad_scale *= (float)R / (float)rv;
   }
-  const long long src = row_index[r];
+  long long src = row_index != nullptr ? row_index[r] : r;
+  // compact_tokens = T: the layers are compact [B, T-1, C] patch-row tensors (no cls row) while row_index holds residual-stream rows b*T+1+p
+  if (compact_tokens > 0) src = src - src / compact_tokens - 1;
+  const long long sample = rows_per_sample > 0 ? src / rows_per_sample : 0;
   float4 acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -77,6 +85,17 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = ld4_stream(row + (i * 32 + lane) * 4);
+    if (aff.p[l] != nullptr) {
+      // F.batch_norm / F.instance_norm over the patch tokens of each channel (engine_for_cyclical.py:94-104,112-115) as one affine map
+      const float2* a = aff.p[l] + sample * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 a01 = *reinterpret_cast<const float4*>(a + (i * 32 + lane) * 4);
+        const float4 a23 = *reinterpret_cast<const float4*>(a + (i * 32 + lane) * 4 + 2);
+        v[i].x = (v[i].x - a01.x) * a01.y; v[i].y = (v[i].y - a01.z) * a01.w;
+        v[i].z = (v[i].z - a23.x) * a23.y; v[i].w = (v[i].w - a23.z) * a23.w;
+      }
+    }
     if (ln_each) ln_inplace<NV>(v, C, 1e-5f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
@@ -107,6 +126,14 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
       }
       g[j] *= grad_scale;
     }
+    if (col_hinge != nullptr) {
+      // var_w0 hinge on the column standard deviation of the student output (engine_for_cyclical.py:130-137):
+      // d/dy[r,c] = k_c * (y[r,c] - mean_c), {mean_c, k_c} prepared by b200vit_column_std
+      const float4 h01 = *reinterpret_cast<const float4*>(col_hinge + c);
+      const float4 h23 = *reinterpret_cast<const float4*>(col_hinge + c + 2);
+      g[0] += h01.y * (yv.x - h01.x); g[1] += h01.w * (yv.y - h01.z);
+      g[2] += h23.y * (yv.z - h23.x); g[3] += h23.w * (yv.w - h23.z);
+    }
     if (dy_bf16 != nullptr) {
       uint2 u;
       u.x = pack_bf16x2(g[0], g[1]);
@@ -121,7 +148,8 @@ __global__ void __launch_bounds__(256) d2v_target_loss_kernel(LayerPtrs layers, 
 
 // deterministic single-CTA sum: out[0] = scale * sum(v[0..n)); with n_valid, scale is rescaled by n / *n_valid (mean over the valid rows)
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out,
-                                                          const int* __restrict__ n_valid) {
+                                                          const int* __restrict__ n_valid, const float* __restrict__ add_term, float add_weight,
+                                                          float mult) {
   __shared__ double sh[32];
   if (n_valid != nullptr) scale *= (float)n / (float)*n_valid;
   double s = 0.0;
@@ -134,7 +162,11 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
     s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) out[0] = (float)(s * (double)scale);
+    if (threadIdx.x == 0) {
+      float r = (float)(s * (double)scale);
+      if (add_term != nullptr) r += add_weight * add_term[0];
+      out[0] = r * mult;
+    }
   }
 }
 
@@ -369,31 +401,64 @@ __global__ void __launch_bounds__(256) wloss_bwd_kernel(const float* __restrict_
 
 #define STREAM static_cast<cudaStream_t>(stream)
 
-extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
-                                       const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
-                                       float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
-                                       const int32_t* n_valid_dev, void* stream) {
-  B200_CHECK_ARG(layers_host != nullptr && num_layers > 0 && num_layers <= MAX_LAYERS, "d2v_target_loss: 1..%d layers", MAX_LAYERS);
-  B200_CHECK_ARG(row_index != nullptr && C % 128 == 0 && C <= 128 * MAXV, "d2v_target_loss: C=%d must be a multiple of 128, <= %d", C, 128 * MAXV);
-  B200_CHECK_ARG(loss_out == nullptr || (row_loss != nullptr && y != nullptr), "d2v_target_loss: loss_out needs y and a row_loss workspace of R floats");
+extern "C" int b200vit_d2v_target_loss_ex(const b200vit_d2v_desc* d, void* stream) {
+  B200_CHECK_ARG(d != nullptr, "d2v_target_loss: null descriptor");
+  const int R = d->R, C = d->C, num_layers = d->num_layers;
+  B200_CHECK_ARG(d->layers != nullptr && num_layers > 0 && num_layers <= MAX_LAYERS, "d2v_target_loss: 1..%d layers", MAX_LAYERS);
+  B200_CHECK_ARG(C % 128 == 0 && C <= 128 * MAXV, "d2v_target_loss: C=%d must be a multiple of 128, <= %d", C, 128 * MAXV);
+  B200_CHECK_ARG(d->loss_out == nullptr || (d->row_loss != nullptr && d->y != nullptr), "d2v_target_loss: loss_out needs y and a row_loss workspace of R floats");
+  B200_CHECK_ARG(d->affine == nullptr || d->rows_per_sample > 0, "d2v_target_loss: channel affine maps need rows_per_sample");
+  B200_CHECK_ARG(d->col_hinge == nullptr || d->y != nullptr, "d2v_target_loss: the column-std hinge needs y");
   if (R == 0) return 0;
+  B200_CHECK_ARG(R > 0, "d2v_target_loss: negative row count");
   LayerPtrs lp;
+  AffinePtrs ap;
+  for (int i = 0; i < MAX_LAYERS; ++i) ap.p[i] = nullptr;
   for (int i = 0; i < num_layers; ++i) {
-    B200_CHECK_ARG(layers_host[i] != nullptr, "d2v_target_loss: layer %d is null", i);
-    lp.p[i] = layers_host[i];
+    B200_CHECK_ARG(d->layers[i] != nullptr, "d2v_target_loss: layer %d is null", i);
+    lp.p[i] = d->layers[i];
+    if (d->affine != nullptr) ap.p[i] = reinterpret_cast<const float2*>(d->affine[i]);
   }
   const int grid = (R + 7) / 8;
-#define TL(NV) d2v_target_loss_kernel<NV><<<grid, 256, 0, STREAM>>>(lp, num_layers, ld_layer, row_index, y, R, C, ln_each, ln_post, beta, l2_loss, grad_scale, targets, static_cast<bf16*>(dy_bf16), dy_f32, row_loss, n_valid_dev)
+#define TL(NV)                                                                                                                        \
+  d2v_target_loss_kernel<NV><<<grid, 256, 0, STREAM>>>(lp, num_layers, d->ld_layer, d->row_index, d->y, R, C, d->ln_each, d->ln_post, \
+                                                       d->beta, d->l2_loss, d->grad_scale, d->targets, static_cast<bf16*>(d->dy_bf16), \
+                                                       d->dy_f32, d->row_loss, d->n_valid_dev, ap, d->rows_per_sample, d->compact_tokens, \
+                                                       reinterpret_cast<const float2*>(d->col_hinge))
   switch (C / 128) {
     case 1: TL(1); break; case 2: TL(2); break; case 3: TL(3); break; case 4: TL(4); break;
     case 5: TL(5); break; case 6: TL(6); break; case 7: TL(7); break; default: TL(8); break;
   }
 #undef TL
   B200_CHECK_LAUNCH("d2v_target_loss");
-  if (loss_out != nullptr) {
-    reduce_sum_kernel<<<1, 1024, 0, STREAM>>>(row_loss, R, 1.0f / ((float)R * (float)C), loss_out, n_valid_dev);
+  if (d->loss_out != nullptr) {
+    reduce_sum_kernel<<<1, 1024, 0, STREAM>>>(d->row_loss, R, 1.0f / ((float)R * (float)C), d->loss_out, d->n_valid_dev, d->loss_add,
+                                              d->loss_add_weight, d->loss_mult);
     B200_CHECK_LAUNCH("d2v_loss_reduce");
   }
+  return 0;
+}
+
+extern "C" int b200vit_d2v_target_loss(const float* const* layers_host, int32_t num_layers, int64_t ld_layer, const int32_t* row_index,
+                                       const float* y, int32_t R, int32_t C, int32_t ln_each, int32_t ln_post, float beta, int32_t l2_loss,
+                                       float grad_scale, float* targets, void* dy_bf16, float* dy_f32, float* row_loss, float* loss_out,
+                                       const int32_t* n_valid_dev, void* stream) {
+  B200_CHECK_ARG(row_index != nullptr, "d2v_target_loss: null row_index");
+  b200vit_d2v_desc d = {};
+  d.layers = layers_host; d.num_layers = num_layers; d.ld_layer = ld_layer; d.row_index = row_index; d.y = y; d.R = R; d.C = C;
+  d.ln_each = ln_each; d.ln_post = ln_post; d.beta = beta; d.l2_loss = l2_loss; d.grad_scale = grad_scale; d.targets = targets;
+  d.dy_bf16 = dy_bf16; d.dy_f32 = dy_f32; d.row_loss = row_loss; d.loss_out = loss_out; d.n_valid_dev = n_valid_dev; d.loss_mult = 1.0f;
+  return b200vit_d2v_target_loss_ex(&d, stream);
+}
+
+// out = wa * *a + wb * *b  (device scalars; b may be NULL): total loss of the --stochastic step, (loss_cyc + loss_stochastic) * loss_scale
+__global__ void scalar_fma_kernel(float* out, const float* a, float wa, const float* b, float wb) {
+  out[0] = wa * a[0] + (b != nullptr ? wb * b[0] : 0.f);
+}
+extern "C" int b200vit_scalar_fma(float* out, const float* a, float wa, const float* b, float wb, void* stream) {
+  B200_CHECK_ARG(out != nullptr && a != nullptr, "scalar_fma: null pointer");
+  scalar_fma_kernel<<<1, 1, 0, STREAM>>>(out, a, wa, b, wb);
+  B200_CHECK_LAUNCH("scalar_fma");
   return 0;
 }
 

@@ -139,6 +139,39 @@ __global__ void __launch_bounds__(ROWS_THREADS) mask_rows_kernel(const uint8_t* 
   if (threadIdx.x == 0) count[B] = bad_sh ? -1 : base_sh;
 }
 
+// mask_dropout_prob of the pre-training loop (engine_for_cyclical.py:62-66): mask &= bernoulli(1 - p), per patch. One CTA per image;
+// keep_in (uint8, optional) injects the Bernoulli draws, otherwise Philox4x32-10 keyed on (seed; image, patch).
+__global__ void __launch_bounds__(256) mask_dropout_kernel(uint8_t* __restrict__ mask, int32_t* __restrict__ count, int np, float p_drop,
+                                                           uint32_t k0, uint32_t k1, unsigned long long first_image,
+                                                           const uint8_t* __restrict__ keep_in) {
+  __shared__ int sh[8];
+  const int b = blockIdx.x;
+  int n = 0;
+  for (int q = threadIdx.x; q < np; q += blockDim.x) {
+    const size_t i = (size_t)b * np + q;
+    bool keep;
+    if (keep_in != nullptr) {
+      keep = keep_in[i] != 0;
+    } else {
+      const unsigned long long img = first_image + (unsigned long long)b;
+      const Philox4 r = philox4x32_10((uint32_t)q, 0x3c6ef372u, (uint32_t)img, (uint32_t)(img >> 32), k0, k1);
+      keep = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p_drop;       // bernoulli(1 - p)
+    }
+    const uint8_t m = (mask[i] != 0 && keep) ? 1 : 0;
+    mask[i] = m;
+    n += m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    count[b] = t;
+  }
+}
+
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
@@ -163,6 +196,18 @@ extern "C" int b200vit_block_masks(uint8_t* mask, int32_t* count, int32_t* rows,
   block_masks_kernel<<<(B + 31) / 32, 32, 0, STREAM>>>(p, mask, count);
   B200_CHECK_LAUNCH("block_masks");
   mask_rows_kernel<<<1, ROWS_THREADS, 0, STREAM>>>(mask, count, B, height * width, tokens, rows);
+  B200_CHECK_LAUNCH("mask_rows");
+  return 0;
+}
+
+extern "C" int b200vit_mask_dropout(uint8_t* mask, int32_t* count, int32_t* rows, int32_t B, int32_t num_patches, int32_t tokens, float p_drop,
+                                    uint64_t seed, uint64_t first_image, const uint8_t* keep_in, void* stream) {
+  B200_CHECK_ARG(mask != nullptr && count != nullptr && B > 0 && num_patches > 0, "mask_dropout: null pointer or empty batch");
+  B200_CHECK_ARG(tokens >= num_patches + 1, "mask_dropout: tokens %d < patches + cls", tokens);
+  B200_CHECK_ARG(p_drop >= 0.f && p_drop <= 1.f, "mask_dropout: p_drop %f outside [0, 1]", (double)p_drop);
+  mask_dropout_kernel<<<B, 256, 0, STREAM>>>(mask, count, num_patches, p_drop, (uint32_t)seed, (uint32_t)(seed >> 32), first_image, keep_in);
+  B200_CHECK_LAUNCH("mask_dropout");
+  mask_rows_kernel<<<1, ROWS_THREADS, 0, STREAM>>>(mask, count, B, num_patches, tokens, rows);
   B200_CHECK_LAUNCH("mask_rows");
   return 0;
 }

@@ -116,12 +116,14 @@ class DistVisionTransformerForCyclicalTraining(_DistBase):
         self.init_std = init_std
         self.lm_head = nn.Linear(embed_dim, embed_dim)
         self.cov_lm_head = nn.Linear(embed_dim, embed_dim)
-        tn = lambda t: _trunc_normal_(t, std=init_std, a=-init_std, b=init_std)
-        tn(self.cls_token)
-        tn(self.cov_cls_token)                      # mask tokens stay zero (modeling_cyclical_dist.py:37-38 vs 66-67)
+        # modeling_cyclical_dist.py:65-71,84-93: timm trunc_normal_(std=.02) with its default ABSOLUTE bounds +-2 (effectively untruncated,
+        # unlike the deterministic cyclical model's +-1 sigma), applied to nn.Linear / LayerNorm only: both patch-embedding convolutions
+        # keep nn.Conv2d's default init; mask tokens stay zero (:37-38)
+        _trunc_normal_(self.cls_token, std=0.02)
+        _trunc_normal_(self.cov_cls_token, std=0.02)
         for m in self.modules():
-            if isinstance(m, (nn.Linear, nn.Conv2d)):
-                tn(m.weight)
+            if isinstance(m, nn.Linear):
+                _trunc_normal_(m.weight, std=0.02)
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
             elif isinstance(m, nn.LayerNorm):

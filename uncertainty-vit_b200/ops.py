@@ -8,7 +8,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (EPI_BF16, EPI_DGELU, EPI_ELU1, EPI_F32, EPI_F32_ATOMIC, EPI_GELU, EPI_RESIDUAL, GemmDesc, check)
+from ._lib import (EPI_BF16, EPI_DGELU, EPI_ELU1, EPI_F32, EPI_F32_ATOMIC, EPI_GELU, EPI_RESIDUAL, GemmDesc)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 GEMM_TIMING = None  # bench.py sets this to a list to collect (start_event, end_event, algorithmic_flops) per GEMM launch
@@ -19,16 +19,39 @@ def _count(n: int = 1) -> None:
     LAUNCHES += n
 
 
+_LAST_DEV = None   # device of the most recent tensor argument: kernels are enqueued on THAT device's current stream
+
+
 def _p(t: Optional[torch.Tensor]):
+    global _LAST_DEV
     if t is None:
         return None
     if not t.is_cuda:
         raise _lib.B200VitError("libb200vit ops need CUDA tensors (no CPU fallback)")
+    _LAST_DEV = t.device
     return t.data_ptr()
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Current stream of the device the call's tensors live on (not of torch's current device: an engine on cuda:1 must not launch on
+    cuda:0's stream). Every wrapper evaluates its tensor arguments (_p) before this."""
+    global _RESTORE_DEV
+    dev = _LAST_DEV
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        _RESTORE_DEV = torch.cuda.current_device()
+        torch.cuda.set_device(dev)          # the launch itself needs the tensors' device current; check() switches back
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+_RESTORE_DEV = None
+
+
+def check(rc: int, what: str = "") -> None:
+    global _RESTORE_DEV
+    if _RESTORE_DEV is not None:
+        torch.cuda.set_device(_RESTORE_DEV)
+        _RESTORE_DEV = None
+    _lib.check(rc, what)
 
 
 def sm_count() -> int:
@@ -318,6 +341,127 @@ def d2v_target_loss(layers: Sequence[torch.Tensor], ld_layer, row_index, y, R, C
                                              int(l2_loss), grad_scale, _p(targets), _p(dy_bf16), _p(dy_f32), _p(row_loss), _p(loss_out),
                                              _p(n_valid), _stream()), "d2v_target_loss")
     _count(2 if loss_out is not None else 1)
+
+
+def d2v_target_loss_ex(layers: Sequence[torch.Tensor], ld_layer, row_index, y, R, C_, ln_each=True, ln_post=True, beta=2.0, l2_loss=False,
+                       grad_scale=1.0, targets=None, dy_bf16=None, dy_f32=None, row_loss=None, loss_out=None, n_valid=None, affine=None,
+                       rows_per_sample=0, compact_tokens=0, col_hinge=None, loss_add=None, loss_add_weight=0.0, loss_mult=1.0):
+    """b200vit_d2v_target_loss_ex: the target builder + loss with the optional instance / batch-norm maps (`affine`: one float2 [samples, C]
+    tensor per layer from channel_stats), compact layers, the var_w0 hinge and the loss_scale multiplier (see include/b200vit.h)."""
+    d = _lib.D2VDesc()
+    arr = (C.c_void_p * len(layers))(*[_p(t) for t in layers])
+    d.layers, d.num_layers, d.ld_layer = arr, len(layers), ld_layer
+    d.row_index, d.y, d.R, d.C = _p(row_index), _p(y), R, C_
+    d.ln_each, d.ln_post, d.beta, d.l2_loss, d.grad_scale = int(ln_each), int(ln_post), beta, int(l2_loss), grad_scale
+    d.targets, d.dy_bf16, d.dy_f32, d.row_loss, d.loss_out, d.n_valid_dev = _p(targets), _p(dy_bf16), _p(dy_f32), _p(row_loss), _p(loss_out), _p(n_valid)
+    aff = None
+    if affine is not None:
+        aff = (C.c_void_p * len(layers))(*[_p(t) for t in affine])
+        d.affine = aff
+    d.rows_per_sample, d.compact_tokens = rows_per_sample, compact_tokens
+    d.col_hinge, d.loss_add, d.loss_add_weight, d.loss_mult = _p(col_hinge), _p(loss_add), loss_add_weight, loss_mult
+    check(_lib.lib().b200vit_d2v_target_loss_ex(C.byref(d), _stream()), "d2v_target_loss_ex")
+    _count(2 if loss_out is not None else 1)
+
+
+def channel_stats(layers: Sequence[torch.Tensor], ld_layer, samples, sample_rows, row0, nrows, C_, batch_norm, instance_norm, eps=1e-5, out=None):
+    """{shift, scale} maps of target_batch_norm / target_instance_norm (engine_for_cyclical.py:94-104): float2 [len(layers), samples, C]."""
+    if out is None:
+        out = torch.empty(len(layers), samples, C_, 2, dtype=torch.float32, device=layers[0].device)
+    arr = (C.c_void_p * len(layers))(*[_p(t) for t in layers])
+    check(_lib.lib().b200vit_channel_stats(arr, len(layers), ld_layer, samples, sample_rows, row0, nrows, C_, int(batch_norm), int(instance_norm), eps,
+                                           _p(out), _stream()), "channel_stats")
+    _count(2)
+    return out
+
+
+def column_std(y, R, C_, n_valid=None, eps=1e-6, margin=0.5, k_scale=0.0, want_hinge_grad=False, work=None, z0=None, hinge=None, col_hinge=None):
+    """z0 = sqrt(y.var(0) + eps), std_loss0 = sum relu(margin - z0) / C and (optionally) the {mean_c, k_c} gradient map of k_scale * std_loss0."""
+    dev = y.device
+    if work is None:
+        work = torch.empty(int(_lib.lib().b200vit_column_std_workspace_bytes(C_)) // 4, dtype=torch.float32, device=dev)
+    z0 = torch.empty(C_, dtype=torch.float32, device=dev) if z0 is None else z0
+    hinge = torch.empty(1, dtype=torch.float32, device=dev) if hinge is None else hinge
+    if want_hinge_grad and col_hinge is None:
+        col_hinge = torch.empty(C_, 2, dtype=torch.float32, device=dev)
+    check(_lib.lib().b200vit_column_std(_p(y), R, C_, _p(n_valid), eps, margin, k_scale, _p(work), _p(z0), _p(hinge), _p(col_hinge), _stream()),
+          "column_std")
+    _count(2)
+    return z0, hinge, col_hinge
+
+
+def scalar_fma(out, a, wa, b=None, wb=0.0):
+    check(_lib.lib().b200vit_scalar_fma(_p(out), _p(a), wa, _p(b), wb, _stream()), "scalar_fma")
+    _count()
+
+
+def mask_dropout(mask_u8, B, num_patches, tokens, p_drop, seed=0, first_image=0, keep_in=None, rows=None, count=None):
+    """mask &= bernoulli(1 - p) in place (engine_for_cyclical.py:62-66) -> (count int32 [B+1], rows int32 [capacity])."""
+    dev = mask_u8.device
+    if count is None:
+        count = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    if rows is None:
+        rows = torch.zeros(B * num_patches, dtype=torch.int32, device=dev)
+    check(_lib.lib().b200vit_mask_dropout(_p(mask_u8), _p(count), _p(rows), B, num_patches, tokens, p_drop, int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                          int(first_image) & 0xFFFFFFFFFFFFFFFF, _p(keep_in), _stream()), "mask_dropout")
+    _count(2)
+    return count, rows
+
+
+def gaussian_sample(mean, cov, eps_in=None, seed=0, stream_id=0, want_eps=False, out_f32=None, out_bf16=None):
+    """z = mean + sqrt(max(cov, 0)) * eps (Philox / Box-Muller or injected eps) -> (z fp32 or None, z bf16 or None, eps or None)."""
+    n = mean.numel()
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = torch.empty_like(mean)
+    eps_out = torch.empty_like(mean) if want_eps else None
+    check(_lib.lib().b200vit_gaussian_sample(_p(mean), _p(cov), _p(eps_in), n, int(seed) & 0xFFFFFFFFFFFFFFFF, stream_id, _p(eps_out), _p(out_f32),
+                                             _p(out_bf16), _stream()), "gaussian_sample")
+    _count()
+    return out_f32, out_bf16, eps_out
+
+
+def gaussian_sample_bwd(dz, cov, eps, dmean=None, dcov=None):
+    check(_lib.lib().b200vit_gaussian_sample_bwd(_p(dz), _p(cov), _p(eps), dz.numel(), _p(dmean), _p(dcov), _stream()), "gaussian_sample_bwd")
+    _count()
+
+
+def finetune_loss(logits, targets, K, feats=None, lam_ft=1e-4, lam_pvn=1e-4, grad_scale=1.0, dlogits=None, dlogits_bf16=None, work=None,
+                  loss_out=None):
+    """Soft-target cross-entropy (+ WassersteinLossFineTuning when feats = (mean, cov, pos_mean, pos_cov, neg_mean, neg_cov), fp32 [B, C]).
+    logits fp32 [B, >= K] (row stride taken from the tensor); returns (loss_out[3] = {total, ce, wloss}, d_mean_feat, d_cov_feat)."""
+    B = logits.shape[0]
+    dev = logits.device
+    if work is None:
+        work = torch.empty(int(_lib.lib().b200vit_finetune_loss_workspace_floats(B)), dtype=torch.float32, device=dev)
+    if loss_out is None:
+        loss_out = torch.empty(3, dtype=torch.float32, device=dev)
+    dfm = dfc = None
+    f = [None] * 6
+    Cf = 0
+    if feats is not None:
+        f = [t.contiguous() for t in feats]
+        Cf = f[0].shape[1]
+        dfm, dfc = torch.empty_like(f[0]), torch.empty_like(f[1])
+    check(_lib.lib().b200vit_finetune_loss(_p(logits), logits.stride(0), _p(targets), B, K, *[_p(t) for t in f], Cf, lam_ft, lam_pvn, grad_scale,
+                                           _p(work), _p(dlogits), dlogits.stride(0) if dlogits is not None else 0, _p(dlogits_bf16),
+                                           dlogits_bf16.stride(0) if dlogits_bf16 is not None else 0,
+                                           dlogits_bf16.shape[1] if dlogits_bf16 is not None else 0, _p(dfm), _p(dfc), _p(loss_out), _stream()),
+          "finetune_loss")
+    _count(3 if feats is not None else 2)
+    return loss_out, dfm, dfc
+
+
+def tace_auroc(logits, labels_i32, is_prob=False, threshold=0.01, n_bins=30):
+    """(TACE, TACE as the reference computes it, macro one-vs-rest AUROC) of fp32 [N, K] logits / probabilities: device tensor [3]."""
+    N, K = logits.shape
+    dev = logits.device
+    work = torch.empty(int(_lib.lib().b200vit_tace_auroc_workspace_bytes(N, K)) + 256, dtype=torch.uint8, device=dev)
+    off = (-work.data_ptr()) % 256
+    out = torch.empty(3, dtype=torch.float32, device=dev)
+    check(_lib.lib().b200vit_tace_auroc(_p(logits), int(is_prob), _p(labels_i32), N, K, threshold, n_bins, work.data_ptr() + off, _p(out),
+                                        _stream()), "tace_auroc")
+    _count(3 if is_prob else 4)
+    return out
 
 
 def ema_update(ema, model, decay, ema_bf16=None):
