@@ -260,6 +260,10 @@ int b200vit_mask_dropout(uint8_t* mask, int32_t* count, int32_t* rows, int32_t B
                          uint64_t first_image, const uint8_t* keep_in, void* stream);
 /* EMA teacher update e = d*e + (1-d)*m (engine_for_cyclical.py:182-185, timm ModelEmaV2._update) + bf16 shadow */
 int b200vit_ema_update(float* ema, const float* model, int64_t n, double decay, void* ema_bf16, void* stream);
+/* The same update applied to the teacher's INTEGER relative_position_index buffer, as ModelEmaV2._update does by walking the whole state
+ * dict: e = trunc(fp32(d) * fp32(e) + fp32(1 - d) * fp32(m)). For many decays (0.9; about half of the values on the 0.999 -> 0.9998 anneal)
+ * some entries come back one lower, i.e. the reference's teacher reads a drifting bias index; reproduced for parity. */
+int b200vit_ema_index_update(int32_t* ema_index, const int32_t* model_index, int32_t n, double decay, void* stream);
 /* out_accum += sum g^2 (clip_grad_norm_, utils.py:374-377) */
 int b200vit_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
 /* clip + torch.optim.AdamW + bf16 weight shadow + EMA over flat arenas (utils.py:364-390, optim_factory.py:58-97).

@@ -18,12 +18,12 @@ def test_library_exports_every_declared_symbol():
     import uncertainty_vit_b200 as pkg
     lib = pkg._lib.lib()
     names = _declared()
-    assert len(names) >= 24
+    assert len(names) >= 40
     raw = ctypes.CDLL(pkg._lib.LIB_PATH)
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/b200vit.h but not exported"
     assert sorted(pkg._lib.exported_symbols()) == names, "python prototypes and header disagree"
-    assert lib.b200vit_abi_version() == 3
+    assert lib.b200vit_abi_version() == 4
 
 
 def test_header_cites_reference_lines():

@@ -1,5 +1,5 @@
-"""CPU: host-side logic of the engines against the oracle (which is pinned to the reference): the fine-tune loss front-end
-(SoftTargetCrossEntropy, WassersteinLossFineTuning), the layer-decay group assignment, the lr schedule and the pass sharding."""
+"""CPU: host-side logic of the engines against the oracle (which is pinned to the reference): label smoothing as soft targets, the
+layer-decay group assignment, the lr schedule and the pass sharding."""
 import math
 
 import numpy as np
@@ -7,35 +7,19 @@ import pytest
 import torch
 
 
-def test_wasserstein_loss_finetuning_matches_oracle_value_and_gradients():
+def test_smoothed_targets_are_label_smoothing_cross_entropy():
+    """The fine-tune engine turns index labels into (1 - s) one-hot + s / K soft targets and runs the soft-target CE kernel: that is
+    timm's LabelSmoothingCrossEntropy(s) (run_class_finetuning.py:619-624), (1 - s) * nll + s * mean(-log p)."""
     from oracle import vit_oracle as O
-    from uncertainty_vit_b200 import engine as E
-    g = torch.Generator().manual_seed(0)
-    B, C = 6, 32
-    args = [torch.randn(B, C, generator=g) for _ in range(6)]
-    a = [t.clone().requires_grad_(True) for t in args]
-    b = [t.clone().requires_grad_(True) for t in args]
-    lo = O.wasserstein_loss_finetune(*a, lam_ft=1e-2, lam_pvn=1e-3)
-    lm = E.wasserstein_loss_finetuning(*b, lambda_finetuning=1e-2, lambda_pvn=1e-3)
-    assert abs(float(lo) - float(lm)) <= 1e-6 * abs(float(lo))
-    lo.backward()
-    lm.backward()
-    for x, y in zip(a, b):
-        assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-9)
-
-
-def test_soft_target_cross_entropy_loss_and_gradient():
-    from uncertainty_vit_b200 import engine as E
     g = torch.Generator().manual_seed(1)
-    z = torch.randn(5, 17, generator=g, requires_grad=True)
-    t = torch.softmax(torch.randn(5, 17, generator=g), -1)
-    ref = torch.sum(-t * torch.log_softmax(z, -1), -1).mean()          # timm.loss.SoftTargetCrossEntropy
-    ref.backward()
-    loss, dz = E.soft_target_cross_entropy(z.detach(), t)
-    assert abs(float(loss) - float(ref)) < 1e-6 and torch.allclose(dz, z.grad, rtol=1e-5, atol=1e-8)
+    z = torch.randn(5, 17, generator=g)
     hard = torch.tensor([3, 0, 16, 7, 7])
-    loss_h, _ = E.soft_target_cross_entropy(z.detach(), torch.nn.functional.one_hot(hard, 17).float())
-    assert abs(float(loss_h) - float(torch.nn.functional.cross_entropy(z.detach(), hard))) < 1e-6
+    for s_ in (0.0, 0.1):
+        logp = torch.log_softmax(z, -1)
+        expect = ((1 - s_) * -logp.gather(1, hard[:, None]).squeeze(1) + s_ * -logp.mean(-1)).mean()
+        got = O.soft_target_cross_entropy(z, O.smoothed_targets(hard, 17, s_))
+        assert abs(float(got) - float(expect)) < 1e-6
+    assert torch.allclose(O.smoothed_targets(hard, 17, 0.1), O.mixup_target(hard, 17, lam=1.0, smoothing=0.1))
 
 
 def test_layer_ids_match_oracle_for_every_reference_parameter_name():

@@ -34,7 +34,20 @@ def _worker(rank, world, port, q):
     g = torch.full((1024,), float(rank + 1))
     dist.all_reduce(g)
     ok_grad = torch.allclose(g / world, torch.full((1024,), (1 + world) / 2.0))
-    q.put((rank, ok_gather, ok_grad))
+    # the engines replace DDP: rank 0's freshly initialised parameter arena is broadcast at construction (run_cyclical.py:316-322 seeds
+    # every rank differently, :515-519 DDP makes them equal), and equal arenas + all-reduced gradients stay equal after a step
+    from uncertainty_vit_b200.engine import sync_initial_parameters
+    torch.manual_seed(100 + rank)
+    arena = torch.randn(4096)
+    mine_before = arena.clone()
+    sync_initial_parameters(arena, world, None)
+    grad = torch.randn(4096)                       # per-rank gradient (different seeds)
+    dist.all_reduce(grad)
+    arena -= 0.1 * grad / world                    # any deterministic optimiser on identical inputs
+    gathered = [torch.empty_like(arena) for _ in range(world)]
+    dist.all_gather(gathered, arena)
+    ok_sync = all(torch.equal(gathered[0], t) for t in gathered) and (rank == 0 or not torch.equal(mine_before, arena))
+    q.put((rank, ok_gather, ok_grad and ok_sync))
     dist.destroy_process_group()
 
 

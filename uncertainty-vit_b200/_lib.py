@@ -76,6 +76,7 @@ _PROTOS = {
     "b200vit_tace_auroc_workspace_bytes": (C.c_size_t, [i32, i32]),
     "b200vit_tace_auroc": (i32, [vp, i32, vp, i32, i32, f32, i32, vp, vp, vp]),
     "b200vit_ema_update": (i32, [vp, vp, i64, C.c_double, vp, vp]),
+    "b200vit_ema_index_update": (i32, [vp, vp, i32, C.c_double, vp]),
     "b200vit_sumsq": (i32, [vp, i64, vp, vp]),
     "b200vit_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, C.c_double, vp, vp]),
     "b200vit_wasserstein_loss": (i32, [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]),

@@ -36,6 +36,8 @@ class VitConfig:
     attn_drop_rate: float = 0.0
     has_gamma: bool = True
     use_abs_pos_emb: bool = False
+    sample_head: bool = False       # dual-stream classifier: logits = head(mean + sqrt(max(cov, 0)) * eps) instead of head(mean); the draw the
+                                    # reference sketches and leaves commented out (modeling_finetune_dist.py:314-325). Default off.
 
     @property
     def grid(self):
@@ -86,6 +88,7 @@ class Noise:
     seed_dev: Optional[torch.Tensor] = None             # int64 [1] on the device: overrides `seed` for attention dropout (CUDA-graph replays)
     drop_path_scale: Optional[torch.Tensor] = None      # fp32 [L, draws, B] = keep / (1 - p_l)
     attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
+    head_eps: Optional[torch.Tensor] = None             # fp32 [B, C]: injected N(0,1) noise of the reparameterised head sample (cfg.sample_head)
     drop_path_active: bool = True                       # applies only to training forwards
     attn_drop_active: Optional[bool] = None             # None: follow `train`; True: dropout even in eval (MC-dropout, enable_dropout())
 
@@ -475,12 +478,18 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
         fmean = _empty((2 * B,), torch.float32, dev)
         frstd = _empty((2 * B,), torch.float32, dev)
         ops.layernorm_fwd(pooled, ps.f32("fc_norm.weight"), ps.f32("fc_norm.bias"), cfg.ln_eps, 2 * B, C, y_bf16=fb, y_f32=feat, mean=fmean, rstd=frstd)
+        head_in = fb[:B]
+        eps = None
+        if cfg.sample_head or noise.head_eps is not None:
+            head_in = _empty((B, C), torch.bfloat16, dev)
+            _, _, eps = ops.gaussian_sample(feat[:B], feat[B:], eps_in=noise.head_eps, seed=noise.seed, stream_id=0x48454144, want_eps=save,
+                                            out_bf16=head_in)
         if save:
-            ctx.update(pooled=pooled, fb=fb, fmean=fmean, frstd=frstd)
+            ctx.update(pooled=pooled, fb=head_in, fmean=fmean, frstd=frstd, head_eps=eps, feat_cov=feat[B:] if eps is not None else None)
         w, hb = ps.head_padded()
         Kp = w.shape[0]
         logits = _empty((B, Kp), torch.float32, dev)
-        ops.gemm(fb[:B], w, B, Kp, C, epilogue=EPI_F32, bias=hb, out_f32=logits)
+        ops.gemm(head_in, w, B, Kp, C, epilogue=EPI_F32, bias=hb, out_f32=logits)
         return (feat[:B], feat[B:], logits[:, :cfg.num_classes]), ctx
     raise B200VitError(f"unknown forward mode {mode!r}")
 
@@ -566,31 +575,39 @@ def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, do
 # classifier (fine-tune) backward: logits = head(fc_norm(mean_{t>=1} x_L))   (modeling_finetune.py:512-523, modeling_finetune_dist.py:311-326)
 # ------------------------------------------------------------------------------------------------------------------
 def _head_backward(ps: ParamSource, cfg: VitConfig, ctx, dlogits: torch.Tensor, dfeat_extra: Optional[torch.Tensor], grads, streams: int) -> torch.Tensor:
-    """Returns dx [streams*B*T, C] fp32 (gradient of the final residual stream). dfeat_extra: optional fp32 [streams*B, C] gradient
-    flowing directly into the fc_norm outputs (the W-loss of the dual-stream fine-tune step)."""
+    """Returns dx [streams*B*T, C] fp32 (gradient of the final residual stream). dlogits: fp32 [B, K], or bf16 [B, Kp] already zero-padded to
+    the GEMM's N (b200vit_finetune_loss writes that directly). dfeat_extra: optional fp32 [streams*B, C] gradient flowing directly into the
+    fc_norm outputs (the W-loss of the dual-stream fine-tune step); it is consumed (accumulated into)."""
     B = ctx["B"]
     T, C, K = cfg.tokens, cfg.embed_dim, cfg.num_classes
     dev = dlogits.device
     SB = streams * B
     w, _ = ps.head_padded()
     Kp = w.shape[0]
-    dl = torch.zeros((B, Kp), dtype=torch.float32, device=dev)
-    dl[:, :K].copy_(dlogits)
-    dl16 = ops.cast_bf16(dl)
+    if dlogits.dtype == torch.bfloat16 and dlogits.shape[1] == Kp:
+        dl16 = dlogits
+    else:
+        dl = torch.zeros((B, Kp), dtype=torch.float32, device=dev)
+        dl[:, :K].copy_(dlogits)
+        dl16 = ops.cast_bf16(dl)
     fb = ctx["fb"]
-    gw = grads["head.weight"]
-    if Kp == K:
+    gw, gb = grads.get("head.weight__padded"), grads.get("head.bias__padded")
+    if gw is not None and gb is not None:            # engine arenas reserve the padded classifier rows: accumulate in place
         ops.linear_wgrad(dl16, fb[:B], gw)
+        ops.colsum_bf16(dl16, B, Kp, gb)
     else:
         tmp = torch.zeros((Kp, C), dtype=torch.float32, device=dev)
+        tmpb = torch.zeros((Kp,), dtype=torch.float32, device=dev)
         ops.linear_wgrad(dl16, fb[:B], tmp)
-        gw.add_(tmp[:K])
-    grads["head.bias"].add_(dlogits.sum(0))                                # [K] column sum of a [B, K] matrix: negligible
-    dfeat16 = torch.zeros((SB, C), dtype=torch.bfloat16, device=dev)
-    ops.gemm(dl16, w, B, C, Kp, b_mn=True, epilogue=EPI_BF16, out_bf16=dfeat16[:B])
-    dfeat = dfeat16.float()
-    if dfeat_extra is not None:
-        dfeat = dfeat + dfeat_extra
+        ops.colsum_bf16(dl16, B, Kp, tmpb)
+        grads["head.weight"].add_(tmp[:K])
+        grads["head.bias"].add_(tmpb[:K])
+    dfeat = dfeat_extra if dfeat_extra is not None else torch.zeros((SB, C), dtype=torch.float32, device=dev)
+    dhead = torch.empty((B, C), dtype=torch.float32, device=dev)
+    ops.gemm(dl16, w, B, C, Kp, b_mn=True, epilogue=EPI_F32, out_f32=dhead)
+    dfeat[:B].add_(dhead)
+    if ctx.get("head_eps") is not None:      # head input = mean + sqrt(max(cov, 0)) * eps: the cov feature receives dhead * eps / (2 sqrt(cov))
+        ops.gaussian_sample_bwd(dhead, ctx["feat_cov"].contiguous(), ctx["head_eps"], dcov=dfeat[B:])
     dpool = torch.zeros((SB, C), dtype=torch.float32, device=dev)
     ops.layernorm_bwd(dfeat.contiguous(), ctx["pooled"], ps.f32("fc_norm.weight"), ctx["fmean"], ctx["frstd"], SB, C, dpool, grads["fc_norm.weight"],
                       grads["fc_norm.bias"])

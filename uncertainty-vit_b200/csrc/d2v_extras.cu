@@ -220,6 +220,13 @@ __global__ void __launch_bounds__(256) gaussian_sample_bwd_kernel(const float* _
   }
 }
 
+// ModelEmaV2._update walks the WHOLE state dict (engine_for_cyclical.py:182-185), so the teacher's int64 relative_position_index buffer
+// goes through `d * e + (1 - d) * m` too: int64 * python float -> fp32 products, fp32 sum, truncated back to int64 by copy_.
+__global__ void __launch_bounds__(256) ema_index_kernel(int* __restrict__ e, const int* __restrict__ m, int n, float d, float od) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) e[i] = (int)__fadd_rn(__fmul_rn(d, (float)e[i]), __fmul_rn(od, (float)m[i]));
+}
+
 }  // namespace
 
 #define STREAM static_cast<cudaStream_t>(stream)
@@ -281,5 +288,13 @@ extern "C" int b200vit_gaussian_sample_bwd(const float* dz, const float* cov, co
   if (blocks > cap) blocks = cap;
   gaussian_sample_bwd_kernel<<<(int)blocks, 256, 0, STREAM>>>(dz, cov, eps, n, dmean, dcov);
   B200_CHECK_LAUNCH("gaussian_sample_bwd");
+  return 0;
+}
+
+extern "C" int b200vit_ema_index_update(int32_t* ema_index, const int32_t* model_index, int32_t n, double decay, void* stream) {
+  B200_CHECK_ARG(ema_index != nullptr && model_index != nullptr && n >= 0, "ema_index_update: null pointer");
+  if (n == 0) return 0;
+  ema_index_kernel<<<(n + 255) / 256, 256, 0, STREAM>>>(ema_index, model_index, n, (float)decay, (float)(1.0 - decay));
+  B200_CHECK_LAUNCH("ema_index_update");
   return 0;
 }

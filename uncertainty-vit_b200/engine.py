@@ -49,6 +49,14 @@ def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epoch
     return schedule
 
 
+def sync_initial_parameters(arena: torch.Tensor, world_size: int, process_group=None) -> None:
+    """Every rank seeds torch with seed + rank before it builds the model (run_cyclical.py:316-322), so the ranks start from DIFFERENT
+    weights; the reference makes them identical through the DistributedDataParallel constructor's broadcast from rank 0 (:515-519).
+    The engines replace DDP, so they do the same on the flat fp32 arena (one collective)."""
+    if world_size > 1:
+        torch.distributed.broadcast(arena, 0, group=process_group)
+
+
 class ArenaParams(core.ParamSource):
     """ParamSource over one fp32 arena + its bf16 shadow arena."""
 
@@ -97,7 +105,12 @@ class D2VEngine:
                  ema_decay_init=0.999, ema_start_at=0, target_layers: Sequence[int] = (6, 7, 8, 9, 10, 11), l1_beta=2.0, l2_loss=False,
                  target_layer_norm_last=True, post_target_layer_norm=True, layer_decay: Optional[float] = None, loss_scale=-1.0,
                  skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0,
-                 lambda_pretraining: float = 1e-5, use_graph: bool = True, with_ema: bool = True):
+                 lambda_pretraining: float = 1e-5, use_graph: bool = True, with_ema: bool = True, target_batch_norm=False,
+                 target_instance_norm=False, post_target_instance_norm=False, var_w0: float = 0.0, var_margin0: float = 0.5,
+                 start_lr_decay_at_step: int = -1, mask_dropout_prob: float = -1.0, track_z0: bool = True):
+        """Keyword names follow engine_for_cyclical.train_one_epoch (:24-32) / run_cyclical.py's flags. world_size > 1: rank 0's parameters
+        are broadcast at construction (what the DistributedDataParallel constructor does in run_cyclical.py:515-519), then only gradients
+        are all-reduced."""
         self.model = model
         self.cfg: VitConfig = model.cfg
         dev = model.cls_token.device
@@ -115,6 +128,11 @@ class D2VEngine:
         self.target_layers = list(target_layers)
         self.l1_beta, self.l2_loss, self.ln_each, self.ln_post = l1_beta, l2_loss, target_layer_norm_last, post_target_layer_norm
         self.loss_scale = loss_scale
+        self.bn_targets, self.in_targets, self.post_in_targets = bool(target_batch_norm), bool(target_instance_norm), bool(post_target_instance_norm)
+        self.var_w0, self.var_margin0, self.track_z0 = float(var_w0), float(var_margin0), bool(track_z0)
+        self.start_lr_decay_at_step = int(start_lr_decay_at_step)
+        self.mask_dropout_prob = float(mask_dropout_prob)
+        self.z0_dev = self.std_loss0_dev = None
         self.lam = lambda_pretraining
         self.world_size, self.pg = world_size, process_group
         self.seed = seed
@@ -179,18 +197,23 @@ class D2VEngine:
                 view = self.p32[o: o + p.numel()].view(shape)
                 view.copy_(p.detach())
                 p.data = view                     # the module now aliases the arena
+        sync_initial_parameters(self.p32, world_size, process_group)      # before the bf16 shadows and the EMA copy are derived
         ops.cast_bf16(self.p32, self.p16)
         if with_ema:
             self.e32.copy_(self.p32)              # ModelEmaV2: deepcopy of the student at construction (run_cyclical.py:503)
             ops.cast_bf16(self.e32, self.e16)
         rel = model.rel_pos_bias.relative_position_index.to(torch.int32).contiguous() if model.rel_pos_bias is not None else None
         self.student = ArenaParams(layout, self.p32, self.p16, rel)
-        self.teacher = ArenaParams(layout, self.e32, self.e16, rel) if with_ema else None
+        # the teacher owns a COPY of the integer index buffer: ModelEmaV2._update walks the whole state dict, so the reference's EMA passes
+        # relative_position_index through `d*e + (1-d)*m` in fp32 and truncates it back (b200vit_ema_index_update) — entries can drift
+        self.rel_e = rel.clone() if (with_ema and rel is not None) else None
+        self.teacher = ArenaParams(layout, self.e32, self.e16, self.rel_e) if with_ema else None
         self.grads = {name: self.g32[o: o + int(np.prod(s))].view(s) for name, (o, s) in layout.items()}
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.opt_step = 0
-        self.cur_decay = ema_decay
+        self.cur_decay = ema_decay          # the reference's loop variable (engine_for_cyclical.py:44): train_one_epoch() resets it per epoch
+        self.ema_updated = True
         if hasattr(model, "_ps"):
             model._ps.invalidate()
 
@@ -214,14 +237,15 @@ class D2VEngine:
         return (b * T + 1 + p).astype(np.int32)
 
     def decay_at(self, it: int) -> float:
-        """engine_for_cyclical.py:55-56."""
+        """engine_for_cyclical.py:55-56: the annealed value while it < ema_start_at; afterwards the loop variable keeps whatever it held
+        (the last annealed value for the rest of that epoch, `decay` from the next epoch on, 0 after a skipped update, :182-185)."""
         if it < self.ema_start_at:
             return self.ema_decay_init + it * (self.ema_decay - self.ema_decay_init) / self.ema_start_at
-        return self.ema_decay
+        return self.cur_decay
 
     def step(self, images: torch.Tensor, mask_u8: torch.Tensor, rows: torch.Tensor, *, lr: Optional[float] = None,
              weight_decay: Optional[float] = None, noise: Optional[Noise] = None, graph: Optional[bool] = None,
-             n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+             n_valid: Optional[torch.Tensor] = None, mask_keep: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step on device-resident inputs. images fp32 [B,3,H,W]; mask_u8 uint8 [B*np]; rows int32 [R].
         n_valid (device int32 [1]): `rows` is padded to a fixed capacity and only its first n_valid entries are masked patches (the
         padding must hold valid row numbers, e.g. 0); the step then has the same launch shapes whatever the block-wise generator drew.
@@ -233,17 +257,77 @@ class D2VEngine:
         lr = self.lr if lr is None else lr
         wd = self.wd if weight_decay is None else weight_decay
         self.cur_decay = self.decay_at(self.it)
+        if self.mask_dropout_prob > 0:
+            mask_u8, rows, n_valid = self.apply_mask_dropout(mask_u8, B, mask_keep)
+            R = rows.numel()
         injected = noise
         if noise is None:
             noise = Noise(seed=(self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF)
         if graph is None:
             graph = self.use_graph
-        if graph and injected is None and ops.GEMM_TIMING is None and R > 0:
+        if R == 0:
+            raise B200VitError("D2VEngine.step: empty masked-row list (the loss is a mean over the masked patches)")
+        if graph and injected is None and ops.GEMM_TIMING is None:
             self._fwd_bwd_graphed(images, mask_u8, rows, noise.seed, n_valid)
         else:
             self._fwd_bwd(images, mask_u8, rows, noise, n_valid)
             self._eager_steps += 1
         return self._optimizer_step(lr, wd)
+
+    def apply_mask_dropout(self, mask_u8: torch.Tensor, B: int, keep: Optional[torch.Tensor] = None):
+        """mask_dropout_prob (engine_for_cyclical.py:62-66): mask &= bernoulli(1 - p) on the device (or an injected keep tensor), the masked-row
+        list rebuilt at capacity (padding = row 0) with the true count in device memory. Returns (mask, rows, n_valid)."""
+        npat = self.cfg.num_patches
+        m = mask_u8.clone()
+        seed = (self.seed * 0x9E3779B97F4A7C15 + 0x51ED270B * (self.it + 1)) & 0xFFFFFFFFFFFFFFFF
+        cap = int(B * npat)
+        count, rows = ops.mask_dropout(m, B, npat, self.cfg.tokens, self.mask_dropout_prob, seed=seed, first_image=self.it * B,
+                                       keep_in=keep.reshape(-1).to(torch.uint8).contiguous() if keep is not None else None,
+                                       rows=torch.zeros(cap, dtype=torch.int32, device=self.dev))
+        return m, rows, count[B:B + 1]
+
+    def _targets_and_loss(self, layers, rows, y, R, n_valid, *, targets=None, dy_bf16=None, dy_f32=None, loss_mult=1.0, with_loss=True,
+                          mean_stream=True):
+        """Target builder + loss of engine_for_cyclical.py:90-150 for one stream. `layers`: the teacher's block outputs [B*T, C] fp32.
+        mean_stream=False (the cov targets of --stochastic, :74-86) only ever gets the per-layer LayerNorm, the mean and the post LayerNorm."""
+        cfg = self.cfg
+        C, T = cfg.embed_dim, cfg.tokens
+        B = layers[0].shape[0] // T
+        dev = self.dev
+        ls = self.loss_scale if self.loss_scale != -1 else 1.0
+        bn, inorm, post_in = (self.bn_targets, self.in_targets, self.post_in_targets) if mean_stream else (False, False, False)
+        affine = None
+        if bn or inorm:
+            st = ops.channel_stats(layers, C, B, T, 1, T - 1, C, bn, inorm)
+            affine = [st[i] for i in range(len(layers))]
+        col_hinge = loss_add = None
+        row_loss = torch.empty((R,), dtype=torch.float32, device=dev) if with_loss else None
+        if with_loss and y is not None and (self.track_z0 or self.var_w0 > 0):
+            if self.z0_dev is None:
+                self.z0_dev = torch.zeros(C, dtype=torch.float32, device=dev)
+                self.std_loss0_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            _, _, col_hinge = ops.column_std(y, R, C, n_valid, 1e-6, self.var_margin0, self.var_w0 * ls, want_hinge_grad=self.var_w0 > 0,
+                                             z0=self.z0_dev, hinge=self.std_loss0_dev)
+            if self.var_w0 > 0:
+                loss_add = self.std_loss0_dev
+        common = dict(beta=self.l1_beta, l2_loss=self.l2_loss if mean_stream else False, n_valid=n_valid)
+        if not post_in:
+            ops.d2v_target_loss_ex(layers, C, rows, y, R, C, self.ln_each, self.ln_post, grad_scale=ls / (R * C) if with_loss else 1.0,
+                                   targets=targets, dy_bf16=dy_bf16, dy_f32=dy_f32, row_loss=row_loss, loss_out=self.loss_dev if with_loss else None,
+                                   affine=affine, rows_per_sample=T if affine is not None else 0, col_hinge=col_hinge, loss_add=loss_add,
+                                   loss_add_weight=self.var_w0, loss_mult=loss_mult, **common)
+            return
+        # post_target_instance_norm (:112-115) normalises the AVERAGED target over the patch tokens of each (image, channel): it needs
+        # the target of every patch row first -> pass 1 over all B*(T-1) rows, statistics, pass 2 over the masked rows of that tensor
+        NP = B * (T - 1)
+        full = torch.empty((NP, C), dtype=torch.float32, device=dev)
+        ops.d2v_target_loss_ex(layers, C, core.all_patch_rows(B, T, dev), None, NP, C, self.ln_each, False, targets=full, affine=affine,
+                               rows_per_sample=T if affine is not None else 0)
+        st2 = ops.channel_stats([full], C, B, T - 1, 0, T - 1, C, False, True)
+        ops.d2v_target_loss_ex([full], C, rows, y, R, C, False, self.ln_post, grad_scale=ls / (R * C) if with_loss else 1.0, targets=targets,
+                               dy_bf16=dy_bf16, dy_f32=dy_f32, row_loss=row_loss, loss_out=self.loss_dev if with_loss else None, affine=[st2[0]],
+                               rows_per_sample=T - 1, compact_tokens=T, col_hinge=col_hinge, loss_add=loss_add, loss_add_weight=self.var_w0,
+                               loss_mult=loss_mult, **common)
 
     def _fwd_bwd(self, images, mask_u8, rows, noise, n_valid=None):
         """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser).
@@ -262,10 +346,8 @@ class D2VEngine:
                                     patches=patches)
         # targets + loss + dLoss/dy: :90-150 (masked rows only; LayerNorm is per row)
         dy = torch.empty((R, C), dtype=torch.bfloat16, device=self.dev)
-        row_loss = torch.empty((R,), dtype=torch.float32, device=self.dev)
         ls = self.loss_scale if self.loss_scale != -1 else 1.0
-        ops.d2v_target_loss([layers[i].view(B * T, C) for i in self.target_layers], C, rows, out, R, C, self.ln_each, self.ln_post, self.l1_beta,
-                            self.l2_loss, ls / (R * C), None, dy, None, row_loss, self.loss_dev, n_valid=n_valid)
+        self._targets_and_loss([layers[i].view(B * T, C) for i in self.target_layers], rows, out, R, n_valid, dy_bf16=dy, loss_mult=ls)
         del layers
         self.g32.zero_()
         core.vit_backward(self.student, cfg, ctx, dy, self.grads)
@@ -340,17 +422,15 @@ class D2VEngine:
         tgt_c = torch.empty((R, C), dtype=torch.float32, device=dev)
         d_m = torch.empty((R, C), dtype=torch.float32, device=dev)
         d_c = torch.zeros((R, C), dtype=torch.float32, device=dev)
-        row_loss = torch.empty((R,), dtype=torch.float32, device=dev)
-        ops.d2v_target_loss([lm[i].view(M, C) for i in self.target_layers], C, rows, om, R, C, self.ln_each, self.ln_post, self.l1_beta, self.l2_loss,
-                            ls / (R * C), tgt_m, None, d_m, row_loss, self.loss_dev, n_valid=n_valid)
-        ops.d2v_target_loss([lc[i].view(M, C) for i in self.target_layers], C, rows, None, R, C, self.ln_each, self.ln_post, self.l1_beta, False,
-                            1.0, tgt_c, None, None, None, None, n_valid=n_valid)
+        self._targets_and_loss([lm[i].view(M, C) for i in self.target_layers], rows, om, R, n_valid, targets=tgt_m, dy_f32=d_m)
+        self._targets_and_loss([lc[i].view(M, C) for i in self.target_layers], rows, None, R, n_valid, targets=tgt_c, with_loss=False,
+                               mean_stream=False)
         del lm, lc
         work = torch.empty((2 * R + 8,), dtype=torch.float32, device=dev)
         if self.wloss_dev is None:
             self.wloss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev, n_valid=n_valid)
-        self.loss_dev.add_(self.wloss_dev, alpha=ls)          # loss = (loss_cyc + loss_stochastic) * loss_scale  (:160-163)
+        ops.scalar_fma(self.loss_dev, self.loss_dev, ls, self.wloss_dev, ls)      # loss = (loss_cyc + std_loss0*var_w0 + loss_stochastic) * loss_scale  (:160-163)
         self.g32.zero_()
         core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads)
 
@@ -360,10 +440,16 @@ class D2VEngine:
         self.gnorm_sq.zero_()
         ops.sumsq(self.g32, self.gnorm_sq)
         self.opt_step += 1
-        do_ema = self.cur_decay != 1 and self.e32 is not None
+        # engine_for_cyclical.py:182-185: no EMA update when the decay is 1 or past start_lr_decay_at_step; the loop variable then drops to 0
+        do_ema = self.e32 is not None and self.cur_decay != 1 and (self.start_lr_decay_at_step == -1 or self.it <= self.start_lr_decay_at_step)
         ops.adamw_step(self.p32, self.g32, self.m32, self.v32, self.hp, self.opt_step, lr, wd, self.betas[0], self.betas[1], self.eps,
                        gnorm_sq=self.gnorm_sq, max_norm=self.clip if self.clip else 0.0, grad_div=float(self.world_size), p_bf16=self.p16,
                        ema=self.e32 if do_ema else None, ema_decay=self.cur_decay, ema_bf16=self.e16 if do_ema else None)
+        if do_ema and self.rel_e is not None:
+            ops.ema_index_update(self.rel_e, self.student.rel_index_i32(), self.cur_decay)
+        self.ema_updated = do_ema
+        if self.e32 is not None and not do_ema:
+            self.cur_decay = 0
         self.it += 1
         # the module aliases the arena, but its bf16 weight shadows / captured eval graphs are keyed on autograd version counters, which a
         # raw-pointer kernel update does not touch: tell the module its weights moved
@@ -439,84 +525,121 @@ class D2VEngine:
         return self.step_staged(self.stage_host(images_pinned, mask_host), **kw)
 
 
-def soft_target_cross_entropy(logits: torch.Tensor, targets: torch.Tensor):
-    """SoftTargetCrossEntropy of timm (run_class_finetuning.py:619-621 after Mixup / CutMix): loss = mean_b sum_k -t log_softmax(z);
-    returns (loss, dLoss/dlogits). [B, K] tensors: a handful of tiny torch ops, not hot-path work."""
-    logp = torch.log_softmax(logits.float(), -1)
-    loss = -(targets * logp).sum(-1).mean()
-    dlogits = (torch.exp(logp) * targets.sum(-1, keepdim=True) - targets) / logits.shape[0]
-    return loss, dlogits
-
-
-def wasserstein_loss_finetuning(mean_out, cov_out, pos_mean, pos_cov, neg_mean, neg_cov, lambda_finetuning=1e-4, lambda_pvn=1e-4):
-    """WassersteinLossFineTuning.forward (distloss.py:39-70) on the [B, C] pooled features of anchor / positive / negative: every input goes
-    through a sigmoid; d(a, b) = |m_a - m_b|^2 + |sqrt(c_a) - sqrt(c_b)|^2 per row; the three distance vectors and the two loss vectors are
-    each divided by their max-abs (differentiated through, like autograd does in the reference)."""
-    mo, co, pm, pc, nm, nc = (torch.sigmoid(t.float()) for t in (mean_out, cov_out, pos_mean, pos_cov, neg_mean, neg_cov))
-
-    def dist(m1, c1, m2, c2):
-        return ((m1 - m2) ** 2).sum(-1) + ((torch.sqrt(c1.clamp_min(1e-24)) - torch.sqrt(c2.clamp_min(1e-24))) ** 2).sum(-1)
-    pos, neg, pvn = dist(mo, co, pm, pc), dist(mo, co, nm, nc), dist(pm, pc, nm, nc)
-    pos, neg, pvn = pos / pos.abs().max(), neg / neg.abs().max(), pvn / pvn.abs().max()
-    triplet = -torch.log(torch.sigmoid(neg - pos + 1e-24))
-    triplet = (triplet / triplet.abs().max() * lambda_finetuning).sum()
-    margin = torch.clamp(pos - pvn, 0)
-    margin = (margin / margin.abs().max() * lambda_pvn).sum()
-    return triplet + margin
-
-
 class FinetuneEngine(D2VEngine):
     """Fused fine-tune TRAIN step (run_class_finetuning.py / engine_for_finetuning(_dist).py) over the same flat arenas as the pre-training
     engine: classifier forward + backward on the CUDA schedules, the reference's layer-decay parameter groups as per-chunk lr scales of the
     fused clip + AdamW kernel (optim_factory.py:33-97, LayerDecayValueAssigner), no EMA teacher.
-      det   : loss = SoftTargetCrossEntropy(model(x), targets)
-      dist  : loss = CE(logits) + WassersteinLossFineTuning(anchor, positive, negative features); the positive / negative forwards run
-              without gradients on the live weights (engine_for_finetuning_dist.py:286-304 uses a per-batch deepcopy: same gradients)."""
+      det   : loss = SoftTargetCrossEntropy / LabelSmoothingCrossEntropy(model(x), targets)
+      dist  : loss = CE(logits) + WassersteinLossFineTuning(anchor, positive, negative features); the positive / negative forwards run in
+              EVAL mode (no drop-path, no dropout) and without a gradient path, like the eval-mode deep copy of
+              engine_for_finetuning_dist.py:293-296.
+    The criterion and its gradients are one C-ABI call (b200vit_finetune_loss); forward + loss + backward replay from a CUDA graph."""
 
     def __init__(self, model, *, lr=5e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, clip_grad=None, layer_decay: Optional[float] = 0.65,
-                 lambda_finetuning=1e-4, lambda_pvn=1e-4, world_size=1, process_group=None, seed=0):
+                 lambda_finetuning=1e-4, lambda_pvn=1e-4, smoothing: float = 0.1, world_size=1, process_group=None, seed=0, use_graph: bool = True):
         if model.cfg.kind != "finetune":
             raise B200VitError("FinetuneEngine needs a classifier (VisionTransformer / DistVisionTransformer)")
         super().__init__(model, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps, clip_grad=clip_grad, ema_decay=1.0, ema_decay_init=1.0,
-                         ema_start_at=0, layer_decay=layer_decay, world_size=world_size, process_group=process_group, seed=seed, use_graph=False,
-                         with_ema=False)
+                         ema_start_at=0, layer_decay=layer_decay, world_size=world_size, process_group=process_group, seed=seed,
+                         use_graph=use_graph, with_ema=False)
         self.lam_ft, self.lam_pvn = lambda_finetuning, lambda_pvn
+        self.smoothing = float(smoothing)           # run_class_finetuning.py:619-624: LabelSmoothingCrossEntropy(args.smoothing) for index labels
+        K, C = model.cfg.num_classes, model.cfg.embed_dim
+        kp = (K + 7) // 8 * 8
+        ow, ob = self.layout["head.weight"][0], self.layout["head.bias"][0]
+        # gradient views over the classifier rows INCLUDING the zero padding up to a multiple of 8 (the GEMM's N): core._head_backward
+        # accumulates straight into them
+        self.grads["head.weight__padded"] = self.g32[ow: ow + kp * C].view(kp, C)
+        self.grads["head.bias__padded"] = self.g32[ob: ob + kp]
+        self.loss3 = torch.zeros(3, dtype=torch.float32, device=self.dev)
+        self._ft_graphs = {}
+        self.last_logits = None
+
+    def soft_targets(self, targets: torch.Tensor) -> torch.Tensor:
+        """[B, K] fp32 targets: soft targets pass through; index labels become (1 - s) one-hot + s / K (== LabelSmoothingCrossEntropy)."""
+        K = self.cfg.num_classes
+        if targets.dim() == 1:
+            s_ = self.smoothing
+            return ops.mixup_batch(None, 1.0, labels=targets.to(self.dev).long().contiguous(), num_classes=K, on_value=1.0 - s_ + s_ / K,
+                                   off_value=s_ / K)
+        return targets.to(self.dev).float().contiguous()
+
+    def _fwd_bwd_ft(self, images, soft, pos_images, neg_images, noise):
+        cfg = self.cfg
+        K = cfg.num_classes
+        B = images.shape[0]
+        kp = (K + 7) // 8 * 8
+        dl16 = torch.empty((B, kp), dtype=torch.bfloat16, device=self.dev)
+        if cfg.dist:
+            (fm, fc, logits), ctx = core.dist_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
+            feats = None
+            if pos_images is not None and neg_images is not None:
+                quiet = Noise(drop_path_active=False, attn_drop_active=False)
+                (pm, pc, _), _ = core.dist_forward(self.student, cfg, pos_images, mode="logits", train=False, save=False, noise=quiet)
+                (nm, nc, _), _ = core.dist_forward(self.student, cfg, neg_images, mode="logits", train=False, save=False, noise=quiet)
+                feats = (fm, fc, pm, pc, nm, nc)
+            _, dfm, dfc = ops.finetune_loss(logits, soft, K, feats=feats, lam_ft=self.lam_ft, lam_pvn=self.lam_pvn, dlogits_bf16=dl16,
+                                            loss_out=self.loss3)
+            self.g32.zero_()
+            core.dist_backward_logits(self.student, cfg, ctx, dfm, dfc, dl16, self.grads)
+        else:
+            logits, ctx = core.vit_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
+            ops.finetune_loss(logits, soft, K, dlogits_bf16=dl16, loss_out=self.loss3)
+            self.g32.zero_()
+            core.vit_backward_logits(self.student, cfg, ctx, dl16, self.grads)
+        return logits
+
+    def _fwd_bwd_ft_graphed(self, images, soft, pos_images, neg_images, seed):
+        cfg = self.cfg
+        trip = pos_images is not None and neg_images is not None
+        key = (tuple(images.shape), trip)
+        g = self._ft_graphs.get(key)
+        if g is None and (self._eager_steps < 2 or len(self._ft_graphs) >= self.max_graphs):
+            self._eager_steps += 1
+            return self._fwd_bwd_ft(images, soft, pos_images, neg_images, Noise(seed=seed))
+        if g is None:
+            st = dict(images=torch.empty_like(images), soft=torch.empty_like(soft), seed=torch.zeros(1, dtype=torch.int64, device=self.dev),
+                      dps=torch.empty(cfg.depth, 4 if cfg.dist else 2, images.shape[0], dtype=torch.float32, device=self.dev),
+                      pos=torch.empty_like(images) if trip else None, neg=torch.empty_like(images) if trip else None)
+            noise = Noise(seed=0, seed_dev=st["seed"], drop_path_scale=st["dps"] if cfg.drop_path_rate > 0 else None)
+            graph = torch.cuda.CUDAGraph()
+            launches0 = ops.LAUNCHES
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(graph):
+                logits = self._fwd_bwd_ft(st["images"], st["soft"], st["pos"], st["neg"], noise)
+            g = dict(graph=graph, st=st, launches=ops.LAUNCHES - launches0, logits=logits)
+            ops.LAUNCHES = launches0
+            self._ft_graphs[key] = g
+        st = g["st"]
+        st["images"].copy_(images, non_blocking=True)
+        st["soft"].copy_(soft, non_blocking=True)
+        if trip:
+            st["pos"].copy_(pos_images, non_blocking=True)
+            st["neg"].copy_(neg_images, non_blocking=True)
+        st["seed"].fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+        if cfg.drop_path_rate > 0:
+            ops.drop_path_scales(cfg.drop_path_probs, 4 if cfg.dist else 2, images.shape[0], seed, self.dev, out=st["dps"])
+        g["graph"].replay()
+        ops.LAUNCHES += g["launches"]
+        return g["logits"]
 
     def step(self, images: torch.Tensor, targets: torch.Tensor, pos_images: Optional[torch.Tensor] = None, neg_images: Optional[torch.Tensor] = None,
-             *, lr: Optional[float] = None, weight_decay: Optional[float] = None, noise: Optional[Noise] = None) -> torch.Tensor:
+             *, lr: Optional[float] = None, weight_decay: Optional[float] = None, noise: Optional[Noise] = None, graph: Optional[bool] = None) -> torch.Tensor:
         """images fp32 [B,3,H,W]; targets: soft targets [B,K] (Mixup / CutMix) or class indices [B]. Returns the device scalar loss."""
-        cfg = self.cfg
         lr = self.lr if lr is None else lr
         wd = self.wd if weight_decay is None else weight_decay
         self.cur_decay = 1.0
-        base_seed = (self.seed * 0x9E3779B97F4A7C15 + 3 * self.it + 1) & 0xFFFFFFFFFFFFFFFF
-        if noise is None:
-            noise = Noise(seed=base_seed)
-        if targets.dim() == 1:
-            targets = torch.nn.functional.one_hot(targets.long(), cfg.num_classes).float()
-        targets = targets.to(self.dev).float()
-        if cfg.dist:
-            (fm, fc, logits), ctx = core.dist_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
-            loss, dlogits = soft_target_cross_entropy(logits, targets)
-            dfm = dfc = None
-            if pos_images is not None and neg_images is not None:
-                (pm, pc, _), _ = core.dist_forward(self.student, cfg, pos_images, mode="logits", train=True, save=False,
-                                                   noise=Noise(seed=(base_seed + 1) & 0xFFFFFFFFFFFFFFFF))
-                (nm, nc, _), _ = core.dist_forward(self.student, cfg, neg_images, mode="logits", train=True, save=False,
-                                                   noise=Noise(seed=(base_seed + 2) & 0xFFFFFFFFFFFFFFFF))
-                with torch.enable_grad():
-                    a, b = fm.detach().float().requires_grad_(True), fc.detach().float().requires_grad_(True)
-                    wl = wasserstein_loss_finetuning(a, b, pm, pc, nm, nc, self.lam_ft, self.lam_pvn)
-                    dfm, dfc = torch.autograd.grad(wl, (a, b))
-                loss = loss + wl.detach()
-            self.g32.zero_()
-            core.dist_backward_logits(self.student, cfg, ctx, dfm, dfc, dlogits.contiguous(), self.grads)
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self.it + 1) & 0xFFFFFFFFFFFFFFFF
+        soft = self.soft_targets(targets)
+        images = images.float().contiguous()
+        if graph is None:
+            graph = self.use_graph
+        if graph and noise is None and ops.GEMM_TIMING is None:
+            logits = self._fwd_bwd_ft_graphed(images, soft, pos_images, neg_images, seed)
         else:
-            logits, ctx = core.vit_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
-            loss, dlogits = soft_target_cross_entropy(logits, targets)
-            self.g32.zero_()
-            core.vit_backward_logits(self.student, cfg, ctx, dlogits.contiguous(), self.grads)
-        self.loss_dev.copy_(loss.reshape(1))
+            logits = self._fwd_bwd_ft(images, soft, pos_images, neg_images, noise if noise is not None else Noise(seed=seed))
+            self._eager_steps += 1
+        self.loss_dev = self.loss3[0:1]
         self.last_logits = logits               # class_acc of the training log (engine_for_finetuning.py:132-133)
         return self._optimizer_step(lr, wd)
 
@@ -577,29 +700,41 @@ def evaluate(data_loader: Iterable, model, device=None, num_classes: Optional[in
     dist_criterion=(lambda_finetuning, lambda_pvn) and a loader of (images, pos, neg, labels): the loss then includes
     WassersteinLossFineTuning of the three forwards): deterministic evaluation with the per-batch metrics of the reference,
     averaged over the batches weighted by batch size (loss: plain mean over batches, as MetricLogger.update(loss=...) does): cross-entropy,
-    acc@1 / acc@5 (percent), 15-bin ECE and NLL, all reduced on the device by the MC-metrics kernel with one sample (S = 1).
-    TACE and AUROC of the reference's printout are not computed (outside the scoped hot path)."""
+    acc@1 / acc@5 (percent), 15-bin ECE, TACE (threshold 0.01, 30 adaptive bins per class), NLL and macro one-vs-rest AUROC, all reduced on
+    the device (b200vit_mc_reduce with one sample, b200vit_tace_auroc, b200vit_finetune_loss). TACE needs at least 30 images per batch
+    (its bin edges are order statistics of the batch); smaller batches report NaN for it, where the reference would index out of range."""
     dev = device if device is not None else next(model.parameters()).device
-    sums = {"acc1": 0.0, "acc5": 0.0, "ECE": 0.0, "ECE_as_reference_computes_it": 0.0, "NLL": 0.0}
+    sums = {"acc1": 0.0, "acc5": 0.0, "ECE": 0.0, "ECE_as_reference_computes_it": 0.0, "NLL": 0.0, "TACE": 0.0, "TACE_as_reference_computes_it": 0.0,
+            "AUROC": 0.0}
     loss_sum, nb, ntot = 0.0, 0, 0
     was_training = model.training
     model.eval()
+    K = model.cfg.num_classes
     for batch in data_loader:
         images, target = batch[0].to(dev).float().contiguous(), batch[-1].to(dev)
         out = model(images)
-        logits = (out[-1] if isinstance(out, (tuple, list)) else out).float()
-        _, _, _, summary = ops.mc_reduce(logits.unsqueeze(0).contiguous(), target.to(torch.int32))
+        logits = (out[-1] if isinstance(out, (tuple, list)) else out).float().contiguous()
+        labels32 = target.to(torch.int32)
+        _, _, _, summary = ops.mc_reduce(logits.unsqueeze(0).contiguous(), labels32)
         a1, a5, ece, ece_ref, nll = summary.tolist()[:5]
         b = images.shape[0]
-        loss = torch.nn.functional.cross_entropy(logits, target.long())
+        if b >= 30:
+            tace, tace_ref, auroc = ops.tace_auroc(logits, labels32).tolist()
+        else:
+            tace, tace_ref, auroc = float("nan"), float("nan"), ops.tace_auroc(logits, labels32, n_bins=max(1, min(30, b))).tolist()[2]
+        onehot = ops.mixup_batch(None, 1.0, labels=target.long().contiguous(), num_classes=K, on_value=1.0, off_value=0.0)   # nn.CrossEntropyLoss
+        feats = None
+        lam = (1e-4, 1e-4)
         if dist_criterion is not None and len(batch) == 4 and isinstance(out, (tuple, list)):
             pm, pc, _ = model(batch[1].to(dev).float().contiguous())
             nm, nc, _ = model(batch[2].to(dev).float().contiguous())
-            loss = loss + wasserstein_loss_finetuning(out[0], out[1], pm, pc, nm, nc, dist_criterion[0], dist_criterion[1])
-        loss_sum += float(loss.item())
+            feats = tuple(t.float().contiguous() for t in (out[0], out[1], pm, pc, nm, nc))
+            lam = dist_criterion
+        loss3, _, _ = ops.finetune_loss(logits, onehot, K, feats=feats, lam_ft=lam[0], lam_pvn=lam[1])
+        loss_sum += float(loss3[0].item())
         nb += 1
         ntot += b
-        for k, v in zip(sums, (a1, a5, ece, ece_ref, nll)):
+        for k, v in zip(sums, (a1, a5, ece, ece_ref, nll, tace, tace_ref, auroc)):
             sums[k] += v * b
     model.train(was_training)
     out = {k: v / max(ntot, 1) for k, v in sums.items()}
@@ -613,6 +748,7 @@ def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, st
     EMA-decay anneal, non-finite loss aborts (:166-168). With `mask_generator` (masking_generator.MaskingGenerator) the masks of each
     batch are drawn on the device and whatever mask the loader yields is ignored (the loader may then yield bare image batches)."""
     total, n = 0.0, 0
+    engine.cur_decay = engine.ema_decay                                     # engine_for_cyclical.py:44
 
     def staged_batches():
         for batch, _ in data_loader:

@@ -117,5 +117,9 @@ def evaluate_mc_dropout(model, batches: Sequence[Tuple[torch.Tensor, torch.Tenso
     labels = torch.cat([y for _, y in batches]).to(dev).to(torch.int32)
     mean_logits, row_stats, hist, summary = ops.mc_reduce(logits.contiguous(), labels)
     s = summary.tolist()
-    return dict(acc1=s[0], acc5=s[1], ece=s[2], ece_reference=s[3], nll=s[4], entropy=s[5], variance=s[6], mutual_info=s[7],
-                mean_logits=mean_logits, row_stats=row_stats, hist=hist)
+    res = dict(acc1=s[0], acc5=s[1], ece=s[2], ece_reference=s[3], nll=s[4], entropy=s[5], variance=s[6], mutual_info=s[7],
+               mean_logits=mean_logits, row_stats=row_stats, hist=hist)
+    if N >= 30:      # TACE (30 adaptive bins per class) and AUROC of the printout, on the mean logits (uncertainty_evaluations.py:83,85)
+        t = ops.tace_auroc(mean_logits, labels).tolist()
+        res.update(tace=t[0], tace_reference=t[1], auroc=t[2])
+    return res

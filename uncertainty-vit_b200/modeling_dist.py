@@ -160,7 +160,7 @@ class DistVisionTransformer(_DistBase):
                  qkv_bias=False, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, norm_layer=nn.LayerNorm, init_values=None,
                  use_abs_pos_emb=True, use_rel_pos_bias=False, use_shared_rel_pos_bias=False, use_mean_pooling=True, init_scale=0.001,
                  linear_classifier=False, has_masking=False, learn_layer_weights=False, layernorm_before_combine=False, gp_layer=False,
-                 het_layer=False, sinkformer=False, gumbel_softmax=False, h_sto_trans=False, sngp=False, **unused):
+                 het_layer=False, sinkformer=False, gumbel_softmax=False, h_sto_trans=False, sngp=False, sample_head=False, **unused):
         super().__init__()
         _reject_unsupported(gp_layer=gp_layer, het_layer=het_layer, sinkformer=sinkformer, gumbel_softmax=gumbel_softmax, h_sto_trans=h_sto_trans,
                             sngp=sngp, use_rel_pos_bias=use_rel_pos_bias, learn_layer_weights=learn_layer_weights, drop_rate=drop_rate > 0,
@@ -192,7 +192,8 @@ class DistVisionTransformer(_DistBase):
                 w.data.div_(math.sqrt(2.0 * (layer_id + 1)))              # no init_scale on the head here (§A.2-5)
         self.cfg = VitConfig(img_size=self.patch_embed.img_size[0], patch_size=self.patch_embed.patch_size[0], in_chans=in_chans, embed_dim=embed_dim,
                              depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio, num_classes=num_classes, ln_eps=self.fc_norm.eps, kind="finetune",
-                             dist=True, drop_path_rate=drop_path_rate, attn_drop_rate=attn_drop_rate, has_gamma=self.blocks[0].gamma_1 is not None)
+                             dist=True, drop_path_rate=drop_path_rate, attn_drop_rate=attn_drop_rate, has_gamma=self.blocks[0].gamma_1 is not None,
+                             sample_head=bool(sample_head))
         self._finish_init()
 
     def get_classifier(self):

@@ -469,6 +469,11 @@ def ema_update(ema, model, decay, ema_bf16=None):
     _count()
 
 
+def ema_index_update(ema_index_i32, model_index_i32, decay):
+    check(_lib.lib().b200vit_ema_index_update(_p(ema_index_i32), _p(model_index_i32), ema_index_i32.numel(), decay, _stream()), "ema_index_update")
+    _count()
+
+
 def sumsq(g, out_accum):
     check(_lib.lib().b200vit_sumsq(_p(g), g.numel(), _p(out_accum), _stream()), "sumsq")
     _count()
