@@ -392,12 +392,14 @@ def test_finetune_loop_and_evaluate(cuda, golden_dir):
             assert abs(ev[k] - v / 7) < 2e-3 * max(1.0, abs(v / 7)), (name, k, ev[k], v / 7)
         ce = np.mean([float(torch.nn.functional.cross_entropy(o, t)) for o, (_, t) in zip(outs, loader)])
         assert abs(ev["loss"] - ce) < 1e-3
+        auroc = sum(O.auroc_macro_ovr(torch.softmax(o, 1), t) * o.shape[0] for o, (_, t) in zip(outs, loader)) / 7
+        assert abs(ev["AUROC"] - auroc) < 1e-4 and np.isnan(ev["TACE"])         # TACE's 30 adaptive bins need >= 30 images per batch
         if arch.dist:      # dist_evaluate: triplet batches, loss = CE + WassersteinLossFineTuning(anchor, positive, negative)
             trip = [(x, x.roll(1, 0), x.flip(0), y)]
             ev3 = E.evaluate(trip, model, cuda, K, dist_criterion=(1e-2, 1e-4))
             with torch.no_grad():
                 a, p_, n_ = (model(t.to(cuda)) for t in trip[0][:3])
-                expect = torch.nn.functional.cross_entropy(a[2].float(), y.to(cuda)) + E.wasserstein_loss_finetuning(a[0], a[1], p_[0], p_[1], n_[0], n_[1], 1e-2, 1e-4)
+                expect = torch.nn.functional.cross_entropy(a[2].float(), y.to(cuda)) + O.wasserstein_loss_finetune(a[0].float(), a[1].float(), p_[0].float(), p_[1].float(), n_[0].float(), n_[1].float(), 1e-2, 1e-4)
             assert abs(ev3["loss"] - float(expect)) < 1e-4 * max(1.0, abs(float(expect))) and ev3["loss"] > E.evaluate(trip, model, cuda, K)["loss"]
 
 

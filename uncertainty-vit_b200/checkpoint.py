@@ -122,6 +122,9 @@ def engine_state_dict(engine, epoch: Optional[int] = None) -> dict:
         ema = {k: v.detach().clone().cpu() for k, v in engine.ema_state_dict().items()}
         for k, v in out["model"].items():           # buffers (relative_position_index) are not in the arena: ModelEmaV2 deep-copies them
             ema.setdefault(k, v.clone())
+        if getattr(engine, "rel_e", None) is not None:
+            # the teacher's OWN index buffer: ModelEmaV2._update runs it through the EMA arithmetic as well (see b200vit_ema_index_update)
+            ema["rel_pos_bias.relative_position_index"] = engine.rel_e.detach().to(torch.int64).cpu()
         out["model_ema"] = {k: ema[k] for k in out["model"]}
     return out
 
@@ -138,6 +141,9 @@ def load_engine_state_dict(engine, ckpt: dict, load_optimizer: bool = True) -> N
         else:
             for name in engine.ema_state_dict():
                 _arena_view(engine, engine.e32, name).copy_(ema[name].to(engine.dev, torch.float32))
+            idx = ema.get("rel_pos_bias.relative_position_index")
+            if idx is not None and getattr(engine, "rel_e", None) is not None:
+                engine.rel_e.copy_(idx.to(engine.dev, torch.int32))
         ops.cast_bf16(engine.e32, engine.e16)
     if load_optimizer and "optimizer" in ckpt:
         load_optimizer_state_dict(engine, ckpt["optimizer"])
