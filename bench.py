@@ -100,10 +100,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU legs (oracle port of the reference algorithm; the only places that execute oracle/)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
+def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH, stochastic=False):
     from oracle import vit_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    arch = O.Arch(kind="cyclical", **O.VIT_B)
+    arch = O.Arch(kind="cyclical", dist=stochastic, **O.VIT_B)
     sd = O.make_state(arch, 0)
     ema = {k: v.clone() for k, v in sd.items()}
     opt = O.new_opt_state(sd)
@@ -111,7 +111,7 @@ def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     mask_t = torch.from_numpy(mask.astype(np.int64))
     g = torch.Generator().manual_seed(1)
     probs = [float(p) for p in torch.linspace(0, 0.25, arch.depth)]
-    noise = O.Noise(drop_path_keep=[(torch.rand(2, batch, generator=g) >= p).float() for p in probs], drop_path_prob=probs,
+    noise = O.Noise(drop_path_keep=[(torch.rand(4 if stochastic else 2, batch, generator=g) >= p).float() for p in probs], drop_path_prob=probs,
                     attn_keep=[(torch.rand(batch, arch.num_heads, arch.tokens, arch.tokens, generator=g) >= 0.05).float() for _ in range(arch.depth)],
                     attn_drop=0.05)
     times = []
@@ -123,18 +123,25 @@ def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     return batch * len(t) / sum(t), sum(t) / len(t), torch.get_num_threads()
 
 
+def workload_config(world, stochastic=False):
+    return {"workload": ("beit_base_patch16_224 --stochastic (dual-stream mean/cov + Wasserstein loss) " if stochastic else "beit_base_patch16_224 ")
+                        + "data2vec cyclical pretrain step (run_cyclical.py recipe), batch 128/GPU, 120 masked patches, "
+                        "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
+            "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"}
+
+
 def run_reference(args):
+    """The reference algorithm on the host cores: exactly --steps timed steps after --warmup untimed ones, each step one full data2vec
+    optimisation step of the same workload on a BOUNDED sample of CPU_SAMPLE_BATCH images (a 128-image step takes ~11 s on 16 threads)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 4))
-    v, sec, cores = cpu_reference_steps(steps, min(args.warmup, 1))
-    sample = f"{steps} full data2vec steps of {CPU_SAMPLE_BATCH} images (fp32, oracle port of the reference algorithm), {cores} threads"
+    v, sec, cores = cpu_reference_steps(args.steps, args.warmup, stochastic=args.stochastic)
+    sample = (f"{args.steps} timed + {args.warmup} warm-up full data2vec steps, each on a bounded sample of {CPU_SAMPLE_BATCH} images of the workload "
+              f"(fp32 oracle port of the reference algorithm: the reference has no packaging and cannot be launched, DESIGN.md section 9), {cores} threads")
     print(json.dumps({"impl": "reference", "metric": "data2vec ViT-B/16 pretrain throughput", "value": v, "unit": "img/s", "n_gpus": args.gpus,
-                      "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "beit_base_patch16_224 data2vec cyclical pretrain step, 120 masked patches, target_layers 6-11, EMA 0.9998",
-                                 "batch_per_step": CPU_SAMPLE_BATCH},
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus, args.stochastic),
                       "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -176,11 +183,84 @@ def run_mc_inference(dev, rank, world, M, barrier, max_over_ranks):
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / reps
-        out[key] = {"img_per_s": MC_BATCH / (ms * 1e-3), "forward_img_per_s": MC_PASSES * MC_BATCH / (ms * 1e-3), "ms_per_eval": ms,
-                    "ece": res["ece"], "nll": res["nll"], "entropy": res["entropy"]}
+        fwd = MC_PASSES * MC_BATCH / (ms * 1e-3)
+        gf = 70.25e9 if key == "stochastic" else 35.27e9                       # algorithmic forward FLOPs per image
+        pk = peaks()
+        out[key] = {"img_per_s": MC_BATCH / (ms * 1e-3), "forward_img_per_s": fwd, "ms_per_eval": ms,
+                    "ece": res["ece"], "nll": res["nll"], "entropy": res["entropy"], "tace": res.get("tace"), "auroc": res.get("auroc"),
+                    "roofline": {"bound": "tensor", "achieved": fwd * gf / 1e12 / world, "peak": pk["bf16_sustained"], "unit": "TFLOP/s per GPU",
+                                 "frac": fwd * gf / 1e12 / world / pk["bf16_sustained"], "flops_per_image": gf}}
         del model
     out["config"] = {"workload": "beit_base_patch16_224 fine-tune model, MC-sample uncertainty eval", "passes": MC_PASSES, "eval_batch": MC_BATCH,
                      "attn_drop": 0.05, "sharding": f"{MC_PASSES} passes over {world} rank(s), logits all-gathered", "scaling": "strong"}
+    return out
+
+
+def timed_steps(step_fn, steps, warmup, barrier, max_over_ranks):
+    for i in range(warmup):
+        step_fn(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = step_fn(i)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
+
+def run_stochastic_block(dev, rank, world, E, M, barrier, max_over_ranks, steps):
+    """BASELINE.json configs[2]: the --stochastic (dual-stream mean / cov + WassersteinLoss) data2vec step at the same N, same recipe."""
+    torch.manual_seed(0 + rank)
+    model = M.create_model("beit_base_patch16_224", pretrained=False, drop_path_rate=0.25, drop_rate=0.0, use_shared_rel_pos_bias=True,
+                           use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05, stochastic=True).to(dev)
+    eng = E.D2VEngine(model, lr=2e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.9998, ema_decay_init=0.999, ema_start_at=0,
+                      target_layers=[6, 7, 8, 9, 10, 11], l1_beta=2.0, post_target_layer_norm=True, world_size=world, seed=rank)
+    batches = []
+    for i in range(2):
+        x, m = synth_batch(BATCH, 300 * rank + i, pin=False)
+        mu8 = np.ascontiguousarray(m.reshape(BATCH, -1))
+        batches.append((x.to(dev), torch.from_numpy(mu8.reshape(-1)).to(dev), torch.from_numpy(eng.rows_from_host_mask(mu8, 197)).to(dev)))
+    ms, loss = timed_steps(lambda i: eng.step(*batches[i % 2], lr=1e-3), steps, 3, barrier, max_over_ranks)
+    pk = peaks()
+    tf = 281.86e9 * BATCH / (ms * 1e-3) / 1e12
+    out = {"value": world * BATCH / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms, "steps": steps, "final_loss": float(loss.item()),
+           "config": workload_config(world, True),
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s per GPU (whole step, algorithmic 281.86 GFLOP/image)",
+                        "frac": tf / pk["bf16_sustained"]}}
+    del eng, model, batches
+    torch.cuda.empty_cache()
+    return out
+
+
+FT_BATCH = 64
+
+
+def run_finetune_large_block(dev, rank, world, E, M, barrier, max_over_ranks, steps):
+    """BASELINE.json configs[4]: beit_large_patch16_224 --stochastic fine-tune TRAIN step (layer_decay 0.65, drop_path 0.2), batch 64 per GPU:
+    anchor forward + backward, eval-mode positive / negative forwards, soft-target CE + WassersteinLossFineTuning (one device kernel),
+    gradient all-reduce, fused clip + layer-decay AdamW; forward + loss + backward replayed from a CUDA graph."""
+    torch.manual_seed(0 + rank)
+    model = M.create_model("beit_large_patch16_224", pretrained=False, stochastic=True, num_classes=1000, drop_rate=0.0, drop_path_rate=0.2,
+                           attn_drop_rate=0.0, use_mean_pooling=True, init_scale=0.001, use_rel_pos_bias=False, use_shared_rel_pos_bias=True,
+                           use_abs_pos_emb=False, init_values=0.1).to(dev)
+    eng = E.FinetuneEngine(model, lr=5e-4, weight_decay=0.05, layer_decay=0.65, clip_grad=3.0, lambda_finetuning=1e-2, lambda_pvn=1e-4,
+                           world_size=world, seed=rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = [torch.randn(FT_BATCH, 3, 224, 224, generator=g).to(dev) for _ in range(3)]
+    tgt = torch.softmax(torch.randn(FT_BATCH, 1000, generator=g) * 4, -1).to(dev)
+    ms, loss = timed_steps(lambda i: eng.step(x[0], tgt, x[1], x[2]), steps, 3, barrier, max_over_ranks)
+    pk = peaks()
+    tf = 1231e9 * FT_BATCH / (ms * 1e-3) / 1e12
+    out = {"value": world * FT_BATCH / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms, "steps": steps, "final_loss": float(loss.item()),
+           "graphs": len(eng._ft_graphs),
+           "config": {"workload": "beit_large_patch16_224 --stochastic fine-tune train step (anchor fwd+bwd, eval-mode pos/neg fwd, soft-target CE + "
+                                  "WassersteinLossFineTuning, AdamW with layer_decay 0.65 groups), drop_path 0.2, batch 64/GPU, bf16",
+                      "global_batch": world * FT_BATCH, "parallelism": f"dp{world}"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s per GPU (whole step, algorithmic 1231 GFLOP/image)",
+                        "frac": tf / pk["bf16_sustained"]}}
+    del eng, model, x
+    torch.cuda.empty_cache()
     return out
 
 
@@ -207,9 +287,6 @@ def run_b200(args):
     extra = {"stochastic": True} if args.stochastic else {}      # --stochastic: the dual-stream (mean / cov) model + Wasserstein loss
     model = M.create_model("beit_base_patch16_224", pretrained=False, drop_path_rate=0.25, drop_rate=0.0, use_shared_rel_pos_bias=True,
                            use_abs_pos_emb=False, init_values=1e-4, attn_drop_rate=0.05, **extra).to(dev)
-    if world > 1:                                                 # DDP broadcasts rank 0's parameters at construction
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
     eng = E.D2VEngine(model, lr=2e-3, weight_decay=0.05, clip_grad=3.0, ema_decay=0.9998, ema_decay_init=0.999, ema_start_at=0,
                       target_layers=[6, 7, 8, 9, 10, 11], l1_beta=2.0, post_target_layer_norm=True, world_size=world, seed=rank)
     lr_sched = E.cosine_scheduler(2e-3, 1e-5, 800, 10, warmup_epochs=10)       # per-step lr as the runner computes it
@@ -251,6 +328,7 @@ def run_b200(args):
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (ops.LAUNCHES - launches0)
     final_loss = float(loss.item())
+    z0_mean = float(eng.z0_dev.mean().item()) if eng.z0_dev is not None else None
     # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs. Every step's inputs are copied from
     # pinned host memory inside the timed region; as in engine.train_one_epoch the copy of batch i+1 is enqueued on the copy stream
     # before step i is launched (a one-batch look-ahead data loader), and the loss of every step is read back.
@@ -317,10 +395,16 @@ def run_b200(args):
                 "gemm_ms_per_step": t_ms / 2, "gemm_share_of_step": (t_ms / 2) / ms, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / pk["bf16_burst"]}
     barrier()
+    # ---- the other BASELINE configs at the same N (skipped when this run IS the --stochastic step): driver-visible sub-blocks
+    del eng, dev_batches
+    torch.cuda.empty_cache()
+    sub_steps = max(3, min(args.steps, 10))
+    stoch_res = None if (args.stochastic or args.no_sub) else run_stochastic_block(dev, rank, world, E, M, barrier, max_over_ranks, sub_steps)
+    ft_res = None if args.no_sub else run_finetune_large_block(dev, rank, world, E, M, barrier, max_over_ranks, sub_steps)
     mc_res = None if args.no_mc else run_mc_inference(dev, rank, world, M, barrier, max_over_ranks)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_steps(2, 1)
+        v, sec, cores = cpu_reference_steps(2, 1, stochastic=args.stochastic)
         cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
                "sample": f"2 full data2vec steps of {CPU_SAMPLE_BATCH} images after 1 warm-up ({sec:.2f} s/step), fp32 oracle port, {cores} threads"}
     if rank == 0:
@@ -329,13 +413,10 @@ def run_b200(args):
             "metric": "data2vec ViT-B/16 pretrain throughput", "value": world * BATCH / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": ("beit_base_patch16_224 --stochastic (dual-stream mean/cov + Wasserstein loss) " if args.stochastic else "beit_base_patch16_224 ")
-                                   + "data2vec cyclical pretrain step (run_cyclical.py recipe), batch 128/GPU, 120 masked patches, "
-                                   "target_layers 6-11, EMA 0.9998, bf16 GEMMs / fp32 master weights", "global_batch": world * BATCH,
-                       "parallelism": f"dp{world}", "l2": "working set per step (>9 GB of activations) is far larger than the 126 MB L2; two alternating input batches"},
+            "config": workload_config(world, args.stochastic),
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "mc_inference": mc_res, "blockwise_masks_e2e": blockwise,
-            "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "stochastic": stoch_res, "finetune_large": ft_res, "mc_inference": mc_res, "blockwise_masks_e2e": blockwise,
+            "final_loss": final_loss, "z0_mean": z0_mean,
             "step_tflops_algorithmic": (281.86e9 if args.stochastic else 140.93e9) * BATCH / (ms * 1e-3) / 1e12}))
     if world > 1:
         dist.destroy_process_group()
@@ -351,6 +432,7 @@ def main():
     ap.add_argument("--stochastic", action="store_true",
                     help="BASELINE.json configs[2] variant: the dual-stream --stochastic pre-training step (not the headline metric)")
     ap.add_argument("--no-mc", action="store_true", help="skip the MC-sample uncertainty-inference measurement (BASELINE.json configs[3])")
+    ap.add_argument("--no-sub", action="store_true", help="skip the --stochastic step and ViT-L fine-tune sub-blocks (BASELINE.json configs[2] and [4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
