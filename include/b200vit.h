@@ -23,9 +23,11 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 4   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+#define B200VIT_ABI_VERSION 5   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
                                    3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8;
-                                   4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss */
+                                   4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss;
+                                   5: tcgen05 Wasserstein attention (wattn_fwd / wattn_bwd take the transformed-operand workspace and the bias
+                                      row maxima), rel_pos_bias rowmax output */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -114,22 +116,28 @@ int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const f
                      const uint8_t* keep_bits, void* work, int32_t ld_ds, const int32_t* rel_index, float* dtable,
                      float* dq_bias, float* dv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
                      void* dqkv, void* stream);
-/* Wasserstein-distance attention of the dual-stream (--stochastic) model: dist Attention.forward (modeling_finetune_dist.py:111-179)
- * with wasserstein_distance_matmul (uncertainty_evaluations.py:276-294). qkv_mean / qkv_cov: bf16 [B, N, 3, H, 64]; qkv_cov holds
- * elu(.)+1 already (GEMM epilogue B200VIT_EPI_ELU1). bias (required) in the padded layout of b200vit_rel_pos_bias.
- * out_mean = P~ v, out_cov = (P~)^2 cv, both bf16 [B, N, H*64]. */
-int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N,
-                      int32_t head_dim, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
-                      const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
-/* Backward of b200vit_wattn_fwd (two kernels: key-tile owners -> dV, dCV, dK, dCK and dD^T; query-tile owners -> dQ, dCQ).
- * dqkv_cov is the gradient w.r.t. the PRE-activation of elu(.)+1, i.e. ready for the QKV wgrad / dgrad GEMMs.
- * work_dD / work_dA: bf16 workspaces [B, H, N, ld_ds] (dA only when dtable != NULL). Bias gradients (optional, +=, [H*64]):
- * dq_bias / dv_bias (q_bias, v_bias) and dcq_bias / dcv_bias (cov_q_bias, cov_v_bias). */
-int b200vit_wattn_bwd(const void* qkv_mean, const void* qkv_cov, const void* out_mean, const void* out_cov, const void* dout_mean,
-                      const void* dout_cov, const float* lse, const float* bias_t, int64_t ld_bias, const uint8_t* keep_bits,
-                      void* work_dD, void* work_dA, int32_t ld_ds, const int32_t* rel_index, float* dtable, float* dq_bias,
-                      float* dv_bias, float* dcq_bias, float* dcv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
-                      float scale, float p_drop, void* dqkv_mean, void* dqkv_cov, void* stream);
+/* Wasserstein-distance attention of the dual-stream (--stochastic) model on tcgen05 / TMEM: dist Attention.forward
+ * (modeling_finetune_dist.py:111-179) with wasserstein_distance_matmul (uncertainty_evaluations.py:276-294). qkv_mean / qkv_cov: bf16
+ * [B, N, 3, H, 64]; qkv_cov holds elu(.)+1 already (GEMM epilogue B200VIT_EPI_ELU1). bias (required) and bias_rowmax ([H, N] = max_j bias) in the
+ * layouts of b200vit_rel_pos_bias (log2(e)-scaled). out_mean = P~ v, out_cov = (P~)^2 cv, both bf16 [B, N, H*64].
+ * xwork: caller-owned, 256-byte aligned, b200vit_wattn_workspace_bytes(B, H, N) bytes: the forward stores the transformed operands
+ * [sigmoid(scale q) | sqrt(sigmoid(cq))], [sigmoid(k) | sqrt(sigmoid(ck))] (bf16 [B, N, 2, H, 128]) and their row norms there; the backward of the
+ * same forward must be given the same (unmodified) buffer. */
+size_t b200vit_wattn_workspace_bytes(int32_t B, int32_t H, int32_t N);
+int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, const float* bias_rowmax, void* xwork,
+                      int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                      uint32_t stream_id, const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
+/* Backward of b200vit_wattn_fwd (prep: Delta_i and the transposed keep bits; key-tile kernel -> dV, dCV and dD^T; per-(batch, head) kernel ->
+ * dQ, dCQ, dK, dCK from dD^T and the transformed operands). dqkv_cov is the gradient w.r.t. the PRE-activation of elu(.)+1, i.e. ready for the
+ * QKV wgrad / dgrad GEMMs. work: caller-owned, 256-byte aligned, b200vit_wattn_bwd_workspace_bytes(B, H, N, dtable != NULL) bytes (dD^T, Delta,
+ * transposed keep bits and, for the bias-table gradient, dA^T). Bias gradients (optional, +=, [H*64]): dq_bias / dv_bias (q_bias, v_bias) and
+ * dcq_bias / dcv_bias (cov_q_bias, cov_v_bias). */
+size_t b200vit_wattn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N, int32_t with_dtable);
+int b200vit_wattn_bwd(const void* qkv_mean, const void* qkv_cov, const void* xwork, const void* out_mean, const void* out_cov,
+                      const void* dout_mean, const void* dout_cov, const float* lse, const float* bias_t, int64_t ld_bias,
+                      const uint8_t* keep_bits, void* work, const int32_t* rel_index, float* dtable, float* dq_bias, float* dv_bias,
+                      float* dcq_bias, float* dcv_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop,
+                      void* dqkv_mean, void* dqkv_cov, void* stream);
 /* The Philox keep mask of b200vit_attn_fwd as uint8 [BH, N, N] (parity tests inject it into the CPU oracle). */
 int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 
@@ -178,9 +186,10 @@ int b200vit_block_masks(uint8_t* mask, int32_t* count, int32_t* rows, int32_t B,
 /* RelativePositionBias.forward (modeling_finetune.py:359-364) in the padded layouts the attention kernels read:
  *   out_fwd  [H, N, ld]: scale * table[index[i,j], h] for j < N, -inf for N <= j < ld  (key mask baked into the padding)
  *   out_bwd_t[H, N, ld]: the transpose (row = key j, column = query i), 0 in the padding.   Either may be NULL.
+ *   rowmax_fwd[H, N]  : max_j scale * table[index[i,j], h] (optional): the stabiliser of the single-pass Wasserstein attention forward.
  * The attention kernels expect scale = log2(e) and ld = N rounded up to 16. */
 int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t ld, float scale, float* out_fwd,
-                         float* out_bwd_t, void* stream);
+                         float* out_bwd_t, float* rowmax_fwd, void* stream);
 /* x[:, 1:].mean(1) (modeling_finetune.py:512-514) */
 int b200vit_meanpool_tokens(const float* x, int32_t B, int32_t T, int32_t C, float* out, void* stream);
 /* backward of the mean pooling: dx[b, t>=1, :] += dpool[b, :] / (T-1) */

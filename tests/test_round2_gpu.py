@@ -131,6 +131,66 @@ def test_gemm_a_mn_only_large_k(ops, cuda):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# 1b. Wasserstein attention (tcgen05 / TMEM) forward + backward against fp32 torch autograd of the reference formulas
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,N,p", [(2, 2, 17, 0.0), (2, 3, 197, 0.0), (3, 2, 197, 0.1), (1, 2, 64, 0.25), (2, 2, 208, 0.05), (1, 1, 5, 0.0),
+                                     (1, 2, 129, 0.0), (40, 12, 197, 0.05)])
+def test_wattention_fwd_bwd(ops, cuda, B, H, N, p):
+    """dist Attention.forward (modeling_finetune_dist.py:119-162) with wasserstein_distance_matmul (uncertainty_evaluations.py:276-294): outputs,
+    log-sum-exp and every gradient (q, k, v, cov q / k / v through elu + 1, the four bias gradients, the relative-position table) against
+    torch autograd in fp32 on the SAME bf16-rounded inputs and the same dropout mask; multi-item persistence at B = 40, H = 12."""
+    from oracle import vit_oracle as O
+    g = torch.Generator(device=cuda).manual_seed(1000 * B + N)
+    scale = 64 ** -0.5
+    qkv_m = _bf(torch.randn(B, N, 3, H, 64, generator=g, device=cuda) * 1.5)
+    z = (torch.randn(B, N, 3, H, 64, generator=g, device=cuda) * 1.5)
+    qkv_c = _bf(torch.nn.functional.elu(z) + 1)
+    zr = qkv_c.float() - 1                               # pre-activation consistent with the ROUNDED elu + 1 values where z > 0 ...
+    zr = torch.where(qkv_c.float() <= 1, torch.log(qkv_c.float().clamp_min(1e-30)), zr).requires_grad_(True)     # ... and log(c') where z <= 0
+    bias = torch.randn(H, N, N, generator=g, device=cuda) * 2.0
+    bias_fwd, bias_t = ops.pad_attn_bias(bias)
+    keep = None
+    if p > 0:
+        keep = (torch.rand(B, H, N, N, generator=g, device=cuda) >= p).to(torch.uint8).contiguous()
+    om = torch.full((B, N, H * 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+    oc = torch.full_like(om, float("nan"))
+    lse = torch.empty(B, H, N, device=cuda)
+    keep_bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=cuda) if p > 0 else None
+    xwork = ops.wattn_fwd(qkv_m, qkv_c, bias_fwd, B, H, N, scale, p, seed=3, stream_id=1, keep_in=keep, out_mean=om, out_cov=oc, lse=lse, keep_bits=keep_bits)
+    # ---- fp32 reference
+    qm = qkv_m.float().requires_grad_(True)
+    q, k, v = (qm[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    cq, ck, cv = ((torch.nn.functional.elu(zr) + 1)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    biasg = bias.clone().requires_grad_(True)
+    A = torch.sigmoid(-O.wasserstein_distance_matmul(q * scale, cq, k, ck) + 1e-24) + biasg
+    P = A.softmax(-1)
+    Pt = P * keep.float() / (1 - p) if p > 0 else P
+    om_r = (Pt @ v).transpose(1, 2).reshape(B, N, H * 64)
+    oc_r = ((Pt ** 2) @ cv).transpose(1, 2).reshape(B, N, H * 64)
+    assert rel(om.float(), om_r) < 2e-2 and rel(oc.float(), oc_r) < 2e-2
+    assert rel(lse, torch.logsumexp(A, -1)) < 1e-3
+    dom = _bf(torch.randn(B, N, H * 64, generator=g, device=cuda))
+    doc = _bf(torch.randn(B, N, H * 64, generator=g, device=cuda))
+    ((om_r * dom.float()).sum() + (oc_r * doc.float()).sum()).backward()
+    # ---- backward kernels (the table gradient through an identity-like index: every (i, j) pair its own bin)
+    dqm = torch.full_like(qkv_m, float("nan"))
+    dqc = torch.full_like(qkv_c, float("nan"))
+    rel_index = torch.arange(N * N, dtype=torch.int32, device=cuda).view(N, N)
+    dtable = torch.zeros(N * N, H, device=cuda)
+    db = [torch.zeros(H * 64, device=cuda) for _ in range(4)]
+    ops.wattn_bwd(qkv_m, qkv_c, xwork, om, oc, dom, doc, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p, dqm, dqc,
+                  dq_bias=db[0], dv_bias=db[1], dcq_bias=db[2], dcv_bias=db[3])
+    gm, gz = qm.grad, zr.grad
+    names = ["dq", "dk", "dv"]
+    for i in range(3):
+        assert rel(dqm[:, :, i].float(), gm[:, :, i]) < 3e-2, (names[i], rel(dqm[:, :, i].float(), gm[:, :, i]))
+        assert rel(dqc[:, :, i].float(), gz[:, :, i]) < 3e-2, ("c" + names[i], rel(dqc[:, :, i].float(), gz[:, :, i]))
+    assert rel(dtable.view(N, N, H).permute(2, 0, 1), biasg.grad) < 3e-2
+    assert rel(db[0], gm[:, :, 0].sum((0, 1)).reshape(-1)) < 3e-2 and rel(db[1], gm[:, :, 2].sum((0, 1)).reshape(-1)) < 3e-2
+    assert rel(db[2], gz[:, :, 0].sum((0, 1)).reshape(-1)) < 3e-2 and rel(db[3], gz[:, :, 2].sum((0, 1)).reshape(-1)) < 3e-2
+
+
+# ------------------------------------------------------------------------------------------------------------
 # 2. target-builder variants, z0 / hinge, mask dropout, sampler, fine-tune criterion, TACE / AUROC (fp32 kernels: 1e-4)
 # ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("bn,inorm,post_in,ln_each,ln_post", [(False, True, False, True, True), (True, False, False, False, True),

@@ -44,8 +44,10 @@ _PROTOS = {
     "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp]),
     "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp]),
     "b200vit_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
-    "b200vit_wattn_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp, vp]),
-    "b200vit_wattn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
+    "b200vit_wattn_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
+    "b200vit_wattn_fwd": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp, vp]),
+    "b200vit_wattn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
+    "b200vit_wattn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
     "b200vit_dropout_mask": (i32, [vp, i32, i32, f32, u64, u32, vp]),
     "b200vit_layernorm_fwd": (i32, [vp, i64, vp, vp, vp, f32, i32, i32, vp, vp, vp, vp, vp]),
     "b200vit_layernorm_bwd": (i32, [vp, i32, vp, i64, vp, vp, vp, vp, i32, i32, vp, i64, vp, vp, vp]),
@@ -59,7 +61,7 @@ _PROTOS = {
     "b200vit_mixup_batch": (i32, [vp, i32, i32, i32, i32, f32, f32, i32, i32, i32, i32, i32, vp, i32, f32, f32, vp, vp]),
     "b200vit_normalize_u8": (i32, [vp, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), vp, vp]),
     "b200vit_block_masks": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, C.c_double, C.c_double, u64, u64, vp, i32, vp]),
-    "b200vit_rel_pos_bias": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
+    "b200vit_rel_pos_bias": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
     "b200vit_meanpool_tokens": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_meanpool_tokens_bwd": (i32, [vp, i32, i32, i32, vp, vp]),
     "b200vit_d2v_target_loss": (i32, [C.POINTER(vp), i32, i64, vp, vp, i32, i32, i32, i32, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
@@ -103,7 +105,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 4:
+        if l.b200vit_abi_version() != 5:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

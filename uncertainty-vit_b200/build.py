@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200vit.so")
-SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "wattention.cu", "rowwise.cu", "d2v.cu", "mc_metrics.cu", "maskgen.cu", "mixup.cu", "imgnorm.cu", "d2v_extras.cu", "calibration.cu", "ft_loss.cu"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "wattention_sm100.cu", "rowwise.cu", "d2v.cu", "mc_metrics.cu", "maskgen.cu", "mixup.cu", "imgnorm.cu", "d2v_extras.cu", "calibration.cu", "ft_loss.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas",
               "-v" if os.environ.get("B200VIT_PTXAS_V") else "-O3"]
 NVCC_FLAGS += os.environ.get("B200VIT_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DB200VIT_KV_TRACE for tools/micro/kv_trace.py
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    if procs or not os.path.exists(LIB):
+    if procs or not os.path.exists(LIB) or any(_newer(o, LIB) for o in objs):
         cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:

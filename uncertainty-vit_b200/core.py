@@ -219,11 +219,12 @@ def stem_backward(ps: ParamSource, cfg: VitConfig, patches: torch.Tensor, dx: to
 
 
 def rel_bias(ps: ParamSource, cfg: VitConfig, dev, want_bwd: bool = True):
-    """(bias_fwd, bias_bwd_t) padded log2(e)-scaled relative position bias, or (None, None)."""
+    """(bias_fwd, bias_bwd_t) padded log2(e)-scaled relative position bias, or (None, None). The dual-stream forward also gets the row maxima
+    (bias_fwd.rowmax), the stabiliser of its single-pass softmax."""
     table = ps.f32("rel_pos_bias.relative_position_bias_table")
     if table is None:
         return None, None
-    return ops.rel_pos_bias(table, ps.rel_index_i32(), cfg.tokens, cfg.num_heads, want_bwd)
+    return ops.rel_pos_bias(table, ps.rel_index_i32(), cfg.tokens, cfg.num_heads, want_bwd, want_rowmax=cfg.dist)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -367,7 +368,7 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
 # ------------------------------------------------------------------------------------------------------------------
 def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: torch.Tensor, *, save: bool,
                        dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
-                       seed_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                       seed_dev: Optional[torch.Tensor] = None, xwork_scratch: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
     M2 = 2 * M
@@ -385,7 +386,11 @@ def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tens
     att = _empty((M2, C), bf, dev)
     lse = _empty((B, H, T), torch.float32, dev) if save else None
     keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
-    ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits, seed_dev=seed_dev)
+    # the transformed operands [sigmoid(q) | sqrt(sigmoid(cq))], [sigmoid(k) | sqrt(sigmoid(ck))]: kept for the backward when saving, else one
+    # scratch buffer shared by all blocks of the forward
+    xwork = ops.wattn_workspace(B, H, T, dev) if (save or xwork_scratch is None) else xwork_scratch
+    ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits, seed_dev=seed_dev,
+                  xwork=xwork)
     x_mid = _empty((M2, C), torch.float32, dev)
     t1 = _empty((M2, C), bf, dev) if save else None
     g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
@@ -409,7 +414,7 @@ def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tens
              rowscale=dp_mlp, rows_per_scale=T, residual=x_mid, out_f32=x_out, out2_bf16=t2)
     if not save:
         return {"x_out": x_out, "x_mid": x_mid}
-    return dict(x_in=x_in, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, keep_bits=keep_bits, t1=t1, x_mid=x_mid, h2=h2,
+    return dict(x_in=x_in, h1=h1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, keep_bits=keep_bits, xwork=xwork, t1=t1, x_mid=x_mid, h2=h2,
                 mean2=mean2, rstd2=rstd2, act=act, pre=pre, t2=t2, x_out=x_out, dp_attn_m=dpv(0), dp_attn_c=dpv(2), dp_mlp=dp_mlp, p_attn=p_attn)
 
 
@@ -438,10 +443,11 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
     p_attn = cfg.attn_drop_rate if attn_drop_on else 0.0
     saved, lm, lc = [], {}, {}
     collect = collect or []
+    scratch = None if save else ops.wattn_workspace(B, cfg.num_heads, T, dev)
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = dist_block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn,
-                               seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev)
+                               seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev, xwork_scratch=scratch)
         x = s["x_out"]
         if i in collect:
             lm[i] = x[:M].view(B, T, C)
@@ -524,10 +530,9 @@ def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, to
     ops.gemm(dt[:M], ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh[:M])
     ops.gemm(dt[M:], ps.bf16(p + "attn.cov_proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh[M:])
     qkv = s["qkv"]
-    ops.wattn_bwd(qkv[:M], qkv[M:], att[:M], att[M:], dh[:M], dh[M:], s["lse"], bias_t, s["keep_bits"],
+    ops.wattn_bwd(qkv[:M], qkv[M:], s["xwork"], att[:M], att[M:], dh[:M], dh[M:], s["lse"], bias_t, s["keep_bits"],
                   ps.rel_index_i32() if dtable is not None else None, dtable, B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv[:M], dqkv[M:],
-                  ws["ds"], ws["ds2"] if dtable is not None else None, dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"),
-                  dcq_bias=g("attn.cov_q_bias"), dcv_bias=g("attn.cov_v_bias"))
+                  work=ws["wattn"], dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"), dcq_bias=g("attn.cov_q_bias"), dcv_bias=g("attn.cov_v_bias"))
     ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))        # both streams multiply by qkv.weight (cov_qkv.weight stays unused, §A.2-1)
     ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M2, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"))
@@ -560,9 +565,9 @@ def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, do
     M2, Hd = 2 * M, cfg.hidden
     bf = torch.bfloat16
     ld = (T + 15) // 16 * 16
-    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
-              ds=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev), ds2=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev))
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
+              wattn=ops.wattn_bwd_workspace(B, cfg.num_heads, T, dtable is not None, dev))
     for i in reversed(range(cfg.depth)):
         dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
         ctx["saved"][i] = None
@@ -641,9 +646,9 @@ def dist_backward_logits(ps: ParamSource, cfg: VitConfig, ctx, dmean_feat, dcov_
     M2, Hd = 2 * M, cfg.hidden
     bf = torch.bfloat16
     ld = (T + 15) // 16 * 16
-    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
-              ds=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev), ds2=torch.zeros((B, cfg.num_heads, T, ld), dtype=bf, device=dev))
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
+    ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
+              wattn=ops.wattn_bwd_workspace(B, cfg.num_heads, T, dtable is not None, dev))
     for i in reversed(range(cfg.depth)):
         dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
         ctx["saved"][i] = None

@@ -40,6 +40,17 @@ __global__ void rel_pos_bias_kernel(const float* __restrict__ table, const int* 
   }
 }
 
+// rowmax[h, i] = max_j scale * table[index[i, j], h]: the softmax stabiliser of the single-pass Wasserstein attention forward
+__global__ void rel_pos_bias_rowmax_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, float scale,
+                                           float* __restrict__ rowmax) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * N) return;
+  const int i = t % N, h = t / N;
+  float m = -INFINITY;
+  for (int j = 0; j < N; ++j) m = fmaxf(m, scale * __ldg(table + (long long)index[i * N + j] * H + h));
+  rowmax[t] = m;
+}
+
 // Relative-position-bias table gradient: dtable[index[i, j], h] += sum_b dS[b, h, i, j]  (dS^T stored [B, H, j, ld] by attn_bwd)
 __global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restrict__ ds, int B, int H, int N, int ld,
                                                            const int* __restrict__ rel_index, float* __restrict__ dtable) {
@@ -92,11 +103,17 @@ extern "C" int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p
 }
 
 extern "C" int b200vit_rel_pos_bias(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t ld, float scale, float* out_fwd,
-                                    float* out_bwd_t, void* stream) {
-  B200_CHECK_ARG(table != nullptr && index != nullptr && (out_fwd != nullptr || out_bwd_t != nullptr) && N > 0 && H > 0 && ld >= N,
-                 "rel_pos_bias: bad arguments");
+                                    float* out_bwd_t, float* rowmax_fwd, void* stream) {
+  B200_CHECK_ARG(table != nullptr && index != nullptr && (out_fwd != nullptr || out_bwd_t != nullptr || rowmax_fwd != nullptr) && N > 0 && H > 0 &&
+                     ld >= N, "rel_pos_bias: bad arguments");
   const int sms = b200vit_num_sms();
-  rel_pos_bias_kernel<<<sms * 4, 256, 0, STREAM>>>(table, index, N, H, ld, scale, out_fwd, out_bwd_t);
-  B200_CHECK_LAUNCH("rel_pos_bias");
+  if (out_fwd != nullptr || out_bwd_t != nullptr) {
+    rel_pos_bias_kernel<<<sms * 4, 256, 0, STREAM>>>(table, index, N, H, ld, scale, out_fwd, out_bwd_t);
+    B200_CHECK_LAUNCH("rel_pos_bias");
+  }
+  if (rowmax_fwd != nullptr) {
+    rel_pos_bias_rowmax_kernel<<<(H * N + 127) / 128, 128, 0, STREAM>>>(table, index, N, H, scale, rowmax_fwd);
+    B200_CHECK_LAUNCH("rel_pos_bias_rowmax");
+  }
   return 0;
 }

@@ -144,20 +144,46 @@ def attn_bwd(qkv, out, dout, lse, bias_t, keep_bits, rel_index, dtable, B, H, N,
     _count((4 if p_drop > 0 else 3) + (1 if dtable is not None else 0))
 
 
+def _aligned_bytes(nbytes: int, device) -> torch.Tensor:
+    """uint8 buffer whose data pointer is 256-byte aligned (torch's CUDA allocator hands out 512-byte aligned blocks)."""
+    t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    assert t.data_ptr() % 256 == 0
+    return t
+
+
+def wattn_workspace(B, H, N, device) -> torch.Tensor:
+    """Transformed-operand workspace of the Wasserstein attention (written by wattn_fwd, read by wattn_bwd of the same forward)."""
+    return _aligned_bytes(_lib.lib().b200vit_wattn_workspace_bytes(B, H, N), device)
+
+
+def wattn_bwd_workspace(B, H, N, with_dtable: bool, device) -> torch.Tensor:
+    return _aligned_bytes(_lib.lib().b200vit_wattn_bwd_workspace_bytes(B, H, N, int(with_dtable)), device)
+
+
 def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out_mean=None, out_cov=None, lse=None,
-              keep_bits=None, seed_dev=None):
-    check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), B, H, N, 64, scale, p_drop, seed, _p(seed_dev), stream_id,
-                                       _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), _stream()), "wattn_fwd")
-    _count()
+              keep_bits=None, seed_dev=None, xwork=None, bias_rowmax=None):
+    """bias: padded fwd layout of rel_pos_bias(); its row maxima ride along as `bias.rowmax` (or pass bias_rowmax)."""
+    if bias_rowmax is None:
+        bias_rowmax = getattr(bias, "rowmax", None)
+    if bias_rowmax is None:
+        raise _lib.B200VitError("wattn_fwd: the padded bias must come from ops.rel_pos_bias / ops.pad_attn_bias (row maxima attached)")
+    if xwork is None:
+        xwork = wattn_workspace(B, H, N, qkv_mean.device)
+    check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), _p(bias_rowmax), _p(xwork), B, H, N, 64, scale, p_drop,
+                                       seed, _p(seed_dev), stream_id, _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), _stream()),
+          "wattn_fwd")
+    _count(2)
+    return xwork
 
 
-def wattn_bwd(qkv_mean, qkv_cov, out_mean, out_cov, dout_mean, dout_cov, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p_drop,
-              dqkv_mean, dqkv_cov, work_dD, work_dA=None, dq_bias=None, dv_bias=None, dcq_bias=None, dcv_bias=None):
-    check(_lib.lib().b200vit_wattn_bwd(_p(qkv_mean), _p(qkv_cov), _p(out_mean), _p(out_cov), _p(dout_mean), _p(dout_cov), _p(lse), _p(bias_t),
-                                       bias_t.stride(1), _p(keep_bits), _p(work_dD), _p(work_dA), work_dD.shape[-1], _p(rel_index), _p(dtable),
-                                       _p(dq_bias), _p(dv_bias), _p(dcq_bias), _p(dcv_bias), B, H, N, 64, scale, p_drop, _p(dqkv_mean),
-                                       _p(dqkv_cov), _stream()), "wattn_bwd")
-    _count(3 if dtable is not None else 2)
+def wattn_bwd(qkv_mean, qkv_cov, xwork, out_mean, out_cov, dout_mean, dout_cov, lse, bias_t, keep_bits, rel_index, dtable, B, H, N, scale, p_drop,
+              dqkv_mean, dqkv_cov, work=None, dq_bias=None, dv_bias=None, dcq_bias=None, dcv_bias=None):
+    if work is None:
+        work = wattn_bwd_workspace(B, H, N, dtable is not None, qkv_mean.device)
+    check(_lib.lib().b200vit_wattn_bwd(_p(qkv_mean), _p(qkv_cov), _p(xwork), _p(out_mean), _p(out_cov), _p(dout_mean), _p(dout_cov), _p(lse),
+                                       _p(bias_t), bias_t.stride(1), _p(keep_bits), _p(work), _p(rel_index), _p(dtable), _p(dq_bias), _p(dv_bias),
+                                       _p(dcq_bias), _p(dcv_bias), B, H, N, 64, scale, p_drop, _p(dqkv_mean), _p(dqkv_cov), _stream()), "wattn_bwd")
+    _count(3 + (1 if p_drop > 0 else 0) + (1 if dtable is not None else 0))
 
 
 def dropout_mask(BH, N, p_drop, seed, stream_id, device) -> torch.Tensor:
@@ -299,13 +325,16 @@ def attn_ld(N: int) -> int:
     return (N + 15) // 16 * 16
 
 
-def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True):
+def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True, want_rowmax: bool = False):
     """(bias_fwd [H,N,ld], bias_bwd_t [H,N,ld] or None) in the padded, log2(e)-scaled layout of the attention kernels."""
     ld = attn_ld(N)
     fwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device)
     bwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device) if want_bwd else None
-    check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, ld, LOG2E, _p(fwd), _p(bwd), _stream()), "rel_pos_bias")
-    _count()
+    rowmax = torch.empty(H, N, dtype=torch.float32, device=table.device) if want_rowmax else None
+    check(_lib.lib().b200vit_rel_pos_bias(_p(table), _p(index_i32), N, H, ld, LOG2E, _p(fwd), _p(bwd), _p(rowmax), _stream()), "rel_pos_bias")
+    _count(2 if want_rowmax else 1)
+    if rowmax is not None:
+        fwd.rowmax = rowmax            # stabiliser of the single-pass Wasserstein attention forward (rides along with the padded bias)
     return fwd, bwd
 
 
@@ -317,7 +346,9 @@ def pad_attn_bias(bias: torch.Tensor):
     fwd[:, :, :N] = bias * LOG2E
     bwd = torch.zeros((H, N, ld), dtype=torch.float32, device=bias.device)
     bwd[:, :, :N] = bias.transpose(1, 2) * LOG2E
-    return fwd.contiguous(), bwd.contiguous()
+    fwd = fwd.contiguous()
+    fwd.rowmax = (bias * LOG2E).amax(-1).contiguous()
+    return fwd, bwd.contiguous()
 
 
 def meanpool_tokens(x, B, T, C_, out):
