@@ -33,6 +33,12 @@ const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
 /* number of SMs of the current device (148 on B200); <0 when no CUDA device is usable */
 int b200vit_device_sm_count(void);
+/* Caps the number of SMs the library's persistent kernels size their grids for (0 = no cap; rounded down to an even number); returns the
+ * previous cap. The data-parallel engine lowers it while the NCCL gradient all-reduce of the upper layers runs beside the backward pass of
+ * the lower ones (replaces DDP's bucketed overlap, run_cyclical.py:515-519): a persistent kernel with a static tile schedule that cannot get
+ * all its CTAs resident at once would otherwise run its last CTAs as a second wave. Process-wide, not thread-safe by design (one process
+ * per GPU). b200vit_device_sm_count() reports the capped value. */
+int b200vit_set_sm_limit(int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM (tcgen05.mma, TMEM accumulators, TMA-fed, persistent, warp-specialised).

@@ -19,6 +19,7 @@ def rel(a, b):
 @pytest.fixture(scope="module")
 def ops(cuda):
     import uncertainty_vit_b200 as pkg
+    from uncertainty_vit_b200 import modeling, modeling_dist  # noqa: F401
     torch.backends.cuda.matmul.allow_tf32 = False          # the fp32 torch.matmul references below must be true fp32
     torch.backends.cudnn.allow_tf32 = False
     return pkg.ops
@@ -367,7 +368,7 @@ def test_engine_against_reference_training_loop_golden(cuda, golden_dir, name):
     on (tools/make_golden.py::case_train_loop): per-step losses, mean gradient norm, weights and EMA teacher after the loop, the teacher's
     truncated index buffer (bit-exact), the logged cur_decay and loss_var0."""
     import uncertainty_vit_b200 as pkg
-    from uncertainty_vit_b200 import engine as E
+    from uncertainty_vit_b200 import engine as E, modeling, modeling_dist  # noqa: F401
     from tests.test_model_gpu import _build_dist, _build_from_gold
     gold = torch.load(os.path.join(golden_dir, name + ".pt"))
     kw = gold["loop_kw"]

@@ -40,6 +40,7 @@ _PROTOS = {
     "b200vit_last_error": (C.c_char_p, []),
     "b200vit_abi_version": (i32, []),
     "b200vit_device_sm_count": (i32, []),
+    "b200vit_set_sm_limit": (i32, [i32]),
     "b200vit_gemm_bf16": (i32, [C.POINTER(GemmDesc), vp]),
     "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, vp]),
     "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp]),

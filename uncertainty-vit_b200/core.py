@@ -328,9 +328,11 @@ def all_patch_rows(B: int, T: int, dev) -> torch.Tensor:
     return t
 
 
-def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads: Dict[str, torch.Tensor], dout_is_bf16_rows: bool = False):
+def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads: Dict[str, torch.Tensor], dout_is_bf16_rows: bool = False,
+                 after_block=None):
     """Accumulates parameter gradients into `grads` (fp32 tensors by reference name, caller zero-initialises).
-    dout: gradient of the forward output ('masked'/'all' modes): fp32 or bf16 [R, C]."""
+    dout: gradient of the forward output ('masked'/'all' modes): fp32 or bf16 [R, C].
+    after_block(i): called once block i's backward has been enqueued (the gradients of blocks i.. and of the head are final then)."""
     B = ctx["B"]
     T, C = cfg.tokens, cfg.embed_dim
     M = B * T
@@ -356,6 +358,8 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
     for i in reversed(range(cfg.depth)):
         block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
         ctx["saved"][i] = None   # free activations as we go
+        if after_block is not None:
+            after_block(i)
     stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)
 
 
@@ -538,7 +542,7 @@ def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, to
     ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"))
 
 
-def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, dout_c: torch.Tensor, grads: Dict[str, torch.Tensor]):
+def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, dout_c: torch.Tensor, grads: Dict[str, torch.Tensor], after_block=None):
     """Backward of dist_forward in the 'masked' / 'all' modes: gradients of (mean output, cov output) -> parameter gradients."""
     B = ctx["B"]
     T, C = cfg.tokens, cfg.embed_dim
@@ -571,6 +575,8 @@ def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, do
     for i in reversed(range(cfg.depth)):
         dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
         ctx["saved"][i] = None
+        if after_block is not None:
+            after_block(i)
     stem_backward(ps, cfg, ctx["patches"], dx[:M], B, ctx["mask_u8"], grads)
     stem_backward(ps, cfg, ctx["patches"], dx[M:], B, ctx["mask_u8"], grads, prefix="cov_")
 

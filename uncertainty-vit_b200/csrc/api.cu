@@ -14,6 +14,8 @@ void b200vit_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_sm_limit = 0;   // 0 = all SMs
+
 int b200vit_num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -23,9 +25,16 @@ int b200vit_num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     cached[dev] = n;
   }
-  return cached[dev];
+  // every persistent kernel of the library sizes its grid from this number: a limit leaves the remaining SMs to a concurrent kernel
+  // (the NCCL all-reduce overlapped with the backward pass)
+  return (g_sm_limit > 0 && g_sm_limit < cached[dev]) ? g_sm_limit : cached[dev];
 }
 
 extern "C" const char* b200vit_last_error(void) { return g_err; }
 extern "C" int b200vit_abi_version(void) { return B200VIT_ABI_VERSION; }
 extern "C" int b200vit_device_sm_count(void) { return b200vit_num_sms(); }
+extern "C" int b200vit_set_sm_limit(int32_t n) {
+  const int prev = g_sm_limit;
+  g_sm_limit = n > 0 ? (n & ~1) : 0;       // CTA pairs: keep it even
+  return prev;
+}

@@ -144,9 +144,16 @@ __global__ void __launch_bounds__(1024) colstat_finalize_kernel(const float* __r
   float hsum = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    float nbs[32], mbs[32], qbs[32];                 // all partials of the column in flight at once (chunks <= 32)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
       const float* p = part + (long long)k * 3 * C;
-      const double nb = p[c], mb = p[C + c], qb = p[2 * C + c];
+      const bool in = k < chunks;
+      nbs[k] = in ? p[c] : 0.f; mbs[k] = in ? p[C + c] : 0.f; qbs[k] = in ? p[2 * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const double nb = nbs[k], mb = mbs[k], qb = qbs[k];
       if (nb <= 0.0) continue;
       const double d = mb - mean, nt = n + nb;
       mean += d * nb / nt;
@@ -252,12 +259,13 @@ extern "C" int b200vit_channel_stats(const float* const* layers_host, int32_t nu
   return 0;
 }
 
-extern "C" size_t b200vit_column_std_workspace_bytes(int32_t C) { return (size_t)64 * 3 * (size_t)C * sizeof(float); }
+constexpr int COLSTAT_CHUNKS = 32;
+extern "C" size_t b200vit_column_std_workspace_bytes(int32_t C) { return (size_t)COLSTAT_CHUNKS * 3 * (size_t)C * sizeof(float); }
 
 extern "C" int b200vit_column_std(const float* y, int32_t R, int32_t C, const int32_t* n_valid_dev, float eps, float margin, float k_scale,
                                   float* work, float* z0, float* hinge_out, float* col_hinge, void* stream) {
   B200_CHECK_ARG(y != nullptr && work != nullptr && R > 0 && C % 128 == 0, "column_std: bad arguments (C=%d must be a multiple of 128)", C);
-  const int chunks = 64;
+  const int chunks = COLSTAT_CHUNKS;
   colstat_partial_kernel<<<dim3(C / 128, chunks), 256, 0, STREAM>>>(y, R, C, n_valid_dev, chunks, work);
   B200_CHECK_LAUNCH("column_std_partial");
   colstat_finalize_kernel<<<1, 1024, 0, STREAM>>>(work, chunks, C, eps, margin, k_scale, z0, hinge_out, reinterpret_cast<float2*>(col_hinge));

@@ -75,15 +75,17 @@ __device__ __forceinline__ void w_wait(uint32_t bar, uint32_t parity) {
 // 16 lanes per (token, q|k, head) unit: lanes 0..7 transform the 64 mean elements (8 each), lanes 8..15 the 64 cov elements.
 __global__ void __launch_bounds__(256) wattn_prep_kernel(const bf16* __restrict__ qkv_m, const bf16* __restrict__ qkv_c, bf16* __restrict__ X,
                                                          float* __restrict__ rn, float* __restrict__ cn, int B, int H, int N, float scale) {
-  const long long units = (long long)B * N * 2 * H;          // even: both half-warps of a warp are in range together
+  // unit = (token bn, q|k, head): 2 H units per token, 16 lanes each. All index math in 32 bits (B N 2 H < 2^31 is checked by the host).
+  const int units = B * N * 2 * H;                           // even: both half-warps of a warp are in range together
   const int l16 = threadIdx.x & 15;
-  for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4; u < units; u += ((long long)gridDim.x * blockDim.x) >> 4) {
-    const int h = (int)(u % H);
-    const int which = (int)((u / H) & 1);
-    const long long bn = u / (2 * H);
-    const bool is_cov = l16 >= 8;
-    const bf16* src = (is_cov ? qkv_c : qkv_m) + bn * (3LL * H * HD) + (long long)which * H * HD + h * HD + (l16 & 7) * 8;
-    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+  const bool is_cov = l16 >= 8;
+  const int upt = 2 * H;                                     // units per token
+  const bf16* src_base = (is_cov ? qkv_c : qkv_m) + (l16 & 7) * 8;
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; u < units; u += (gridDim.x * blockDim.x) >> 4) {
+    const int bn = u / upt;
+    const int wh = u - bn * upt;                             // which * H + h : also the 64-column slot inside the q | k part of the qkv row
+    const int which = wh >= H ? 1 : 0;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src_base + (size_t)bn * (3 * H * HD) + wh * HD);
     const uint32_t* pr = &raw.x;
     // sigmoid(a x) = 1 / (1 + 2^(-a x log2e)) ; sqrt(sigmoid(x)) = rsqrt(1 + 2^(-x log2e))   (sigmoid of elu + 1 > 0 is > 1/2: the 1e-24 clamp never binds)
     const float a = -(is_cov ? 1.0f : (which == 0 ? scale : 1.0f)) * LOG2E;
@@ -99,14 +101,14 @@ __global__ void __launch_bounds__(256) wattn_prep_kernel(const bf16* __restrict_
       const float2 r = unpack_bf16x2(po[k]);
       nrm += r.x * r.x + r.y * r.y;
     }
-    *reinterpret_cast<uint4*>(X + ((bn * 2 + which) * H + h) * XW + l16 * 8) = outv;
+    *reinterpret_cast<uint4*>(X + (size_t)u * XW + l16 * 8) = outv;          // X is [B N, 2, H, 128] = [unit, 128]
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 4);
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 2);
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
     if (l16 == 0) {
-      const long long b = bn / N, n = bn - b * N;
-      (which == 0 ? rn : cn)[(b * H + h) * N + n] = nrm * LOG2E;
+      const int b = bn / N, n = bn - b * N, h = wh - which * H;
+      (which == 0 ? rn : cn)[(size_t)(b * H + h) * N + n] = nrm * LOG2E;
     }
   }
 }
@@ -238,7 +240,7 @@ wattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
   if (warp == F_EW_WARPS) {
     if (lane == 0) {
       ptx::mbar_init(qk_full, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, F_EW_WARPS * 32);
-      ptx::mbar_init(o_full, 1); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, F_EW_WARPS);
+      ptx::mbar_init(o_full, 2); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, F_EW_WARPS);
       for (int s = 0; s < F_BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), F_EW_WARPS / 2); }
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_x1); ptx::prefetch_tmap(&tm_x2); ptx::prefetch_tmap(&tm_v); ptx::prefetch_tmap(&tm_cv);
@@ -255,28 +257,34 @@ wattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == F_EW_WARPS) {
-    if (lane == 0 && n_items > 0) {
-      // ---------------- MMA issue ----------------
+    if (lane < 2 && n_items > 0) {
+      // ---------------- MMA issue: thread 0 issues S; the two independent O chains are issued SIMT, one per thread (an MMA costs ~100 cycles to
+      // issue, 26 of them in a row would sit on the critical path between the softmax and the epilogue) ----------------
+      const int m = lane;
       const uint64_t dQm = ptx::make_smem_desc(base + F_SM_Q, 16, 1024), dQc = ptx::make_smem_desc(base + F_SM_Q + TILE_M * 128, 16, 1024);
       const uint64_t dKm = ptx::make_smem_desc(base + F_SM_K, 16, 1024), dKc = ptx::make_smem_desc(base + F_SM_K + KT_BYTES, 16, 1024);
-      const uint64_t dV = ptx::make_smem_desc(base + F_SM_V, KT_BYTES, 1024), dCV = ptx::make_smem_desc(base + F_SM_CV, KT_BYTES, 1024);   // MN-major
+      const uint64_t dVx = ptx::make_smem_desc(base + (m == 0 ? F_SM_V : F_SM_CV), KT_BYTES, 1024);   // MN-major: V | CV
+      const uint32_t t_o = tmem_base + (m == 0 ? F_T_OM : F_T_OC), t_a = tmem_base + (m == 0 ? 0 : F_T_PSQ);
       const uint32_t idesc_s = ptx::make_idesc_bf16(TILE_M, n_pad, false, false), idesc_o = ptx::make_idesc_bf16(TILE_M, HD, false, true);
       const int ksteps = n_pad >> 4;
       for (int it = 0; it < n_items; ++it) {
         const uint32_t ph = (uint32_t)(it & 1);
         w_wait(qk_full, ph);
-        // S = X1m X2m^T + X1u X2u^T : the K = 128 contraction as two 64-wide swizzle atoms (4 k-steps each)
+        if (m == 0) {
+          // S = X1m X2m^T + X1u X2u^T : the K = 128 contraction as two 64-wide swizzle atoms (4 k-steps each)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem_base, dQm + 2 * ks, dKm + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem_base, dQm + 2 * ks, dKm + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem_base, dQc + 2 * ks, dKc + 2 * ks, idesc_s, 1u);
-        ptx::umma_commit(s_full);                 // also: X1 / X2 have been read (the TMA thread may fetch the next item's)
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(tmem_base, dQc + 2 * ks, dKc + 2 * ks, idesc_s, 1u);
+          ptx::umma_commit(s_full);               // also: X1 / X2 have been read (the TMA thread may fetch the next item's)
+        }
+        __syncwarp(0x3u);
         w_wait(v_full, ph);
         w_wait(p_full, ph);
         if (it > 0) w_wait(t_free, ph ^ 1u);      // the epilogue has drained O_m / O_c of the previous item
         ptx::tc_fence_after();
-        for (int kk = 0; kk < ksteps; ++kk) ptx::umma_bf16_ts(tmem_base + F_T_OM, tmem_base + kk * 8, dV + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
-        for (int kk = 0; kk < ksteps; ++kk) ptx::umma_bf16_ts(tmem_base + F_T_OC, tmem_base + F_T_PSQ + kk * 8, dCV + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
+        // thread 0: O_m = P~ V (A = TMEM columns [0, n_pad/2)); thread 1: O_c = (P~)^2 CV (A = the squared copy). Same accumulate flags in both lanes.
+        for (int kk = 0; kk < ksteps; ++kk) ptx::umma_bf16_ts(t_o, t_a + kk * 8, dVx + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
         ptx::umma_commit(o_full);
       }
     }
@@ -1136,6 +1144,7 @@ extern "C" int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, cons
   const uintptr_t addrs[] = {(uintptr_t)qkv_mean, (uintptr_t)qkv_cov, (uintptr_t)out_mean, (uintptr_t)out_cov, (uintptr_t)xwork};
   for (uintptr_t a : addrs) B200_CHECK_ARG((a & 15) == 0, "wattn_fwd: tensors must be 16-byte aligned");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(xwork) & 255) == 0, "wattn_fwd: xwork must be 256-byte aligned");
+  B200_CHECK_ARG((long long)B * N * 2 * H < (1LL << 31), "wattn_fwd: B * N * H too large");
   const XWork xw = split_xwork(xwork, B, H, N);
   const int sms = b200vit_num_sms();
   wattn_prep_kernel<<<sms * 8, 256, 0, stream>>>(static_cast<const bf16*>(qkv_mean), static_cast<const bf16*>(qkv_cov), xw.X, xw.rn, xw.cn, B, H, N, scale);

@@ -107,7 +107,8 @@ class D2VEngine:
                  skip_weight_decay: Iterable[str] = ("pos_embed", "cls_token"), world_size=1, process_group=None, seed=0,
                  lambda_pretraining: float = 1e-5, use_graph: bool = True, with_ema: bool = True, target_batch_norm=False,
                  target_instance_norm=False, post_target_instance_norm=False, var_w0: float = 0.0, var_margin0: float = 0.5,
-                 start_lr_decay_at_step: int = -1, mask_dropout_prob: float = -1.0, track_z0: bool = True):
+                 start_lr_decay_at_step: int = -1, mask_dropout_prob: float = -1.0, track_z0: bool = True, overlap_allreduce: Optional[bool] = None,
+                 allreduce_cut_block: Optional[int] = None, allreduce_sm_reserve: int = 16):
         """Keyword names follow engine_for_cyclical.train_one_epoch (:24-32) / run_cyclical.py's flags. world_size > 1: rank 0's parameters
         are broadcast at construction (what the DistributedDataParallel constructor does in run_cyclical.py:515-519), then only gradients
         are all-reduced."""
@@ -135,6 +136,18 @@ class D2VEngine:
         self.z0_dev = self.std_loss0_dev = None
         self.lam = lambda_pretraining
         self.world_size, self.pg = world_size, process_group
+        # Gradient all-reduce overlapped with the backward pass (what DDP's buckets do in the reference, run_cyclical.py:515-519): the arena is
+        # laid out in named_parameters() order, so once block `cut`'s backward has run, everything from blocks.<cut> to the head is final. That
+        # upper part is all-reduced on NCCL's stream while the lower blocks' backward continues (inside the captured graph too: the fork and
+        # the join are graph edges); the persistent kernels are sized for `allreduce_sm_reserve` fewer SMs meanwhile, so NCCL's CTAs are resident
+        # from the start instead of delaying a persistent GEMM's last CTAs into a second wave.
+        import os as _os
+        if overlap_allreduce is None:
+            overlap_allreduce = _os.environ.get("B200VIT_AR_OVERLAP", "1") != "0"
+        self.overlap_ar = bool(overlap_allreduce) and world_size > 1
+        self.ar_cut = allreduce_cut_block if allreduce_cut_block is not None else int(_os.environ.get("B200VIT_AR_CUT", str(max(1, (self.cfg.depth * 5) // 12))))
+        self.ar_reserve = int(_os.environ.get("B200VIT_AR_SM_RESERVE", str(allreduce_sm_reserve)))
+        self._ar_done_in_step = False
         self.seed = seed
         self.it = 0
         self.layer_decay, self.skip_weight_decay = layer_decay, tuple(skip_weight_decay)
@@ -329,6 +342,30 @@ class D2VEngine:
                                rows_per_sample=T - 1, compact_tokens=T, col_hinge=col_hinge, loss_add=loss_add, loss_add_weight=self.var_w0,
                                loss_mult=loss_mult, **common)
 
+    def _overlapped_backward(self, run_backward):
+        """Runs `run_backward(after_block)` with the gradient all-reduce of the arena's upper part (blocks.<cut> .. head) issued as soon as it is
+        final, on NCCL's stream, and the lower part right after the backward; see __init__. Without data parallelism it is a plain call."""
+        if not self.overlap_ar:
+            run_backward(None)
+            return
+        cut = min(max(self.ar_cut, 1), self.cfg.depth - 1)
+        off = self.layout[f"blocks.{cut}.gamma_1"][0] if f"blocks.{cut}.gamma_1" in self.layout else self.layout[f"blocks.{cut}.norm1.weight"][0]
+        upper, lower = self.g32[off:], self.g32[:off]
+        state = {}
+
+        def after_block(i):
+            if i == cut:
+                state["work"] = torch.distributed.all_reduce(upper, group=self.pg, async_op=True)
+                state["prev"] = ops.set_sm_limit(max(2, ops.sm_count() - self.ar_reserve))
+        try:
+            run_backward(after_block)
+        finally:
+            if "prev" in state:
+                ops.set_sm_limit(state["prev"])
+        state["work"].wait()
+        torch.distributed.all_reduce(lower, group=self.pg)
+        self._ar_done_in_step = True
+
     def _fwd_bwd(self, images, mask_u8, rows, noise, n_valid=None):
         """Teacher forward, student forward, targets + loss, student backward into the gradient arena (everything but the optimiser).
         With n_valid the padded rows of `rows` get dy = 0 from the loss kernel, so they add nothing to any gradient."""
@@ -350,7 +387,7 @@ class D2VEngine:
         self._targets_and_loss([layers[i].view(B * T, C) for i in self.target_layers], rows, out, R, n_valid, dy_bf16=dy, loss_mult=ls)
         del layers
         self.g32.zero_()
-        core.vit_backward(self.student, cfg, ctx, dy, self.grads)
+        self._overlapped_backward(lambda cb: core.vit_backward(self.student, cfg, ctx, dy, self.grads, after_block=cb))
 
     def _fwd_bwd_graphed(self, images, mask_u8, rows, seed: int, n_valid=None):
         """The same launch sequence replayed from a CUDA graph: ~400 stream-ordered, allocation-free launches whose Python issue time
@@ -405,6 +442,7 @@ class D2VEngine:
             ops.drop_path_scales(cfg.drop_path_probs, 4 if cfg.dist else 2, images.shape[0], seed, self.dev, out=st["dps"])
         g["graph"].replay()
         ops.LAUNCHES += g["launches"]
+        self._ar_done_in_step = self.overlap_ar        # the captured graph contains both gradient all-reduces
 
     def _fwd_bwd_dist(self, images, mask_u8, rows, noise, n_valid=None):
         """--stochastic step (engine_for_cyclical.py:69-86,125-126,152-158): dual-stream teacher/student, targets for both streams,
@@ -432,11 +470,12 @@ class D2VEngine:
         ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev, n_valid=n_valid)
         ops.scalar_fma(self.loss_dev, self.loss_dev, ls, self.wloss_dev, ls)      # loss = (loss_cyc + std_loss0*var_w0 + loss_stochastic) * loss_scale  (:160-163)
         self.g32.zero_()
-        core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads)
+        self._overlapped_backward(lambda cb: core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads, after_block=cb))
 
     def _optimizer_step(self, lr, wd):
-        if self.world_size > 1:
+        if self.world_size > 1 and not self._ar_done_in_step:
             torch.distributed.all_reduce(self.g32, group=self.pg)       # DDP gradient mean = sum / world (folded into grad_div)
+        self._ar_done_in_step = False
         self.gnorm_sq.zero_()
         ops.sumsq(self.g32, self.gnorm_sq)
         self.opt_step += 1

@@ -58,6 +58,11 @@ def sm_count() -> int:
     return _lib.lib().b200vit_device_sm_count()
 
 
+def set_sm_limit(n: int) -> int:
+    """Caps the SM count the persistent kernels size their grids for (0 = none); returns the previous cap."""
+    return _lib.lib().b200vit_set_sm_limit(int(n))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # GEMM
 # ----------------------------------------------------------------------------------------------------------------
