@@ -108,7 +108,7 @@ class D2VEngine:
                  lambda_pretraining: float = 1e-5, use_graph: bool = True, with_ema: bool = True, target_batch_norm=False,
                  target_instance_norm=False, post_target_instance_norm=False, var_w0: float = 0.0, var_margin0: float = 0.5,
                  start_lr_decay_at_step: int = -1, mask_dropout_prob: float = -1.0, track_z0: bool = True, overlap_allreduce: Optional[bool] = None,
-                 allreduce_cut_block: Optional[int] = None, allreduce_sm_reserve: int = 16):
+                 allreduce_cut_block: Optional[int] = None, allreduce_sm_reserve: int = 0):
         """Keyword names follow engine_for_cyclical.train_one_epoch (:24-32) / run_cyclical.py's flags. world_size > 1: rank 0's parameters
         are broadcast at construction (what the DistributedDataParallel constructor does in run_cyclical.py:515-519), then only gradients
         are all-reduced."""
@@ -139,13 +139,15 @@ class D2VEngine:
         # Gradient all-reduce overlapped with the backward pass (what DDP's buckets do in the reference, run_cyclical.py:515-519): the arena is
         # laid out in named_parameters() order, so once block `cut`'s backward has run, everything from blocks.<cut> to the head is final. That
         # upper part is all-reduced on NCCL's stream while the lower blocks' backward continues (inside the captured graph too: the fork and
-        # the join are graph edges); the persistent kernels are sized for `allreduce_sm_reserve` fewer SMs meanwhile, so NCCL's CTAs are resident
-        # from the start instead of delaying a persistent GEMM's last CTAs into a second wave.
+        # the join are graph edges). `allreduce_sm_reserve` > 0 additionally sizes the persistent kernels for that many fewer SMs during the
+        # window. Measured at N = 2 (profiles/r2_allreduce_overlap_n2.md): 29.65 ms without overlap, 29.44 ms with cut = 2 / no reserve; an
+        # SM reserve of 16-32 never paid (the lower blocks' GEMMs lose more than NCCL gains), so the default is 0. The gain is small because
+        # NCCL's CTAs cannot co-reside with the ~200 KB-smem persistent GEMM / attention CTAs: they mostly run in the gaps.
         import os as _os
         if overlap_allreduce is None:
             overlap_allreduce = _os.environ.get("B200VIT_AR_OVERLAP", "1") != "0"
         self.overlap_ar = bool(overlap_allreduce) and world_size > 1
-        self.ar_cut = allreduce_cut_block if allreduce_cut_block is not None else int(_os.environ.get("B200VIT_AR_CUT", str(max(1, (self.cfg.depth * 5) // 12))))
+        self.ar_cut = allreduce_cut_block if allreduce_cut_block is not None else int(_os.environ.get("B200VIT_AR_CUT", "2")))
         self.ar_reserve = int(_os.environ.get("B200VIT_AR_SM_RESERVE", str(allreduce_sm_reserve)))
         self._ar_done_in_step = False
         self.seed = seed
@@ -356,7 +358,8 @@ class D2VEngine:
         def after_block(i):
             if i == cut:
                 state["work"] = torch.distributed.all_reduce(upper, group=self.pg, async_op=True)
-                state["prev"] = ops.set_sm_limit(max(2, ops.sm_count() - self.ar_reserve))
+                if self.ar_reserve > 0:
+                    state["prev"] = ops.set_sm_limit(max(2, ops.sm_count() - self.ar_reserve))
         try:
             run_backward(after_block)
         finally:
