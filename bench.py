@@ -192,7 +192,7 @@ def run_mc_inference(dev, rank, world, M, barrier, max_over_ranks):
                                  "frac": fwd * gf / 1e12 / world / pk["bf16_sustained"], "flops_per_image": gf}}
         del model
     out["config"] = {"workload": "beit_base_patch16_224 fine-tune model, MC-sample uncertainty eval", "passes": MC_PASSES, "eval_batch": MC_BATCH,
-                     "attn_drop": 0.05, "sharding": f"{MC_PASSES} passes over {world} rank(s), logits all-gathered", "scaling": "strong"}
+                     "attn_drop": 0.05, "sharding": f"sample x batch: {MC_BATCH} images split over {world} rank(s), the {MC_PASSES} passes of a rank batched into forwards of <= 1536 rows; per-image statistics gathered", "scaling": "strong"}
     return out
 
 

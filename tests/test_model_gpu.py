@@ -193,19 +193,21 @@ def test_mc_dropout_eval_matches_oracle_on_same_masks(pkg, cuda, golden_dir):
     mc.enable_dropout(model)
     assert model.blocks[0].attn.attn_drop.training and not model.blocks[1].drop_path.training
     res = mc.evaluate_mc_dropout(model, [(x, labels)], S)
-    # re-run the passes manually to capture per-pass logits and the exact masks of each pass
+    # the S passes of the 3 images are batched into ONE forward of S x 3 rows (row s * 3 + n = pass s of image n): re-run it to capture the
+    # per-pass logits and the exact Philox masks of every row
     model._seed_calls = 0
+    B = gold["B"]
+    model.eval(); mc.enable_dropout(model)
+    noise_seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * 1) & 0xFFFFFFFFFFFFFFFF
+    with torch.no_grad():
+        logits_all = model(x.repeat(S, 1, 1, 1).contiguous())
+    keeps_all = [pkg.ops.dropout_mask(S * B * arch.num_heads, arch.tokens, 0.1, noise_seed, l, cuda).view(S * B, arch.num_heads, arch.tokens, arch.tokens)
+                 for l in range(arch.depth)]
     per_pass = []
     for s in range(S):
-        model.eval(); mc.enable_dropout(model)
-        noise_seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (s + 1)) & 0xFFFFFFFFFFFFFFFF
-        with torch.no_grad():
-            logits = model(x)
-        keeps = [pkg.ops.dropout_mask(gold["B"] * arch.num_heads, arch.tokens, 0.1, noise_seed, l, cuda).view(gold["B"], arch.num_heads, arch.tokens, arch.tokens)
-                 for l in range(arch.depth)]
-        onoise = O.Noise(attn_keep=[k.float().cpu() for k in keeps], attn_drop=0.1)
+        onoise = O.Noise(attn_keep=[k[s * B:(s + 1) * B].float().cpu() for k in keeps_all], attn_drop=0.1)
         ref = O.finetune_forward(sd, arch, gold["x"], noise=onoise)
-        assert rel(logits.cpu(), ref) < 2e-2, s
+        assert rel(logits_all[s * B:(s + 1) * B].cpu(), ref) < 2e-2, s
         per_pass.append(ref)
     r = O.mc_reduce(torch.stack(per_pass), labels)
     assert rel(res["mean_logits"].cpu(), r["mean_logits"]) < 2e-2

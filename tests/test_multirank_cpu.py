@@ -30,6 +30,10 @@ def _worker(rank, world, port, q):
     s0, s1 = mc.shard_passes(S, world)[rank]
     got = mc.gather_passes(full[s0:s1].clone(), S, rank, world)
     ok_gather = torch.equal(got, full)
+    # sample x batch sharding of the MC evaluation: images split across ranks, gathered back in image order
+    rows = torch.arange(N * K, dtype=torch.float32).reshape(N, K)
+    i0, i1 = mc.shard_images(N, world)[rank]
+    ok_gather = ok_gather and torch.equal(mc.gather_rows(rows[i0:i1].clone(), N, rank, world), rows)
     # data-parallel gradient arena: all_reduce(sum) then grad_div = world (what D2VEngine.step does) == mean of per-rank grads
     g = torch.full((1024,), float(rank + 1))
     dist.all_reduce(g)

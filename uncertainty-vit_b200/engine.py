@@ -147,7 +147,7 @@ class D2VEngine:
         if overlap_allreduce is None:
             overlap_allreduce = _os.environ.get("B200VIT_AR_OVERLAP", "1") != "0"
         self.overlap_ar = bool(overlap_allreduce) and world_size > 1
-        self.ar_cut = allreduce_cut_block if allreduce_cut_block is not None else int(_os.environ.get("B200VIT_AR_CUT", "2")))
+        self.ar_cut = allreduce_cut_block if allreduce_cut_block is not None else int(_os.environ.get("B200VIT_AR_CUT", "2"))
         self.ar_reserve = int(_os.environ.get("B200VIT_AR_SM_RESERVE", str(allreduce_sm_reserve)))
         self._ar_done_in_step = False
         self.seed = seed

@@ -529,15 +529,23 @@ def wasserstein_loss(mean_out, cov_out, pos_mean, pos_cov, lam, grad_scale, work
     _count(3 if d_mean is not None else 2)
 
 
-def mc_reduce(logits, labels_i32, n_bins=15):
+def mc_reduce(logits, labels_i32, n_bins=15, finalize=True):
+    """logits fp32 [S, N, K] -> (mean_logits [N, K], row_stats [N, 8], hist [n_bins, 3], summary [8] or None when finalize=False: the
+    multi-rank evaluation reduces its own images, gathers row_stats / sums hist across ranks and calls mc_finalize once)."""
     S, N, K = logits.shape
     dev = logits.device
     mean_logits = torch.empty(N, K, dtype=torch.float32, device=dev)
     row_stats = torch.empty(N, 8, dtype=torch.float32, device=dev)
     hist = torch.zeros(n_bins, 3, dtype=torch.float32, device=dev)
-    summary = torch.empty(8, dtype=torch.float32, device=dev)
     check(_lib.lib().b200vit_mc_reduce(_p(logits), _p(labels_i32), S, N, K, n_bins, _p(mean_logits), _p(row_stats), _p(hist), _stream()),
           "mc_reduce")
-    check(_lib.lib().b200vit_mc_finalize(_p(row_stats), _p(hist), N, n_bins, _p(summary), _stream()), "mc_finalize")
-    _count(2)
+    _count()
+    summary = mc_finalize(row_stats, hist, N, n_bins) if finalize else None
     return mean_logits, row_stats, hist, summary
+
+
+def mc_finalize(row_stats, hist, N, n_bins=15):
+    summary = torch.empty(8, dtype=torch.float32, device=row_stats.device)
+    check(_lib.lib().b200vit_mc_finalize(_p(row_stats), _p(hist), N, n_bins, _p(summary), _stream()), "mc_finalize")
+    _count()
+    return summary
