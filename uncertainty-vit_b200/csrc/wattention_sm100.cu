@@ -6,11 +6,11 @@
 //
 // Kernels
 //   wattn_prep_kernel   : element-wise, HBM-bound: X1 = [m1 | u1], X2 = [m2 | u2] as bf16 [B, N, 2, H, 128] and the row norms r_i, c_j (taken from the
-//                         SAME bf16-rounded values the tensor cores multiply, times log2 e). sqrt(sigmoid(c)) = rsqrt(1 + e^-c): 2 MUFU per element.
+//                         SAME bf16-rounded values the tensor cores multiply, halved). sigmoid = 0.5 + 0.5 tanh(x/2): 1 MUFU; sqrt(sigmoid(c)) = rsqrt(1 + e^-c): 2.
 //                         The forward writes this workspace, the backward reads it (no transform is ever repeated).
 //   wattn_fwd_kernel    : persistent, one CTA per SM. TMA: X1 tile, X2, V, CV (3-D boxes, rows past N zero-filled), bias ring. tcgen05: S = X1 X2^T
 //                         (128 x n_pad x 128) into TMEM; EIGHT element-wise warps = two threads per query row (TMEM lane quadrant = warp & 3,
-//                         column half = warp >> 2) run ONE pass: t = 1 / (1 + 2^(D log2e)), p = 2^(t log2e + bias - m_i) with the stabiliser
+//                         column half = warp >> 2) run ONE pass: t = sigmoid(-D) = 0.5 - 0.5 tanh(D/2), p = 2^(t log2e + bias - m_i) with the stabiliser
 //                         m_i = max_j bias_ij + log2e >= max_j A_ij (t < 1), so no running max and no rescaling; P~ and (P~)^2 go back to TMEM as
 //                         bf16 and feed two TS-MMAs (A operand from tensor memory): O_m = P~ V, O_c = (P~)^2 CV; epilogue via smem + TMA store.
 //   wattn_bwd_kv_kernel : key-tile owner (TMEM lane = key row), 64-query boxes, two ping-pong groups: S^T = X2 X1^T, Gm^T = V dOm^T, Gc^T = CV dOc^T
@@ -41,6 +41,11 @@ constexpr int BIAS_STAGE_BYTES = TILE_M * 128;  // [128 rows x 32 fp32]
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {      // one MUFU; |error| ~ 2^-11, far below the bf16 resolution of what it feeds
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -81,22 +86,31 @@ __global__ void __launch_bounds__(256) wattn_prep_kernel(const bf16* __restrict_
   const bool is_cov = l16 >= 8;
   const int upt = 2 * H;                                     // units per token
   const bf16* src_base = (is_cov ? qkv_c : qkv_m) + (l16 & 7) * 8;
+  // one unit per iteration: a 4-way unrolled variant (4 loads in flight per thread, 60 registers) measured SLOWER (113 vs 90 us): at 32
+  // registers 8 CTAs per SM are resident and the warps hide the latency themselves
   for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; u < units; u += (gridDim.x * blockDim.x) >> 4) {
     const int bn = u / upt;
     const int wh = u - bn * upt;                             // which * H + h : also the 64-column slot inside the q | k part of the qkv row
     const int which = wh >= H ? 1 : 0;
     const uint4 raw = *reinterpret_cast<const uint4*>(src_base + (size_t)bn * (3 * H * HD) + wh * HD);
     const uint32_t* pr = &raw.x;
-    // sigmoid(a x) = 1 / (1 + 2^(-a x log2e)) ; sqrt(sigmoid(x)) = rsqrt(1 + 2^(-x log2e))   (sigmoid of elu + 1 > 0 is > 1/2: the 1e-24 clamp never binds)
-    const float a = -(is_cov ? 1.0f : (which == 0 ? scale : 1.0f)) * LOG2E;
+    // mean half: sigmoid(a x) = 0.5 + 0.5 tanh(a x / 2) (ONE MUFU); cov half: sqrt(sigmoid(x)) = rsqrt(1 + 2^(-x log2e)) (two)
+    // (sigmoid of elu + 1 > 0 is > 1/2: the 1e-24 clamp of the reference never binds)
+    const float a = is_cov ? -LOG2E : 0.5f * (which == 0 ? scale : 1.0f);
     uint4 outv;
     uint32_t* po = &outv.x;
     float nrm = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 v = unpack_bf16x2(pr[k]);
-      const float e0 = 1.0f + ex2(v.x * a), e1 = 1.0f + ex2(v.y * a);
-      const float y0 = is_cov ? rsqrt_approx(e0) : rcp_approx(e0), y1 = is_cov ? rsqrt_approx(e1) : rcp_approx(e1);
+      float y0, y1;
+      if (is_cov) {
+        y0 = rsqrt_approx(1.0f + ex2(v.x * a));
+        y1 = rsqrt_approx(1.0f + ex2(v.y * a));
+      } else {
+        y0 = fmaf(tanh_approx(v.x * a), 0.5f, 0.5f);
+        y1 = fmaf(tanh_approx(v.y * a), 0.5f, 0.5f);
+      }
       po[k] = pack_bf16x2(y0, y1);
       const float2 r = unpack_bf16x2(po[k]);
       nrm += r.x * r.x + r.y * r.y;
@@ -108,7 +122,7 @@ __global__ void __launch_bounds__(256) wattn_prep_kernel(const bf16* __restrict_
     nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
     if (l16 == 0) {
       const int b = bn / N, n = bn - b * N, h = wh - which * H;
-      (which == 0 ? rn : cn)[(size_t)(b * H + h) * N + n] = nrm * LOG2E;
+      (which == 0 ? rn : cn)[(size_t)(b * H + h) * N + n] = 0.5f * nrm;       // HALF squared norms: D / 2 = rn + cn - x1.x2
     }
   }
 }
@@ -134,8 +148,8 @@ static_assert(F_SM_K % 1024 == 0 && F_SM_V % 1024 == 0 && F_SM_CV % 1024 == 0 &&
 static_assert(F_SMEM <= 232448, "forward kernel smem");
 
 struct WFwdParams {
-  const float* rn;          // [B, H, N] query norms x log2e
-  const float* cn;          // [B, H, N] key norms x log2e
+  const float* rn;          // [B, H, N] half squared query norms
+  const float* cn;          // [B, H, N] half squared key norms
   const float* rowmax;      // [H, N] max_j bias_ij (log2 domain)
   float* lse;               // [B, H, N] or null
   uint8_t* keep_bits;       // [B, H, N, 32]
@@ -172,42 +186,46 @@ __device__ __forceinline__ uint32_t w_keep_word(const WFwdParams& p, uint64_t se
   return w;
 }
 
-// 16 scores of one query row -> probabilities; P~ and (P~)^2 back to TMEM as bf16 pairs
-template <bool DROP>
-__device__ __forceinline__ void wfwd_step16(uint32_t t_src, uint32_t t_p, uint32_t t_psq, const uint8_t* bias_row, int q0, int row, const float* cn,
-                                            float rl2, float mst, float& l, uint32_t w16) {
-  uint32_t s[16];
-  ptx::tmem_ld_x16_sync(t_src, s);
-  float pr[16];
+// NC (16 or 32) scores of one query row -> probabilities; P~ and (P~)^2 back to TMEM as bf16 pairs. Both 16-column TMEM loads of a 32-column
+// chunk are in flight before the single wait. k0 = log2e / 2 - m_i folds the sigmoid's offset and the stabiliser into one constant.
+template <bool DROP, int NC>
+__device__ __forceinline__ void wfwd_chunk(uint32_t t_src, uint32_t t_p, uint32_t t_psq, const uint8_t* bias_row, int row, const float* cn,
+                                           float rnh, float k0, float& l, uint32_t w) {
+  uint32_t s[32];
+  if constexpr (NC == 32) {
+    ptx::tmem_ld_x16_pair_sync(t_src, reinterpret_cast<uint32_t(&)[16]>(s[0]), t_src + 16, reinterpret_cast<uint32_t(&)[16]>(s[16]));
+  } else {
+    ptx::tmem_ld_x16_sync(t_src, reinterpret_cast<uint32_t(&)[16]>(s[0]));
+  }
   float acc = 0.f;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bias_row + (((q0 + q) ^ (row & 7)) << 4));
+  for (int q = 0; q < NC / 4; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias_row + ((q ^ (row & 7)) << 4));
     const float4 c4 = *reinterpret_cast<const float4*>(cn + 4 * q);
     const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float d2 = fmaf(__uint_as_float(s[4 * q + e]), -2.0f * LOG2E, rl2 + cc[e]);      // D log2e
-      const float t = rcp_approx(1.0f + ex2(d2));                                            // sigmoid(-D)
-      const float pv = ex2(fmaf(t, LOG2E, bb[e]) - mst);                                     // bias padding = -inf -> 0
-      pr[4 * q + e] = pv;
+      const float hd = (rnh + cc[e]) - __uint_as_float(s[4 * q + e]);                          // D / 2
+      const float th = tanh_approx(hd);                                                        // sigmoid(-D) = 0.5 - 0.5 tanh(D / 2)
+      float pv = ex2(fmaf(th, -0.5f * LOG2E, bb[e] + k0));                                     // bias padding = -inf -> 0
       acc += pv;
+      if (DROP && !(w & (1u << (4 * q + e)))) pv = 0.f;
+      s[4 * q + e] = __float_as_uint(pv);
     }
   }
   l += acc;
-  if (DROP) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (!(w16 & (1u << e))) pr[e] = 0.f;
-  }
-  uint32_t pk[8], pq[8];
+  for (int hlf = 0; hlf < NC / 16; ++hlf) {
+    uint32_t pk[8], pq[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    pk[e] = pack_bf16x2(pr[2 * e], pr[2 * e + 1]);
-    pq[e] = pack_bf16x2(pr[2 * e] * pr[2 * e], pr[2 * e + 1] * pr[2 * e + 1]);
+    for (int e = 0; e < 8; ++e) {
+      const float p0 = __uint_as_float(s[hlf * 16 + 2 * e]), p1 = __uint_as_float(s[hlf * 16 + 2 * e + 1]);
+      pk[e] = pack_bf16x2(p0, p1);
+      pq[e] = pack_bf16x2(p0 * p0, p1 * p1);
+    }
+    ptx::tmem_st_x8(t_p + hlf * 8, pk);
+    ptx::tmem_st_x8(t_psq + hlf * 8, pq);
   }
-  ptx::tmem_st_x8(t_p, pk);
-  ptx::tmem_st_x8(t_psq, pq);
 }
 
 template <bool DROP>
@@ -335,8 +353,9 @@ wattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
       const bool active = m0 + quad * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
       float* s_cn = reinterpret_cast<float*>(gbase + F_SM_CN) + (it & 1) * NMAX;
       if (tid < n_pad) s_cn[tid] = tid < p.N ? __ldg(p.cn + (long long)bh * p.N + tid) : 0.f;
-      const float rl2 = i < p.N ? __ldg(p.rn + (long long)bh * p.N + i) : 0.f;
+      const float rnh = i < p.N ? __ldg(p.rn + (long long)bh * p.N + i) : 0.f;
       const float mst = i < p.N ? __ldg(p.rowmax + (long long)h * p.N + i) + LOG2E : 0.f;
+      const float k0 = 0.5f * LOG2E - mst;
       ptx::named_bar_sync(1, F_EW_WARPS * 32);
       w_wait(s_full, ph);
       ptx::tc_fence_after();
@@ -352,8 +371,8 @@ wattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
             w = full ? w_keep_word<32>(p, seed, bh, i, c) : w_keep_word<16>(p, seed, bh, i, c);
             if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
           }
-          wfwd_step16<DROP>(trow + c * 32, trow + c * 16, trow + F_T_PSQ + c * 16, bias_row, 0, row, s_cn + c * 32, rl2, mst, l, w);
-          if (full) wfwd_step16<DROP>(trow + c * 32 + 16, trow + c * 16 + 8, trow + F_T_PSQ + c * 16 + 8, bias_row, 4, row, s_cn + c * 32 + 16, rl2, mst, l, w >> 16);
+          if (full) wfwd_chunk<DROP, 32>(trow + c * 32, trow + c * 16, trow + F_T_PSQ + c * 16, bias_row, row, s_cn + c * 32, rnh, k0, l, w);
+          else wfwd_chunk<DROP, 16>(trow + c * 32, trow + c * 16, trow + F_T_PSQ + c * 16, bias_row, row, s_cn + c * 32, rnh, k0, l, w);
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bias_empty(s));
@@ -537,8 +556,8 @@ static_assert(KV_SM_BOX % 1024 == 0 && KV_SM_BIAS % 1024 == 0 && KV_SMEM <= 2324
 struct WKvParams {
   const float* lse;          // [B, H, N]
   const float* dvec;         // [B, H, N]
-  const float* rn;           // [B, H, N] x log2e
-  const float* cn;           // [B, H, N] x log2e
+  const float* rn;           // [B, H, N] half squared norms
+  const float* cn;
   const uint32_t* keep_t;    // [B, H, N(key), 8]
   const bf16* qkv_c;         // raw elu(.)+1 values (chain rule of dCV)
   bf16* dd_out;              // [B, H, N(key), ld(query)]  dD^T
@@ -553,13 +572,26 @@ struct WKvParams {
 };
 
 // 16 queries of one key row out of TMEM: P, P~, dP~, dA, dD; P~^T / (P~^2)^T written back as bf16 pairs behind the read pointer
+// three x16 loads in flight, one wait, ONE asm block (the destination registers are defined only after the wait)
+__device__ __forceinline__ void w_tmem_ld_x16_triple_sync(uint32_t ta, uint32_t (&a)[16], uint32_t tb, uint32_t (&b)[16], uint32_t tc, uint32_t (&c)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+        "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]),
+        "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]), "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
+      : "r"(ta), "r"(tb), "r"(tc)
+      : "memory");
+}
+
 template <bool DROP>
 __device__ __forceinline__ void wkv_step16(const WKvParams& p, uint32_t t_st, uint32_t t_gm, uint32_t t_gc, uint32_t t_p, uint32_t t_psq,
                                            const uint8_t* bias_row, int row, const float* s_lse, const float* s_dl, const float* s_rn, float cnj,
                                            uint32_t kw, bool valid, bf16* dd_row, bf16* da_row) {
   uint32_t x[16], gm[16], gc[16];
-  ptx::tmem_ld_x16_pair_sync(t_st, x, t_gm, gm);
-  ptx::tmem_ld_x16_sync(t_gc, gc);
+  w_tmem_ld_x16_triple_sync(t_st, x, t_gm, gm, t_gc, gc);
   uint32_t pk[8], pq[8], dd[8], da[8];
   if (valid) {
 #pragma unroll
@@ -573,14 +605,13 @@ __device__ __forceinline__ void wkv_step16(const WKvParams& p, uint32_t t_st, ui
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = 4 * q + e;
-        const float d2 = fmaf(__uint_as_float(x[idx]), -2.0f * LOG2E, rr[e] + cnj);
-        const float t = rcp_approx(1.0f + ex2(d2));
-        const float pv = ex2(fmaf(t, LOG2E, bb[e]) - ll[e]);                       // lse2 = +inf past N -> 0
+        const float th = tanh_approx((rr[e] + cnj) - __uint_as_float(x[idx]));     // tanh(D / 2); t = sigmoid(-D) = 0.5 - 0.5 th
+        const float pv = ex2(fmaf(th, -0.5f * LOG2E, bb[e] + (0.5f * LOG2E - ll[e])));   // lse2 = +inf past N -> 0
         const float f = (!DROP || (kw & (1u << idx))) ? p.inv_keep : 0.f;
         pt[e] = f * pv;
         const float dpt = fmaf(2.0f * pt[e], __uint_as_float(gc[idx]), __uint_as_float(gm[idx]));
         dAv[e] = pv * fmaf(f, dpt, -dl[e]);
-        dDv[e] = -dAv[e] * t * (1.0f - t);
+        dDv[e] = dAv[e] * fmaf(th * 0.25f, th, -0.25f);                          // -dA t (1 - t), t (1 - t) = (1 - th^2) / 4
         pt2[e] = pt[e] * pt[e];
       }
       pk[2 * q] = pack_bf16x2(pt[0], pt[1]); pk[2 * q + 1] = pack_bf16x2(pt[2], pt[3]);
@@ -981,7 +1012,9 @@ wattn_bwd_dx_kernel(const __grid_constant__ CUtensorMap tm_dd, const __grid_cons
             const uint8_t* rowp = gbase + DX_SM_A + c * KT_BYTES + n * 128;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const uint4 v4 = *reinterpret_cast<const uint4*>(rowp + (q << 4));      // the swizzle only permutes the chunks of a row
+              // the swizzle only permutes the 16-byte chunks of a row and a sum does not care about the order: start each lane at a
+              // different chunk, or the 32 rows of a warp (128 B apart) would all hit the same four banks
+              const uint4 v4 = *reinterpret_cast<const uint4*>(rowp + (((q + lane) & 7) << 4));
               const uint32_t* pv = &v4.x;
 #pragma unroll
               for (int k = 0; k < 4; ++k) { const float2 f2 = unpack_bf16x2(pv[k]); acc += f2.x + f2.y; }
