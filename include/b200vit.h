@@ -23,11 +23,12 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 5   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+#define B200VIT_ABI_VERSION 6   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
                                    3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8;
                                    4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss;
                                    5: tcgen05 Wasserstein attention (wattn_fwd / wattn_bwd take the transformed-operand workspace and the bias
-                                      row maxima), rel_pos_bias rowmax output */
+                                      row maxima), rel_pos_bias rowmax output;
+                                   6: keep_bits (the dropout mask as its own kernel), keep_ready in attn_fwd / wattn_fwd, set_sm_limit */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -108,7 +109,13 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                      float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
-                     float* lse, uint8_t* keep_bits, void* stream);
+                     float* lse, uint8_t* keep_bits, int32_t keep_ready, void* stream);
+/* The packed keep mask of one attention layer, [B*H, N, 32] bytes (bit j%8 of byte j/8 of row i = keep(i, j)), from Philox4x32-7 keyed on
+ * (seed or *seed_dev, stream_id) or from an injected uint8 [B*H, N, N] mask. b200vit_attn_fwd / b200vit_wattn_fwd run it themselves unless
+ * they are called with keep_ready != 0 — then keep_bits must already hold the mask: it depends only on the key, so the engine draws the masks
+ * of all layers of a step on a side stream, next to the EMA-teacher forward (the draw costs ~40 us per ViT-B layer, integer-multiply bound). */
+int b200vit_keep_bits(uint8_t* keep_bits, int32_t BH, int32_t N, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                      const uint8_t* keep_in, void* stream);
 /* Bytes of the caller-owned workspace of b200vit_attn_bwd: dS^T bf16 [B, H, N, ld_ds] | D fp32 [B, H, N] | transposed keep bits. */
 size_t b200vit_attn_bwd_workspace_bytes(int32_t B, int32_t H, int32_t N);
 /* bias_t: the TRANSPOSED padded bias (b200vit_rel_pos_bias out_bwd_t) or NULL.
@@ -132,7 +139,8 @@ int b200vit_attn_bwd(const void* qkv, const void* out, const void* dout, const f
 size_t b200vit_wattn_workspace_bytes(int32_t B, int32_t H, int32_t N);
 int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, const float* bias_rowmax, void* xwork,
                       int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                      uint32_t stream_id, const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, void* stream);
+                      uint32_t stream_id, const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse, uint8_t* keep_bits, int32_t keep_ready,
+                      void* stream);
 /* Backward of b200vit_wattn_fwd (prep: Delta_i and the transposed keep bits; key-tile kernel -> dV, dCV and dD^T; per-(batch, head) kernel ->
  * dQ, dCQ, dK, dCK from dD^T and the transformed operands). dqkv_cov is the gradient w.r.t. the PRE-activation of elu(.)+1, i.e. ready for the
  * QKV wgrad / dgrad GEMMs. work: caller-owned, 256-byte aligned, b200vit_wattn_bwd_workspace_bytes(B, H, N, dtable != NULL) bytes (dD^T, Delta,
@@ -160,6 +168,14 @@ int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_index,
 int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
                           const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma,
                           float* dbeta, void* stream);
+/* b200vit_layernorm_bwd (all rows, no row list) followed, in the same pass over the rows, by b200vit_scale_residual_bwd of the residual
+ * branch BELOW this LayerNorm in the backward order (the attention branch after norm2's backward; the previous block's MLP branch after
+ * norm1's): dx += LN-backward(dy); dt = rowscale * gamma2 * dx; dgamma2 += sum rowscale * t * dx; dbias2 += sum dt. The 77 MB fp32 gradient
+ * stream is read once instead of twice per LayerNorm. */
+int b200vit_layernorm_bwd_scale_residual(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const float* gamma, const float* mean,
+                                         const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma, float* dbeta,
+                                         const void* t_bf16, const float* rowscale, int32_t rows_per_scale, const float* gamma2, void* dt_bf16,
+                                         float* dgamma2, float* dbias2, void* stream);
 /* backward of x + drop_path(gamma * t) (Block.forward, modeling_finetune.py:296-298):
  * dt = rowscale[r / rows_per_scale] * gamma * dx (bf16); dgamma += sum rowscale * t * dx; dbias += sum dt */
 int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const void* t_bf16, const float* rowscale, int32_t rows_per_scale,

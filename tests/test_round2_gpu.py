@@ -603,3 +603,45 @@ def test_vit_large_dims_fwd_bwd_vs_oracle(cuda, dist):
             if e > (GRAD_TOL_CANCELLING if _is_cancelling(k) else GRAD_TOL):
                 bad.append((k, round(e, 4)))
     assert not bad, bad
+
+
+# ------------------------------------------------------------------ fused LayerNorm backward + scale-residual backward
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,C,T,with_gamma", [(394, 768, 197, True), (2 * 197 * 3, 1024, 197, True), (64, 256, 16, False), (788, 128, 197, True)])
+def test_layernorm_bwd_scale_residual_matches_separate_kernels(ops, rows, C, T, with_gamma):
+    """b200vit_layernorm_bwd_scale_residual == b200vit_layernorm_bwd followed by b200vit_scale_residual_bwd on the same buffers
+    (dx bit-exact: same per-row arithmetic; the column reductions within fp32 atomics reordering)."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device="cpu").manual_seed(rows + C)
+    r = lambda *s: torch.randn(*s, generator=gen).to(dev)
+    dy = r(rows, C).bfloat16()
+    x = r(rows, C)                      # the fp32 residual stream
+    gamma = (1 + 0.1 * r(C)).contiguous()
+    xf = x
+    mean = xf.mean(1).contiguous()
+    rstd = (xf.var(1, unbiased=False) + 1e-6).rsqrt().contiguous()
+    dx0 = r(rows, C)
+    t = r(rows, C).bfloat16()
+    scale = (torch.rand(rows // T, generator=gen) > 0.3).float().mul(1.25).to(dev)
+    g2 = (0.1 * r(C)).contiguous() if with_gamma else None
+
+    def run(fused):
+        dx = dx0.clone()
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        dg2 = torch.zeros(C, device=dev) if with_gamma else None
+        db2 = torch.zeros(C, device=dev)
+        dt = torch.empty(rows, C, dtype=torch.bfloat16, device=dev)
+        if fused:
+            ops.layernorm_bwd_scale_residual(dy, x, gamma, mean, rstd, rows, C, dx, dg, db, t, scale, T, g2, dt, dg2, db2)
+        else:
+            ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows, C, dx, dg, db)
+            ops.scale_residual_bwd(dx, t, scale, T, g2, rows, C, dt, dg2, db2)
+        torch.cuda.synchronize()
+        return dx, dt, dg, db, dg2, db2
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(a[1], b[1])
+    for u, v in zip(a[2:], b[2:]):
+        if u is not None:
+            torch.testing.assert_close(u, v, rtol=2e-4, atol=2e-4 * float(v.abs().max()) + 1e-6)

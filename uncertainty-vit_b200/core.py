@@ -89,6 +89,8 @@ class Noise:
     drop_path_scale: Optional[torch.Tensor] = None      # fp32 [L, draws, B] = keep / (1 - p_l)
     attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
     head_eps: Optional[torch.Tensor] = None             # fp32 [B, C]: injected N(0,1) noise of the reparameterised head sample (cfg.sample_head)
+    keep_bits_all: Optional[torch.Tensor] = None        # uint8 [L, B, H, N, 32]: packed attention-dropout masks of ALL layers, drawn ahead of the
+    keep_join: Optional[object] = None                  # forward on this side stream (draw_keep_bits); the forward joins it before block 0
     drop_path_active: bool = True                       # applies only to training forwards
     attn_drop_active: Optional[bool] = None             # None: follow `train`; True: dropout even in eval (MC-dropout, enable_dropout())
 
@@ -102,7 +104,8 @@ def _empty(shape, dtype, dev):
 # ------------------------------------------------------------------------------------------------------------------
 def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: Optional[torch.Tensor], *, save: bool,
                   dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
-                  x_mid: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None, seed_dev: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                  x_mid: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None, seed_dev: Optional[torch.Tensor] = None,
+                  keep_pre: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """x_in: fp32 [B*T, C] residual stream. Returns the saved tensors (x_out under 'x_out')."""
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
@@ -117,8 +120,9 @@ def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B
     ops.gemm(h1, ps.bf16(p + "attn.qkv.weight"), M, 3 * C, C, epilogue=EPI_BF16, bias=ps.qkv_bias(p), out_bf16=qkv)
     attn_out = _empty((M, C), bf, dev)
     lse = _empty((B, H, T), torch.float32, dev) if save else None
-    keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
-    ops.attn_fwd(qkv, bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, attn_out, lse, keep_bits, seed_dev=seed_dev)
+    keep_bits = (keep_pre if keep_pre is not None else torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev)) if p_attn > 0 else None
+    ops.attn_fwd(qkv, bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, attn_out, lse, keep_bits, seed_dev=seed_dev,
+                 keep_ready=keep_pre is not None and p_attn > 0)
     if x_mid is None:
         x_mid = _empty((M, C), torch.float32, dev)
     t1 = _empty((M, C), bf, dev) if save else None
@@ -147,8 +151,12 @@ def block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B
 
 
 def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.Tensor], dx: torch.Tensor, B: int,
-                   bias: Optional[torch.Tensor], grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor]):
-    """dx: fp32 [B*T, C] gradient of the block output; updated IN PLACE to the gradient of the block input."""
+                   bias: Optional[torch.Tensor], grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor],
+                   first_srb_done: bool = False, below: Optional[Dict[str, torch.Tensor]] = None):
+    """dx: fp32 [B*T, C] gradient of the block output; updated IN PLACE to the gradient of the block input.
+    Each LayerNorm backward is fused with the scale-residual backward that consumes the dx it produces (one pass over the fp32 gradient
+    stream instead of two): norm2's with this block's attention branch, norm1's with the MLP branch of the block BELOW (`below` = that
+    block's saved tensors; its block_backward is then called with first_srb_done=True)."""
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
     p = f"blocks.{i}."
@@ -157,22 +165,40 @@ def block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.T
     g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
     g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
     # ---- MLP branch: x_out = x_mid + dp2 * gamma_2 * (fc2(gelu(fc1(LN2 x_mid))))
-    ops.scale_residual_bwd(dx, s["t2"], s["dp2"], T, g2, M, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
+    if not first_srb_done:
+        ops.scale_residual_bwd(dx, s["t2"], s["dp2"], T, g2, M, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
     ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
-    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
-    ops.colsum_bf16(dpre, M, Hd, g("mlp.fc1.bias"))
+    # fc1.bias gradient = column sums of dpre: fused into the dGELU epilogue (one launch and one 155 MB read less per block)
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre, colsum=g("mlp.fc1.bias"))
     ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
     ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
-    ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M, C, dx, g("norm2.weight"), g("norm2.bias"))
-    # ---- attention branch: x_mid = x_in + dp1 * gamma_1 * proj(attn(LN1 x_in))
-    ops.scale_residual_bwd(dx, s["t1"], s["dp1"], T, g1, M, C, dt, g("gamma_1") if cfg.has_gamma else None, g("attn.proj.bias"))
+    # ---- norm2 backward + attention branch: x_mid = x_in + dp1 * gamma_1 * proj(attn(LN1 x_in))
+    ops.layernorm_bwd_scale_residual(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M, C, dx, g("norm2.weight"), g("norm2.bias"),
+                                     s["t1"], s["dp1"], T, g1, dt, g("gamma_1") if cfg.has_gamma else None, g("attn.proj.bias"))
     ops.linear_wgrad(dt, s["attn_out"], g("attn.proj.weight"))
     ops.gemm(dt, ps.bf16(p + "attn.proj.weight"), M, C, C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
     ops.attn_bwd(s["qkv"], s["attn_out"], dh, s["lse"], bias, s["keep_bits"], ps.rel_index_i32() if dtable is not None else None, dtable,
                  B, H, T, (C // H) ** -0.5, s["p_attn"], dqkv, ds_work=ws.get("attn_ws"), dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"))
     ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))
     ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
-    ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"))
+    if below is None:
+        ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"))
+    else:
+        q = f"blocks.{i - 1}."
+        ops.layernorm_bwd_scale_residual(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M, C, dx, g("norm1.weight"), g("norm1.bias"),
+                                         below["t2"], below["dp2"], T, ps.f32(q + "gamma_2") if cfg.has_gamma else None, dt,
+                                         grads.get(q + "gamma_2") if cfg.has_gamma else None, grads.get(q + "mlp.fc2.bias"))
+
+
+def _backward_blocks(block_fn, cfg: VitConfig, saved, after_block, *args):
+    """Runs block_fn(i, saved[i], first_srb_done, below) for i = depth-1 .. 0, chaining the LayerNorm / scale-residual fusion across blocks and
+    releasing each block's activations as soon as the block below no longer needs them."""
+    for i in reversed(range(cfg.depth)):
+        below = saved[i - 1] if i > 0 else None
+        block_fn(i, saved[i], i < cfg.depth - 1, below)
+        saved[i] = None
+        if after_block is not None:
+            after_block(i)
 
 
 def backward_workspace(cfg: VitConfig, B: int, dev) -> Dict[str, torch.Tensor]:
@@ -230,6 +256,23 @@ def rel_bias(ps: ParamSource, cfg: VitConfig, dev, want_bwd: bool = True):
 # ------------------------------------------------------------------------------------------------------------------
 # whole network
 # ------------------------------------------------------------------------------------------------------------------
+def draw_keep_bits(cfg: VitConfig, B: int, noise: Noise, dev, side_stream) -> None:
+    """Draws the packed attention-dropout masks of all layers of one training forward on `side_stream` (they depend only on the Philox key),
+    so that the integer-multiply-bound draw (~40 us per ViT-B layer) runs beside whatever the main stream does next — the EMA-teacher
+    forward in the data2vec step. vit_forward / dist_forward join the side stream before their first block. No-op with injected masks."""
+    if cfg.attn_drop_rate <= 0.0 or noise.attn_keep is not None or noise.attn_drop_active is False:
+        return
+    H, T = cfg.num_heads, cfg.tokens
+    kb = torch.empty((cfg.depth, B, H, T, 32), dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side_stream.wait_stream(cur)
+    with torch.cuda.stream(side_stream):
+        for l in range(cfg.depth):
+            ops.keep_bits(kb[l], B * H, T, cfg.attn_drop_rate, seed=noise.seed, stream_id=l, seed_dev=noise.seed_dev)
+    kb.record_stream(side_stream)
+    noise.keep_bits_all, noise.keep_join = kb, side_stream
+
+
 def make_drop_path_scales(cfg: VitConfig, B: int, noise: Noise, dev, draws: int = 2) -> Optional[torch.Tensor]:
     if not noise.drop_path_active or cfg.drop_path_rate <= 0.0:
         return None
@@ -265,10 +308,13 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
     saved = []
     layers: Dict[int, torch.Tensor] = {}
     collect = collect or []
+    kb_all = noise.keep_bits_all if p_attn > 0 else None
+    if kb_all is not None and noise.keep_join is not None:
+        torch.cuda.current_stream(dev).wait_stream(noise.keep_join)        # the masks were drawn on a side stream
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn, seed=noise.seed,
-                          keep_in=keep_in, seed_dev=noise.seed_dev)
+                          keep_in=keep_in, seed_dev=noise.seed_dev, keep_pre=kb_all[i] if kb_all is not None else None)
         if i in collect:
             if collect_what == "fc":      # fc_feature = x_out - x_mid (modeling_cyclical.py:203-205); rarely used
                 layers[i] = (s["x_out"] - s["x_mid"]).view(B, T, C)
@@ -355,11 +401,8 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
                           row_index=row_index)
     ws = backward_workspace(cfg, B, dev)
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
-    for i in reversed(range(cfg.depth)):
-        block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
-        ctx["saved"][i] = None   # free activations as we go
-        if after_block is not None:
-            after_block(i)
+    _backward_blocks(lambda i, sv, done, below: block_backward(ps, cfg, i, sv, dx, B, ctx["bias"], grads, dtable, ws, done, below),
+                     cfg, ctx["saved"], after_block)
     stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)
 
 
@@ -372,7 +415,8 @@ def vit_backward(ps: ParamSource, cfg: VitConfig, ctx, dout: torch.Tensor, grads
 # ------------------------------------------------------------------------------------------------------------------
 def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tensor, B: int, bias: torch.Tensor, *, save: bool,
                        dp_scale: Optional[torch.Tensor], p_attn: float, seed: int, keep_in: Optional[torch.Tensor],
-                       seed_dev: Optional[torch.Tensor] = None, xwork_scratch: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                       seed_dev: Optional[torch.Tensor] = None, xwork_scratch: Optional[torch.Tensor] = None,
+                       keep_pre: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
     M2 = 2 * M
@@ -389,12 +433,12 @@ def dist_block_forward(ps: ParamSource, cfg: VitConfig, i: int, x_in: torch.Tens
     ops.gemm(h1[M:], w, M, 3 * C, C, epilogue=ops.EPI_ELU1, bias=ps.qkv_bias(p, cov=True), out_bf16=qkv[M:])     # elu(.)+1 (:127)
     att = _empty((M2, C), bf, dev)
     lse = _empty((B, H, T), torch.float32, dev) if save else None
-    keep_bits = torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev) if p_attn > 0 else None
+    keep_bits = (keep_pre if keep_pre is not None else torch.empty((B, H, T, 32), dtype=torch.uint8, device=dev)) if p_attn > 0 else None
     # the transformed operands [sigmoid(q) | sqrt(sigmoid(cq))], [sigmoid(k) | sqrt(sigmoid(ck))]: kept for the backward when saving, else one
     # scratch buffer shared by all blocks of the forward
     xwork = ops.wattn_workspace(B, H, T, dev) if (save or xwork_scratch is None) else xwork_scratch
     ops.wattn_fwd(qkv[:M], qkv[M:], bias, B, H, T, (C // H) ** -0.5, p_attn, seed, i, keep_in, att[:M], att[M:], lse, keep_bits, seed_dev=seed_dev,
-                  xwork=xwork)
+                  xwork=xwork, keep_ready=keep_pre is not None and p_attn > 0)
     x_mid = _empty((M2, C), torch.float32, dev)
     t1 = _empty((M2, C), bf, dev) if save else None
     g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
@@ -448,10 +492,14 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
     saved, lm, lc = [], {}, {}
     collect = collect or []
     scratch = None if save else ops.wattn_workspace(B, cfg.num_heads, T, dev)
+    kb_all = noise.keep_bits_all if p_attn > 0 else None
+    if kb_all is not None and noise.keep_join is not None:
+        torch.cuda.current_stream(dev).wait_stream(noise.keep_join)
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = dist_block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn,
-                               seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev, xwork_scratch=scratch)
+                               seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev, xwork_scratch=scratch,
+                               keep_pre=kb_all[i] if kb_all is not None else None)
         x = s["x_out"]
         if i in collect:
             lm[i] = x[:M].view(B, T, C)
@@ -505,9 +553,11 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
 
 
 def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, torch.Tensor], dx: torch.Tensor, B: int, bias_t: torch.Tensor,
-                        grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor]):
+                        grads: Dict[str, torch.Tensor], dtable: Optional[torch.Tensor], ws: Dict[str, torch.Tensor],
+                        first_srb_done: bool = False, below: Optional[Dict[str, torch.Tensor]] = None):
     """dx: fp32 [2*B*T, C] (mean rows then cov rows), updated IN PLACE. Shared weights (qkv, fc1, fc2, norms, gammas) receive the sum of
-    both streams' gradients simply because the GEMMs / reductions run over the stacked rows."""
+    both streams' gradients simply because the GEMMs / reductions run over the stacked rows. LayerNorm backward fused with the following
+    scale-residual backward as in block_backward (norm2: one launch per stream, because proj / cov_proj have their own bias gradients)."""
     T, C, H, Hd = cfg.tokens, cfg.embed_dim, cfg.num_heads, cfg.hidden
     M = B * T
     M2 = 2 * M
@@ -517,17 +567,19 @@ def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, to
     g1 = ps.f32(p + "gamma_1") if cfg.has_gamma else None
     g2 = ps.f32(p + "gamma_2") if cfg.has_gamma else None
     # ---- shared MLP over the stacked rows
-    ops.scale_residual_bwd(dx, s["t2"], s["dp_mlp"], T, g2, M2, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
+    if not first_srb_done:
+        ops.scale_residual_bwd(dx, s["t2"], s["dp_mlp"], T, g2, M2, C, dt, g("gamma_2") if cfg.has_gamma else None, g("mlp.fc2.bias"))
     ops.linear_wgrad(dt, s["act"], g("mlp.fc2.weight"))
-    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M2, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre)
-    ops.colsum_bf16(dpre, M2, Hd, g("mlp.fc1.bias"))
+    ops.gemm(dt, ps.bf16(p + "mlp.fc2.weight"), M2, Hd, C, b_mn=True, epilogue=EPI_DGELU, aux=s["pre"], out_bf16=dpre, colsum=g("mlp.fc1.bias"))
     ops.linear_wgrad(dpre, s["h2"], g("mlp.fc1.weight"))
     ops.gemm(dpre, ps.bf16(p + "mlp.fc1.weight"), M2, C, Hd, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
-    ops.layernorm_bwd(dh, s["x_mid"], ps.f32(p + "norm2.weight"), s["mean2"], s["rstd2"], M2, C, dx, g("norm2.weight"), g("norm2.bias"))
-    # ---- attention branch: mean rows through proj, cov rows through cov_proj (shared gamma_1)
+    # ---- norm2 backward + attention branch: mean rows through proj, cov rows through cov_proj (shared gamma_1)
     gg1 = g("gamma_1") if cfg.has_gamma else None
-    ops.scale_residual_bwd(dx[:M], s["t1"][:M], s["dp_attn_m"], T, g1, M, C, dt[:M], gg1, g("attn.proj.bias"))
-    ops.scale_residual_bwd(dx[M:], s["t1"][M:], s["dp_attn_c"], T, g1, M, C, dt[M:], gg1, g("attn.cov_proj.bias"))
+    n2w, gn2w, gn2b = ps.f32(p + "norm2.weight"), g("norm2.weight"), g("norm2.bias")
+    ops.layernorm_bwd_scale_residual(dh[:M], s["x_mid"][:M], n2w, s["mean2"][:M], s["rstd2"][:M], M, C, dx[:M], gn2w, gn2b,
+                                     s["t1"][:M], s["dp_attn_m"], T, g1, dt[:M], gg1, g("attn.proj.bias"))
+    ops.layernorm_bwd_scale_residual(dh[M:], s["x_mid"][M:], n2w, s["mean2"][M:], s["rstd2"][M:], M, C, dx[M:], gn2w, gn2b,
+                                     s["t1"][M:], s["dp_attn_c"], T, g1, dt[M:], gg1, g("attn.cov_proj.bias"))
     att = s["att"]
     ops.linear_wgrad(dt[:M], att[:M], g("attn.proj.weight"))
     ops.linear_wgrad(dt[M:], att[M:], g("attn.cov_proj.weight"))
@@ -539,7 +591,13 @@ def dist_block_backward(ps: ParamSource, cfg: VitConfig, i: int, s: Dict[str, to
                   work=ws["wattn"], dq_bias=g("attn.q_bias"), dv_bias=g("attn.v_bias"), dcq_bias=g("attn.cov_q_bias"), dcv_bias=g("attn.cov_v_bias"))
     ops.linear_wgrad(dqkv, s["h1"], g("attn.qkv.weight"))        # both streams multiply by qkv.weight (cov_qkv.weight stays unused, §A.2-1)
     ops.gemm(dqkv, ps.bf16(p + "attn.qkv.weight"), M2, C, 3 * C, b_mn=True, epilogue=EPI_BF16, out_bf16=dh)
-    ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"))
+    if below is None:
+        ops.layernorm_bwd(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"))
+    else:
+        q = f"blocks.{i - 1}."
+        ops.layernorm_bwd_scale_residual(dh, s["x_in"], ps.f32(p + "norm1.weight"), s["mean1"], s["rstd1"], M2, C, dx, g("norm1.weight"), g("norm1.bias"),
+                                         below["t2"], below["dp_mlp"], T, ps.f32(q + "gamma_2") if cfg.has_gamma else None, dt,
+                                         grads.get(q + "gamma_2") if cfg.has_gamma else None, grads.get(q + "mlp.fc2.bias"))
 
 
 def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, dout_c: torch.Tensor, grads: Dict[str, torch.Tensor], after_block=None):
@@ -572,11 +630,8 @@ def dist_backward(ps: ParamSource, cfg: VitConfig, ctx, dout_m: torch.Tensor, do
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
     ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
               wattn=ops.wattn_bwd_workspace(B, cfg.num_heads, T, dtable is not None, dev))
-    for i in reversed(range(cfg.depth)):
-        dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
-        ctx["saved"][i] = None
-        if after_block is not None:
-            after_block(i)
+    _backward_blocks(lambda i, sv, done, below: dist_block_backward(ps, cfg, i, sv, dx, B, ctx["bias"], grads, dtable, ws, done, below),
+                     cfg, ctx["saved"], after_block)
     stem_backward(ps, cfg, ctx["patches"], dx[:M], B, ctx["mask_u8"], grads)
     stem_backward(ps, cfg, ctx["patches"], dx[M:], B, ctx["mask_u8"], grads, prefix="cov_")
 
@@ -632,9 +687,8 @@ def vit_backward_logits(ps: ParamSource, cfg: VitConfig, ctx, dlogits: torch.Ten
     dx = _head_backward(ps, cfg, ctx, dlogits, None, grads, 1)
     ws = backward_workspace(cfg, B, dlogits.device)
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
-    for i in reversed(range(cfg.depth)):
-        block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
-        ctx["saved"][i] = None
+    _backward_blocks(lambda i, sv, done, below: block_backward(ps, cfg, i, sv, dx, B, ctx["bias"], grads, dtable, ws, done, below),
+                     cfg, ctx["saved"], None)
     stem_backward(ps, cfg, ctx["patches"], dx, B, ctx["mask_u8"], grads)
 
 
@@ -655,8 +709,7 @@ def dist_backward_logits(ps: ParamSource, cfg: VitConfig, ctx, dmean_feat, dcov_
     dtable = grads.get("rel_pos_bias.relative_position_bias_table")
     ws = dict(dt=_empty((M2, C), bf, dev), dpre=_empty((M2, Hd), bf, dev), dh=_empty((M2, C), bf, dev), dqkv=_empty((M2, 3 * C), bf, dev),
               wattn=ops.wattn_bwd_workspace(B, cfg.num_heads, T, dtable is not None, dev))
-    for i in reversed(range(cfg.depth)):
-        dist_block_backward(ps, cfg, i, ctx["saved"][i], dx, B, ctx["bias"], grads, dtable, ws)
-        ctx["saved"][i] = None
+    _backward_blocks(lambda i, sv, done, below: dist_block_backward(ps, cfg, i, sv, dx, B, ctx["bias"], grads, dtable, ws, done, below),
+                     cfg, ctx["saved"], None)
     stem_backward(ps, cfg, ctx["patches"], dx[:M], B, None, grads)
     stem_backward(ps, cfg, ctx["patches"], dx[M:], B, None, grads, prefix="cov_")

@@ -27,6 +27,48 @@ __global__ void dropout_mask_kernel(uint8_t* out, int BH, int N, float p_drop, u
   }
 }
 
+// Packed keep mask of one attention layer, [B*H, N, 8 words] (bit e of word c = key 32c + e of that query row), from the Philox stream of
+// dropout_mask_kernel or from an injected uint8 mask. One thread per (row, 32-key word). Generating the mask here — a 20 us, fully
+// occupied kernel — instead of inside the attention forward takes ~11 instructions per decision off the one-thread-per-row softmax loop,
+// which is latency-bound (the forward with dropout was 129 us against 87 us without).
+__global__ void __launch_bounds__(256) keep_bits_kernel(uint32_t* __restrict__ keep_bits, int BH, int N, uint32_t thresh, uint64_t seed,
+                                                        const uint64_t* __restrict__ seed_dev, uint32_t stream_id, const uint8_t* __restrict__ keep_in) {
+  const long long total = (long long)BH * N * 8;
+  const uint64_t sd = seed_dev != nullptr ? *seed_dev : seed;
+  const int words = (N + 31) >> 5;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 7);
+    const long long row = idx >> 3;              // bh * N + i
+    uint32_t w = 0u;
+    if (c < words) {
+      const int i = (int)(row % N);
+      const int bh = (int)(row / N);
+      if (keep_in == nullptr) {
+        // word n4 of a Philox draw holds the two 16-bit lanes of keys (n4 * 8 + quad * 2, + 1): both compared at once (vset2), the two
+        // result bits (0 and 16) folded into adjacent bit positions
+        const uint32_t th2 = thresh | (thresh << 16);
+#pragma unroll
+        for (int quad = 0; quad < 4; ++quad) {
+          const Philox4 r = dropout_group(sd, stream_id, bh, i, quad, c);
+          const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int n4 = 0; n4 < 4; ++n4) {
+            const uint32_t ge = __vcmpgeu2(rw[n4], th2) & 0x00010001u;      // bit 0: low lane kept, bit 16: high lane kept
+            w |= ((ge | (ge >> 15)) & 3u) << (n4 * 8 + quad * 2);
+          }
+        }
+      } else {
+        const uint8_t* src = keep_in + row * N;
+        for (int e = 0; e < 32; ++e) {
+          const int j = c * 32 + e;
+          if (j < N && src[j]) w |= 1u << e;
+        }
+      }
+    }
+    keep_bits[idx] = w;
+  }
+}
+
 // RelativePositionBias.forward (modeling_finetune.py:359-364) in the layout the attention kernels read:
 //   out_fwd[h, i, j] = scale * table[index[i, j], h] for j < N, -inf for N <= j < ld     (forward: key mask baked in)
 //   out_bwd[h, j, i] = scale * table[index[i, j], h] for i < N, 0 for N <= i < ld        (backward: transposed)
@@ -92,6 +134,23 @@ int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld
   relbias_grad_kernel<<<sms * 8, 256, 0, STREAM>>>(static_cast<const bf16*>(ds_work), B, H, N, ld_ds, rel_index, dtable);
   B200_CHECK_LAUNCH("relbias_grad");
   return 0;
+}
+
+// internal: shared by the dot-product and the Wasserstein attention forwards
+int b200vit_keep_bits_launch(uint8_t* keep_bits, int BH, int N, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                             const uint8_t* keep_in, void* stream) {
+  const int sms = b200vit_num_sms();
+  keep_bits_kernel<<<sms * 8, 256, 0, STREAM>>>(reinterpret_cast<uint32_t*>(keep_bits), BH, N, (uint32_t)(p_drop * 65536.0f + 0.5f), seed, seed_dev,
+                                                stream_id, keep_in);
+  B200_CHECK_LAUNCH("keep_bits");
+  return 0;
+}
+
+extern "C" int b200vit_keep_bits(uint8_t* keep_bits, int32_t BH, int32_t N, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                                 const uint8_t* keep_in, void* stream) {
+  B200_CHECK_ARG(keep_bits != nullptr && BH > 0 && N > 0 && N <= NMAX && p_drop >= 0.f && p_drop < 1.f, "keep_bits: bad arguments");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(keep_bits) & 3) == 0, "keep_bits: the mask must be 4-byte aligned");
+  return b200vit_keep_bits_launch(keep_bits, BH, N, p_drop, seed, seed_dev, stream_id, keep_in, stream);
 }
 
 extern "C" int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {

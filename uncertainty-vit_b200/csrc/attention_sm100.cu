@@ -54,29 +54,10 @@ struct Fwd100Params {
   uint32_t stream_id;
 };
 
-// Keep bits of the 32 (or 16) keys [32c, 32c + COLS) of query row i — bit e = key 32c + e. Same Philox stream layout as the
-// mma.sync kernels (dropout_group / dropout_u16 in attn_common.cuh), so b200vit_dropout_mask and the backward agree.
-template <int COLS>
-__device__ __forceinline__ uint32_t keep_word(const Fwd100Params& p, uint64_t seed, int bh, int i, int c) {
-  uint32_t w = 0u;
-  if (p.keep_in == nullptr) {
-#pragma unroll
-    for (int quad = 0; quad < 4; ++quad) {
-      const Philox4 r = dropout_group(seed, p.stream_id, bh, i, quad, c);
-#pragma unroll
-      for (int n4 = 0; n4 < COLS / 8; ++n4) {
-        w |= (dropout_u16(r, n4 * 2) >= p.thresh ? 1u : 0u) << (n4 * 8 + quad * 2);
-        w |= (dropout_u16(r, n4 * 2 + 1) >= p.thresh ? 1u : 0u) << (n4 * 8 + quad * 2 + 1);
-      }
-    }
-  } else if (i < p.N) {
-    const uint8_t* src = p.keep_in + ((long long)bh * p.N + i) * p.N;
-    for (int e = 0; e < COLS; ++e) {
-      const int j = c * 32 + e;
-      if (j < p.N && src[j]) w |= 1u << e;
-    }
-  }
-  return w;
+// Keep bits of the 32 keys [32c, 32c + 32) of query row i — bit e = key 32c + e — from the packed mask b200vit_keep_bits_launch wrote
+// before this kernel (Philox stream of dropout_group / dropout_u16 in attn_common.cuh, or the injected mask).
+__device__ __forceinline__ uint32_t keep_word(const Fwd100Params& p, int bh, int i, int c) {
+  return i < p.N ? __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits) + ((long long)bh * p.N + i) * 8 + c) : 0u;
 }
 
 template <int COLS, bool HAS_BIAS>
@@ -130,10 +111,7 @@ __device__ __forceinline__ void pass2_step16(uint32_t t_src, uint32_t t_dst, flo
 template <int COLS, bool DROP>
 __device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint64_t seed, uint32_t trow, int bh, int i, int c, float mx, float& l) {
   uint32_t w = 0xffffffffu;
-  if (DROP) {
-    w = keep_word<COLS>(p, seed, bh, i, c);
-    if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
-  }
+  if (DROP) w = keep_word(p, bh, i, c);
   pass2_step16<DROP>(trow + c * 32, trow + c * 16, mx, l, w);
   if constexpr (COLS == 32) pass2_step16<DROP>(trow + c * 32 + 16, trow + c * 16 + 8, mx, l, w >> 16);
 }
@@ -1156,7 +1134,7 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
 
 extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                                 float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
-                                float* lse, uint8_t* keep_bits, void* stream_) {
+                                float* lse, uint8_t* keep_bits, int32_t keep_ready, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_fwd: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0, "attn_fwd: bad B=%d H=%d", B, H);
@@ -1184,6 +1162,9 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
     tb = tq;
   }
   cudaError_t e;
+  if (p_drop > 0.f && !keep_ready) {
+    if ((rc = b200vit_keep_bits_launch(keep_bits, B * H, N, p_drop, seed, seed_dev, stream_id, keep_in, stream_))) return rc;
+  }
   if (p_drop > 0.f) e = bias != nullptr ? launch_fwd100<true, true>(tq, tkv, tb, to, p, stream) : launch_fwd100<true, false>(tq, tkv, tb, to, p, stream);
   else e = bias != nullptr ? launch_fwd100<false, true>(tq, tkv, tb, to, p, stream) : launch_fwd100<false, false>(tq, tkv, tb, to, p, stream);
   if (e != cudaSuccess) { b200vit_set_error("attn_fwd: launch failed: %s", cudaGetErrorString(e)); return (int)e; }

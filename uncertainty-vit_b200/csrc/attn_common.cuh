@@ -3,6 +3,8 @@
 #include "common.cuh"
 
 int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld_ds, const int32_t* rel_index, float* dtable, void* stream);
+int b200vit_keep_bits_launch(uint8_t* keep_bits, int BH, int N, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                             const uint8_t* keep_in, void* stream);
 
 namespace attn {
 

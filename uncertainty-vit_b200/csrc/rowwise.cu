@@ -77,14 +77,27 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // LayerNorm backward. dx[src_row] += rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));
 // dgamma += sum dy*xhat ; dbeta += sum dy.   Each warp loops over rows; per-CTA smem reduction; atomics at the end.
 // ------------------------------------------------------------------------------------------------
-template <int NV, typename DY>
+// Optional second stage on the SAME rows, fused (the next op of the backward pass reads the dx this kernel has just produced): the backward
+// of x_out = x_in + rowscale * gamma2 * t (scale_residual_bwd below): dt = rowscale gamma2 dx (bf16), dgamma2 += sum rowscale t dx,
+// dbias2 += sum dt. Saves the 77 MB re-read of dx and one launch per LayerNorm of a block.
+struct SrbStage {
+  const bf16* t;            // null: stage off
+  const float* rowscale;
+  int rows_per_scale;
+  const float* gamma2;
+  bf16* dt;
+  float* dgamma2;
+  float* dbias2;
+};
+
+template <int NV, typename DY, bool SRB>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, const float* __restrict__ x, long long ldx,
                                                      const int* __restrict__ row_index, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                      int rows, int C, float* __restrict__ dx, long long lddx,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float red[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, const SrbStage srb) {
+  extern __shared__ float red[];  // [2][C] (+ [2][C] for the fused stage)
+  for (int i = threadIdx.x; i < (SRB ? 4 : 2) * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -95,6 +108,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
 #pragma unroll
   for (int i = 0; i < NV; ++i)
     g[i] = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 ag2[SRB ? NV : 1], ab2[SRB ? NV : 1], g2[SRB ? NV : 1];
+  if constexpr (SRB) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      ag2[i] = ab2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      g2[i] = srb.gamma2 != nullptr ? __ldg(reinterpret_cast<const float4*>(srb.gamma2 + (i * 32 + lane) * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+  }
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const long long src = row_index != nullptr ? row_index[r] : r;
     const float* xr = x + src * ldx;
@@ -120,10 +141,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
     // A row whose dy is all zero adds nothing. It is skipped rather than added as zeros because dx[src] is updated with a plain
     // read-modify-write: the padding entries of a fixed-capacity row list (b200vit_d2v_target_loss, n_valid_dev) may repeat a row
     // number that a live row of another warp is updating at the same time.
-    if (!__any_sync(0xffffffffu, live)) continue;
+    if (!SRB && !__any_sync(0xffffffffu, live)) continue;      // (the fused stage must write dt for every row; it is never used with a row list)
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
     float* dxr = dx + src * lddx;
+    float rs = 1.0f;
+    if constexpr (SRB) rs = srb.rowscale != nullptr ? __ldg(srb.rowscale + r / srb.rows_per_scale) : 1.0f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -133,6 +156,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
       o.z += rstd * (d[i].z - s1 - xh[i].z * s2);
       o.w += rstd * (d[i].w - s1 - xh[i].w * s2);
       st4(dxr + c, o);
+      if constexpr (SRB) {
+        const float4 tv = ld_bf16x4(srb.t + (long long)r * C + c);
+        const float4 q = make_float4(rs * g2[i].x * o.x, rs * g2[i].y * o.y, rs * g2[i].z * o.z, rs * g2[i].w * o.w);
+        st_bf16x4(srb.dt + (long long)r * C + c, q);
+        ag2[i].x += rs * tv.x * o.x; ag2[i].y += rs * tv.y * o.y; ag2[i].z += rs * tv.z * o.z; ag2[i].w += rs * tv.w * o.w;
+        ab2[i].x += q.x; ab2[i].y += q.y; ab2[i].z += q.z; ab2[i].w += q.w;
+      }
+    }
+  }
+  if constexpr (SRB) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&red[2 * C + c], ag2[i].x); atomicAdd(&red[2 * C + c + 1], ag2[i].y); atomicAdd(&red[2 * C + c + 2], ag2[i].z); atomicAdd(&red[2 * C + c + 3], ag2[i].w);
+      atomicAdd(&red[3 * C + c], ab2[i].x); atomicAdd(&red[3 * C + c + 1], ab2[i].y); atomicAdd(&red[3 * C + c + 2], ab2[i].z); atomicAdd(&red[3 * C + c + 3], ab2[i].w);
     }
   }
   if (dgamma != nullptr || dbeta != nullptr) {
@@ -146,6 +184,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
       if (dgamma != nullptr) atomicAdd(dgamma + i, red[i]);
       if (dbeta != nullptr) atomicAdd(dbeta + i, red[C + i]);
+    }
+  }
+  if constexpr (SRB) {
+    if (dgamma == nullptr && dbeta == nullptr) __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (srb.dgamma2 != nullptr) atomicAdd(srb.dgamma2 + i, red[2 * C + i]);
+      if (srb.dbias2 != nullptr) atomicAdd(srb.dbias2 + i, red[3 * C + i]);
     }
   }
 }
@@ -383,19 +428,22 @@ extern "C" int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t*
   return 0;
 }
 
-extern "C" int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index,
-                                     const float* gamma, const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx,
-                                     int64_t lddx, float* dgamma, float* dbeta, void* stream) {
-  B200_CHECK_ARG(dy != nullptr && x != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr, "layernorm_bwd: null pointer");
-  B200_CHECK_ARG(C > 0 && C % 128 == 0 && C <= 128 * LN_MAXV, "layernorm_bwd: C=%d must be a multiple of 128, <= %d", C, 128 * LN_MAXV);
-  if (rows == 0) return 0;
+static int launch_ln_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
+                         const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma, float* dbeta,
+                         const SrbStage& srb, void* stream) {
   const int sms = b200vit_num_sms();
   int grid = (rows + 7) / 8;
   if (grid > sms * 2) grid = sms * 2;
-  const size_t smem = 2 * C * sizeof(float);
-#define LN_BWD(NV)                                                                                                              \
-  if (dy_is_f32) ln_bwd_kernel<NV, float><<<grid, 256, smem, STREAM>>>(static_cast<const float*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta); \
-  else ln_bwd_kernel<NV, bf16><<<grid, 256, smem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta)
+  const bool fused = srb.t != nullptr;
+  const size_t smem = (fused ? 4 : 2) * C * sizeof(float);
+#define LN_BWD(NV)                                                                                                                             \
+  if (fused) {                                                                                                                                 \
+    if (dy_is_f32) ln_bwd_kernel<NV, float, true><<<grid, 256, smem, STREAM>>>(static_cast<const float*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb); \
+    else ln_bwd_kernel<NV, bf16, true><<<grid, 256, smem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);          \
+  } else {                                                                                                                                     \
+    if (dy_is_f32) ln_bwd_kernel<NV, float, false><<<grid, 256, smem, STREAM>>>(static_cast<const float*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb); \
+    else ln_bwd_kernel<NV, bf16, false><<<grid, 256, smem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);          \
+  }
   switch (C / 128) {
     case 1: LN_BWD(1); break; case 2: LN_BWD(2); break; case 3: LN_BWD(3); break; case 4: LN_BWD(4); break;
     case 5: LN_BWD(5); break; case 6: LN_BWD(6); break; case 7: LN_BWD(7); break; default: LN_BWD(8); break;
@@ -403,6 +451,32 @@ extern "C" int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const fl
 #undef LN_BWD
   B200_CHECK_LAUNCH("layernorm_bwd");
   return 0;
+}
+
+extern "C" int b200vit_layernorm_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index,
+                                     const float* gamma, const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx,
+                                     int64_t lddx, float* dgamma, float* dbeta, void* stream) {
+  B200_CHECK_ARG(dy != nullptr && x != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr, "layernorm_bwd: null pointer");
+  B200_CHECK_ARG(C > 0 && C % 128 == 0 && C <= 128 * LN_MAXV, "layernorm_bwd: C=%d must be a multiple of 128, <= %d", C, 128 * LN_MAXV);
+  if (rows == 0) return 0;
+  SrbStage off = {};
+  return launch_ln_bwd(dy, dy_is_f32, x, ldx, row_index, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, off, stream);
+}
+
+extern "C" int b200vit_layernorm_bwd_scale_residual(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const float* gamma,
+                                                    const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx,
+                                                    float* dgamma, float* dbeta, const void* t_bf16, const float* rowscale,
+                                                    int32_t rows_per_scale, const float* gamma2, void* dt_bf16, float* dgamma2, float* dbias2,
+                                                    void* stream) {
+  B200_CHECK_ARG(dy != nullptr && x != nullptr && mean != nullptr && rstd != nullptr && dx != nullptr, "layernorm_bwd_scale_residual: null pointer");
+  B200_CHECK_ARG(t_bf16 != nullptr && dt_bf16 != nullptr, "layernorm_bwd_scale_residual: the fused stage needs t and dt");
+  B200_CHECK_ARG(C > 0 && C % 128 == 0 && C <= 128 * LN_MAXV, "layernorm_bwd_scale_residual: C=%d must be a multiple of 128, <= %d", C, 128 * LN_MAXV);
+  B200_CHECK_ARG(rowscale == nullptr || rows_per_scale > 0, "layernorm_bwd_scale_residual: rows_per_scale must be > 0");
+  if (rows == 0) return 0;
+  SrbStage st;
+  st.t = static_cast<const bf16*>(t_bf16); st.rowscale = rowscale; st.rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1; st.gamma2 = gamma2;
+  st.dt = static_cast<bf16*>(dt_bf16); st.dgamma2 = dgamma2; st.dbias2 = dbias2;
+  return launch_ln_bwd(dy, dy_is_f32, x, ldx, nullptr, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, st, stream);
 }
 
 extern "C" int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const void* t_bf16, const float* rowscale, int32_t rows_per_scale,

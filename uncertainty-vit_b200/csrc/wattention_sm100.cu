@@ -162,28 +162,9 @@ struct WFwdParams {
   uint32_t stream_id;
 };
 
-// keep bits of keys [32c, 32c + COLS) of query row i (bit e = key 32c + e): the Philox stream layout of the det kernels / b200vit_dropout_mask
-template <int COLS>
-__device__ __forceinline__ uint32_t w_keep_word(const WFwdParams& p, uint64_t seed, int bh, int i, int c) {
-  uint32_t w = 0u;
-  if (p.keep_in == nullptr) {
-#pragma unroll
-    for (int quad = 0; quad < 4; ++quad) {
-      const Philox4 r = dropout_group(seed, p.stream_id, bh, i, quad, c);
-#pragma unroll
-      for (int n4 = 0; n4 < COLS / 8; ++n4) {
-        w |= (dropout_u16(r, n4 * 2) >= p.thresh ? 1u : 0u) << (n4 * 8 + quad * 2);
-        w |= (dropout_u16(r, n4 * 2 + 1) >= p.thresh ? 1u : 0u) << (n4 * 8 + quad * 2 + 1);
-      }
-    }
-  } else if (i < p.N) {
-    const uint8_t* src = p.keep_in + ((long long)bh * p.N + i) * p.N;
-    for (int e = 0; e < COLS; ++e) {
-      const int j = c * 32 + e;
-      if (j < p.N && src[j]) w |= 1u << e;
-    }
-  }
-  return w;
+// keep bits of keys [32c, 32c + 32) of query row i (bit e = key 32c + e) from the packed mask b200vit_keep_bits_launch wrote before this kernel
+__device__ __forceinline__ uint32_t w_keep_word(const WFwdParams& p, int bh, int i, int c) {
+  return i < p.N ? __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits) + ((long long)bh * p.N + i) * 8 + c) : 0u;
 }
 
 // NC (16 or 32) scores of one query row -> probabilities; P~ and (P~)^2 back to TMEM as bf16 pairs. Both 16-column TMEM loads of a 32-column
@@ -367,10 +348,7 @@ wattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constan
           const uint8_t* bias_row = gbase + F_SM_BIAS + s * BIAS_STAGE_BYTES + row * 128;
           const bool full = c + 1 < nchunks || tail_cols == 32;
           uint32_t w = 0xffffffffu;
-          if (DROP) {
-            w = full ? w_keep_word<32>(p, seed, bh, i, c) : w_keep_word<16>(p, seed, bh, i, c);
-            if (i < p.N) *reinterpret_cast<uint32_t*>(p.keep_bits + ((long long)bh * p.N + i) * 32 + c * 4) = w;
-          }
+          if (DROP) w = w_keep_word(p, bh, i, c);
           if (full) wfwd_chunk<DROP, 32>(trow + c * 32, trow + c * 16, trow + F_T_PSQ + c * 16, bias_row, row, s_cn + c * 32, rnh, k0, l, w);
           else wfwd_chunk<DROP, 16>(trow + c * 32, trow + c * 16, trow + F_T_PSQ + c * 16, bias_row, row, s_cn + c * 32, rnh, k0, l, w);
         }
@@ -1163,7 +1141,7 @@ extern "C" size_t b200vit_wattn_workspace_bytes(int32_t B, int32_t H, int32_t N)
 extern "C" int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, const float* bias, int64_t ld_bias, const float* bias_rowmax, void* xwork,
                                  int32_t B, int32_t H, int32_t N, int32_t head_dim, float scale, float p_drop, uint64_t seed,
                                  const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out_mean, void* out_cov, float* lse,
-                                 uint8_t* keep_bits, void* stream_) {
+                                 uint8_t* keep_bits, int32_t keep_ready, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv_mean && qkv_cov && out_mean && out_cov && xwork, "wattn_fwd: null pointer (xwork of b200vit_wattn_workspace_bytes is required)");
   B200_CHECK_ARG(B > 0 && H > 0, "wattn_fwd: bad B=%d H=%d", B, H);
@@ -1205,6 +1183,9 @@ extern "C" int b200vit_wattn_fwd(const void* qkv_mean, const void* qkv_cov, cons
                          : cudaFuncSetAttribute(wattn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
     if (e != cudaSuccess) { b200vit_set_error("wattn_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured[drop] = true;
+  }
+  if (drop && !keep_ready) {
+    if ((rc = b200vit_keep_bits_launch(keep_bits, B * H, N, p_drop, seed, seed_dev, stream_id, keep_in, stream_))) return rc;
   }
   const int ctas = p.items < sms ? p.items : sms;
   if (drop) wattn_fwd_kernel<true><<<ctas, F_THREADS, F_SMEM, stream>>>(tx1, tx2, tv, tcv, tb, tom, toc, p);

@@ -119,6 +119,7 @@ class D2VEngine:
             raise B200VitError("D2VEngine needs the model on a CUDA (B200) device")
         self.dev = dev
         self._copy_stream = None
+        self._side_stream = None
         self.use_graph = use_graph
         self.max_graphs = 2
         self.wloss_dev = None
@@ -344,6 +345,15 @@ class D2VEngine:
                                rows_per_sample=T - 1, compact_tokens=T, col_hinge=col_hinge, loss_add=loss_add, loss_add_weight=self.var_w0,
                                loss_mult=loss_mult, **common)
 
+    def _draw_masks(self, B, noise):
+        """The student's attention-dropout masks of this step, drawn on a side stream while the teacher forward runs (core.draw_keep_bits)."""
+        import os as _os
+        if _os.environ.get("B200VIT_SIDE_MASKS", "1") == "0":       # A/B switch: the attention forwards then draw their own masks in-stream
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.dev)
+        core.draw_keep_bits(self.cfg, B, noise, self.dev, self._side_stream)
+
     def _overlapped_backward(self, run_backward):
         """Runs `run_backward(after_block)` with the gradient all-reduce of the arena's upper part (blocks.<cut> .. head) issued as soon as it is
         final, on NCCL's stream, and the lower part right after the backward; see __init__. Without data parallelism it is a plain call."""
@@ -379,6 +389,7 @@ class D2VEngine:
         C, T = cfg.embed_dim, cfg.tokens
         R = rows.numel()
         patches = core.patches_bf16(cfg, images)
+        self._draw_masks(B, noise)
         # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88
         layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers, patches=patches)
         # student: :124-128
@@ -456,6 +467,7 @@ class D2VEngine:
         M = B * T
         R = rows.numel()
         dev = self.dev
+        self._draw_masks(B, noise)
         (lm, lc), _ = core.dist_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers)
         (om, oc), ctx = core.dist_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise)
         ls = self.loss_scale if self.loss_scale != -1 else 1.0

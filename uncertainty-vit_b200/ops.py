@@ -126,10 +126,17 @@ def linear_wgrad(dy_bf16, x_bf16, dw_f32, alpha: float = 1.0):
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None, seed_dev=None):
+def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None, seed_dev=None,
+             keep_ready=False):
     ld_bias = bias.stride(1) if bias is not None else 0
     check(_lib.lib().b200vit_attn_fwd(_p(qkv), _p(bias), ld_bias, B, H, N, 64, scale, p_drop, seed, _p(seed_dev), stream_id, _p(keep_in), _p(out),
-                                      _p(lse), _p(keep_bits), _stream()), "attn_fwd")
+                                      _p(lse), _p(keep_bits), int(keep_ready), _stream()), "attn_fwd")
+    _count(2 if (p_drop > 0 and not keep_ready) else 1)           # + the packed keep-mask kernel
+
+
+def keep_bits(out, BH, N, p_drop, seed=0, stream_id=0, keep_in=None, seed_dev=None):
+    """Packed dropout keep mask of one attention layer into `out` (uint8 [BH, N, 32]): Philox stream (seed / *seed_dev, stream_id) or injected mask."""
+    check(_lib.lib().b200vit_keep_bits(_p(out), BH, N, p_drop, seed, _p(seed_dev), stream_id, _p(keep_in), _stream()), "keep_bits")
     _count()
 
 
@@ -166,7 +173,7 @@ def wattn_bwd_workspace(B, H, N, with_dtable: bool, device) -> torch.Tensor:
 
 
 def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out_mean=None, out_cov=None, lse=None,
-              keep_bits=None, seed_dev=None, xwork=None, bias_rowmax=None):
+              keep_bits=None, seed_dev=None, xwork=None, bias_rowmax=None, keep_ready=False):
     """bias: padded fwd layout of rel_pos_bias(); its row maxima ride along as `bias.rowmax` (or pass bias_rowmax)."""
     if bias_rowmax is None:
         bias_rowmax = getattr(bias, "rowmax", None)
@@ -175,9 +182,9 @@ def wattn_fwd(qkv_mean, qkv_cov, bias, B, H, N, scale, p_drop=0.0, seed=0, strea
     if xwork is None:
         xwork = wattn_workspace(B, H, N, qkv_mean.device)
     check(_lib.lib().b200vit_wattn_fwd(_p(qkv_mean), _p(qkv_cov), _p(bias), bias.stride(1), _p(bias_rowmax), _p(xwork), B, H, N, 64, scale, p_drop,
-                                       seed, _p(seed_dev), stream_id, _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), _stream()),
-          "wattn_fwd")
-    _count(2)
+                                       seed, _p(seed_dev), stream_id, _p(keep_in), _p(out_mean), _p(out_cov), _p(lse), _p(keep_bits), int(keep_ready),
+                                       _stream()), "wattn_fwd")
+    _count(3 if (p_drop > 0 and not keep_ready) else 2)
     return xwork
 
 
@@ -211,6 +218,15 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma=None, dbeta=Non
     check(_lib.lib().b200vit_layernorm_bwd(_p(dy), int(dy.dtype == torch.float32), _p(x), ldx if ldx is not None else C_, _p(row_index),
                                            _p(gamma), _p(mean), _p(rstd), rows, C_, _p(dx), lddx if lddx is not None else C_,
                                            _p(dgamma), _p(dbeta), _stream()), "layernorm_bwd")
+    _count()
+
+
+def layernorm_bwd_scale_residual(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma, dbeta, t_bf16, rowscale, rows_per_scale, gamma2, dt_bf16,
+                                 dgamma2=None, dbias2=None):
+    """layernorm_bwd on all rows fused with the scale_residual_bwd that reads the dx it produces (one pass over the gradient stream)."""
+    check(_lib.lib().b200vit_layernorm_bwd_scale_residual(_p(dy), int(dy.dtype == torch.float32), _p(x), C_, _p(gamma), _p(mean), _p(rstd), rows, C_,
+                                                          _p(dx), C_, _p(dgamma), _p(dbeta), _p(t_bf16), _p(rowscale), rows_per_scale, _p(gamma2),
+                                                          _p(dt_bf16), _p(dgamma2), _p(dbias2), _stream()), "layernorm_bwd_scale_residual")
     _count()
 
 
