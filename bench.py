@@ -377,9 +377,18 @@ def run_b200(args):
     roof = None
     if rank == 0:
         ops.GEMM_TIMING = []
+    # the instrumented steps run the step's launches on ONE stream (the timed steps overlap the EMA-teacher forward with the student's on a
+    # second stream; events around a GEMM would then also time the kernels it shares the SMs with)
+    serial = {k: os.environ.get(k) for k in ("B200VIT_TEACHER_STREAM",)}
+    os.environ.update({k: "0" for k in serial})
     for i in range(2):                       # every rank steps (the step contains the gradient all-reduce); rank 0 records
         eng.step(*dev_batches[i % 2], lr=lr_at(i))
     torch.cuda.synchronize()
+    for k, v in serial.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     if rank == 0:
         rec, ops.GEMM_TIMING = ops.GEMM_TIMING, None
         flops = sum(f for _, _, f in rec)

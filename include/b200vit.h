@@ -23,12 +23,13 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 6   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+#define B200VIT_ABI_VERSION 7   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
                                    3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8;
                                    4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss;
                                    5: tcgen05 Wasserstein attention (wattn_fwd / wattn_bwd take the transformed-operand workspace and the bias
                                       row maxima), rel_pos_bias rowmax output;
-                                   6: keep_bits (the dropout mask as its own kernel), keep_ready in attn_fwd / wattn_fwd, set_sm_limit */
+                                   6: keep_bits (the dropout mask as its own kernel), keep_ready in attn_fwd / wattn_fwd, set_sm_limit;
+                                   7: layernorm_bwd_scale_residual */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);

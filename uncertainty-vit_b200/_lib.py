@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200vit.so")
+LIB_PATH = os.environ.get("B200VIT_LIB") or os.path.join(HERE, "libb200vit.so")     # B200VIT_LIB: an alternative build (kernel A/B runs)
 
 EPI_BF16, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC, EPI_ELU1 = range(7)
 
@@ -108,7 +108,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 6:
+        if l.b200vit_abi_version() != 7:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

@@ -9,6 +9,7 @@ The model's nn.Parameters are re-pointed at views of the arenas, so state_dict()
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -120,6 +121,8 @@ class D2VEngine:
         self.dev = dev
         self._copy_stream = None
         self._side_stream = None
+        self._teacher_stream = None
+        self._teacher_forked = False
         self.use_graph = use_graph
         self.max_graphs = 2
         self.wloss_dev = None
@@ -354,6 +357,23 @@ class D2VEngine:
             self._side_stream = torch.cuda.Stream(device=self.dev)
         core.draw_keep_bits(self.cfg, B, noise, self.dev, self._side_stream)
 
+    def _teacher_stream_ctx(self):
+        """Context that issues the teacher forward on a second stream (B200VIT_TEACHER_STREAM=0: on the step's own stream)."""
+        import contextlib
+        if os.environ.get("B200VIT_TEACHER_STREAM", "1") == "0":
+            self._teacher_forked = False
+            return contextlib.nullcontext()
+        if self._teacher_stream is None:
+            self._teacher_stream = torch.cuda.Stream(device=self.dev)
+        self._teacher_stream.wait_stream(torch.cuda.current_stream(self.dev))
+        self._teacher_forked = True
+        return torch.cuda.stream(self._teacher_stream)
+
+    def _teacher_join(self):
+        if self._teacher_forked:
+            torch.cuda.current_stream(self.dev).wait_stream(self._teacher_stream)
+            self._teacher_forked = False
+
     def _overlapped_backward(self, run_backward):
         """Runs `run_backward(after_block)` with the gradient all-reduce of the arena's upper part (blocks.<cut> .. head) issued as soon as it is
         final, on NCCL's stream, and the lower part right after the backward; see __init__. Without data parallelism it is a plain call."""
@@ -390,11 +410,15 @@ class D2VEngine:
         R = rows.numel()
         patches = core.patches_bf16(cfg, images)
         self._draw_masks(B, noise)
-        # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88
-        layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers, patches=patches)
+        # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88. It shares nothing with the student forward but the
+        # patches, so it runs on its own stream: its kernels fill the SMs the student's persistent GEMMs leave idle in their last wave.
+        with self._teacher_stream_ctx():
+            layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers,
+                                         patches=patches)
         # student: :124-128
         out, ctx = core.vit_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise,
                                     patches=patches)
+        self._teacher_join()
         # targets + loss + dLoss/dy: :90-150 (masked rows only; LayerNorm is per row)
         dy = torch.empty((R, C), dtype=torch.bfloat16, device=self.dev)
         ls = self.loss_scale if self.loss_scale != -1 else 1.0
@@ -468,8 +492,10 @@ class D2VEngine:
         R = rows.numel()
         dev = self.dev
         self._draw_masks(B, noise)
-        (lm, lc), _ = core.dist_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers)
+        with self._teacher_stream_ctx():
+            (lm, lc), _ = core.dist_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers)
         (om, oc), ctx = core.dist_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise)
+        self._teacher_join()
         ls = self.loss_scale if self.loss_scale != -1 else 1.0
         tgt_m = torch.empty((R, C), dtype=torch.float32, device=dev)
         tgt_c = torch.empty((R, C), dtype=torch.float32, device=dev)

@@ -3,6 +3,7 @@ hand-written sm_100a kernel of libb200vit.so. Tensors must be CUDA tensors; ther
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -223,7 +224,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma=None, dbeta=Non
 
 def layernorm_bwd_scale_residual(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma, dbeta, t_bf16, rowscale, rows_per_scale, gamma2, dt_bf16,
                                  dgamma2=None, dbias2=None):
-    """layernorm_bwd on all rows fused with the scale_residual_bwd that reads the dx it produces (one pass over the gradient stream)."""
+    """layernorm_bwd on all rows fused with the scale_residual_bwd that reads the dx it produces (one pass over the gradient stream).
+    The default launches the two kernels separately: on B200 the fused kernel (228 registers, one CTA per SM) measured 0.5 ms per step SLOWER than
+    the pair (tools/ab.sh B200VIT_FUSED_LN, profiles/README.md); B200VIT_FUSED_LN=1 selects it."""
+    if os.environ.get("B200VIT_FUSED_LN", "0") == "0":
+        layernorm_bwd(dy, x, gamma, mean, rstd, rows, C_, dx, dgamma, dbeta)
+        scale_residual_bwd(dx, t_bf16, rowscale, rows_per_scale, gamma2, rows, C_, dt_bf16, dgamma2, dbias2)
+        return
     check(_lib.lib().b200vit_layernorm_bwd_scale_residual(_p(dy), int(dy.dtype == torch.float32), _p(x), C_, _p(gamma), _p(mean), _p(rstd), rows, C_,
                                                           _p(dx), C_, _p(dgamma), _p(dbeta), _p(t_bf16), _p(rowscale), rows_per_scale, _p(gamma2),
                                                           _p(dt_bf16), _p(dgamma2), _p(dbias2), _stream()), "layernorm_bwd_scale_residual")
