@@ -113,6 +113,10 @@ def bench():
         us = timeit(lambda i: ops.attn_fwd(qkvs[i % R], bias_f, B, H, N, scale, p, 1, 2, None, outs[i % R], lse, bits if p > 0 else None))
         fl = 4.0 * B * H * N * N * 64
         print(f"attn_fwd p={p}: {us:8.1f} us   {fl / us * 1e-6:7.1f} TFLOP/s algorithmic")
+    us = timeit(lambda i: ops.attn_fwd(qkvs[i % R], None, B, H, N, scale, 0.0, 1, 2, None, outs[i % R], lse, None))
+    print(f"attn_fwd p=0.0 no bias (no bias ring traffic): {us:8.1f} us")
+    if "--fwd-only" in sys.argv:
+        return
     if "--bwd" in sys.argv:
         douts = [torch.randn(B, N, H * 64, device=dev).bfloat16() for _ in range(R)]
         dqkv = torch.empty(B, N, 3, H, 64, dtype=torch.bfloat16, device=dev)

@@ -7,10 +7,12 @@
 //                      [128 x 32] fp32 SWIZZLE_128B boxes), tcgen05.mma S = Q K^T (128 x n_pad x 64, accumulator in TMEM columns
 //                      [0, n_pad)), later tcgen05.mma O = P~ V with the A operand read straight from TENSOR MEMORY (the bf16
 //                      probabilities overlay the S columns they were computed from) and V as an MN-major smem operand.
-//   warps 0..3       : one thread per query row (TMEM lane == row): no shuffles, no shared-memory round trip for the scores.
+//   warps 0..7       : TWO threads per query row (TMEM lane == row; warps w and w + 4 share lane quadrant w): the even 32-key chunks of a
+//                      row belong to one, the odd chunks to the other, the row maximum and the row sum meet through shared memory
+//                      (the kernel is bound by this element-wise phase: one thread per row left the SM at 12 of 64 warps).
 //                      pass 1: s2 = s * scale*log2e + bias, running max, s2 written back to TMEM;
-//                      pass 2: p = 2^(s2 - max), row sum, Philox4x32-7 dropout (or injected mask), keep bits packed for the
-//                      backward, bf16 pairs stored to TMEM columns [0, n_pad/2);
+//                      pass 2: p = 2^(s2 - max), row sum, dropout by the precomputed keep bits, bf16 pairs stored over score columns
+//                      the SAME thread has already consumed (p_col below), so the two threads of a row never touch each other's columns;
 //                      epilogue: O (TMEM columns [128, 192)) * 1/((1-p) * rowsum) -> bf16 -> swizzled smem tile -> TMA store
 //                      (rows past N clipped by the tensor map), log-sum-exp to global.
 #include <cstdlib>
@@ -33,9 +35,11 @@ constexpr int SM_K = SM_Q + TILE_M * 128;                 // NMAX rows x 128 B
 constexpr int SM_V = SM_K + NMAX * 128;                   // NMAX rows x 128 B; its first 16 KB double as the bf16 O staging tile of the epilogue
 constexpr int SM_BIAS = SM_V + NMAX * 128;
 constexpr int SM_BAR = SM_BIAS + BIAS_STAGES * BIAS_STAGE_BYTES;
-constexpr int FWD_LANE_BYTES = SM_BAR + 1024;             // 103424
+constexpr int SM_XCH = SM_BAR + 1024;                     // [2 halves][128 rows] row maxima, then [2][128] row sums (fp32)
+constexpr int FWD_LANE_BYTES = SM_XCH + 2048;             // 105472
 constexpr int FWD_LANES = 2;
-constexpr int FWD_EW_WARPS = 4;                           // softmax warps per lane (one thread per query row)
+constexpr int FWD_QUADS = 4;                              // TMEM lane quadrants of a 128-row tile
+constexpr int FWD_EW_WARPS = 2 * FWD_QUADS;               // softmax warps per lane: two threads per query row
 constexpr int FWD100_THREADS = FWD_LANES * (FWD_EW_WARPS + 2) * 32;   // + MMA warp + TMA warp per lane
 constexpr int FWD100_SMEM = FWD_LANES * FWD_LANE_BYTES + 1024;
 constexpr int O_COL = 128;                                // O accumulator: TMEM columns [128, 192) of the lane's 256-column half
@@ -108,12 +112,17 @@ __device__ __forceinline__ void pass2_step16(uint32_t t_src, uint32_t t_dst, flo
   ptx::tmem_st_x8(t_dst, pk);
 }
 
+// TMEM column (fp32 units) of the 16 bf16 pairs of key chunk c: chunks 0..3 overwrite the lower half of their own score columns, chunks
+// 4..6 the upper half of the scores of chunk c - 4 — same parity, hence the same thread, which has consumed them by then. All of P lands
+// in columns [0, 128), clear of the O accumulator at [128, 192) (the dead scores of chunks 4 and 5).
+__host__ __device__ __forceinline__ constexpr int p_col(int c) { return c < 4 ? 32 * c : 32 * (c - 4) + 16; }
+
 template <int COLS, bool DROP>
 __device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint64_t seed, uint32_t trow, int bh, int i, int c, float mx, float& l) {
   uint32_t w = 0xffffffffu;
   if (DROP) w = keep_word(p, bh, i, c);
-  pass2_step16<DROP>(trow + c * 32, trow + c * 16, mx, l, w);
-  if constexpr (COLS == 32) pass2_step16<DROP>(trow + c * 32 + 16, trow + c * 16 + 8, mx, l, w >> 16);
+  pass2_step16<DROP>(trow + c * 32, trow + p_col(c), mx, l, w);
+  if constexpr (COLS == 32) pass2_step16<DROP>(trow + c * 32 + 16, trow + p_col(c) + 8, mx, l, w >> 16);
 }
 
 // Persistent: one CTA per SM holds FWD_LANES independent lanes (own smem, own 256-column TMEM half, own barriers); lane L of CTA c
@@ -126,8 +135,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                       const __grid_constant__ CUtensorMap tm_bias, const __grid_constant__ CUtensorMap tm_out, const Fwd100Params p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA warps 0..7: softmax warps (lane L = warp >> 2; TMEM lane quadrant = CTA warp index & 3, a hardware rule); 8, 9: MMA and TMA warp
-  // of lane 0; 10, 11: of lane 1.   `warp` = role inside the lane: 0..3 softmax, 4 MMA, 5 TMA
+  // CTA warps 0..15: softmax warps (lane L = warp >> 3; TMEM lane quadrant = CTA warp index & 3, a hardware rule; chunk parity = bit 2);
+  // 16, 17: MMA and TMA warp of lane 0; 18, 19: of lane 1.   `warp` = role inside the lane: 0..7 softmax, 8 MMA, 9 TMA
   const int L = warp_cta < FWD_LANES * FWD_EW_WARPS ? warp_cta / FWD_EW_WARPS : (warp_cta - FWD_LANES * FWD_EW_WARPS) >> 1;
   const int warp = warp_cta < FWD_LANES * FWD_EW_WARPS ? warp_cta % FWD_EW_WARPS : FWD_EW_WARPS + ((warp_cta - FWD_LANES * FWD_EW_WARPS) & 1);
   const uint32_t cta_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -156,7 +165,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (lane == 0) {
       ptx::mbar_init(qk_full, 1); ptx::mbar_init(v_full, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, FWD_EW_WARPS * 32);
       ptx::mbar_init(o_full, 1); ptx::mbar_init(v_free, 1); ptx::mbar_init(t_free, FWD_EW_WARPS);
-      for (int s = 0; s < BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), FWD_EW_WARPS); }
+      for (int s = 0; s < BIAS_STAGES; ++s) { ptx::mbar_init(bias_full(s), 1); ptx::mbar_init(bias_empty(s), FWD_QUADS); }   // a chunk is read by one parity
       ptx::fence_barrier_init();
       ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_kv); ptx::prefetch_tmap(&tm_out);
       if (HAS_BIAS) ptx::prefetch_tmap(&tm_bias);
@@ -194,7 +203,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ptx::mbar_wait(v_full, ph);
         ptx::mbar_wait(p_full, ph);
         ptx::tc_fence_after();
-        for (int kk = 0; kk < ksteps; ++kk) ptx::umma_bf16_ts(tmem_base + O_COL, tmem_base + kk * 8, dV + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < ksteps; ++kk)
+          ptx::umma_bf16_ts(tmem_base + O_COL, tmem_base + p_col(kk >> 1) + 8 * (kk & 1), dV + 128 * kk, idesc_o, kk > 0 ? 1u : 0u);
         ptx::umma_commit(o_full);
       }
     }
@@ -227,22 +237,25 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
   } else {
-    // ---------------- softmax warps: one thread per query row ----------------
-    const int row = warp * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ---------------- softmax warps: two threads per query row ----------------
+    const int quad = warp & 3, par = warp >> 2;              // TMEM lane quadrant; parity of the key chunks this thread owns
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint64_t seed = (DROP && p.seed_dev != nullptr) ? __ldg(reinterpret_cast<const unsigned long long*>(p.seed_dev)) : p.seed;
-    int gc = 0;
+    float* xch_mx = reinterpret_cast<float*>(gbase + SM_XCH);          // [2][128]
+    float* xch_l = xch_mx + 2 * TILE_M;                                 // [2][128]
     for (int it = 0; it < n_items; ++it) {
       int b, h, m0, bh;
       item_of(it, b, h, m0, bh);
       const uint32_t ph = (uint32_t)(it & 1);
       const int i = m0 + row;
-      const bool active = m0 + warp * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
+      const bool active = m0 + quad * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
+      const int gc0 = it * nchunks;                         // the bias ring counts chunks across items
       ptx::mbar_wait(s_full, ph);
       ptx::tc_fence_after();
       float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c, ++gc) {
-        const int s = gc % BIAS_STAGES;
+      for (int c = par; c < nchunks; c += 2) {
+        const int gc = gc0 + c, s = gc % BIAS_STAGES;
         if (HAS_BIAS) ptx::mbar_wait(bias_full(s), (uint32_t)((gc / BIAS_STAGES) & 1));
         if (active) {
           const uint8_t* bias_row = gbase + SM_BIAS + s * BIAS_STAGE_BYTES + row * 128;
@@ -254,38 +267,41 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           if (lane == 0) ptx::mbar_arrive(bias_empty(s));
         }
       }
+      xch_mx[par * TILE_M + row] = mx;
       ptx::tmem_st_wait();
+      ptx::named_bar_sync(1 + L, FWD_EW_WARPS * 32);
+      mx = fmaxf(mx, xch_mx[(par ^ 1) * TILE_M + row]);
       float l = 0.f;
       if (active) {
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = par; c < nchunks; c += 2) {
           if (c + 1 < nchunks || tail_cols == 32) pass2_chunk<32, DROP>(p, seed, trow, bh, i, c, mx, l);
           else pass2_chunk<16, DROP>(p, seed, trow, bh, i, c, mx, l);
         }
       }
+      xch_l[par * TILE_M + row] = l;
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
-      // ---------------- epilogue ----------------
+      ptx::named_bar_sync(1 + L, FWD_EW_WARPS * 32);
+      l += xch_l[(par ^ 1) * TILE_M + row];
+      // ---------------- epilogue: this thread's 32 of the row's 64 output columns ----------------
       ptx::mbar_wait(o_full, ph);
       ptx::tc_fence_after();
       if (active) {
         const float inv = p.inv_keep / l;
         uint8_t* orow = gbase + SM_V + row * 128;           // V is dead (o_full) and the previous store has drained the tile (v_free)
+        uint32_t o[32];
+        ptx::tmem_ld_x32_sync(trow + O_COL + par * 32, o);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t o[32];
-          ptx::tmem_ld_x32_sync(trow + O_COL + half * 32, o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + (((half * 4 + q) ^ (row & 7)) << 4)) = u;
-          }
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((par * 4 + q) ^ (row & 7)) << 4)) = u;
         }
-        if (i < p.N && p.lse != nullptr) p.lse[(long long)bh * p.N + i] = (mx + log2f(l)) / LOG2E;
+        if (par == 0 && i < p.N && p.lse != nullptr) p.lse[(long long)bh * p.N + i] = (mx + log2f(l)) / LOG2E;
       }
       ptx::tc_fence_before();
       __syncwarp();
