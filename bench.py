@@ -396,11 +396,11 @@ def run_b200(args):
         pk = peaks()
         achieved = flops / (t_ms * 1e-3) / 1e12
         traffic = None            # DRAM bytes per GEMM launch (ncu capture of the same step, committed under profiles/)
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_gemm_dram.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("bytes_per_launch")
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_dram.json)", "kernel": "gemm_bf16_kernel (tcgen05, all 4 operand-major instantiations)", "launches_timed": len(rec),
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_gemm_dram.json)", "kernel": "gemm_bf16_kernel (tcgen05, all 4 operand-major instantiations)", "launches_timed": len(rec),
                 "gemm_ms_per_step": t_ms / 2, "gemm_share_of_step": (t_ms / 2) / ms, "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                 "frac_of_burst": achieved / pk["bf16_burst"]}
     barrier()
