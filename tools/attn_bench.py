@@ -128,6 +128,10 @@ def bench():
             us = timeit(lambda i: ops.attn_bwd(qkvs[0], outs[0], douts[i % R], lse, bias_t, bits if p > 0 else None, idx, dtable, B, H, N, scale, p, dqkv,
                                                ds_work=ds_work))
             print(f"attn_bwd (+relbias_grad) p={p}: {us:8.1f} us")
+        us = timeit(lambda i: ops.attn_bwd(qkvs[0], outs[0], douts[i % R], lse, None, None, None, None, B, H, N, scale, 0.0, dqkv, ds_work=ds_work))
+        print(f"attn_bwd p=0.0 no bias, no table gradient: {us:8.1f} us")
+        us = timeit(lambda i: ops.attn_bwd(qkvs[0], outs[0], douts[i % R], lse, bias_t, None, None, None, B, H, N, scale, 0.0, dqkv, ds_work=ds_work))
+        print(f"attn_bwd p=0.0 bias, no table gradient: {us:8.1f} us")
 
 
 def ncu_run():

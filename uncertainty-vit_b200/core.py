@@ -90,7 +90,7 @@ class Noise:
     attn_keep: Optional[List[torch.Tensor]] = None      # per layer uint8 [B, H, N, N]
     head_eps: Optional[torch.Tensor] = None             # fp32 [B, C]: injected N(0,1) noise of the reparameterised head sample (cfg.sample_head)
     keep_bits_all: Optional[torch.Tensor] = None        # uint8 [L, B, H, N, 32]: packed attention-dropout masks of ALL layers, drawn ahead of the
-    keep_join: Optional[object] = None                  # forward on this side stream (draw_keep_bits); the forward joins it before block 0
+    keep_join: Optional[object] = None                  # forward on a side stream (draw_keep_bits): one event per layer, block i waits for event i
     drop_path_active: bool = True                       # applies only to training forwards
     attn_drop_active: Optional[bool] = None             # None: follow `train`; True: dropout even in eval (MC-dropout, enable_dropout())
 
@@ -256,21 +256,43 @@ def rel_bias(ps: ParamSource, cfg: VitConfig, dev, want_bwd: bool = True):
 # ------------------------------------------------------------------------------------------------------------------
 # whole network
 # ------------------------------------------------------------------------------------------------------------------
-def draw_keep_bits(cfg: VitConfig, B: int, noise: Noise, dev, side_stream) -> None:
-    """Draws the packed attention-dropout masks of all layers of one training forward on `side_stream` (they depend only on the Philox key),
-    so that the integer-multiply-bound draw (~40 us per ViT-B layer) runs beside whatever the main stream does next — the EMA-teacher
-    forward in the data2vec step. vit_forward / dist_forward join the side stream before their first block. No-op with injected masks."""
+_MASK_STREAMS: Dict[int, torch.cuda.Stream] = {}
+
+
+def _mask_stream(dev) -> torch.cuda.Stream:
+    st = _MASK_STREAMS.get(dev.index)
+    if st is None:
+        st = _MASK_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def draw_keep_bits(cfg: VitConfig, B: int, noise: Noise, dev, side_stream=None) -> None:
+    """Draws the packed attention-dropout masks of all layers of one forward on a side stream (they depend only on the Philox key), so that
+    the integer-multiply-bound draw (~40 us per ViT-B layer at B=128) runs beside whatever the main stream does — the EMA-teacher forward
+    in the data2vec step, the previous layers of the same forward in MC-sample inference. One event per layer: block i of vit_forward /
+    dist_forward waits for the mask of layer i only. No-op with injected masks."""
     if cfg.attn_drop_rate <= 0.0 or noise.attn_keep is not None or noise.attn_drop_active is False:
         return
+    side_stream = side_stream if side_stream is not None else _mask_stream(dev)
     H, T = cfg.num_heads, cfg.tokens
     kb = torch.empty((cfg.depth, B, H, T, 32), dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream(dev)
     side_stream.wait_stream(cur)
+    events = []
     with torch.cuda.stream(side_stream):
         for l in range(cfg.depth):
             ops.keep_bits(kb[l], B * H, T, cfg.attn_drop_rate, seed=noise.seed, stream_id=l, seed_dev=noise.seed_dev)
+            events.append(side_stream.record_event())
     kb.record_stream(side_stream)
-    noise.keep_bits_all, noise.keep_join = kb, side_stream
+    noise.keep_bits_all, noise.keep_join = kb, events
+
+
+def _keep_for_block(noise: Noise, kb_all, i: int, dev):
+    if kb_all is None:
+        return None
+    if noise.keep_join is not None:
+        torch.cuda.current_stream(dev).wait_event(noise.keep_join[i])
+    return kb_all[i]
 
 
 def make_drop_path_scales(cfg: VitConfig, B: int, noise: Noise, dev, draws: int = 2) -> Optional[torch.Tensor]:
@@ -308,13 +330,13 @@ def vit_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_u
     saved = []
     layers: Dict[int, torch.Tensor] = {}
     collect = collect or []
+    if p_attn > 0 and noise.keep_bits_all is None:
+        draw_keep_bits(cfg, B, noise, dev)                 # not pre-drawn by the engine: layer i+1's mask is drawn while layer i computes
     kb_all = noise.keep_bits_all if p_attn > 0 else None
-    if kb_all is not None and noise.keep_join is not None:
-        torch.cuda.current_stream(dev).wait_stream(noise.keep_join)        # the masks were drawn on a side stream
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn, seed=noise.seed,
-                          keep_in=keep_in, seed_dev=noise.seed_dev, keep_pre=kb_all[i] if kb_all is not None else None)
+                          keep_in=keep_in, seed_dev=noise.seed_dev, keep_pre=_keep_for_block(noise, kb_all, i, dev))
         if i in collect:
             if collect_what == "fc":      # fc_feature = x_out - x_mid (modeling_cyclical.py:203-205); rarely used
                 layers[i] = (s["x_out"] - s["x_mid"]).view(B, T, C)
@@ -492,14 +514,14 @@ def dist_forward(ps: ParamSource, cfg: VitConfig, images: torch.Tensor, *, mask_
     saved, lm, lc = [], {}, {}
     collect = collect or []
     scratch = None if save else ops.wattn_workspace(B, cfg.num_heads, T, dev)
+    if p_attn > 0 and noise.keep_bits_all is None:
+        draw_keep_bits(cfg, B, noise, dev)
     kb_all = noise.keep_bits_all if p_attn > 0 else None
-    if kb_all is not None and noise.keep_join is not None:
-        torch.cuda.current_stream(dev).wait_stream(noise.keep_join)
     for i in range(cfg.depth):
         keep_in = noise.attn_keep[i] if (noise.attn_keep is not None and p_attn > 0) else None
         s = dist_block_forward(ps, cfg, i, x, B, bias, save=save, dp_scale=dps[i] if dps is not None else None, p_attn=p_attn,
                                seed=noise.seed, keep_in=keep_in, seed_dev=noise.seed_dev, xwork_scratch=scratch,
-                               keep_pre=kb_all[i] if kb_all is not None else None)
+                               keep_pre=_keep_for_block(noise, kb_all, i, dev))
         x = s["x_out"]
         if i in collect:
             lm[i] = x[:M].view(B, T, C)

@@ -93,34 +93,58 @@ __global__ void rel_pos_bias_rowmax_kernel(const float* __restrict__ table, cons
   rowmax[t] = m;
 }
 
-// Relative-position-bias table gradient: dtable[index[i, j], h] += sum_b dS[b, h, i, j]  (dS^T stored [B, H, j, ld] by attn_bwd)
-__global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restrict__ ds, int B, int H, int N, int ld,
-                                                           const int* __restrict__ rel_index, float* __restrict__ dtable) {
-  const int half = ld >> 1;                       // pairs of queries
-  const long long total = (long long)H * N * half;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int ip = (int)(t % half);
-    const int j = (int)((t / half) % N);
-    const int h = (int)(t / ((long long)half * N));
-    const int i = ip * 2;
-    if (i >= N) continue;
-    float s0 = 0.f, s1 = 0.f;
-    const bf16* src = ds + ((long long)h * N + j) * ld + i;
+// Relative-position-bias table gradient: dtable[index[i, j], h] += sum_b dS[b, h, i, j]  (dS^T stored [B, H, j, ld] by attn_bwd).
+// One pass over the 126 MB workspace of a ViT-B layer: a thread owns 8 consecutive queries of one (h, key) row (16-byte loads, 8 batches in
+// flight), RB_SPLIT threads share the batch dimension and meet in shared memory, so the scatter issues one atomic per (h, i, j).
+constexpr int RB_ITEMS = 64, RB_SPLIT = 4;
+__global__ void __launch_bounds__(RB_ITEMS * RB_SPLIT) relbias_grad_kernel(const bf16* __restrict__ ds, int B, int H, int N, int ld,
+                                                                          const int* __restrict__ rel_index, float* __restrict__ dtable) {
+  __shared__ float part[RB_SPLIT][RB_ITEMS][8];
+  const int vecs = ld >> 3;                       // 16-byte vectors per (h, key) row
+  const long long total = (long long)H * N * vecs;
+  const long long t = (long long)blockIdx.x * RB_ITEMS + threadIdx.x;
+  const int q = threadIdx.y;
+  const int v = (int)(t % vecs);
+  const int j = (int)((t / vecs) % N);
+  const int h = (int)(t / ((long long)vecs * N));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (t < total && v * 8 < N) {
+    const int per = (B + RB_SPLIT - 1) / RB_SPLIT;
+    const int b0 = q * per, b1 = min(B, b0 + per);
     const long long bstride = (long long)H * N * ld;
-    int b = 0;
-    for (; b + 8 <= B; b += 8) {     // 8 independent loads in flight
-      uint32_t w[8];
+    const bf16* src = ds + ((long long)h * N + j) * ld + v * 8;
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      uint4 w[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const uint32_t*>(src + (long long)(b + u) * bstride);
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (long long)(b + u) * bstride));
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { const float2 v = unpack_bf16x2(w[u]); s0 += v.x; s1 += v.y; }
+      for (int u = 0; u < 8; ++u) {
+        const float2 f0 = unpack_bf16x2(w[u].x), f1 = unpack_bf16x2(w[u].y), f2 = unpack_bf16x2(w[u].z), f3 = unpack_bf16x2(w[u].w);
+        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+      }
     }
-    for (; b < B; ++b) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + (long long)b * bstride));
-      s0 += v.x; s1 += v.y;
+    for (; b < b1; ++b) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (long long)b * bstride));
+      const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
+      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
     }
-    atomicAdd(dtable + (long long)rel_index[i * N + j] * H + h, s0);
-    if (i + 1 < N) atomicAdd(dtable + (long long)rel_index[(i + 1) * N + j] * H + h, s1);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[q][threadIdx.x][e] = acc[e];
+  __syncthreads();
+  // 512 (item, query) sums per CTA, two per thread
+  for (int k = threadIdx.y * RB_ITEMS + threadIdx.x; k < RB_ITEMS * 8; k += RB_ITEMS * RB_SPLIT) {
+    const int it = k >> 3, e = k & 7;
+    const long long tt = (long long)blockIdx.x * RB_ITEMS + it;
+    if (tt >= total) continue;
+    const int vv = (int)(tt % vecs), jj = (int)((tt / vecs) % N), hh = (int)(tt / ((long long)vecs * N));
+    const int i = vv * 8 + e;
+    if (i >= N) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < RB_SPLIT; ++qq) s += part[qq][it][e];
+    atomicAdd(dtable + (long long)rel_index[i * N + jj] * H + hh, s);
   }
 }
 
@@ -130,8 +154,10 @@ __global__ void __launch_bounds__(256) relbias_grad_kernel(const bf16* __restric
 
 // internal (not part of the public ABI): shared by the dual-stream backward in wattention.cu
 int b200vit_relbias_grad_launch(const void* ds_work, int B, int H, int N, int ld_ds, const int32_t* rel_index, float* dtable, void* stream) {
-  const int sms = b200vit_num_sms();
-  relbias_grad_kernel<<<sms * 8, 256, 0, STREAM>>>(static_cast<const bf16*>(ds_work), B, H, N, ld_ds, rel_index, dtable);
+  B200_CHECK_ARG(ld_ds % 8 == 0 && (reinterpret_cast<uintptr_t>(ds_work) & 15) == 0, "relbias_grad: dS^T rows must be 16-byte aligned (ld %% 8 == 0)");
+  const long long items = (long long)H * N * (ld_ds / 8);
+  relbias_grad_kernel<<<(unsigned)((items + RB_ITEMS - 1) / RB_ITEMS), dim3(RB_ITEMS, RB_SPLIT), 0, STREAM>>>(static_cast<const bf16*>(ds_work), B, H, N, ld_ds,
+                                                                                                              rel_index, dtable);
   B200_CHECK_LAUNCH("relbias_grad");
   return 0;
 }
