@@ -5,6 +5,9 @@
 // atomicAdd per column per CTA.
 #include "../../include/b200vit.h"
 #include "common.cuh"
+#include "ptx_sm100.cuh"
+#include <type_traits>
+#include <stdlib.h>
 
 namespace {
 
@@ -196,6 +199,326 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm backward, column-owner layout (dense rows, no row list): a thread owns 4 columns of LNC_RB rows per iteration, blockDim =
+// (C/4, LNC_TY) — each y-slice of C/4 threads works on its own rows. The column sums (dgamma, dbeta and, fused, dgamma2 / dbias2) are 4 + 4
+// (+ 4 + 4) registers per thread instead of 2 (4) x C/32 per lane of the warp-per-row kernel above (202 / 228 registers, one CTA of 8 warps
+// per SM, 4.35 TB/s); the two row sums per row cross the slice through shared memory (one named barrier pair per LNC_RB rows). The dx / t
+// loads of the second phase are issued before the reduction, so they are in flight across it. SRB: the scale-residual backward of the
+// branch that consumes this dx (scale_residual_bwd_kernel below) runs in the same pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int LNC_RB = 2, LNC_TY_MAX = 8, LNC_THREADS = 768;   // blockDim = (C/4, LNC_THREADS / (C/4)): one CTA of ~768 threads per SM
+template <typename DY, bool SRB>
+struct LncRaw {                      // the global loads of one iteration, issued one iteration ahead (software pipeline)
+  typename std::conditional<sizeof(DY) == 2, uint2, float4>::type dy[LNC_RB];
+  float4 x[LNC_RB], dx[LNC_RB];
+  uint2 t[SRB ? LNC_RB : 1];
+  float mean[LNC_RB], rstd[LNC_RB], rsc[SRB ? LNC_RB : 1];
+};
+
+template <typename DY, bool SRB>
+__global__ void __launch_bounds__(LNC_THREADS, 1) ln_bwd_cols_kernel(const DY* __restrict__ dy, const float* __restrict__ x, long long ldx,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                                   const float* __restrict__ rstd_in, int rows, int C, float* __restrict__ dx,
+                                                                   long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   const SrbStage srb) {
+  extern __shared__ float sm[];
+  const int TX = blockDim.x, TY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y, nw = TX >> 5, w = tx >> 5, lane = tx & 31;
+  float* part = sm + ty * (8 * 2 * LNC_RB + 2 * LNC_RB);   // [8 warps][2 RB] partial row sums of this slice
+  float* fin = part + 8 * 2 * LNC_RB;                     // [2 RB]
+  float* colred = sm + LNC_TY_MAX * (8 * 2 * LNC_RB + 2 * LNC_RB);   // [4][C] cross-slice column sums
+  const int c = tx * 4;
+  const float invC = 1.0f / (float)C;
+  const float4 g = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 g2 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if constexpr (SRB) { if (srb.gamma2 != nullptr) g2 = __ldg(reinterpret_cast<const float4*>(srb.gamma2 + c)); }
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ag2 = ag, ab2 = ag;
+  const int ngroups = (rows + TY * LNC_RB - 1) / (TY * LNC_RB);
+  using Raw = LncRaw<DY, SRB>;
+  auto load = [&](int grp, Raw& q) {
+    const int r0 = (grp * TY + ty) * LNC_RB;
+#pragma unroll
+    for (int u = 0; u < LNC_RB; ++u) {
+      const int r = r0 + u;
+      const bool ok = grp < ngroups && r < rows;
+      if constexpr (sizeof(DY) == 2) q.dy[u] = ok ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) + (long long)r * C + c) : make_uint2(0u, 0u);
+      else q.dy[u] = ok ? ld4(reinterpret_cast<const float*>(dy) + (long long)r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q.x[u] = ok ? ld4(x + (long long)r * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q.dx[u] = ok ? ld4(dx + (long long)r * lddx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q.mean[u] = ok ? __ldg(mean_in + r) : 0.f;
+      q.rstd[u] = ok ? __ldg(rstd_in + r) : 0.f;
+      if constexpr (SRB) {
+        q.t[u] = ok ? __ldg(reinterpret_cast<const uint2*>(srb.t + (long long)r * C + c)) : make_uint2(0u, 0u);
+        q.rsc[u] = ok ? (srb.rowscale != nullptr ? __ldg(srb.rowscale + r / srb.rows_per_scale) : 1.0f) : 0.0f;
+      }
+    }
+  };
+  auto process = [&](int grp, const Raw& cur) {
+    const int r0 = (grp * TY + ty) * LNC_RB;
+    float4 xh[LNC_RB], d[LNC_RB];
+    float p1[LNC_RB], p2[LNC_RB];
+#pragma unroll
+    for (int u = 0; u < LNC_RB; ++u) {
+      float4 dv;
+      if constexpr (sizeof(DY) == 2) {
+        const float2 a0 = unpack_bf16x2(cur.dy[u].x), a1 = unpack_bf16x2(cur.dy[u].y);
+        dv = make_float4(a0.x, a0.y, a1.x, a1.y);
+      } else {
+        dv = cur.dy[u];
+      }
+      const float mean = cur.mean[u], rstd = cur.rstd[u];
+      const float4 xv = cur.x[u];
+      xh[u] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      ag.x += dv.x * xh[u].x; ag.y += dv.y * xh[u].y; ag.z += dv.z * xh[u].z; ag.w += dv.w * xh[u].w;
+      ab.x += dv.x; ab.y += dv.y; ab.z += dv.z; ab.w += dv.w;
+      d[u] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+      p1[u] = d[u].x + d[u].y + d[u].z + d[u].w;
+      p2[u] = d[u].x * xh[u].x + d[u].y * xh[u].y + d[u].z * xh[u].z + d[u].w * xh[u].w;
+    }
+#pragma unroll
+    for (int u = 0; u < LNC_RB; ++u) {
+      p1[u] = warp_sum(p1[u]);
+      p2[u] = warp_sum(p2[u]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < LNC_RB; ++u) { part[w * 2 * LNC_RB + 2 * u] = p1[u]; part[w * 2 * LNC_RB + 2 * u + 1] = p2[u]; }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + ty), "r"(TX) : "memory");
+    if (tx < 2 * LNC_RB) {
+      float a = 0.f;
+      for (int k = 0; k < nw; ++k) a += part[k * 2 * LNC_RB + tx];
+      fin[tx] = a * invC;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + ty), "r"(TX) : "memory");
+#pragma unroll
+    for (int u = 0; u < LNC_RB; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) continue;
+      const float s1 = fin[2 * u], s2 = fin[2 * u + 1], rstd = cur.rstd[u];
+      float4 o = cur.dx[u];
+      o.x += rstd * (d[u].x - s1 - xh[u].x * s2);
+      o.y += rstd * (d[u].y - s1 - xh[u].y * s2);
+      o.z += rstd * (d[u].z - s1 - xh[u].z * s2);
+      o.w += rstd * (d[u].w - s1 - xh[u].w * s2);
+      st4(dx + (long long)r * lddx + c, o);
+      if constexpr (SRB) {
+        const float2 t0 = unpack_bf16x2(cur.t[u].x), t1 = unpack_bf16x2(cur.t[u].y);
+        const float rs = cur.rsc[u];
+        const float4 q = make_float4(rs * g2.x * o.x, rs * g2.y * o.y, rs * g2.z * o.z, rs * g2.w * o.w);
+        st_bf16x4(srb.dt + (long long)r * C + c, q);
+        ag2.x += rs * t0.x * o.x; ag2.y += rs * t0.y * o.y; ag2.z += rs * t1.x * o.z; ag2.w += rs * t1.y * o.w;
+        ab2.x += q.x; ab2.y += q.y; ab2.z += q.z; ab2.w += q.w;
+      }
+    }
+  };
+  // two register buffers in ping-pong (no copies: a move out of a register with a load in flight would wait for it): the loads of group
+  // k + 1 are in flight across the reduction, barriers and stores of group k
+  Raw qa, qb;
+  const int stride = gridDim.x;
+  load(blockIdx.x, qa);
+  for (int grp = blockIdx.x; grp < ngroups; grp += 2 * stride) {
+    load(grp + stride, qb);
+    process(grp, qa);
+    load(grp + 2 * stride, qa);
+    if (grp + stride < ngroups) process(grp + stride, qb);
+  }
+  // column sums: slices add into shared memory one after the other, then ONE vector atomic per 4 columns and quantity per CTA
+  for (int s = 0; s < TY; ++s) {
+    if (ty == s) {
+      float4* cr = reinterpret_cast<float4*>(colred);
+      const int q4 = C >> 2;
+      auto put = [&](int k, const float4& v) {
+        float4 cur = s == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : cr[k * q4 + tx];
+        cr[k * q4 + tx] = make_float4(cur.x + v.x, cur.y + v.y, cur.z + v.z, cur.w + v.w);
+      };
+      put(0, ag); put(1, ab);
+      if constexpr (SRB) { put(2, ag2); put(3, ab2); }
+    }
+    __syncthreads();
+  }
+  if (ty == 0) {
+    const float4* cr = reinterpret_cast<const float4*>(colred);
+    const int q4 = C >> 2;
+    auto red4 = [](float* p, const float4& v) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    };
+    if (dgamma != nullptr) red4(dgamma + c, cr[tx]);
+    if (dbeta != nullptr) red4(dbeta + c, cr[q4 + tx]);
+    if constexpr (SRB) {
+      if (srb.dgamma2 != nullptr) red4(srb.dgamma2 + c, cr[2 * q4 + tx]);
+      if (srb.dbias2 != nullptr) red4(srb.dbias2 + c, cr[3 * q4 + tx]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (+ fused scale-residual backward) with the operand streams staged through shared memory by bulk async copies.
+// The register-staged kernels above top out at 4.4-4.7 TB/s: the bytes a thread can keep in flight are the registers it can spare
+// (measured: software pipelining, 384 / 768-thread CTAs, ping-pong buffers all land between 57 and 82 us for 271-349 MB). Here one producer
+// lane streams LNB_G-row chunks of dy (bf16), x, dx (fp32), t (bf16) and the rows' mean / rstd into a ring of shared-memory stages with
+// cp.async.bulk + mbarrier (up to ~190 KB in flight per SM, no registers involved), and two consumer groups of C/4 threads (column-owner
+// layout: 4 columns x LNB_G rows per thread, column sums in 16 registers) take alternate stages. Rows are contiguous (ldx == lddx == C) and
+// rows % LNB_G == 0 on this path; everything else uses the kernels above.
+// ------------------------------------------------------------------------------------------------
+constexpr int LNB_G = 4;                 // rows per stage
+constexpr int LNB_GROUPS = 2;            // consumer groups
+constexpr int LNB_MAX_STAGES = 6;
+struct LnbParams {
+  const bf16* dy; const float* x; const float* gamma; const float* mean; const float* rstd;
+  float* dx; float* dgamma; float* dbeta;
+  SrbStage srb;
+  int rows, C, nstages, stage_bytes;
+};
+
+template <bool SRB>
+__global__ void __launch_bounds__(LNB_GROUPS * 256 + 32, 1) ln_bwd_bulk_kernel(const LnbParams p) {
+  extern __shared__ __align__(128) uint8_t lnb_smem[];
+  const int C = p.C, TX = C >> 2;
+  // stage layout: dy [G][C] bf16 | x [G][C] f32 | dx [G][C] f32 | t [G][C] bf16 (SRB) | mean [G] | rstd [G]
+  const int off_x = LNB_G * C * 2, off_dx = off_x + LNB_G * C * 4, off_t = off_dx + LNB_G * C * 4;
+  const int off_ms = off_t + (SRB ? LNB_G * C * 2 : 0);
+  uint8_t* stages = lnb_smem;
+  float* red = reinterpret_cast<float*>(lnb_smem + (size_t)p.nstages * p.stage_bytes);      // [GROUPS][8 warps][2 G] + [GROUPS][2 G] + [4][C]
+  const uint32_t bar0 = ptx::smem_u32(red + LNB_GROUPS * (8 * 2 * LNB_G + 2 * LNB_G) + 4 * C);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (LNB_MAX_STAGES + s); };
+  const int tid = threadIdx.x;
+  const int nchunks = p.rows / LNB_G;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int ctid = tid - 32;                      // consumer thread index (tid >= 32)
+  if (tid < 32) {
+    if (tid == 0) {
+      // ---------------- producer ----------------
+      const uint32_t tx_bytes = (uint32_t)(LNB_G * C * (SRB ? 12 : 10) + 2 * LNB_G * 4);
+      for (int i = 0; i < my; ++i) {
+        const int s = i % p.nstages;
+        if (i >= p.nstages) ptx::mbar_wait(empty(s), (uint32_t)(((i / p.nstages) - 1) & 1));
+        const long long r0 = (long long)(first + i * stride) * LNB_G;
+        const uint32_t dst = ptx::smem_u32(stages + (size_t)s * p.stage_bytes);
+        ptx::mbar_arrive_expect_tx(full(s), tx_bytes);
+        ptx::bulk_load_1d(dst, p.dy + r0 * C, LNB_G * C * 2, full(s));
+        ptx::bulk_load_1d(dst + off_x, p.x + r0 * C, LNB_G * C * 4, full(s));
+        ptx::bulk_load_1d(dst + off_dx, p.dx + r0 * C, LNB_G * C * 4, full(s));
+        if (SRB) ptx::bulk_load_1d(dst + off_t, p.srb.t + r0 * C, LNB_G * C * 2, full(s));
+        ptx::bulk_load_1d(dst + off_ms, p.mean + r0, LNB_G * 4, full(s));
+        ptx::bulk_load_1d(dst + off_ms + LNB_G * 4, p.rstd + r0, LNB_G * 4, full(s));
+      }
+    }
+    return;
+  }
+  // ---------------- consumers ----------------
+  const int grp = ctid / TX, tx = ctid - grp * TX;
+  if (grp >= LNB_GROUPS) return;                  // blockDim is 32 + GROUPS * TX exactly; defensive
+  const int w = tx >> 5, lane = tx & 31, nw = TX >> 5;
+  float* part = red + grp * (8 * 2 * LNB_G + 2 * LNB_G);
+  float* fin = part + 8 * 2 * LNB_G;
+  float* colred = red + LNB_GROUPS * (8 * 2 * LNB_G + 2 * LNB_G);
+  const int c = tx * 4;
+  const float invC = 1.0f / (float)C;
+  const float4 g = p.gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(p.gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 g2 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if constexpr (SRB) { if (p.srb.gamma2 != nullptr) g2 = __ldg(reinterpret_cast<const float4*>(p.srb.gamma2 + c)); }
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ag2 = ag, ab2 = ag;
+  for (int i = grp; i < my; i += LNB_GROUPS) {
+    const int s = i % p.nstages;
+    const long long r0 = (long long)(first + i * stride) * LNB_G;
+    const uint8_t* st = stages + (size_t)s * p.stage_bytes;
+    ptx::mbar_wait(full(s), (uint32_t)((i / p.nstages) & 1));
+    float4 xh[LNB_G], d[LNB_G];
+    float p1[LNB_G], p2[LNB_G], rstd[LNB_G];
+#pragma unroll
+    for (int u = 0; u < LNB_G; ++u) {
+      const uint2 dr = *reinterpret_cast<const uint2*>(st + (u * C + c) * 2);
+      const float4 xv = *reinterpret_cast<const float4*>(st + off_x + (u * C + c) * 4);
+      const float mean = *reinterpret_cast<const float*>(st + off_ms + u * 4);
+      rstd[u] = *reinterpret_cast<const float*>(st + off_ms + (LNB_G + u) * 4);
+      const float2 a0 = unpack_bf16x2(dr.x), a1 = unpack_bf16x2(dr.y);
+      const float4 dv = make_float4(a0.x, a0.y, a1.x, a1.y);
+      xh[u] = make_float4((xv.x - mean) * rstd[u], (xv.y - mean) * rstd[u], (xv.z - mean) * rstd[u], (xv.w - mean) * rstd[u]);
+      ag.x += dv.x * xh[u].x; ag.y += dv.y * xh[u].y; ag.z += dv.z * xh[u].z; ag.w += dv.w * xh[u].w;
+      ab.x += dv.x; ab.y += dv.y; ab.z += dv.z; ab.w += dv.w;
+      d[u] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+      p1[u] = d[u].x + d[u].y + d[u].z + d[u].w;
+      p2[u] = d[u].x * xh[u].x + d[u].y * xh[u].y + d[u].z * xh[u].z + d[u].w * xh[u].w;
+    }
+#pragma unroll
+    for (int u = 0; u < LNB_G; ++u) {
+      p1[u] = warp_sum(p1[u]);
+      p2[u] = warp_sum(p2[u]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < LNB_G; ++u) { part[w * 2 * LNB_G + 2 * u] = p1[u]; part[w * 2 * LNB_G + 2 * u + 1] = p2[u]; }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TX) : "memory");
+    if (tx < 2 * LNB_G) {
+      float a = 0.f;
+      for (int k = 0; k < nw; ++k) a += part[k * 2 * LNB_G + tx];
+      fin[tx] = a * invC;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TX) : "memory");
+    float rsc[LNB_G];
+    if constexpr (SRB) {
+#pragma unroll
+      for (int u = 0; u < LNB_G; ++u)
+        rsc[u] = p.srb.rowscale != nullptr ? __ldg(p.srb.rowscale + ((int)r0 + u) / p.srb.rows_per_scale) : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < LNB_G; ++u) {
+      const float s1 = fin[2 * u], s2 = fin[2 * u + 1];
+      float4 o = *reinterpret_cast<const float4*>(st + off_dx + (u * C + c) * 4);
+      o.x += rstd[u] * (d[u].x - s1 - xh[u].x * s2);
+      o.y += rstd[u] * (d[u].y - s1 - xh[u].y * s2);
+      o.z += rstd[u] * (d[u].z - s1 - xh[u].z * s2);
+      o.w += rstd[u] * (d[u].w - s1 - xh[u].w * s2);
+      st4(p.dx + (r0 + u) * C + c, o);
+      if constexpr (SRB) {
+        const uint2 tr = *reinterpret_cast<const uint2*>(st + off_t + (u * C + c) * 2);
+        const float2 t0 = unpack_bf16x2(tr.x), t1 = unpack_bf16x2(tr.y);
+        const float rs = rsc[u];
+        const float4 q = make_float4(rs * g2.x * o.x, rs * g2.y * o.y, rs * g2.z * o.z, rs * g2.w * o.w);
+        st_bf16x4(p.srb.dt + (r0 + u) * C + c, q);
+        ag2.x += rs * t0.x * o.x; ag2.y += rs * t0.y * o.y; ag2.z += rs * t1.x * o.z; ag2.w += rs * t1.y * o.w;
+        ab2.x += q.x; ab2.y += q.y; ab2.z += q.z; ab2.w += q.w;
+      }
+    }
+    // every thread of the group has read the stage (fin was read after the second barrier, the stage just above): hand it back
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TX) : "memory");
+    if (tx == 0) ptx::mbar_arrive(empty(s));
+  }
+  // column sums: the groups add into shared memory one after the other (all consumers, barrier 8), then one vector atomic per 4 columns
+  float4* cr = reinterpret_cast<float4*>(colred);
+  for (int sgrp = 0; sgrp < LNB_GROUPS; ++sgrp) {
+    if (grp == sgrp) {
+      auto put = [&](int k, const float4& v) {
+        const float4 cur = sgrp == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : cr[k * TX + tx];
+        cr[k * TX + tx] = make_float4(cur.x + v.x, cur.y + v.y, cur.z + v.z, cur.w + v.w);
+      };
+      put(0, ag); put(1, ab);
+      if constexpr (SRB) { put(2, ag2); put(3, ab2); }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(8), "r"(LNB_GROUPS * TX) : "memory");
+  }
+  if (grp == 0) {
+    auto red4 = [](float* q, const float4& v) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    };
+    if (p.dgamma != nullptr) red4(p.dgamma + c, cr[tx]);
+    if (p.dbeta != nullptr) red4(p.dbeta + c, cr[TX + tx]);
+    if constexpr (SRB) {
+      if (p.srb.dgamma2 != nullptr) red4(p.srb.dgamma2 + c, cr[2 * TX + tx]);
+      if (p.srb.dbias2 != nullptr) red4(p.srb.dbias2 + c, cr[3 * TX + tx]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward of  x_out = x_in + rowscale[b] * gamma * t   (Block.forward, modeling_finetune.py:296-298):
 //   dt = rowscale*gamma*dx (bf16) ; dgamma += sum rowscale*t*dx ; dbias += sum dt      (dbias = grad of the branch's
 //   last Linear bias, i.e. column sum of dt)
@@ -205,6 +528,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const DY* __restrict__ dy, 
 // same-address atomics from many small CTAs were the bottleneck of the first version.
 constexpr int RB_UNROLL = 4;
 
+constexpr int SRB_UNROLL = 2;
 __global__ void scale_residual_bwd_kernel(const float* __restrict__ dx, long long lddx, const bf16* __restrict__ t,
                                           const float* __restrict__ rowscale, int rows_per_scale, const float* __restrict__ gamma, int rows, int C,
                                           bf16* __restrict__ dt, float* __restrict__ dgamma, float* __restrict__ dbias) {
@@ -215,29 +539,47 @@ __global__ void scale_residual_bwd_kernel(const float* __restrict__ dx, long lon
   __syncthreads();
   const float4 gm = gamma != nullptr ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int step = gridDim.x * rowl * RB_UNROLL;
-  for (int r0 = (blockIdx.x * rowl + threadIdx.y) * RB_UNROLL; r0 < rows; r0 += step) {
-    float4 d[RB_UNROLL], tv[RB_UNROLL];
-    float rs[RB_UNROLL];
+  const int step = gridDim.x * rowl * SRB_UNROLL;
+  // software pipeline: the loads of the next SRB_UNROLL rows are in flight while the current ones are scaled and stored (a thread that
+  // loads, computes and stores in turn keeps its bytes in flight only half of the time: 3.5 TB/s before, measured)
+  struct Raw {
+    float4 d[SRB_UNROLL];
+    uint2 t[SRB_UNROLL];
+    float rs[SRB_UNROLL];
+  };
+  auto load = [&](int r0, Raw& q) {
 #pragma unroll
-    for (int u = 0; u < RB_UNROLL; ++u) {
+    for (int u = 0; u < SRB_UNROLL; ++u) {
       const int r = r0 + u;
-      if (r < rows) {
-        d[u] = ld4(dx + (long long)r * lddx + c);
-        tv[u] = t != nullptr ? ld_bf16x4(t + (long long)r * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rs[u] = rowscale != nullptr ? __ldg(rowscale + r / rows_per_scale) : 1.0f;
-      }
+      const bool ok = r < rows;
+      q.d[u] = ok ? ld4(dx + (long long)r * lddx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q.t[u] = (ok && t != nullptr) ? __ldg(reinterpret_cast<const uint2*>(t + (long long)r * C + c)) : make_uint2(0u, 0u);
+      q.rs[u] = ok ? (rowscale != nullptr ? __ldg(rowscale + r / rows_per_scale) : 1.0f) : 0.0f;
     }
+  };
+  auto process = [&](int r0, const Raw& cur) {
 #pragma unroll
-    for (int u = 0; u < RB_UNROLL; ++u) {
+    for (int u = 0; u < SRB_UNROLL; ++u) {
       const int r = r0 + u;
       if (r < rows) {
-        const float4 o = make_float4(rs[u] * gm.x * d[u].x, rs[u] * gm.y * d[u].y, rs[u] * gm.z * d[u].z, rs[u] * gm.w * d[u].w);
+        const float rs = cur.rs[u];
+        const float4 d = cur.d[u];
+        const float2 t0 = unpack_bf16x2(cur.t[u].x), t1 = unpack_bf16x2(cur.t[u].y);
+        const float4 o = make_float4(rs * gm.x * d.x, rs * gm.y * d.y, rs * gm.z * d.z, rs * gm.w * d.w);
         st_bf16x4(dt + (long long)r * C + c, o);
-        ag.x += rs[u] * tv[u].x * d[u].x; ag.y += rs[u] * tv[u].y * d[u].y; ag.z += rs[u] * tv[u].z * d[u].z; ag.w += rs[u] * tv[u].w * d[u].w;
+        ag.x += rs * t0.x * d.x; ag.y += rs * t0.y * d.y; ag.z += rs * t1.x * d.z; ag.w += rs * t1.y * d.w;
         ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
       }
     }
+  };
+  Raw qa, qb;                               // ping-pong (no register copies of in-flight loads)
+  int r0 = (blockIdx.x * rowl + threadIdx.y) * SRB_UNROLL;
+  load(r0, qa);
+  for (; r0 < rows; r0 += 2 * step) {
+    load(r0 + step, qb);
+    process(r0, qa);
+    load(r0 + 2 * step, qa);
+    process(r0 + step, qb);
   }
   atomicAdd(&red[c], ag.x); atomicAdd(&red[c + 1], ag.y); atomicAdd(&red[c + 2], ag.z); atomicAdd(&red[c + 3], ag.w);
   atomicAdd(&red[C + c], ab.x); atomicAdd(&red[C + c + 1], ab.y); atomicAdd(&red[C + c + 2], ab.z); atomicAdd(&red[C + c + 3], ab.w);
@@ -428,13 +770,72 @@ extern "C" int b200vit_layernorm_fwd(const float* x, int64_t ldx, const int32_t*
   return 0;
 }
 
+// B200VIT_LN_BWD_LAYOUT (same-box A/B): 0 = bulk-staged where it applies (default), 1 = register-staged column-owner kernel for dense rows,
+// 2 = warp-per-row kernel everywhere
+static int b200vit_ln_bwd_layout() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200VIT_LN_BWD_LAYOUT"); v = e != nullptr ? atoi(e) : 0; }
+  return v;
+}
+
 static int launch_ln_bwd(const void* dy, int32_t dy_is_f32, const float* x, int64_t ldx, const int32_t* row_index, const float* gamma,
                          const float* mean, const float* rstd, int32_t rows, int32_t C, float* dx, int64_t lddx, float* dgamma, float* dbeta,
                          const SrbStage& srb, void* stream) {
   const int sms = b200vit_num_sms();
+  const bool fused = srb.t != nullptr;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta) | reinterpret_cast<uintptr_t>(srb.dgamma2) |
+                         reinterpret_cast<uintptr_t>(srb.dbias2)) & 15) == 0;          // red.global.add.v4 needs 16-byte aligned gradient rows
+  const bool bulk_ok = row_index == nullptr && aligned && !dy_is_f32 && ldx == C && lddx == C && rows % LNB_G == 0 && C % 128 == 0 && C / 4 <= 256 &&
+                       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(mean) |
+                         reinterpret_cast<uintptr_t>(rstd) | reinterpret_cast<uintptr_t>(srb.t)) & 15) == 0 && b200vit_ln_bwd_layout() == 0;
+  if (bulk_ok) {
+    LnbParams lp;
+    lp.dy = static_cast<const bf16*>(dy); lp.x = x; lp.gamma = gamma; lp.mean = mean; lp.rstd = rstd; lp.dx = dx; lp.dgamma = dgamma; lp.dbeta = dbeta;
+    lp.srb = srb; lp.rows = rows; lp.C = C;
+    lp.stage_bytes = LNB_G * C * (fused ? 12 : 10) + 128;           // + mean / rstd (2 x 16 B), padded to keep every stage 128-byte aligned
+    const size_t tail = (LNB_GROUPS * (8 * 2 * LNB_G + 2 * LNB_G) + 4 * C) * sizeof(float) + 2 * LNB_MAX_STAGES * 8 + 16;
+    int nst = (int)((220 * 1024 - tail) / lp.stage_bytes);
+    if (nst > LNB_MAX_STAGES) nst = LNB_MAX_STAGES;
+    nst &= ~1;       // even: a stage then always belongs to the same consumer group, which therefore observes every phase of its full barrier
+    lp.nstages = nst;
+    const size_t smem = (size_t)nst * lp.stage_bytes + tail;
+    const int nchunks = rows / LNB_G;
+    const int bgrid = nchunks < sms ? nchunks : sms;
+    const int threads = 32 + LNB_GROUPS * (C / 4);
+    static bool cfg_done[2] = {false, false};
+    if (!cfg_done[fused]) {
+      cudaError_t e = fused ? cudaFuncSetAttribute(ln_bwd_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)
+                            : cudaFuncSetAttribute(ln_bwd_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      if (e != cudaSuccess) { b200vit_set_error("layernorm_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return (int)e; }
+      cfg_done[fused] = true;
+    }
+    if (nst >= 2) {
+      if (fused) ln_bwd_bulk_kernel<true><<<bgrid, threads, smem, STREAM>>>(lp);
+      else ln_bwd_bulk_kernel<false><<<bgrid, threads, smem, STREAM>>>(lp);
+      B200_CHECK_LAUNCH("layernorm_bwd (bulk-staged)");
+      return 0;
+    }
+  }
+  if (row_index == nullptr && aligned && b200vit_ln_bwd_layout() != 2) {              // dense rows: column-owner kernel
+    const int tx = C / 4;
+    int ty = LNC_THREADS / tx;
+    if (ty > LNC_TY_MAX) ty = LNC_TY_MAX;
+    const int ngroups = (rows + ty * LNC_RB - 1) / (ty * LNC_RB);
+    const int cgrid = ngroups < sms ? ngroups : sms;
+    const size_t csmem = (LNC_TY_MAX * (8 * 2 * LNC_RB + 2 * LNC_RB) + 4 * C) * sizeof(float);
+    const dim3 blk(tx, ty);
+    if (fused) {
+      if (dy_is_f32) ln_bwd_cols_kernel<float, true><<<cgrid, blk, csmem, STREAM>>>(static_cast<const float*>(dy), x, ldx, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);
+      else ln_bwd_cols_kernel<bf16, true><<<cgrid, blk, csmem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);
+    } else {
+      if (dy_is_f32) ln_bwd_cols_kernel<float, false><<<cgrid, blk, csmem, STREAM>>>(static_cast<const float*>(dy), x, ldx, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);
+      else ln_bwd_cols_kernel<bf16, false><<<cgrid, blk, csmem, STREAM>>>(static_cast<const bf16*>(dy), x, ldx, gamma, mean, rstd, rows, C, dx, lddx, dgamma, dbeta, srb);
+    }
+    B200_CHECK_LAUNCH("layernorm_bwd (column-owner)");
+    return 0;
+  }
   int grid = (rows + 7) / 8;
   if (grid > sms * 2) grid = sms * 2;
-  const bool fused = srb.t != nullptr;
   const size_t smem = (fused ? 4 : 2) * C * sizeof(float);
 #define LN_BWD(NV)                                                                                                                             \
   if (fused) {                                                                                                                                 \
@@ -488,11 +889,11 @@ extern "C" int b200vit_scale_residual_bwd(const float* dx, int64_t lddx, const v
   if (rows == 0) return 0;
   const int sms = b200vit_num_sms();
   const int tx = C / 4;
-  int ty = 768 / tx;                       // ~768 threads per CTA
+  int ty = 512 / tx;                       // ~512 threads per CTA, 3 CTAs per SM, two iterations of SRB_UNROLL rows in flight per thread
   if (ty < 1) ty = 1;
   if (ty > 8) ty = 8;
-  int grid = (rows + ty * RB_UNROLL - 1) / (ty * RB_UNROLL);
-  if (grid > sms * 2) grid = sms * 2;
+  int grid = (rows + ty * SRB_UNROLL - 1) / (ty * SRB_UNROLL);
+  if (grid > sms * 3) grid = sms * 3;
   scale_residual_bwd_kernel<<<grid, dim3(tx, ty), 2 * C * sizeof(float), STREAM>>>(dx, lddx, static_cast<const bf16*>(t_bf16), rowscale, rows_per_scale > 0 ? rows_per_scale : 1,
                                                           gamma, rows, C, static_cast<bf16*>(dt_bf16), dgamma, dbias);
   B200_CHECK_LAUNCH("scale_residual_bwd");
