@@ -383,7 +383,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA thread waits for both CTAs' epilogues
+      if (lane == 0) ptx::mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);   // the leader's MMA thread waits for both CTAs' epilogues
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }

@@ -238,6 +238,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       ::"r"(bar), "r"(rank)
       : "memory");
 }
+// The same without release semantics: no fence over the caller's outstanding global stores (ERRBAR). For signals that only hand back TENSOR
+// memory: tcgen05.wait::ld has already completed the reads, the consumer needs no view of this thread's global writes.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
 
 // ---- vector reduction (sm_90+): 4 fp32 atomic adds in one L2 transaction -----------------
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
