@@ -304,35 +304,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int cg = lane & 7, sub = lane >> 3;      // coalesced view: 4-column group and row-within-4 of this lane
     constexpr int CHUNKS = EPI_COLS / 32;          // 2 or 4 chunks of 32 columns per warp
     const bool io = !p.epi.debug_skip_io;
-    for (int u = pair; u < num_units; u += num_pairs) {
+    // ---- everything that does not depend on the accumulator is fetched ahead of time: for chunk c + 1 while chunk c is being processed, and
+    // for chunk 0 of the NEXT tile while the last chunk of this one is (when the epilogue paces the kernel — the K = 768 shapes — the
+    // accumulator is already waiting, and a load issued at the top of a tile would sit on the critical path once per tile)
+    auto unit_bases = [&](int u, int& m_base, int& n_base) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
-      const int m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
-      const int n_base = n_blk * BLOCK_N + half * EPI_COLS + cg * 4;
-      // ---- everything that does not depend on the accumulator is fetched BEFORE waiting for the MMAs of this tile,
-      // and for chunk c+1 while chunk c is being processed (no global-load latency on the TMEM-drain critical path)
-      auto load_cols = [&](int n, float4& b4, float4& c4) {
-        b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        c4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (MODE != B200VIT_EPI_F32_ATOMIC && n < p.N && io) {
-          if (p.epi.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
-          if ((MODE == B200VIT_EPI_BF16 || MODE == B200VIT_EPI_RESIDUAL) && p.epi.colscale != nullptr)
-            c4 = __ldg(reinterpret_cast<const float4*>(p.epi.colscale + n));
-        }
-      };
-      float4 bias4, cs4;
+      m_base = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + quarter * 32;
+      n_base = n_blk * BLOCK_N + half * EPI_COLS + cg * 4;
+    };
+    auto load_cols = [&](int n, float4& b4, float4& c4) {
+      b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      c4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (MODE != B200VIT_EPI_F32_ATOMIC && n < p.N && io) {
+        if (p.epi.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
+        if ((MODE == B200VIT_EPI_BF16 || MODE == B200VIT_EPI_RESIDUAL) && p.epi.colscale != nullptr)
+          c4 = __ldg(reinterpret_cast<const float4*>(p.epi.colscale + n));
+      }
+    };
+    auto row_scale = [&](int m) {
+      return (MODE == B200VIT_EPI_RESIDUAL && p.epi.rowscale != nullptr && m < p.M) ? __ldg(p.epi.rowscale + m / p.epi.rows_per_scale) : 1.0f;
+    };
+    float4 bias4, cs4;
+    float rs[8];
+    EpiPrefetch pf[8];
+    if (pair < num_units) {
+      int m_base, n_base;
+      unit_bases(pair, m_base, n_base);
       load_cols(n_base, bias4, cs4);
-      float rs[8];
-      EpiPrefetch pf[8];
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         const int m = m_base + rr * 4 + sub;
-        rs[rr] = (MODE == B200VIT_EPI_RESIDUAL && p.epi.rowscale != nullptr && m < p.M) ? __ldg(p.epi.rowscale + m / p.epi.rows_per_scale) : 1.0f;
+        rs[rr] = row_scale(m);
         pf[rr] = epi_prefetch<MODE>(p.epi, m, n_base, io && m < p.M && n_base < p.N);
       }
+    }
+    for (int u = pair; u < num_units; u += num_pairs) {
+      int m_base, n_base;
+      unit_bases(u, m_base, n_base);
+      const bool has_next = u + num_pairs < num_units;
+      int m_next = 0, n_next = 0;
+      if (has_next) unit_bases(u + num_pairs, m_next, n_next);
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * EPI_COLS;
+      bool wrapped = false;                  // chunk 0 of the next tile has been requested
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_base + c * 32;
@@ -348,12 +364,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         float4 bias_n, cs_n;
         EpiPrefetch nxt[8];
-        const bool more = c + 1 < CHUNKS;
-        load_cols(more ? n + 32 : p.N, bias_n, cs_n);
+        float rs_n[8];
+        const bool more = c + 1 < CHUNKS && n + 32 - cg * 4 < p.N;       // another chunk of this tile follows
+        const bool wrap = !more && has_next;                               // otherwise: chunk 0 of the next tile
+        wrapped = wrapped || wrap;
+        const int n_pre = more ? n + 32 : n_next, m_pre = more ? m_base : m_next;
+        load_cols((more || wrap) ? n_pre : p.N, bias_n, cs_n);
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
-          const int m = m_base + rr * 4 + sub;
-          nxt[rr] = epi_prefetch<MODE>(p.epi, m, n + 32, more && io && m < p.M && n + 32 < p.N);
+          const int m = m_pre + rr * 4 + sub;
+          nxt[rr] = epi_prefetch<MODE>(p.epi, m, n_pre, (more || wrap) && io && m < p.M && n_pre < p.N);
+          rs_n[rr] = wrap ? row_scale(m) : rs[rr];
         }
         const bool col_ok = n < p.N;       // N % 8 == 0: a 4-column group is entirely valid or not
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -378,8 +399,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         bias4 = bias_n;
         cs4 = cs_n;
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) pf[rr] = nxt[rr];
+        for (int rr = 0; rr < 8; ++rr) { pf[rr] = nxt[rr]; rs[rr] = rs_n[rr]; }
         __syncwarp();
+      }
+      if (has_next && !wrapped) {            // this warp's columns lie outside the matrix in this tile: nothing was processed, fetch directly
+        load_cols(n_next, bias4, cs4);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int m = m_next + rr * 4 + sub;
+          rs[rr] = row_scale(m);
+          pf[rr] = epi_prefetch<MODE>(p.epi, m, n_next, io && m < p.M && n_next < p.N);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
