@@ -36,7 +36,7 @@ def run(name, m, n, k, a_mn=False, b_mn=False, epi=ops.EPI_BF16, reps=20, nbuf=3
         elif epi == ops.EPI_DGELU:
             ops.gemm(a, b, m, n, k, aux=o16b, out_bf16=o16, **args)
         elif epi == ops.EPI_RESIDUAL:
-            ops.gemm(a, b, m, n, k, bias=bias, colscale=bias, residual=res, out_f32=o32, out2_bf16=o16, **args)
+            ops.gemm(a, b, m, n, k, bias=bias, colscale=bias, residual=res, out_f32=o32, out2_bf16=None if no_out2 else o16, **args)
         else:
             ops.gemm(a, b, m, n, k, out_f32=o32, **args)
     for i in range(3):
@@ -59,6 +59,9 @@ if __name__ == "__main__":
         run("fc2 dgrad dgelu (acc * aux)", M, 3072, 768, b_mn=True, epi=ops.EPI_DGELU)
         run("fc1 dgrad bf16", M, 768, 3072, b_mn=True)
         run("proj fwd residual", M, 768, 768, epi=ops.EPI_RESIDUAL)
+        run("proj fwd residual, no bf16 branch output", M, 768, 768, epi=ops.EPI_RESIDUAL, no_out2=True)
+        run("proj shape, fp32 store only (EPI_F32)", M, 768, 768, epi=ops.EPI_F32)
+        run("proj shape, bf16 store only (EPI_BF16)", M, 768, 768)
         run("fc2 fwd residual", M, 768, 3072, epi=ops.EPI_RESIDUAL)
         run("qkv fwd bf16", M, 2304, 768)
         sys.exit(0)
