@@ -16,8 +16,12 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
 PROFILE_STOCHASTIC=1 python tools/profile_step.py > $O/profile_step_sto.log 2>&1 || exit 1
 PROFILE_STOCHASTIC=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_step_stochastic.csv python tools/profile_step.py > /dev/null 2>&1
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_bf16 --csv --log-file $O/gemm_dram.csv python tools/profile_step.py > /dev/null 2>&1
-PROFILE_STOCHASTIC=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"wattn_fwd_kernel|wattn_bwd_kv|wattn_bwd_dx|wattn_prep" --launch-skip 40 --launch-count 6 -o $O/wattn_step -f python tools/profile_step.py > $O/ncu_wattn.log 2>&1
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"attn_fwd_sm100|attn_bwd_kv|attn_bwd_dq|keep_bits" --launch-skip 36 --launch-count 5 -o $O/attn_step -f python tools/profile_step.py > $O/ncu_attn.log 2>&1
+PROFILE_STOCHASTIC=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"wattn_fwd_kernel|wattn_prep" --launch-skip 26 --launch-count 3 -o $O/wattn_fwd_step -f python tools/profile_step.py > $O/ncu_wattn_fwd.log 2>&1
+PROFILE_STOCHASTIC=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"wattn_bwd_kv|wattn_bwd_dx" --launch-skip 4 --launch-count 2 -o $O/wattn_bwd_step -f python tools/profile_step.py > $O/ncu_wattn_bwd.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"attn_fwd_sm100" --launch-skip 14 --launch-count 2 -o $O/attn_fwd_step -f python tools/profile_step.py > $O/ncu_attn_fwd.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"attn_bwd_kv|attn_bwd_dq" --launch-skip 4 --launch-count 2 -o $O/attn_step -f python tools/profile_step.py > $O/ncu_attn.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"ln_bwd_bulk|ln_fwd_kernel" --launch-skip 20 --launch-count 2 -o $O/rows_step -f python tools/profile_step.py > $O/ncu_rows.log 2>&1
+python tools/row_bench.py > $O/row_bench.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_bf16 --launch-skip 60 --launch-count 8 -o $O/gemm_step -f python tools/profile_step.py > $O/ncu_gemm.log 2>&1
 tail -2 $O/tests_gpu.log
 cut -c1-300 $O/bench_n1.json
