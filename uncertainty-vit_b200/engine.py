@@ -413,6 +413,7 @@ class D2VEngine:
         # teacher (EMA weights, eval mode, unmasked): engine_for_cyclical.py:68-88. It shares nothing with the student forward but the
         # patches, so it runs on its own stream: its kernels fill the SMs the student's persistent GEMMs leave idle in their last wave.
         with self._teacher_stream_ctx():
+            self.g32.zero_()          # 345 MB of fp32 gradients: cleared beside the forward instead of in front of the backward
             layers, _ = core.vit_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers,
                                          patches=patches)
         # student: :124-128
@@ -424,7 +425,6 @@ class D2VEngine:
         ls = self.loss_scale if self.loss_scale != -1 else 1.0
         self._targets_and_loss([layers[i].view(B * T, C) for i in self.target_layers], rows, out, R, n_valid, dy_bf16=dy, loss_mult=ls)
         del layers
-        self.g32.zero_()
         self._overlapped_backward(lambda cb: core.vit_backward(self.student, cfg, ctx, dy, self.grads, after_block=cb))
 
     def _fwd_bwd_graphed(self, images, mask_u8, rows, seed: int, n_valid=None):
@@ -493,6 +493,7 @@ class D2VEngine:
         dev = self.dev
         self._draw_masks(B, noise)
         with self._teacher_stream_ctx():
+            self.g32.zero_()
             (lm, lc), _ = core.dist_forward(self.teacher, cfg, images, mode="layers", train=False, save=False, collect=self.target_layers)
         (om, oc), ctx = core.dist_forward(self.student, cfg, images, mask_u8=mask_u8, row_index=rows, mode="masked", train=True, save=True, noise=noise)
         self._teacher_join()
@@ -510,7 +511,6 @@ class D2VEngine:
             self.wloss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         ops.wasserstein_loss(om, oc, tgt_m, tgt_c, self.lam, ls, work, d_m, d_c, self.wloss_dev, n_valid=n_valid)
         ops.scalar_fma(self.loss_dev, self.loss_dev, ls, self.wloss_dev, ls)      # loss = (loss_cyc + std_loss0*var_w0 + loss_stochastic) * loss_scale  (:160-163)
-        self.g32.zero_()
         self._overlapped_backward(lambda cb: core.dist_backward(self.student, cfg, ctx, d_m, d_c, self.grads, after_block=cb))
 
     def _optimizer_step(self, lr, wd):
@@ -651,13 +651,20 @@ class FinetuneEngine(D2VEngine):
         kp = (K + 7) // 8 * 8
         dl16 = torch.empty((B, kp), dtype=torch.bfloat16, device=self.dev)
         if cfg.dist:
+            trip = pos_images is not None and neg_images is not None
+            if trip:
+                # positive and negative images: ONE eval-mode forward of 2B images (no batch statistics anywhere: identical to two forwards;
+                # engine_for_finetuning_dist.py:293-296 runs them through a deepcopy in eval mode), on the second stream next to the anchor's
+                # training forward, which it shares nothing with
+                quiet = Noise(drop_path_active=False, attn_drop_active=False)
+                both = torch.cat((pos_images, neg_images), 0)
+                with self._teacher_stream_ctx():
+                    (bm, bc, _), _ = core.dist_forward(self.student, cfg, both, mode="logits", train=False, save=False, noise=quiet)
             (fm, fc, logits), ctx = core.dist_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
             feats = None
-            if pos_images is not None and neg_images is not None:
-                quiet = Noise(drop_path_active=False, attn_drop_active=False)
-                (pm, pc, _), _ = core.dist_forward(self.student, cfg, pos_images, mode="logits", train=False, save=False, noise=quiet)
-                (nm, nc, _), _ = core.dist_forward(self.student, cfg, neg_images, mode="logits", train=False, save=False, noise=quiet)
-                feats = (fm, fc, pm, pc, nm, nc)
+            if trip:
+                self._teacher_join()
+                feats = (fm, fc, bm[:B], bc[:B], bm[B:], bc[B:])
             _, dfm, dfc = ops.finetune_loss(logits, soft, K, feats=feats, lam_ft=self.lam_ft, lam_pvn=self.lam_pvn, dlogits_bf16=dl16,
                                             loss_out=self.loss3)
             self.g32.zero_()
