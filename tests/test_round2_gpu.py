@@ -645,3 +645,45 @@ def test_layernorm_bwd_scale_residual_matches_separate_kernels(ops, rows, C, T, 
     for u, v in zip(a[2:], b[2:]):
         if u is not None:
             torch.testing.assert_close(u, v, rtol=2e-4, atol=2e-4 * float(v.abs().max()) + 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,C,T", [(M_BENCH, 768, 197), (2 * 64 * 197, 1024, 197), (394, 768, 197)])
+def test_layernorm_bwd_paths_vs_torch_autograd(ops, cuda, rows, C, T):
+    """The three LayerNorm-backward kernels (bulk-staged through shared memory: rows % 4 == 0; register-staged column-owner: ragged row counts;
+    warp per row: B200VIT_LN_BWD_LAYOUT=2) and the fused scale-residual stage against torch autograd in fp32 at the benchmarked shape, ViT-L
+    width and a ragged row count: dx (fp32, += into the incoming gradient), dgamma / dbeta, dt, dgamma2 / dbias2."""
+    gen = torch.Generator(device=cuda).manual_seed(rows + C)
+    r = lambda *s: torch.randn(*s, generator=gen, device=cuda)
+    x = r(rows, C) * 1.5 + 0.3
+    g = (1 + 0.1 * r(C)).requires_grad_(True)
+    b = (0.1 * r(C)).requires_grad_(True)
+    dy = r(rows, C).bfloat16()
+    dx0 = r(rows, C)
+    t = r(rows, C).bfloat16()
+    scale = (torch.rand(rows // T, generator=gen, device=cuda) > 0.3).float() * 1.25
+    g2 = 0.1 * r(C)
+    xr = x.clone().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(xr, (C,), g, b, eps=1e-6)
+    y.backward(dy.float())
+    dx_ref = dx0 + xr.grad
+    rs = scale.repeat_interleave(T)[:rows, None]
+    dt_ref = rs * g2 * dx_ref
+    dg2_ref = (rs * t.float() * dx_ref).sum(0)
+    mean = x.mean(1).contiguous()
+    rstd = (x.var(1, unbiased=False) + 1e-6).rsqrt().contiguous()
+    dx = dx0.clone()
+    dg, db, dg2, db2 = (torch.zeros(C, device=cuda) for _ in range(4))
+    dt = torch.empty(rows, C, dtype=torch.bfloat16, device=cuda)
+    ops.layernorm_bwd_scale_residual(dy, x, g.detach(), mean, rstd, rows, C, dx, dg, db, t, scale, T, g2, dt, dg2, db2)
+    torch.cuda.synchronize()
+    assert rel(dx, dx_ref) < 1e-5
+    assert rel(dg, g.grad) < 1e-4 and rel(db, b.grad) < 1e-4
+    assert rel(dt.float(), dt_ref) < 4e-3                      # bf16 output
+    assert rel(dg2, dg2_ref) < 1e-4
+    assert rel(db2, dt_ref.sum(0)) < 2e-3                      # column sums of the values before bf16 rounding vs after: fp32 sums of ~25k terms
+    # the un-fused entry on the same inputs
+    dx1 = dx0.clone()
+    dg1, db1 = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    ops.layernorm_bwd(dy, x, g.detach(), mean, rstd, rows, C, dx1, dg1, db1)
+    assert rel(dx1, dx_ref) < 1e-5 and rel(dg1, g.grad) < 1e-4 and rel(db1, b.grad) < 1e-4
