@@ -659,6 +659,7 @@ class FinetuneEngine(D2VEngine):
                 quiet = Noise(drop_path_active=False, attn_drop_active=False)
                 both = torch.cat((pos_images, neg_images), 0)
                 with self._teacher_stream_ctx():
+                    self.g32.zero_()               # the gradient arena (1.6 GB for ViT-L) is cleared beside the forwards
                     (bm, bc, _), _ = core.dist_forward(self.student, cfg, both, mode="logits", train=False, save=False, noise=quiet)
             (fm, fc, logits), ctx = core.dist_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
             feats = None
@@ -667,7 +668,8 @@ class FinetuneEngine(D2VEngine):
                 feats = (fm, fc, bm[:B], bc[:B], bm[B:], bc[B:])
             _, dfm, dfc = ops.finetune_loss(logits, soft, K, feats=feats, lam_ft=self.lam_ft, lam_pvn=self.lam_pvn, dlogits_bf16=dl16,
                                             loss_out=self.loss3)
-            self.g32.zero_()
+            if not trip:
+                self.g32.zero_()
             core.dist_backward_logits(self.student, cfg, ctx, dfm, dfc, dl16, self.grads)
         else:
             logits, ctx = core.vit_forward(self.student, cfg, images, mode="logits", train=True, save=True, noise=noise)
