@@ -23,13 +23,14 @@
 extern "C" {
 #endif
 
-#define B200VIT_ABI_VERSION 7   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
+#define B200VIT_ABI_VERSION 8   /* 2: seed_dev in attn_fwd / wattn_fwd, caller-owned attention-backward workspace;
                                    3: n_valid_dev in d2v_target_loss / wasserstein_loss (padded row lists), block_masks, mixup_batch, normalize_u8;
                                    4: d2v_target_loss_ex, channel_stats, column_std, mask_dropout, gaussian_sample, tace_auroc, finetune_loss;
                                    5: tcgen05 Wasserstein attention (wattn_fwd / wattn_bwd take the transformed-operand workspace and the bias
                                       row maxima), rel_pos_bias rowmax output;
                                    6: keep_bits (the dropout mask as its own kernel), keep_ready in attn_fwd / wattn_fwd, set_sm_limit;
-                                   7: layernorm_bwd_scale_residual */
+                                   7: layernorm_bwd_scale_residual;
+                                   8: indexed relative-position bias in attn_fwd (rel_pos_index_tiles) */
 
 const char* b200vit_last_error(void);
 int b200vit_abi_version(void);
@@ -110,7 +111,19 @@ int b200vit_gemm_bf16(const b200vit_gemm_desc* desc, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                      float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
-                     float* lse, uint8_t* keep_bits, int32_t keep_ready, void* stream);
+                     float* lse, uint8_t* keep_bits, int32_t keep_ready, const uint16_t* bias_idx16, const float* bias_tab, int32_t nbins,
+                     void* stream);
+/* The relative-position bias in INDEXED form (RelativePositionBias.forward gathers table[index], modeling_finetune.py:359-364): when bias_idx16
+ * != NULL b200vit_attn_fwd ignores `bias` and gathers log2(e) * table[index[i, j], h] itself — the uint16 index tile of a 128-query tile
+ * (52 KB) stays resident in shared memory for the whole kernel and the head's table row (3 KB) is reloaded per item, instead of 106 KB of fp32
+ * bias per (batch, head, query tile) streaming through a TMA ring (25 % of the forward's stall samples were waits for that ring).
+ *   tab_out   : fp32 [H, tab_pitch], tab_pitch = (nbins + 1) rounded up to 4; entry nbins = -inf (key mask)
+ *   idx16_out : uint16 [ceil(N / 128), 128, B200VIT_ATTN_IDX_PITCH]; columns >= N hold nbins
+ * N <= 208, nbins < B200VIT_ATTN_TAB_MAX. Values are bit-identical to the dense bias of b200vit_rel_pos_bias. */
+#define B200VIT_ATTN_IDX_PITCH 210
+#define B200VIT_ATTN_TAB_MAX 1024
+int b200vit_rel_pos_index_tiles(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t nbins, float scale, float* tab_out,
+                                uint16_t* idx16_out, void* stream);
 /* The packed keep mask of one attention layer, [B*H, N, 32] bytes (bit j%8 of byte j/8 of row i = keep(i, j)), from Philox4x32-7 keyed on
  * (seed or *seed_dev, stream_id) or from an injected uint8 [B*H, N, N] mask. b200vit_attn_fwd / b200vit_wattn_fwd run it themselves unless
  * they are called with keep_ready != 0 — then keep_bits must already hold the mask: it depends only on the key, so the engine draws the masks

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/b200vit.h but not exported"
     assert sorted(pkg._lib.exported_symbols()) == names, "python prototypes and header disagree"
-    assert lib.b200vit_abi_version() == 7
+    assert lib.b200vit_abi_version() == 8
 
 
 def test_header_cites_reference_lines():

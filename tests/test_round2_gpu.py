@@ -687,3 +687,28 @@ def test_layernorm_bwd_paths_vs_torch_autograd(ops, cuda, rows, C, T):
     dg1, db1 = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
     ops.layernorm_bwd(dy, x, g.detach(), mean, rstd, rows, C, dx1, dg1, db1)
     assert rel(dx1, dx_ref) < 1e-5 and rel(dg1, g.grad) < 1e-4 and rel(db1, b.grad) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,N,p_drop", [(3, 12, 197, 0.0), (2, 3, 197, 0.1), (5, 2, 65, 0.0), (1, 1, 5, 0.0), (2, 4, 208, 0.05), (4, 16, 197, 0.0)])
+def test_attention_indexed_bias_is_the_dense_bias(ops, cuda, B, H, N, p_drop):
+    """b200vit_attn_fwd with the relative-position bias in indexed form (resident uint16 index tile + the head's table row) against the same call
+    with the dense fp32 bias of b200vit_rel_pos_bias: the gathered values are the same fp32 numbers, so out / lse / keep bits are bit-identical."""
+    g = torch.Generator(device=cuda).manual_seed(B * 1000 + N)
+    nb = 732
+    table = torch.randn(nb, H, generator=g, device=cuda) * 0.5
+    index = torch.randint(0, nb, (N, N), generator=g, device=cuda, dtype=torch.int32)
+    qkv = (torch.randn(B, N, 3, H, 64, generator=g, device=cuda) * 0.7).bfloat16()
+    dense, _ = ops.rel_pos_bias(table, index, N, H, want_bwd=False)
+    both, _ = ops.rel_pos_bias(table, index, N, H, want_bwd=False, want_index_tiles=True)
+    assert hasattr(both, "idx16") and torch.equal(dense, both)
+    res = []
+    for bias in (dense, both):
+        out = torch.full((B, N, H * 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+        lse = torch.empty(B, H, N, device=cuda)
+        bits = torch.zeros(B, H, N, 32, dtype=torch.uint8, device=cuda)
+        ops.attn_fwd(qkv, bias, B, H, N, 0.125, p_drop, 7, 3, None, out, lse, bits if p_drop > 0 else None)
+        res.append((out, lse, bits))
+    torch.cuda.synchronize()
+    assert torch.isfinite(res[1][0].float()).all()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])

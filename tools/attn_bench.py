@@ -115,6 +115,15 @@ def bench():
         print(f"attn_fwd p={p}: {us:8.1f} us   {fl / us * 1e-6:7.1f} TFLOP/s algorithmic")
     us = timeit(lambda i: ops.attn_fwd(qkvs[i % R], None, B, H, N, scale, 0.0, 1, 2, None, outs[i % R], lse, None))
     print(f"attn_fwd p=0.0 no bias (no bias ring traffic): {us:8.1f} us")
+    table = torch.randn(732, H, device=dev) * 0.5
+    from uncertainty_vit_b200 import modeling as _M
+    index = _M.relative_position_index(14, 14).to(torch.int32).to(dev).contiguous()      # the reference's index (structured: neighbouring rows -> neighbouring bins)
+    bias_i, _ = ops.rel_pos_bias(table, index, N, H, want_bwd=False, want_index_tiles=True)
+    bias_d, _ = ops.rel_pos_bias(table, index, N, H, want_bwd=False)
+    for name, bb in (("dense fp32 bias ring", bias_d), ("indexed bias (resident index tile + table row)", bias_i)):
+        for p in (0.0, 0.05):
+            us = timeit(lambda i: ops.attn_fwd(qkvs[i % R], bb, B, H, N, scale, p, 1, 2, None, outs[i % R], lse, bits if p > 0 else None, keep_ready=p > 0))
+            print(f"attn_fwd p={p} {name} (masks pre-drawn): {us:8.1f} us")
     if "--fwd-only" in sys.argv:
         return
     if "--bwd" in sys.argv:

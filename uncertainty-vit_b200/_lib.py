@@ -42,7 +42,8 @@ _PROTOS = {
     "b200vit_device_sm_count": (i32, []),
     "b200vit_set_sm_limit": (i32, [i32]),
     "b200vit_gemm_bf16": (i32, [C.POINTER(GemmDesc), vp]),
-    "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, i32, vp]),
+    "b200vit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp, u32, vp, vp, vp, vp, i32, vp, vp, i32, vp]),
+    "b200vit_rel_pos_index_tiles": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "b200vit_keep_bits": (i32, [vp, i32, i32, f32, u64, vp, u32, vp, vp]),
     "b200vit_attn_bwd": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp]),
     "b200vit_attn_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
@@ -108,7 +109,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.b200vit_abi_version() != 7:
+        if l.b200vit_abi_version() != 8:
             raise B200VitError("libb200vit ABI version mismatch")
         _lib = l
     return _lib

@@ -250,7 +250,7 @@ def rel_bias(ps: ParamSource, cfg: VitConfig, dev, want_bwd: bool = True):
     table = ps.f32("rel_pos_bias.relative_position_bias_table")
     if table is None:
         return None, None
-    return ops.rel_pos_bias(table, ps.rel_index_i32(), cfg.tokens, cfg.num_heads, want_bwd, want_rowmax=cfg.dist)
+    return ops.rel_pos_bias(table, ps.rel_index_i32(), cfg.tokens, cfg.num_heads, want_bwd, want_rowmax=cfg.dist, want_index_tiles=not cfg.dist)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -82,6 +82,25 @@ __global__ void rel_pos_bias_kernel(const float* __restrict__ table, const int* 
   }
 }
 
+// Indexed form of the bias for the forward kernel (attention_sm100.cu, BIAS == 2): tab[h][k] = scale * table[k][h] with tab[h][nbins] = -inf
+// (the key mask), and the relative_position_index as uint16 tiles [query tile][128 rows][IDX_PITCH] (row pitch 105 words: conflict-free for
+// one-thread-per-row reads; columns >= N point at the -inf entry). 52 KB per query tile stay resident in shared memory for the whole
+// kernel instead of 106 KB of fp32 bias per (batch, head, query tile) streaming through a TMA ring.
+__global__ void rel_pos_index_tiles_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, int nbins, float scale,
+                                           int tab_pitch, float* __restrict__ tab, int m_tiles, uint16_t* __restrict__ idx16) {
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int t = t0; t < H * tab_pitch; t += stride) {
+    const int k = t % tab_pitch, h = t / tab_pitch;
+    tab[t] = k < nbins ? scale * __ldg(table + (long long)k * H + h) : (k == nbins ? -INFINITY : 0.f);
+  }
+  const int per_tile = 128 * B200VIT_ATTN_IDX_PITCH;
+  for (int t = t0; t < m_tiles * per_tile; t += stride) {
+    const int j = t % B200VIT_ATTN_IDX_PITCH, r = (t / B200VIT_ATTN_IDX_PITCH) % 128, mt = t / per_tile;
+    const int i = mt * 128 + r;
+    idx16[t] = (uint16_t)(j >= N ? nbins : (i < N ? index[i * N + j] : 0));
+  }
+}
+
 // rowmax[h, i] = max_j scale * table[index[i, j], h]: the softmax stabiliser of the single-pass Wasserstein attention forward
 __global__ void rel_pos_bias_rowmax_kernel(const float* __restrict__ table, const int* __restrict__ index, int N, int H, float scale,
                                            float* __restrict__ rowmax) {
@@ -184,6 +203,17 @@ extern "C" int b200vit_dropout_mask(uint8_t* out, int32_t BH, int32_t N, float p
   const int sms = b200vit_num_sms();
   dropout_mask_kernel<<<sms * 8, 256, 0, STREAM>>>(out, BH, N, p_drop, seed, stream_id);
   B200_CHECK_LAUNCH("dropout_mask");
+  return 0;
+}
+
+extern "C" int b200vit_rel_pos_index_tiles(const float* table, const int32_t* index, int32_t N, int32_t H, int32_t nbins, float scale, float* tab_out,
+                                           uint16_t* idx16_out, void* stream) {
+  B200_CHECK_ARG(table != nullptr && index != nullptr && tab_out != nullptr && idx16_out != nullptr && N > 0 && N <= 208 && H > 0 && nbins > 0 &&
+                     nbins < B200VIT_ATTN_TAB_MAX, "rel_pos_index_tiles: bad arguments (N <= 208, nbins < %d)", B200VIT_ATTN_TAB_MAX);
+  const int tab_pitch = (nbins + 1 + 3) & ~3;
+  const int m_tiles = (N + 127) / 128;
+  rel_pos_index_tiles_kernel<<<64, 256, 0, STREAM>>>(table, index, N, H, nbins, scale, tab_pitch, tab_out, m_tiles, idx16_out);
+  B200_CHECK_LAUNCH("rel_pos_index_tiles");
   return 0;
 }
 

@@ -33,18 +33,22 @@ constexpr int BIAS_STAGE_BYTES = TILE_M * 128;           // 128 rows x 32 fp32
 constexpr int SM_Q = 0;                                   // 128 rows x 128 B
 constexpr int SM_K = SM_Q + TILE_M * 128;                 // NMAX rows x 128 B
 constexpr int SM_V = SM_K + NMAX * 128;                   // NMAX rows x 128 B; its first 16 KB double as the bf16 O staging tile of the epilogue
-constexpr int SM_BIAS = SM_V + NMAX * 128;
-constexpr int SM_BAR = SM_BIAS + BIAS_STAGES * BIAS_STAGE_BYTES;
-constexpr int SM_XCH = SM_BAR + 1024;                     // [2 halves][128 rows] row maxima, then [2][128] row sums (fp32)
-constexpr int FWD_LANE_BYTES = SM_XCH + 2048;             // 105472
+constexpr int SM_BIAS = SM_V + NMAX * 128;               // dense bias: the TMA ring; indexed bias: the head's table row (<= 4 KB)
+constexpr int IDX_PITCH_W = B200VIT_ATTN_IDX_PITCH / 2;   // 105 words per index row: rows 9 banks apart, conflict-free one-thread-per-row reads
+constexpr int IDX_TILE_BYTES = TILE_M * B200VIT_ATTN_IDX_PITCH * 2;   // 53 760
 constexpr int FWD_LANES = 2;
 constexpr int FWD_QUADS = 4;                              // TMEM lane quadrants of a 128-row tile
 constexpr int FWD_EW_WARPS = 2 * FWD_QUADS;               // softmax warps per lane: two threads per query row
 constexpr int FWD100_THREADS = FWD_LANES * (FWD_EW_WARPS + 2) * 32;   // + MMA warp + TMA warp per lane
-constexpr int FWD100_SMEM = FWD_LANES * FWD_LANE_BYTES + 1024;
+// BIAS: 0 none, 1 dense fp32 [H, N, ld] through a TMA ring, 2 indexed (table row + resident uint16 index tile shared by both lanes)
+__host__ __device__ constexpr int fwd_sm_bar(int bias) { return SM_BIAS + (bias == 2 ? B200VIT_ATTN_TAB_MAX * 4 : BIAS_STAGES * BIAS_STAGE_BYTES); }
+__host__ __device__ constexpr int fwd_sm_xch(int bias) { return fwd_sm_bar(bias) + 1024; }   // [2 halves][128 rows] row maxima, then row sums
+__host__ __device__ constexpr int fwd_lane_bytes(int bias) { return fwd_sm_xch(bias) + 2048; }
+__host__ __device__ constexpr int fwd_smem(int bias) { return FWD_LANES * fwd_lane_bytes(bias) + (bias == 2 ? IDX_TILE_BYTES : 0) + 1024; }
 constexpr int O_COL = 128;                                // O accumulator: TMEM columns [128, 192) of the lane's 256-column half
-static_assert(SM_K % 1024 == 0 && SM_V % 1024 == 0 && SM_BIAS % 1024 == 0 && FWD_LANE_BYTES % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
-static_assert(FWD100_SMEM <= 232448, "forward kernel smem");
+static_assert(SM_K % 1024 == 0 && SM_V % 1024 == 0 && SM_BIAS % 1024 == 0 && fwd_lane_bytes(1) % 1024 == 0 && fwd_lane_bytes(2) % 1024 == 0,
+              "SWIZZLE_128B tiles need 1024-byte alignment");
+static_assert(fwd_smem(1) <= 232448 && fwd_smem(2) <= 232448, "forward kernel smem");
 
 struct Fwd100Params {
   float* lse;               // [B, H, N]
@@ -56,6 +60,9 @@ struct Fwd100Params {
   uint64_t seed;
   const uint64_t* seed_dev;  // when non-null the Philox key is read from device memory (a captured CUDA graph re-keys every replay)
   uint32_t stream_id;
+  const uint16_t* bias_idx16;   // indexed bias (BIAS == 2): [m_tiles][128][B200VIT_ATTN_IDX_PITCH]
+  const float* bias_tab;        // [H][tab_pitch]
+  int tab_pitch;
 };
 
 // Keep bits of the 32 keys [32c, 32c + 32) of query row i — bit e = key 32c + e — from the packed mask b200vit_keep_bits_launch wrote
@@ -64,18 +71,23 @@ __device__ __forceinline__ uint32_t keep_word(const Fwd100Params& p, int bh, int
   return i < p.N ? __ldg(reinterpret_cast<const uint32_t*>(p.keep_bits) + ((long long)bh * p.N + i) * 8 + c) : 0u;
 }
 
-template <int COLS, bool HAS_BIAS>
-__device__ __forceinline__ void pass1_chunk(const Fwd100Params& p, uint32_t taddr, const uint8_t* bias_row, int row, int c, float& mx) {
+template <int COLS, int BIAS>
+__device__ __forceinline__ void pass1_chunk(const Fwd100Params& p, uint32_t taddr, const uint8_t* bias_row, const uint32_t* idx_row, const float* tab,
+                                            int row, int c, float& mx) {
   uint32_t s[COLS];
   if constexpr (COLS == 32) ptx::tmem_ld_x32_sync(taddr, reinterpret_cast<uint32_t(&)[32]>(s));
   else ptx::tmem_ld_x16_sync(taddr, reinterpret_cast<uint32_t(&)[16]>(s));
 #pragma unroll
   for (int q = 0; q < COLS / 4; ++q) {
     float v[4];
-    if (HAS_BIAS) {   // bias is pre-multiplied by log2(e); padding columns hold -inf (key mask); SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+    if (BIAS == 1) {   // bias is pre-multiplied by log2(e); padding columns hold -inf (key mask); SWIZZLE_128B: 16-byte chunk ^ (row & 7)
       const float4 b4 = *reinterpret_cast<const float4*>(bias_row + ((q ^ (row & 7)) << 4));
       v[0] = fmaf(__uint_as_float(s[4 * q]), p.sl2, b4.x); v[1] = fmaf(__uint_as_float(s[4 * q + 1]), p.sl2, b4.y);
       v[2] = fmaf(__uint_as_float(s[4 * q + 2]), p.sl2, b4.z); v[3] = fmaf(__uint_as_float(s[4 * q + 3]), p.sl2, b4.w);
+    } else if (BIAS == 2) {   // gather from the head's table row through the resident index tile (entry nbins = -inf for the padding columns)
+      const uint32_t w0 = idx_row[2 * q], w1 = idx_row[2 * q + 1];
+      v[0] = fmaf(__uint_as_float(s[4 * q]), p.sl2, tab[w0 & 0xffffu]); v[1] = fmaf(__uint_as_float(s[4 * q + 1]), p.sl2, tab[w0 >> 16]);
+      v[2] = fmaf(__uint_as_float(s[4 * q + 2]), p.sl2, tab[w1 & 0xffffu]); v[3] = fmaf(__uint_as_float(s[4 * q + 3]), p.sl2, tab[w1 >> 16]);
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = (c * 32 + 4 * q + e) < p.N ? __uint_as_float(s[4 * q + e]) * p.sl2 : -INFINITY;
@@ -129,10 +141,12 @@ __device__ __forceinline__ void pass2_chunk(const Fwd100Params& p, uint64_t seed
 // walks items (2c + L) + k * 2 * gridDim of the (batch, head, query-tile) list. Q / K of the next item are requested as soon as the
 // S MMAs of the current one have read them, V once the epilogue's TMA store has drained the staging tile that aliases it, the bias
 // ring simply runs on: the load / launch latency a one-shot CTA exposes per item is paid once per lane.
-template <bool DROP, bool HAS_BIAS>
+template <bool DROP, int BIAS>
 __global__ void __launch_bounds__(FWD100_THREADS, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                       const __grid_constant__ CUtensorMap tm_bias, const __grid_constant__ CUtensorMap tm_out, const Fwd100Params p) {
+  constexpr bool HAS_BIAS = BIAS == 1;          // the dense bias ring and its barriers
+  constexpr int FWD_LANE_BYTES = fwd_lane_bytes(BIAS), SM_BAR = fwd_sm_bar(BIAS), SM_XCH = fwd_sm_xch(BIAS);
   extern __shared__ uint8_t smem_raw[];
   const int warp_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA warps 0..15: softmax warps (lane L = warp >> 3; TMEM lane quadrant = CTA warp index & 3, a hardware rule; chunk parity = bit 2);
@@ -152,14 +166,27 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int n_pad = p.n_pad;
   const int nchunks = (n_pad + 31) >> 5;
   const int tail_cols = n_pad - (nchunks - 1) * 32;   // 16 or 32
-  const int first = blockIdx.x * FWD_LANES + L, stride = gridDim.x * FWD_LANES;
-  const int n_items = first < p.items ? (p.items - first + stride - 1) / stride : 0;
+  // dense / no bias: lane L of CTA c walks items (2c + L) + k * 2 * gridDim of the (batch, head, query-tile) list. Indexed bias: a CTA keeps ONE
+  // query tile (its index tile is resident) and its lanes walk the (batch, head) pairs: mt = c % m_tiles, gridDim % m_tiles == 0 (host)
+  const int cta_mt = BIAS == 2 ? (int)blockIdx.x % p.m_tiles : 0;
+  const int first = BIAS == 2 ? ((int)blockIdx.x / p.m_tiles) * FWD_LANES + L : (int)blockIdx.x * FWD_LANES + L;
+  const int stride = BIAS == 2 ? ((int)gridDim.x / p.m_tiles) * FWD_LANES : (int)gridDim.x * FWD_LANES;
+  const int total_items = BIAS == 2 ? p.B * p.H : p.items;
+  const int n_items = first < total_items ? (total_items - first + stride - 1) / stride : 0;
   auto item_of = [&](int it, int& b, int& h, int& m0, int& bh) {
     const int item = first + it * stride;
-    const int mt = item % p.m_tiles;
-    bh = item / p.m_tiles;
+    const int mt = BIAS == 2 ? cta_mt : item % p.m_tiles;
+    bh = BIAS == 2 ? item : item / p.m_tiles;
     b = bh / p.H; h = bh - b * p.H; m0 = mt * TILE_M;
   };
+  // indexed bias: the uint16 index tile of this CTA's query tile, loaded once (both lanes read it), and the lane's table row
+  const uint32_t* idx_s = reinterpret_cast<const uint32_t*>(smem_raw + (cta_base - ptx::smem_u32(smem_raw)) + FWD_LANES * FWD_LANE_BYTES);
+  float* tab_s = reinterpret_cast<float*>(gbase + SM_BIAS);
+  if constexpr (BIAS == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.bias_idx16 + (size_t)cta_mt * (IDX_TILE_BYTES / 2));
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw + (cta_base - ptx::smem_u32(smem_raw)) + FWD_LANES * FWD_LANE_BYTES);
+    for (int i = threadIdx.x; i < IDX_TILE_BYTES / 16; i += FWD100_THREADS) dst[i] = __ldg(src + i);
+  }
 
   if (warp == FWD_EW_WARPS) {
     if (lane == 0) {
@@ -251,6 +278,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const int i = m0 + row;
       const bool active = m0 + quad * 32 < p.N;            // warps whose 32 rows are all past N only keep the barrier protocol alive
       const int gc0 = it * nchunks;                         // the bias ring counts chunks across items
+      if constexpr (BIAS == 2) {
+        if (it == 0) {                                       // the first item's table row (later ones are fetched during the previous item)
+          const int et = (warp * 32 + lane);
+          for (int k2 = et; k2 < p.tab_pitch; k2 += FWD_EW_WARPS * 32) tab_s[k2] = __ldg(p.bias_tab + (size_t)h * p.tab_pitch + k2);
+          ptx::named_bar_sync(1 + L, FWD_EW_WARPS * 32);
+        }
+      }
       ptx::mbar_wait(s_full, ph);
       ptx::tc_fence_after();
       float mx = -INFINITY;
@@ -259,8 +293,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (HAS_BIAS) ptx::mbar_wait(bias_full(s), (uint32_t)((gc / BIAS_STAGES) & 1));
         if (active) {
           const uint8_t* bias_row = gbase + SM_BIAS + s * BIAS_STAGE_BYTES + row * 128;
-          if (c + 1 < nchunks || tail_cols == 32) pass1_chunk<32, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
-          else pass1_chunk<16, HAS_BIAS>(p, trow + c * 32, bias_row, row, c, mx);
+          const uint32_t* idx_row = idx_s + row * IDX_PITCH_W + c * 16;
+          if (c + 1 < nchunks || tail_cols == 32) pass1_chunk<32, BIAS>(p, trow + c * 32, bias_row, idx_row, tab_s, row, c, mx);
+          else pass1_chunk<16, BIAS>(p, trow + c * 32, bias_row, idx_row, tab_s, row, c, mx);
         }
         if (HAS_BIAS) {
           __syncwarp();
@@ -271,6 +306,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       ptx::tmem_st_wait();
       ptx::named_bar_sync(1 + L, FWD_EW_WARPS * 32);
       mx = fmaxf(mx, xch_mx[(par ^ 1) * TILE_M + row]);
+      // indexed bias: every thread of the lane is past pass 1, the table row is dead: fetch the next item's (in flight across pass 2)
+      float tnext[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (BIAS == 2) {
+        if (it + 1 < n_items) {
+          int b2, h2, m2, bh2;
+          item_of(it + 1, b2, h2, m2, bh2);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const int e = (warp * 32 + lane) + k2 * FWD_EW_WARPS * 32;
+            if (e < p.tab_pitch) tnext[k2] = __ldg(p.bias_tab + (size_t)h2 * p.tab_pitch + e);
+          }
+        }
+      }
       float l = 0.f;
       if (active) {
         for (int c = par; c < nchunks; c += 2) {
@@ -279,6 +327,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
       }
       xch_l[par * TILE_M + row] = l;
+      if constexpr (BIAS == 2) {
+        if (it + 1 < n_items) {
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const int e = (warp * 32 + lane) + k2 * FWD_EW_WARPS * 32;
+            if (e < p.tab_pitch) tab_s[e] = tnext[k2];
+          }
+        }
+      }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
@@ -363,17 +420,21 @@ int make_tmap3(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* 
   return 0;
 }
 
-template <bool DROP, bool HAS_BIAS>
+template <bool DROP, int BIAS>
 cudaError_t launch_fwd100(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tb, const CUtensorMap& to, const Fwd100Params& p,
                           cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<DROP, HAS_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD100_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<DROP, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(BIAS));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int ctas = min(b200vit_num_sms(), (p.items + FWD_LANES - 1) / FWD_LANES);
-  attn_fwd_sm100_kernel<DROP, HAS_BIAS><<<ctas, FWD100_THREADS, FWD100_SMEM, stream>>>(tq, tkv, tb, to, p);
+  int ctas = min(b200vit_num_sms(), (p.items + FWD_LANES - 1) / FWD_LANES);
+  if (BIAS == 2) {                       // a CTA owns one query tile: whole groups of m_tiles CTAs
+    ctas = ctas / p.m_tiles * p.m_tiles;
+    if (ctas < p.m_tiles) ctas = p.m_tiles;
+  }
+  attn_fwd_sm100_kernel<DROP, BIAS><<<ctas, FWD100_THREADS, fwd_smem(BIAS), stream>>>(tq, tkv, tb, to, p);
   return cudaGetLastError();
 }
 
@@ -1150,9 +1211,13 @@ extern "C" int b200vit_attn_bwd(const void* qkv, const void* out, const void* do
 
 extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_bias, int32_t B, int32_t H, int32_t N, int32_t head_dim,
                                 float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, const uint8_t* keep_in, void* out,
-                                float* lse, uint8_t* keep_bits, int32_t keep_ready, void* stream_) {
+                                float* lse, uint8_t* keep_bits, int32_t keep_ready, const uint16_t* bias_idx16, const float* bias_tab, int32_t nbins,
+                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv != nullptr && out != nullptr, "attn_fwd: null pointer");
+  const bool indexed = bias_idx16 != nullptr;
+  B200_CHECK_ARG(!indexed || (bias_tab != nullptr && nbins > 0 && nbins < B200VIT_ATTN_TAB_MAX && (reinterpret_cast<uintptr_t>(bias_idx16) & 15) == 0),
+                 "attn_fwd: the indexed bias needs bias_tab, 0 < nbins < %d and a 16-byte aligned index tile", B200VIT_ATTN_TAB_MAX);
   B200_CHECK_ARG(B > 0 && H > 0, "attn_fwd: bad B=%d H=%d", B, H);
   B200_CHECK_ARG(head_dim == HD, "attn_fwd: head_dim %d unsupported (64 only)", head_dim);
   B200_CHECK_ARG(N > 0 && N <= NMAX, "attn_fwd: N=%d unsupported (1..%d)", N, NMAX);
@@ -1166,13 +1231,14 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
   p.lse = lse; p.keep_bits = keep_bits; p.keep_in = keep_in; p.B = B; p.H = H; p.N = N; p.n_pad = n_pad; p.m_tiles = (N + TILE_M - 1) / TILE_M; p.items = B * H * p.m_tiles;
   p.sl2 = scale * LOG2E; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   p.thresh = (uint32_t)(p_drop * 65536.0f + 0.5f); p.seed = seed; p.seed_dev = seed_dev; p.stream_id = stream_id;
+  p.bias_idx16 = bias_idx16; p.bias_tab = bias_tab; p.tab_pitch = indexed ? ((nbins + 1 + 3) & ~3) : 0;
   const uint64_t row = 3ull * H * HD;
   CUtensorMap tq, tkv, tb, to;
   int rc;
   if ((rc = make_tmap3(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, TILE_M))) return rc;
   if ((rc = make_tmap3(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, row, N, B, row, row * N, HD, n_pad))) return rc;
   if ((rc = make_tmap3(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, (uint64_t)H * HD, N, B, (uint64_t)H * HD, (uint64_t)H * HD * N, HD, TILE_M))) return rc;
-  if (bias != nullptr) {
+  if (bias != nullptr && !indexed) {
     if ((rc = make_tmap3(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, bias, ld_bias, N, H, ld_bias, (uint64_t)ld_bias * N, 32, TILE_M))) return rc;
   } else {
     tb = tq;
@@ -1181,8 +1247,9 @@ extern "C" int b200vit_attn_fwd(const void* qkv, const float* bias, int64_t ld_b
   if (p_drop > 0.f && !keep_ready) {
     if ((rc = b200vit_keep_bits_launch(keep_bits, B * H, N, p_drop, seed, seed_dev, stream_id, keep_in, stream_))) return rc;
   }
-  if (p_drop > 0.f) e = bias != nullptr ? launch_fwd100<true, true>(tq, tkv, tb, to, p, stream) : launch_fwd100<true, false>(tq, tkv, tb, to, p, stream);
-  else e = bias != nullptr ? launch_fwd100<false, true>(tq, tkv, tb, to, p, stream) : launch_fwd100<false, false>(tq, tkv, tb, to, p, stream);
+  const int mode = indexed ? 2 : (bias != nullptr ? 1 : 0);
+  if (p_drop > 0.f) e = mode == 2 ? launch_fwd100<true, 2>(tq, tkv, tb, to, p, stream) : mode == 1 ? launch_fwd100<true, 1>(tq, tkv, tb, to, p, stream) : launch_fwd100<true, 0>(tq, tkv, tb, to, p, stream);
+  else e = mode == 2 ? launch_fwd100<false, 2>(tq, tkv, tb, to, p, stream) : mode == 1 ? launch_fwd100<false, 1>(tq, tkv, tb, to, p, stream) : launch_fwd100<false, 0>(tq, tkv, tb, to, p, stream);
   if (e != cudaSuccess) { b200vit_set_error("attn_fwd: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }

@@ -129,9 +129,14 @@ def linear_wgrad(dy_bf16, x_bf16, dw_f32, alpha: float = 1.0):
 # ----------------------------------------------------------------------------------------------------------------
 def attn_fwd(qkv, bias, B, H, N, scale, p_drop=0.0, seed=0, stream_id=0, keep_in=None, out=None, lse=None, keep_bits=None, seed_dev=None,
              keep_ready=False):
+    """bias: the padded dense bias of rel_pos_bias / pad_attn_bias, or None. When it carries the indexed form (.tab / .idx16, rel_pos_bias with
+    want_index_tiles) the kernel gathers from the table instead of streaming the dense tensor — same values."""
     ld_bias = bias.stride(1) if bias is not None else 0
+    idx16 = getattr(bias, "idx16", None) if bias is not None else None
+    tab = getattr(bias, "tab", None) if idx16 is not None else None
     check(_lib.lib().b200vit_attn_fwd(_p(qkv), _p(bias), ld_bias, B, H, N, 64, scale, p_drop, seed, _p(seed_dev), stream_id, _p(keep_in), _p(out),
-                                      _p(lse), _p(keep_bits), int(keep_ready), _stream()), "attn_fwd")
+                                      _p(lse), _p(keep_bits), int(keep_ready), _p(idx16), _p(tab), int(bias.nbins) if idx16 is not None else 0,
+                                      _stream()), "attn_fwd")
     _count(2 if (p_drop > 0 and not keep_ready) else 1)           # + the packed keep-mask kernel
 
 
@@ -353,8 +358,13 @@ def attn_ld(N: int) -> int:
     return (N + 15) // 16 * 16
 
 
-def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True, want_rowmax: bool = False):
-    """(bias_fwd [H,N,ld], bias_bwd_t [H,N,ld] or None) in the padded, log2(e)-scaled layout of the attention kernels."""
+ATTN_IDX_PITCH, ATTN_TAB_MAX = 210, 1024         # B200VIT_ATTN_IDX_PITCH / B200VIT_ATTN_TAB_MAX of include/b200vit.h
+INDEXED_BIAS = os.environ.get("B200VIT_INDEXED_BIAS", "1") != "0"      # A/B switch: 0 = the forward streams the dense fp32 bias
+
+
+def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True, want_rowmax: bool = False, want_index_tiles: bool = False):
+    """(bias_fwd [H,N,ld], bias_bwd_t [H,N,ld] or None) in the padded, log2(e)-scaled layout of the attention kernels.
+    want_index_tiles: also the INDEXED form of the same bias for b200vit_attn_fwd (attributes .tab / .idx16 / .nbins of bias_fwd)."""
     ld = attn_ld(N)
     fwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device)
     bwd = torch.empty(H, N, ld, dtype=torch.float32, device=table.device) if want_bwd else None
@@ -363,6 +373,13 @@ def rel_pos_bias(table, index_i32, N, H, want_bwd: bool = True, want_rowmax: boo
     _count(2 if want_rowmax else 1)
     if rowmax is not None:
         fwd.rowmax = rowmax            # stabiliser of the single-pass Wasserstein attention forward (rides along with the padded bias)
+    nbins = int(table.shape[0])
+    if want_index_tiles and INDEXED_BIAS and N <= 208 and nbins < ATTN_TAB_MAX:
+        tab = torch.empty(H, (nbins + 4) // 4 * 4, dtype=torch.float32, device=table.device)
+        idx16 = torch.empty((N + 127) // 128, 128, ATTN_IDX_PITCH, dtype=torch.int16, device=table.device)
+        check(_lib.lib().b200vit_rel_pos_index_tiles(_p(table), _p(index_i32), N, H, nbins, LOG2E, _p(tab), _p(idx16), _stream()), "rel_pos_index_tiles")
+        _count()
+        fwd.tab, fwd.idx16, fwd.nbins = tab, idx16, nbins
     return fwd, bwd
 
 
