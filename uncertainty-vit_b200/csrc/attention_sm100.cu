@@ -581,35 +581,23 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restri
   const long long rows = (long long)B * N;
   for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const int b = (int)(r / N), i = (int)(r - (long long)b * N);
-    // four passes of four heads at a time: all eight 16-byte loads of a lane are issued before the first is used
-    for (int hb = 0; hb < H; hb += 16) {
-      uint4 ov[4], dv[4];
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      const int h = h0 + (lane >> 3);
+      float acc = 0.f;
+      if (h < H) {
+        const long long off = (r * H + h) * HD + (lane & 7) * 8;
+        const uint4 ov = *reinterpret_cast<const uint4*>(out + off), dv = *reinterpret_cast<const uint4*>(dout + off);
+        const uint32_t* op = &ov.x; const uint32_t* dp = &dv.x;
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int h = hb + k4 * 4 + (lane >> 3);
-        if (h < H) {
-          const long long off = (r * H + h) * HD + (lane & 7) * 8;
-          ov[k4] = *reinterpret_cast<const uint4*>(out + off);
-          dv[k4] = *reinterpret_cast<const uint4*>(dout + off);
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(op[k]), d = unpack_bf16x2(dp[k]);
+          acc += a.x * d.x + a.y * d.y;
         }
       }
-#pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int h = hb + k4 * 4 + (lane >> 3);
-        float acc = 0.f;
-        if (h < H) {
-          const uint32_t* op = &ov[k4].x; const uint32_t* dp = &dv[k4].x;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 a = unpack_bf16x2(op[k]), d = unpack_bf16x2(dp[k]);
-            acc += a.x * d.x + a.y * d.y;
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (h < H && (lane & 7) == 0) dvec[((long long)b * H + h) * N + i] = acc;
-      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (h < H && (lane & 7) == 0) dvec[((long long)b * H + h) * N + i] = acc;
     }
   }
 }
