@@ -329,17 +329,23 @@ def run_b200(args):
     launches = (ops.LAUNCHES - launches0)
     final_loss = float(loss.item())
     z0_mean = float(eng.z0_dev.mean().item()) if eng.z0_dev is not None else None
-    # ---- e2e: pinned host batch -> H2D -> step -> loss.item(), wall clock between device syncs. Every step's inputs are copied from
+    # ---- e2e: pinned host batch -> H2D -> step -> loss read-back, wall clock between device syncs. Every step's inputs are copied from
     # pinned host memory inside the timed region; as in engine.train_one_epoch the copy of batch i+1 is enqueued on the copy stream
-    # before step i is launched (a one-batch look-ahead data loader), and the loss of every step is read back.
+    # before step i is launched (a one-batch look-ahead data loader), and the loss of every step is read back (its 4-byte copy is enqueued
+    # behind the step and awaited after the NEXT step has been enqueued, D2VEngine.read_loss_async — as train_one_epoch does).
     def e2e_loop(n):
         nxt = eng.stage_host(*host[0])
+        pending = None
         for i in range(n):
-            loss_dev = eng.launch_staged(nxt, lr=lr_at(i))                       # enqueue step i
+            loss_dev = eng.launch_staged(nxt, lr=lr_at(i))                       # enqueue step i and the read-back of its loss behind it
+            handle = eng.read_loss_async(loss_dev)
             nxt = eng.stage_host(*host[(i + 1) % 2]) if i + 1 < n else None      # stage batch i+1 (host work + H2D) while it runs
-            float(loss_dev.item())                                                # read the loss of step i back
+            if pending is not None:
+                pending.wait()                                                    # the loss of step i-1 reaches the host (every step's does)
+            pending = handle
+        pending.wait()
 
-    e2e_loop(2)
+    e2e_loop(max(4, args.warmup))        # untimed: the staging buffers of the look-ahead pipeline (three batches alive) come from the allocator's cache afterwards
     barrier()
     t0 = time.perf_counter()
     e2e_loop(args.steps)
@@ -356,13 +362,18 @@ def run_b200(args):
 
     def blockwise_loop(n):
         nxt = eng.stage_device_masks(host[0][0], gen)
+        pending = None
         for i in range(n):
             loss_dev = eng.launch_staged(nxt, lr=lr_at(i))
+            handle = eng.read_loss_async(loss_dev)
             counts.append(nxt[5])
             nxt = eng.stage_device_masks(host[(i + 1) % 2][0], gen) if i + 1 < n else None
-            float(loss_dev.item())
+            if pending is not None:
+                pending.wait()
+            pending = handle
+        pending.wait()
 
-    blockwise_loop(3)
+    blockwise_loop(max(4, args.warmup))
     barrier()
     del counts[:]
     t0 = time.perf_counter()

@@ -595,6 +595,24 @@ class D2VEngine:
             t.record_stream(cur)
         return self.step(images, mask_u8, rows, n_valid=n_valid, **kw)
 
+    def read_loss_async(self, loss_dev: torch.Tensor):
+        """Enqueues the device->host copy of a step's loss scalar behind the step and returns a handle whose .wait() yields the float. Reading
+        the loss of step i after step i + 1 has been enqueued keeps the GPU's queue non-empty across the host's per-step work (the reference's
+        `loss.item()` right after the step, engine_for_cyclical.py:164, idles the device for the length of that work)."""
+        ring = self.__dict__.setdefault("_loss_ring", [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)])
+        k = self.__dict__.get("_loss_ring_pos", 0)
+        self._loss_ring_pos = (k + 1) % len(ring)
+        host = ring[k]
+        host.copy_(loss_dev.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+
+        class _Pending:
+            def wait(_self) -> float:
+                ev.synchronize()
+                return float(host[0])
+        return _Pending()
+
     def step_staged(self, staged, **kw) -> float:
         """One step on a batch returned by stage_host(); reads the loss back (engine_for_cyclical.py:164)."""
         return float(self.launch_staged(staged, **kw).item())
@@ -852,6 +870,18 @@ def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, st
     it_batches = staged_batches()
     nxt = next(it_batches, None)
     step = 0
+    pending = None                                                         # (handle, step number) of the loss not yet read back
+
+    def settle(p):
+        nonlocal total, n
+        loss = p[0].wait()
+        if not math.isfinite(loss):
+            raise FloatingPointError(f"Loss is {loss}, stopping training")      # engine_for_cyclical.py:166-168 (one step later than the reference)
+        total += loss
+        n += 1
+        if p[1] % print_freq == 0:
+            log(f"Epoch: [{epoch}] step {p[1]} loss {loss:.4f} ema_decay {engine.cur_decay:.6f}")
+
     while nxt is not None:
         cur = nxt
         it = start_steps + step
@@ -859,13 +889,12 @@ def train_one_epoch(engine: D2VEngine, data_loader: Iterable, epoch: int = 0, st
         wd = float(wd_schedule_values[it]) if wd_schedule_values is not None else None
         engine.it = it
         loss_dev = engine.launch_staged(cur, lr=lr, weight_decay=wd)      # enqueue step `step` ...
-        nxt = next(it_batches, None)                                       # ... stage batch step+1 (host work + H2D) while it runs ...
-        loss = float(loss_dev.item())                                      # ... and read the loss back (engine_for_cyclical.py:164)
-        if not math.isfinite(loss):
-            raise FloatingPointError(f"Loss is {loss}, stopping training")
-        total += loss
-        n += 1
-        if step % print_freq == 0:
-            log(f"Epoch: [{epoch}] step {step} loss {loss:.4f} ema_decay {engine.cur_decay:.6f}")
+        handle = engine.read_loss_async(loss_dev)                          # ... and the 4-byte read-back of its loss behind it,
+        nxt = next(it_batches, None)                                       # stage batch step+1 (host work + H2D) while it runs,
+        if pending is not None:
+            settle(pending)                                                # and only now wait for the loss of the PREVIOUS step (:164)
+        pending = (handle, step)
         step += 1
+    if pending is not None:
+        settle(pending)
     return {"loss": total / max(n, 1), "cur_decay": engine.cur_decay}
