@@ -64,6 +64,7 @@ if __name__ == "__main__":
         run("proj shape, bf16 store only (EPI_BF16)", M, 768, 768)
         run("fc2 fwd residual", M, 768, 3072, epi=ops.EPI_RESIDUAL)
         run("qkv fwd bf16", M, 2304, 768)
+        run("cov qkv fwd elu+1", M, 2304, 768, epi=ops.EPI_ELU1)
         sys.exit(0)
     for skip in (0, 1):
         tag = " [no epilogue I/O]" if skip else ""

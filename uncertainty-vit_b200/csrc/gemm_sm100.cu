@@ -33,7 +33,7 @@ constexpr int ACC_STAGES = 2;
 //   I/O epilogues (bf16, residual, fp32, split-K atomics, ELU+1): 8 epilogue warps (128 columns each), 6-stage ring
 template <int MODE>
 struct Cfg {
-  static constexpr bool kWide = (MODE == B200VIT_EPI_GELU || MODE == B200VIT_EPI_DGELU);   // dGELU: 16 warps hide the aux-load latency (8: 190 us, 16: 153 us)
+  static constexpr bool kWide = (MODE == B200VIT_EPI_GELU || MODE == B200VIT_EPI_DGELU || MODE == B200VIT_EPI_ELU1);   // dGELU: 16 warps hide the aux-load latency (8: 190 us, 16: 153 us)
   static constexpr int STAGES = kWide ? 5 : 6;
   static constexpr int NUM_EPI_WARPS = kWide ? 16 : 8;
   static constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);
